@@ -64,8 +64,14 @@ def classify_calc(name, macro, params):
     if "Submat_lookup" in macro:
         if "dna_submat" in macro:
             return abi.CALC_MATCH_DNA, p
-        if "Translate_base" in macro:
+        tq = "Sequence_get_symbol(ud->query, %QP+1)" in macro
+        tt = "Sequence_get_symbol(ud->target, %TP+1)" in macro
+        if tq and tt:
+            return abi.CALC_MATCH_3_3, p
+        if tt:
             return abi.CALC_MATCH_1_3, p
+        if tq:
+            return abi.CALC_MATCH_3_1, p
         return abi.CALC_MATCH_PROTEIN, p
     for key in ("codon_gap_open", "codon_gap_extend", "gap_open", "gap_extend"):
         if "aas->" + key + ")" in macro:
