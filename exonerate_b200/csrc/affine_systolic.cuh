@@ -1,0 +1,255 @@
+// affine_systolic.cuh -- the affine-gap lattice fill (hot kernel of the path).
+//
+// Replaces the generated Viterbi_DP_Func of the affine family
+// (optimal:affine:{local,global,bestfit,overlap}:* find score / find path,
+// generator src/c4/viterbi.c:1638-1727, semantics src/c4/viterbi.c:655-837)
+// for models whose closed form is the 5-state / 9-transition template printed
+// in SURVEY.md §8a:
+//   T0 D->D (0,1) ext   T1 I->I (1,0) ext   T2 M->D (0,1) open  T3 M->I (1,0) open
+//   T4 M->M (1,1) match T5 S->M (0,0)       T6 D->M (0,0)       T7 I->M (0,0)
+//   T8 M->E (0,0)
+// "first valid transition assigns, later ones replace only if strictly greater"
+// (viterbi.c:766-775) in exactly this order is what every max below encodes.
+//
+// Mapping (B200): one CTA = one warp = one query x target lattice.  Lane l owns
+// R consecutive lattice rows in REGISTERS; lanes are skewed by one column
+// (lane l works on column step-l), so the anti-diagonal wavefront is the warp
+// itself: the bottom cell of a lane's strip reaches the next lane through ONE
+// warp shuffle per value per step, the target symbol rides the same shuffle,
+// and no cell value ever touches shared memory or HBM.  Queries longer than
+// 32*R-1 are swept in strips; the strip hand-off row {M,I}[T+1] lives in L2.
+// int32 max-plus on the DPX pipe (VIADDMNMX / VIMNMX3 / VIMNMX.RELU); the
+// substitution score is one PRMT on a byte-packed column of the matrix.
+//
+// TB=true additionally records, per cell, which transition won for M (2 bits),
+// D (1 bit) and I (1 bit): 4 bits/cell, R/2 bytes per lane per step, written as
+// one coalesced vector store in the skewed order the warp produces them.
+#pragma once
+#include "c4b_common.cuh"
+
+namespace c4b {
+
+enum { END_ANYWHERE = 0, END_RESTRICTED = 1 };
+enum { SCORE_PRMT = 0, SCORE_SMEM = 1 };
+
+// score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code))
+//              SCORE_SMEM -> int32[25*24] (row 24 = "no symbol" row)
+template <int R, bool TB, int ENDMODE, int SM>
+__global__ void __launch_bounds__(32)
+affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
+                   const AffModel mdl, const void *__restrict__ score_table) {
+    constexpr int WPL = R / 8;  // traceback words per lane per step
+    __shared__ uint2 xtab[25];
+    __shared__ int32_t subm[SM == SCORE_SMEM ? 25 * 24 : 1];
+
+    const int lane = threadIdx.x;
+    const AffPair P = pairs[blockIdx.x];
+    const int Q = P.Q, T = P.T;
+
+    if (SM == SCORE_PRMT) {
+        if (lane < 25) xtab[lane] = reinterpret_cast<const uint2 *>(score_table)[lane];
+    } else {
+        for (int k = lane; k < 25 * 24; k += 32)
+            subm[k] = reinterpret_cast<const int32_t *>(score_table)[k];
+    }
+    __syncwarp();
+
+    const int openD = mdl.openD, extD = mdl.extD, openI = mdl.openI, extI = mdl.extI;
+    // where may START be entered / END be left (src/c4/layout.c:21-88)
+    const int ss = mdl.start_scope, es = mdl.end_scope;
+    const bool start_any = (ss == C4B_SCOPE_ANYWHERE);
+    const bool start_row0 = start_any || ss == C4B_SCOPE_EDGE || ss == C4B_SCOPE_QUERY;
+    const bool start_col0 = start_any || ss == C4B_SCOPE_EDGE || ss == C4B_SCOPE_TARGET;
+    const bool end_rowQ = (es == C4B_SCOPE_EDGE || es == C4B_SCOPE_QUERY);
+    const bool end_colT = (es == C4B_SCOPE_EDGE || es == C4B_SCOPE_TARGET);
+
+    const int rows_per_sweep = 32 * R;
+    const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    const int nsteps = T + 1 + 31;
+
+    // first strict maximum of END in (target outer, query inner) order
+    // (viterbi.c:778-791) == lexicographic max of (score, -j, -i)
+    int best = INT32_MIN, best_j = 0, best_i = 0;
+
+    for (int sweep = 0; sweep < nsweeps; ++sweep) {
+        const int row0 = sweep * rows_per_sweep + lane * R;  // lattice row of r = 0
+        const bool first_row_lane = (sweep == 0 && lane == 0);
+        // per-row query operand: PRMT selector or matrix row offset
+        uint32_t sel[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + r;  // lattice row; consumes query symbol i-1
+            int c;
+            if (SM == SCORE_PRMT) {
+                c = (i >= 1 && i <= Q) ? P.q[i - 1] : kPadClass;
+                sel[r] = (uint32_t)c * 0x1111u | 0x8880u;  // byte c, sign-extended
+            } else {
+                c = (i >= 1 && i <= Q) ? P.q[i - 1] : 24;
+                sel[r] = (uint32_t)c * 24u;
+            }
+        }
+        int Mp[R], Dp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Mp[r] = NEG2;
+            Dp[r] = NEG2;
+        }
+        // END at the last lattice row: which of my registers holds row Q
+        const int rQ = (Q >= row0 && Q < row0 + R) ? (Q - row0) : -1;
+
+        const int2 *top_in = (sweep & 1) ? P.top0 : P.top1;   // written by sweep-1
+        int2 *top_out = (sweep & 1) ? P.top1 : P.top0;
+        const bool write_top = (sweep + 1 < nsweeps) && (lane == 31);
+
+        int topM = NEG2, topI = NEG2, topMprev = NEG2;  // row above my strip
+        int in_code = kTargetNone;                      // column code handed down
+        int code0 = kTargetNone;                        // lane 0: column 0 has no symbol
+        int2 top0v = make_int2(NEG2, NEG2);
+        if (lane == 0 && sweep > 0) top0v = top_in[0];
+        uint32_t *tbp = nullptr;
+        if (TB) tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * WPL;
+
+        for (int s = 0; s < nsteps; ++s) {
+            const int j = s - lane;
+            int code;
+            if (lane == 0) {
+                code = code0;
+                if (sweep > 0) {
+                    topM = top0v.x;
+                    topI = top0v.y;
+                }
+                // prefetch column s+1 for the next step
+                code0 = (s + 1 <= T) ? (int)P.t[s] : kTargetNone;
+                if (sweep > 0 && s + 1 <= T) top0v = top_in[s + 1];
+            } else {
+                code = in_code;
+            }
+            int botM = NEG2, botI = NEG2;
+            if (j >= 0 && j <= T) {
+                uint2 X = make_uint2(0, 0);
+                const int32_t *subcol = nullptr;
+                if (SM == SCORE_PRMT) X = xtab[code];
+                else subcol = subm + code;
+                // START candidate value per cell (T5); NEG2 where START is out of scope
+                const int sv_col = (start_any || (j == 0 && start_col0)) ? 0 : NEG2;
+                int upM = topM, upI = topI, diag = topMprev;
+                int cm = INT32_MIN;   // column maximum over my rows (END_ANYWHERE)
+                int capt = INT32_MIN; // M at lattice row Q (END_RESTRICTED)
+                uint32_t w[WPL > 0 ? WPL : 1];
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) w[k] = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int sc;
+                    if (SM == SCORE_PRMT) sc = (int)__byte_perm(X.x, X.y, sel[r]);
+                    else sc = subcol[sel[r]];
+                    int sv = sv_col;
+                    if (r == 0) {
+                        // lattice row 0: START scope QUERY/EDGE allows it; corner always
+                        if (first_row_lane && (start_row0 || j == 0)) sv = 0;
+                    }
+                    const int mp = Mp[r];
+                    int Iv, Dv, Mv;
+                    if (!TB) {
+                        Iv = __viaddmax_s32(upI, extI, upM + openI);
+                        Dv = __viaddmax_s32(Dp[r], extD, mp + openD);
+                        Mv = __vimax3_s32(__viaddmax_s32(diag, sc, sv), Dv, Iv);
+                    } else {
+                        // I: T1 extend first, T3 open replaces only if strictly greater
+                        const int ia = upI + extI, ib = upM + openI;
+                        const bool pI = ib > ia;
+                        Iv = max(ia, ib);
+                        // D: T0 extend first, T2 open
+                        const int da = Dp[r] + extD, db = mp + openD;
+                        const bool pD = db > da;
+                        Dv = max(da, db);
+                        // M: T4 match, T5 start, T6 from D, T7 from I
+                        int cur = diag + sc;
+                        int dir = 0;
+                        if (cur < sv) { cur = sv; dir = 1; }
+                        if (cur < Dv) { cur = Dv; dir = 2; }
+                        if (cur < Iv) { cur = Iv; dir = 3; }
+                        Mv = cur;
+                        const uint32_t nib = (uint32_t)pI | ((uint32_t)pD << 1) | ((uint32_t)dir << 2);
+                        w[r / 8] |= nib << (4 * (r % 8));
+                    }
+                    diag = mp;
+                    Mp[r] = Mv;
+                    Dp[r] = Dv;
+                    upM = Mv;
+                    upI = Iv;
+                    if (ENDMODE == END_ANYWHERE) cm = max(cm, Mv);
+                    else if (r == rQ) capt = Mv;
+                }
+                botM = upM;
+                botI = upI;
+                topMprev = topM;
+                if (TB) {
+                    if (WPL == 4) *reinterpret_cast<uint4 *>(tbp) = make_uint4(w[0], w[1], w[2], w[3]);
+                    else if (WPL == 2) *reinterpret_cast<uint2 *>(tbp) = make_uint2(w[0], w[1]);
+                    else tbp[0] = w[0];
+                }
+                if (write_top) top_out[j] = make_int2(botM, botI);
+                // ---- END bookkeeping ----
+                if (ENDMODE == END_ANYWHERE) {
+                    if (cm > best || (cm == best && j < best_j)) {
+                        int bi = 0;
+                        bool found = false;
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (!found && Mp[r] == cm) { bi = row0 + r; found = true; }
+                        best = cm;
+                        best_j = j;
+                        best_i = bi;
+                    }
+                } else {
+                    const bool corner_only = (es == C4B_SCOPE_CORNER);
+                    if (j == T && end_colT) {
+                        // whole last column is an END edge: rows in increasing order
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int i = row0 + r;
+                            if (i <= Q && (Mp[r] > best || (Mp[r] == best && j < best_j))) {
+                                best = Mp[r]; best_j = j; best_i = i;
+                            }
+                        }
+                    } else if (rQ >= 0 && (end_rowQ || (corner_only && j == T))) {
+                        if (capt > best || (capt == best && j < best_j)) {
+                            best = capt; best_j = j; best_i = Q;
+                        }
+                    }
+                }
+            }
+            if (TB) tbp += 32 * WPL;
+            // hand the strip's bottom row and the column code to the next lane
+            const int nM = __shfl_up_sync(0xffffffffu, botM, 1);
+            const int nI = __shfl_up_sync(0xffffffffu, botI, 1);
+            const int nC = __shfl_up_sync(0xffffffffu, code, 1);
+            if (lane > 0) {
+                // topMprev for lane>0 is updated inside the active block from topM
+                topM = nM;
+                topI = nI;
+                in_code = nC;
+            }
+        }
+    }
+    // lexicographic warp reduction: max score, then min j, then min i
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        const bool take = (ob > best) || (ob == best && (oj < best_j || (oj == best_j && oi < best_i)));
+        if (take) { best = ob; best_j = oj; best_i = oi; }
+    }
+    if (lane == 0) {
+        AffOut o;
+        o.best = best;
+        o.end_i = best_i;
+        o.end_j = best_j;
+        o.flags = (best == INT32_MIN) ? 1 : 0;
+        outs[P.out_index] = o;
+    }
+}
+
+}  // namespace c4b

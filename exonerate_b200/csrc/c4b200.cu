@@ -1,0 +1,855 @@
+// c4b200.cu -- the C ABI of include/c4b200.h: engine, staging, kernel dispatch.
+//
+// Host side of the drop-in boundary.  Mirrors, batched, what Optimal_find_score /
+// Optimal_find_path (src/c4/optimal.c:123-133,368-413) do for one lattice:
+// choose the fill variant, run it, trace back, hand an operation list to the
+// caller.  No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "affine_systolic.cuh"
+#include "affine_traceback.cuh"
+#include "generic_wavefront.cuh"
+
+namespace c4b {
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+}  // namespace c4b
+
+using namespace c4b;
+
+struct c4b_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct Chunk {
+    int begin, end;  // range in the ordered lattice list
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        n = count;
+        if (!count) return 0;
+        C4B_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- model analysis ---------------------------------------------------------
+// Is the closed model the affine template of SURVEY.md §8a?  (Checked, not
+// assumed: the order is read from the tables the caller passes.)
+bool analyze_affine(const c4b_model &m, AffModel *am, int *match_kind) {
+    if (m.n_states != 5 || m.n_transitions != 9 || m.n_shadow_slots != 0) return false;
+    if (m.max_query_advance != 1 || m.max_target_advance != 1) return false;
+    const int S = m.start_state, E = m.end_state;
+    const c4b_transition *t = m.transitions;
+    auto is_const = [&](int k) { return t[k].calc >= 0 && m.calcs[t[k].calc].kind == C4B_CALC_CONST &&
+                                        m.calcs[t[k].calc].protect == 0; };
+    auto adv = [&](int k, int aq, int at) { return t[k].advance_query == aq && t[k].advance_target == at; };
+    // T4 fixes the match state, T2/T3 the delete/insert states
+    if (!adv(4, 1, 1) || t[4].input != t[4].output || t[4].calc < 0) return false;
+    const int M = t[4].input;
+    const int mk = m.calcs[t[4].calc].kind;
+    if (mk != C4B_CALC_MATCH_DNA && mk != C4B_CALC_MATCH_PROTEIN) return false;
+    if (m.calcs[t[4].calc].protect != 0) return false;
+    if (!adv(2, 0, 1) || t[2].input != M || !is_const(2)) return false;
+    const int D = t[2].output;
+    if (!adv(3, 1, 0) || t[3].input != M || !is_const(3)) return false;
+    const int I = t[3].output;
+    if (M == S || M == E || D == M || I == M || D == I || D == S || D == E || I == S || I == E) return false;
+    if (!adv(0, 0, 1) || t[0].input != D || t[0].output != D || !is_const(0)) return false;
+    if (!adv(1, 1, 0) || t[1].input != I || t[1].output != I || !is_const(1)) return false;
+    if (!adv(5, 0, 0) || t[5].input != S || t[5].output != M || t[5].calc >= 0) return false;
+    if (!adv(6, 0, 0) || t[6].input != D || t[6].output != M || t[6].calc >= 0) return false;
+    if (!adv(7, 0, 0) || t[7].input != I || t[7].output != M || t[7].calc >= 0) return false;
+    if (!adv(8, 0, 0) || t[8].input != M || t[8].output != E || t[8].calc >= 0) return false;
+    if (t[4].label != C4B_LABEL_MATCH) return false;
+    am->extD = m.calcs[t[0].calc].param[0];
+    am->extI = m.calcs[t[1].calc].param[0];
+    am->openD = m.calcs[t[2].calc].param[0];
+    am->openI = m.calcs[t[3].calc].param[0];
+    // the pad-row argument of the systolic kernel needs strictly negative gaps
+    if (am->extD >= 0 || am->extI >= 0 || am->openD >= 0 || am->openI >= 0) return false;
+    am->start_scope = m.start_scope;
+    am->end_scope = m.end_scope;
+    am->tDD = 0; am->tII = 1; am->tMD = 2; am->tMI = 3; am->tMM = 4;
+    am->tSM = 5; am->tDM = 6; am->tIM = 7; am->tME = 8;
+    *match_kind = mk;
+    return true;
+}
+
+__global__ void encode_kernel(uint8_t *buf, size_t n, const uint8_t *__restrict__ lut, int *bad) {
+    // raw symbol bytes -> matrix codes, 16 bytes per thread; 0xFF marks a symbol
+    // outside the substitution matrix alphabet (src/sequence/submat.c:26-55)
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t base = v * 16;
+    if (base >= n) return;
+    if (base + 16 <= n) {
+        uint4 w = *reinterpret_cast<uint4 *>(buf + base);
+        uint32_t a[4] = {w.x, w.y, w.z, w.w};
+        bool any_bad = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t c = lut[(a[k] >> (8 * b)) & 255u];
+                any_bad |= (c == 0xFFu);
+                o |= c << (8 * b);
+            }
+            a[k] = o;
+        }
+        *reinterpret_cast<uint4 *>(buf + base) = make_uint4(a[0], a[1], a[2], a[3]);
+        if (any_bad) atomicOr(bad, 1);
+    } else {
+        for (size_t k = base; k < n; ++k) {
+            const uint8_t c = lut[buf[k]];
+            if (c == 0xFF) atomicOr(bad, 1);
+            buf[k] = c;
+        }
+    }
+}
+
+__global__ void apply_threshold_kernel(c4b_result *results, int n, int threshold) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (results[p].status == 0 && results[p].score < threshold) {
+        results[p].status = 1;  // Optimal_find_path returns NULL (optimal.c:408-411)
+        results[p].n_ops = 0;
+    }
+}
+
+// exclusive scan of n_ops in result order (single block; n is a batch size)
+__global__ void ops_scan_kernel(const c4b_result *results, int n, int64_t *new_off, int64_t *total) {
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int b = tid * per, e = min(n, b + per);
+    int64_t s = 0;
+    for (int k = b; k < e; ++k) s += results[k].n_ops;
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < 1024; ++k) {
+            const int64_t v = part[k];
+            part[k] = run;
+            run += v;
+        }
+        *total = run;
+    }
+    __syncthreads();
+    int64_t off = part[tid];
+    for (int k = b; k < e; ++k) {
+        new_off[k] = off;
+        off += results[k].n_ops;
+    }
+}
+
+__global__ void ops_compact_kernel(c4b_result *results, int n, const int64_t *new_off,
+                                   const int32_t *__restrict__ slots, int32_t *__restrict__ packed) {
+    const int p = blockIdx.x;
+    if (p >= n) return;
+    const int64_t src = results[p].ops_offset, dst = new_off[p];
+    const int cnt = results[p].n_ops * 2;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) packed[2 * dst + k] = slots[2 * src + k];
+    __syncthreads();
+    if (threadIdx.x == 0) results[p].ops_offset = dst;
+}
+
+}  // namespace
+
+#include "generic_host.inl"
+
+// =============================================================================
+struct c4b_batch {
+    c4b_engine *e = nullptr;
+    int n = 0;
+    bool want_path = false;
+    bool affine = false;
+    c4b_model model;
+    c4b_scoring scoring;
+    int64_t cells = 0;
+    const char *kernel_name = "none";
+    bool ran = false;
+
+    // ---- affine path ----
+    AffModel aff;
+    int R = 32, score_mode = SCORE_PRMT, max_sub = 0, gap_min = 0;
+    std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
+    std::vector<Chunk> band_chunks, direct_chunks;
+    DevBuf<uint8_t> d_seq;
+    DevBuf<uint8_t> d_lut;          // [0,256) query LUT, [256,512) target LUT
+    DevBuf<uint8_t> d_score_table;
+    DevBuf<int> d_bad;
+    DevBuf<AffPair> d_full, d_band, d_direct;
+    DevBuf<AffOut> d_out1, d_out2, d_outd;
+    DevBuf<int32_t> d_band_j0, d_qorg, d_torg;
+    DevBuf<TbJob> d_jobs_band, d_jobs_direct;
+    DevBuf<uint32_t> d_tb;
+    DevBuf<int2> d_top;
+    DevBuf<c4b_result> d_results;
+    DevBuf<int32_t> d_ops_slots, d_ops_packed;
+    DevBuf<int64_t> d_new_off;  // n + 1 (last = total)
+    size_t q_bytes = 0, t_bytes = 0;
+    std::vector<EventPair> fill_events;
+    int fill_events_used = 0;
+
+    // ---- generic path ----
+    GenericBatch *generic = nullptr;
+
+    ~c4b_batch() {
+        d_seq.release(); d_lut.release(); d_score_table.release(); d_bad.release();
+        d_full.release(); d_band.release(); d_direct.release();
+        d_out1.release(); d_out2.release(); d_outd.release();
+        d_band_j0.release(); d_qorg.release(); d_torg.release();
+        d_jobs_band.release(); d_jobs_direct.release();
+        d_tb.release(); d_top.release(); d_results.release();
+        d_ops_slots.release(); d_ops_packed.release(); d_new_off.release();
+        for (auto &ev : fill_events) {
+            if (ev.a) cudaEventDestroy(ev.a);
+            if (ev.b) cudaEventDestroy(ev.b);
+        }
+        if (generic) generic_batch_destroy(generic);
+    }
+};
+
+namespace {
+
+template <int R, bool TB, int ENDMODE>
+void launch_fill_sm(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count) {
+    if (b->score_mode == SCORE_PRMT)
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, 32, 0, b->e->stream>>>(
+            pairs, outs, b->aff, b->d_score_table.p);
+    else
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM><<<count, 32, 0, b->e->stream>>>(
+            pairs, outs, b->aff, b->d_score_table.p);
+}
+
+template <int R>
+void launch_fill_r(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb) {
+    const bool any = (b->aff.end_scope == C4B_SCOPE_ANYWHERE);
+    if (tb) {
+        if (any) launch_fill_sm<R, true, END_ANYWHERE>(b, pairs, outs, count);
+        else launch_fill_sm<R, true, END_RESTRICTED>(b, pairs, outs, count);
+    } else {
+        if (any) launch_fill_sm<R, false, END_ANYWHERE>(b, pairs, outs, count);
+        else launch_fill_sm<R, false, END_RESTRICTED>(b, pairs, outs, count);
+    }
+}
+
+int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb) {
+    if (!count) return 0;
+    if ((size_t)b->fill_events_used >= b->fill_events.size()) {
+        EventPair ev;
+        C4B_CUDA(cudaEventCreate(&ev.a));
+        C4B_CUDA(cudaEventCreate(&ev.b));
+        b->fill_events.push_back(ev);
+    }
+    EventPair &ev = b->fill_events[b->fill_events_used++];
+    C4B_CUDA(cudaEventRecord(ev.a, b->e->stream));
+    switch (b->R) {
+    case 8: launch_fill_r<8>(b, pairs, outs, count, tb); break;
+    case 16: launch_fill_r<16>(b, pairs, outs, count, tb); break;
+    default: launch_fill_r<32>(b, pairs, outs, count, tb); break;
+    }
+    C4B_CUDA(cudaGetLastError());
+    C4B_CUDA(cudaEventRecord(ev.b, b->e->stream));
+    b->e->launches++;
+    return 0;
+}
+
+int launch_traceback(c4b_batch *b, const AffPair *pairs, const AffOut *outs, const AffOut *score_outs,
+                     const int32_t *band_j0, const TbJob *jobs, int count) {
+    if (!count) return 0;
+    const int threads = 64, blocks = (count + threads - 1) / threads;
+    switch (b->R) {
+    case 8:
+        affine_traceback_kernel<8><<<blocks, threads, 0, b->e->stream>>>(
+            pairs, outs, score_outs, band_j0, jobs, count, b->aff, b->d_results.p, b->d_ops_slots.p);
+        break;
+    case 16:
+        affine_traceback_kernel<16><<<blocks, threads, 0, b->e->stream>>>(
+            pairs, outs, score_outs, band_j0, jobs, count, b->aff, b->d_results.p, b->d_ops_slots.p);
+        break;
+    default:
+        affine_traceback_kernel<32><<<blocks, threads, 0, b->e->stream>>>(
+            pairs, outs, score_outs, band_j0, jobs, count, b->aff, b->d_results.p, b->d_ops_slots.p);
+        break;
+    }
+    C4B_CUDA(cudaGetLastError());
+    b->e->launches++;
+    return 0;
+}
+
+size_t tb_words(int R, int Q, int T) {
+    const int rows_per_sweep = 32 * R;
+    const size_t nsweeps = (size_t)(Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    return nsweeps * (size_t)(T + 1 + 31) * 32 * (R / 8);
+}
+
+int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
+    c4b_engine *e = b->e;
+    const int n = b->n;
+    const c4b_scoring &sc = b->scoring;
+    const int32_t *matrix = (match_kind == C4B_CALC_MATCH_DNA) ? sc.dna_matrix : sc.protein_matrix;
+    const uint8_t *index = (match_kind == C4B_CALC_MATCH_DNA) ? sc.dna_index : sc.protein_index;
+
+    // ---- sequence placement (dedupe identical host buffers), lattice geometry
+    std::map<std::pair<const uint8_t *, int>, size_t> qmap, tmap;
+    std::vector<size_t> qoff(n), toff(n);
+    size_t qbytes = 0, tbytes = 0;
+    int maxQ = 0;
+    bool used[24] = {false};
+    for (int p = 0; p < n; ++p) {
+        const c4b_pair &pp = pairs[p];
+        if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
+            pp.query_start + pp.query_length > pp.query_len ||
+            pp.target_start + pp.target_length > pp.target_len) {
+            set_error("pair " + std::to_string(p) + ": region outside the sequences");
+            return -1;
+        }
+        if (pp.n_blocked) {
+            set_error("affine systolic path does not take SubOpt blocked cells");
+            return -2;
+        }
+        auto qk = std::make_pair(pp.query + pp.query_start, pp.query_length);
+        auto it = qmap.find(qk);
+        if (it == qmap.end()) {
+            qmap[qk] = qbytes;
+            qoff[p] = qbytes;
+            qbytes += align_up((size_t)pp.query_length, 16) + 16;
+            for (int k = 0; k < pp.query_length; ++k) {
+                const int c = index[qk.first[k]];
+                if (c >= 24) {
+                    set_error("query " + std::to_string(p) + ": symbol outside the substitution matrix");
+                    return -1;
+                }
+                used[c] = true;
+            }
+        } else {
+            qoff[p] = it->second;
+        }
+        auto tk = std::make_pair(pp.target + pp.target_start, pp.target_length);
+        auto jt = tmap.find(tk);
+        if (jt == tmap.end()) {
+            tmap[tk] = tbytes;
+            toff[p] = tbytes;
+            tbytes += align_up((size_t)pp.target_length, 16) + 16;
+        } else {
+            toff[p] = jt->second;
+        }
+        maxQ = std::max(maxQ, pp.query_length);
+        b->cells += (int64_t)pp.query_length * pp.target_length;
+    }
+    b->q_bytes = qbytes;
+    b->t_bytes = tbytes;
+    b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
+
+    // ---- scoring tables
+    int n_used = 0, cls_of[24], code_of[8];
+    bool fits8 = true;
+    int max_sub = INT32_MIN;
+    for (int a = 0; a < 24; ++a) {
+        cls_of[a] = -1;
+        for (int c = 0; c < 24; ++c) {
+            const int v = matrix[a * 24 + c];
+            max_sub = std::max(max_sub, v);
+            if (used[a] && (v < -127 || v > 127)) fits8 = false;
+        }
+        if (used[a]) {
+            if (n_used < 7) code_of[n_used] = a;
+            cls_of[a] = n_used++;
+        }
+    }
+    b->max_sub = max_sub;
+    b->gap_min = std::min(-b->aff.openD, -b->aff.extD);
+    b->score_mode = (n_used <= 7 && fits8) ? SCORE_PRMT : SCORE_SMEM;
+    b->aff.score_mode = b->score_mode;
+    std::vector<uint8_t> lut(512, 0xFF);
+    std::vector<uint8_t> table;
+    if (b->score_mode == SCORE_PRMT) {
+        table.assign(25 * 8, 0);
+        for (int tc = 0; tc < 25; ++tc) {
+            int8_t *x = reinterpret_cast<int8_t *>(&table[tc * 8]);
+            for (int k = 0; k < n_used; ++k) x[k] = (tc < 24) ? (int8_t)matrix[code_of[k] * 24 + tc] : 0;
+            x[kPadClass] = -100;
+        }
+        for (int c = 0; c < 256; ++c)
+            if (index[c] < 24 && cls_of[index[c]] >= 0) lut[c] = (uint8_t)cls_of[index[c]];
+    } else {
+        std::vector<int32_t> t32(25 * 25, 0);
+        for (int a = 0; a < 25; ++a)
+            for (int c = 0; c < 25; ++c)
+                t32[a * 25 + c] = (a < 24 && c < 24) ? matrix[a * 24 + c] : (a == 24 ? -100 : 0);
+        table.resize(t32.size() * 4);
+        memcpy(table.data(), t32.data(), table.size());
+        for (int c = 0; c < 256; ++c)
+            if (index[c] < 24) lut[c] = index[c];
+    }
+    for (int c = 0; c < 256; ++c)
+        if (index[c] < 24) lut[256 + c] = index[c];
+
+    // ---- which lattices take which route
+    const bool local = (b->aff.start_scope == C4B_SCOPE_ANYWHERE && b->aff.end_scope == C4B_SCOPE_ANYWHERE);
+    std::vector<int64_t> band_cols(n, 0);
+    for (int p = 0; p < n; ++p) {
+        const int Q = pairs[p].query_length, T = pairs[p].target_length;
+        bool two_pass = !b->want_path;
+        if (b->want_path && local) {
+            const int64_t W = std::min<int64_t>(T, affine_band_width(Q, b->max_sub, b->gap_min));
+            band_cols[p] = W;
+            two_pass = (2 * (W + 33) < 3 * ((int64_t)T + 33) / 2);  // band < 75% of the lattice
+        }
+        if (two_pass) b->score_list.push_back(p);
+        else b->direct_list.push_back(p);
+    }
+    auto by_cost = [&](int a, int c) {
+        const int64_t ca = (int64_t)pairs[a].query_length * pairs[a].target_length;
+        const int64_t cc = (int64_t)pairs[c].query_length * pairs[c].target_length;
+        return ca != cc ? ca > cc : a < c;
+    };
+    std::sort(b->score_list.begin(), b->score_list.end(), by_cost);
+    std::sort(b->direct_list.begin(), b->direct_list.end(), by_cost);
+    const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
+
+    // ---- traceback arena, chunked to a memory budget
+    size_t free_b = 0, total_b = 0;
+    C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t fixed = qbytes + tbytes;
+    const size_t tb_budget_words = (free_b > fixed + (1ull << 30) ? (free_b - fixed - (1ull << 30)) : (1ull << 28)) / 4 / 2;
+    std::vector<size_t> tb_off_s(ns, 0), tb_off_d(nd, 0);
+    size_t arena_words = 0;
+    if (b->want_path) {
+        auto chunkify = [&](const std::vector<int> &list, std::vector<size_t> &offs,
+                            std::vector<Chunk> &chunks, bool band) -> int {
+            size_t cur = 0;
+            int begin = 0;
+            for (int k = 0; k < (int)list.size(); ++k) {
+                const int p = list[k];
+                const int Tt = band ? (int)band_cols[p] : pairs[p].target_length;
+                const size_t w = align_up(tb_words(b->R, pairs[p].query_length, Tt), 4);
+                if (w > tb_budget_words) {
+                    set_error("traceback of pair " + std::to_string(p) + " exceeds the device memory budget");
+                    return -1;
+                }
+                if (cur + w > tb_budget_words) {
+                    chunks.push_back({begin, k});
+                    begin = k;
+                    cur = 0;
+                }
+                offs[k] = cur;
+                cur += w;
+                arena_words = std::max(arena_words, cur);
+            }
+            if (begin < (int)list.size()) chunks.push_back({begin, (int)list.size()});
+            return 0;
+        };
+        if (chunkify(b->score_list, tb_off_s, b->band_chunks, true)) return -1;
+        if (chunkify(b->direct_list, tb_off_d, b->direct_chunks, false)) return -1;
+    }
+
+    // ---- device allocations
+    if (b->d_seq.alloc(qbytes + tbytes + 64)) return -1;
+    if (b->d_lut.alloc(512)) return -1;
+    if (b->d_score_table.alloc(table.size())) return -1;
+    if (b->d_bad.alloc(1)) return -1;
+    if (b->d_full.alloc(ns) || b->d_out1.alloc(ns)) return -1;
+    if (b->d_direct.alloc(nd) || b->d_outd.alloc(nd)) return -1;
+    if (b->d_results.alloc(n)) return -1;
+    if (b->d_qorg.alloc(ns) || b->d_torg.alloc(ns)) return -1;
+    if (b->want_path) {
+        if (b->d_band.alloc(ns) || b->d_out2.alloc(ns) || b->d_band_j0.alloc(ns)) return -1;
+        if (b->d_jobs_band.alloc(ns) || b->d_jobs_direct.alloc(nd)) return -1;
+        if (b->d_tb.alloc(arena_words + 4)) return -1;
+        if (b->d_new_off.alloc((size_t)n + 1)) return -1;
+    }
+    // sweep hand-off rows for queries longer than one sweep
+    std::vector<size_t> top_off(n, (size_t)-1);
+    size_t top_elems = 0;
+    for (int p = 0; p < n; ++p)
+        if (pairs[p].query_length + 1 > 32 * b->R) {
+            top_off[p] = top_elems;
+            top_elems += 2 * (size_t)(pairs[p].target_length + 1);
+        }
+    if (b->d_top.alloc(top_elems)) return -1;
+
+    // ---- stage sequences: pinned bounce buffer -> HBM, then encode in place
+    uint8_t *h_seq = nullptr;
+    C4B_CUDA(cudaMallocHost(&h_seq, qbytes + tbytes + 64));
+    for (auto &kv : qmap) memcpy(h_seq + kv.second, kv.first.first, (size_t)kv.first.second);
+    for (auto &kv : tmap) memcpy(h_seq + qbytes + kv.second, kv.first.first, (size_t)kv.first.second);
+    cudaStream_t st = e->stream;
+    C4B_CUDA(cudaMemcpyAsync(b->d_seq.p, h_seq, qbytes + tbytes, cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(b->d_score_table.p, table.data(), table.size(), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), st));
+    if (qbytes) {
+        encode_kernel<<<(unsigned)((qbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(b->d_seq.p, qbytes, b->d_lut.p, b->d_bad.p);
+        e->launches++;
+    }
+    if (tbytes) {
+        encode_kernel<<<(unsigned)((tbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(b->d_seq.p + qbytes, tbytes,
+                                                                                b->d_lut.p + 256, b->d_bad.p);
+        e->launches++;
+    }
+    C4B_CUDA(cudaGetLastError());
+
+    // ---- lattice descriptors and traceback jobs
+    std::vector<AffPair> h_full(ns), h_direct(nd);
+    std::vector<int32_t> h_qorg(ns), h_torg(ns);
+    std::vector<TbJob> h_jb(ns), h_jd(nd);
+    int64_t ops_cursor = 0;
+    auto make_pair_desc = [&](int p, int slot, size_t tbo) {
+        AffPair a;
+        a.q = b->d_seq.p + qoff[p];
+        a.t = b->d_seq.p + qbytes + toff[p];
+        a.Q = pairs[p].query_length;
+        a.T = pairs[p].target_length;
+        a.tb = b->want_path ? b->d_tb.p + tbo : nullptr;
+        a.top0 = a.top1 = nullptr;
+        if (top_off[p] != (size_t)-1) {
+            a.top0 = b->d_top.p + top_off[p];
+            a.top1 = a.top0 + (pairs[p].target_length + 1);
+        }
+        a.out_index = slot;
+        return a;
+    };
+    auto make_job = [&](int p, int slot, bool band) {
+        TbJob j;
+        j.pair = slot;
+        j.result = p;
+        j.q_origin = pairs[p].query_start;
+        j.t_origin = pairs[p].target_start;
+        j.expect = band ? 1 : 0;
+        j.score_slot = band ? slot : -1;
+        const int64_t span = band ? band_cols[p] : pairs[p].target_length;
+        j.ops_cap = (int32_t)std::min<int64_t>(pairs[p].query_length + span + 4, INT32_MAX);
+        j.ops_off = ops_cursor;
+        j.reserved = 0;
+        ops_cursor += j.ops_cap;
+        return j;
+    };
+    for (int k = 0; k < ns; ++k) {
+        const int p = b->score_list[k];
+        h_full[k] = make_pair_desc(p, k, tb_off_s[k]);
+        h_qorg[k] = pairs[p].query_start;
+        h_torg[k] = pairs[p].target_start;
+        if (b->want_path) h_jb[k] = make_job(p, k, true);
+    }
+    for (int k = 0; k < nd; ++k) {
+        const int p = b->direct_list[k];
+        h_direct[k] = make_pair_desc(p, k, tb_off_d[k]);
+        if (b->want_path) h_jd[k] = make_job(p, k, false);
+    }
+    if (b->want_path) {
+        if (b->d_ops_slots.alloc(2 * (size_t)ops_cursor + 2)) return -1;
+        if (b->d_ops_packed.alloc(2 * (size_t)ops_cursor + 2)) return -1;
+    }
+    // score-only results are indexed by original pair: remap out_index for them
+    if (!b->want_path)
+        for (int k = 0; k < ns; ++k) h_full[k].out_index = k;
+    if (ns) {
+        C4B_CUDA(cudaMemcpyAsync(b->d_full.p, h_full.data(), ns * sizeof(AffPair), cudaMemcpyHostToDevice, st));
+        C4B_CUDA(cudaMemcpyAsync(b->d_qorg.p, h_qorg.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        C4B_CUDA(cudaMemcpyAsync(b->d_torg.p, h_torg.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (b->want_path)
+            C4B_CUDA(cudaMemcpyAsync(b->d_jobs_band.p, h_jb.data(), ns * sizeof(TbJob), cudaMemcpyHostToDevice, st));
+    }
+    if (nd) {
+        C4B_CUDA(cudaMemcpyAsync(b->d_direct.p, h_direct.data(), nd * sizeof(AffPair), cudaMemcpyHostToDevice, st));
+        if (b->want_path)
+            C4B_CUDA(cudaMemcpyAsync(b->d_jobs_direct.p, h_jd.data(), nd * sizeof(TbJob), cudaMemcpyHostToDevice, st));
+    }
+    C4B_CUDA(cudaStreamSynchronize(st));
+    cudaFreeHost(h_seq);
+    int bad = 0;
+    C4B_CUDA(cudaMemcpy(&bad, b->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) {
+        set_error("a sequence holds a symbol outside the substitution matrix alphabet");
+        return -1;
+    }
+    b->kernel_name = "affine_systolic";
+    return 0;
+}
+
+int affine_run(c4b_batch *b, c4b_score threshold) {
+    c4b_engine *e = b->e;
+    cudaStream_t st = e->stream;
+    const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
+    b->fill_events_used = 0;
+    // pass 1: score + END cell over the full lattices, nothing written per cell
+    if (launch_fill(b, b->d_full.p, b->d_out1.p, ns, false)) return -1;
+    if (!b->want_path) {
+        if (ns) {
+            // results are indexed by ordered slot here; the host un-permutes on fetch
+            affine_score_results_kernel<<<(ns + 127) / 128, 128, 0, st>>>(b->d_full.p, b->d_out1.p, b->d_qorg.p,
+                                                                         b->d_torg.p, ns, b->d_results.p);
+            e->launches++;
+        }
+        C4B_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (ns) {
+        affine_plan_band_kernel<<<(ns + 127) / 128, 128, 0, st>>>(b->d_full.p, b->d_out1.p, b->d_band.p,
+                                                                  b->d_band_j0.p, ns, b->max_sub, b->gap_min);
+        e->launches++;
+        C4B_CUDA(cudaGetLastError());
+    }
+    // pass 2: refill only the band with the traceback record, then walk it
+    for (const Chunk &c : b->band_chunks) {
+        const int cnt = c.end - c.begin;
+        if (launch_fill(b, b->d_band.p + c.begin, b->d_out2.p, cnt, true)) return -1;
+        if (launch_traceback(b, b->d_band.p, b->d_out2.p, b->d_out1.p, b->d_band_j0.p,
+                             b->d_jobs_band.p + c.begin, cnt)) return -1;
+    }
+    for (const Chunk &c : b->direct_chunks) {
+        const int cnt = c.end - c.begin;
+        if (launch_fill(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, true)) return -1;
+        if (launch_traceback(b, b->d_direct.p, b->d_outd.p, nullptr, nullptr,
+                             b->d_jobs_direct.p + c.begin, cnt)) return -1;
+    }
+    (void)nd;
+    apply_threshold_kernel<<<(b->n + 127) / 128, 128, 0, st>>>(b->d_results.p, b->n, threshold);
+    ops_scan_kernel<<<1, 1024, 0, st>>>(b->d_results.p, b->n, b->d_new_off.p, b->d_new_off.p + b->n);
+    ops_compact_kernel<<<b->n, 64, 0, st>>>(b->d_results.p, b->n, b->d_new_off.p, b->d_ops_slots.p,
+                                            b->d_ops_packed.p);
+    e->launches += 3;
+    C4B_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int affine_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops_capacity) {
+    cudaStream_t st = b->e->stream;
+    const int n = b->n;
+    if (!b->want_path) {
+        std::vector<c4b_result> tmp(n);
+        C4B_CUDA(cudaMemcpyAsync(tmp.data(), b->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
+        C4B_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < n; ++k) results[b->score_list[k]] = tmp[k];
+        return 0;
+    }
+    int64_t total = 0;
+    C4B_CUDA(cudaMemcpyAsync(results, b->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaMemcpyAsync(&total, b->d_new_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < n; ++k)
+        if (results[k].status >= 2) {
+            set_error("internal: traceback of pair " + std::to_string(k) + " failed with status " +
+                      std::to_string(results[k].status));
+            return -1;
+        }
+    if (total > ops_capacity) {
+        set_error("ops buffer too small: need capacity " + std::to_string(total));
+        return -3;
+    }
+    if (total)
+        C4B_CUDA(cudaMemcpy(ops, b->d_ops_packed.p, 2 * (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int c4b_abi_version(void) { return C4B_ABI_VERSION; }
+const char *c4b_last_error(void) { return c4b::g_error.c_str(); }
+
+int c4b_engine_create(int device, c4b_engine **out) {
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device: ") + cudaGetErrorString(err) +
+                  " (libc4b200 has no CPU fallback)");
+        return -1;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device ordinal out of range");
+        return -1;
+    }
+    C4B_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    C4B_CUDA(cudaGetDeviceProperties(&prop, device));
+    c4b_engine *e = new c4b_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete e;
+        return -1;
+    }
+    *out = e;
+    return 0;
+}
+
+void c4b_engine_destroy(c4b_engine *e) {
+    if (!e) return;
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int c4b_engine_set_stream(c4b_engine *e, void *cuda_stream) {
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = false;
+    return 0;
+}
+
+int64_t c4b_engine_kernel_launches(const c4b_engine *e) { return e->launches; }
+
+int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
+                     const c4b_pair *pairs, int want_path, c4b_batch **out) {
+    if (!e || !model || !scoring || n < 0 || (n && !pairs)) {
+        set_error("c4b_batch_create: bad arguments");
+        return -1;
+    }
+    C4B_CUDA(cudaSetDevice(e->device));
+    c4b_batch *b = new c4b_batch();
+    b->e = e;
+    b->n = n;
+    b->want_path = want_path != 0;
+    b->model = *model;
+    b->scoring = *scoring;
+    int match_kind = 0;
+    bool any_blocked = false;
+    for (int p = 0; p < n; ++p) any_blocked |= pairs[p].n_blocked > 0;
+    int rc;
+    if (n == 0) {
+        *out = b;  // an empty batch runs and fetches nothing
+        return 0;
+    }
+    if (!any_blocked && analyze_affine(*model, &b->aff, &match_kind)) {
+        b->affine = true;
+        rc = affine_create(b, pairs, match_kind);
+    } else {
+        rc = generic_batch_create(e->stream, &e->launches, model, scoring, n, pairs, want_path != 0,
+                                  &b->generic);
+        if (!rc) {
+            b->kernel_name = "generic_wavefront";
+            b->cells = generic_batch_cells(b->generic);
+        }
+    }
+    if (rc) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return 0;
+}
+
+int c4b_batch_run(c4b_batch *b, c4b_score threshold) {
+    C4B_CUDA(cudaSetDevice(b->e->device));
+    b->ran = true;
+    if (b->n == 0) return 0;
+    if (b->affine) return affine_run(b, threshold);
+    return generic_batch_run(b->generic, threshold);
+}
+
+int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops_capacity) {
+    if (!b->ran) {
+        set_error("c4b_batch_fetch before c4b_batch_run");
+        return -1;
+    }
+    if (b->n == 0) return 0;
+    if (b->affine) return affine_fetch(b, results, ops, ops_capacity);
+    return generic_batch_fetch(b->generic, results, ops, ops_capacity);
+}
+
+int64_t c4b_batch_cells(const c4b_batch *b) { return b->cells; }
+
+double c4b_batch_last_fill_ms(c4b_batch *b) {
+    if (!b->ran || b->n == 0) return -1.0;
+    if (!b->affine) return generic_batch_fill_ms(b->generic);
+    cudaStreamSynchronize(b->e->stream);
+    double ms = 0;
+    for (int k = 0; k < b->fill_events_used; ++k) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, b->fill_events[k].a, b->fill_events[k].b) == cudaSuccess) ms += f;
+    }
+    return ms;
+}
+
+const char *c4b_batch_kernel_name(const c4b_batch *b) { return b->kernel_name; }
+
+void c4b_batch_destroy(c4b_batch *b) { delete b; }
+
+int c4b_find_score_batch(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
+                         const c4b_pair *pairs, c4b_score *scores) {
+    c4b_batch *b = nullptr;
+    int rc = c4b_batch_create(e, model, scoring, n, pairs, 0, &b);
+    if (rc) return rc;
+    std::vector<c4b_result> res(n);
+    rc = c4b_batch_run(b, C4B_IMPOSSIBLY_LOW_SCORE);
+    if (!rc) rc = c4b_batch_fetch(b, res.data(), nullptr, 0);
+    if (!rc)
+        for (int k = 0; k < n; ++k) scores[k] = res[k].score;
+    c4b_batch_destroy(b);
+    return rc;
+}
+
+int c4b_find_path_batch(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
+                        const c4b_pair *pairs, c4b_score threshold, c4b_result *results, int32_t *ops,
+                        int64_t ops_capacity) {
+    c4b_batch *b = nullptr;
+    int rc = c4b_batch_create(e, model, scoring, n, pairs, 1, &b);
+    if (rc) return rc;
+    rc = c4b_batch_run(b, threshold);
+    if (!rc) rc = c4b_batch_fetch(b, results, ops, ops_capacity);
+    c4b_batch_destroy(b);
+    return rc;
+}
+
+int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
+                          const c4b_pair *pair, int mode, c4b_result *result, int32_t *ops,
+                          int64_t ops_capacity) {
+    // FIND_SCORE and FIND_REGION need no operation list; FIND_REGION's bounding
+    // box is the path's (Viterbi_Data_finalise, viterbi.c:633-653), so it is
+    // served by the path machinery and the ops are dropped.
+    if (mode == 0) {
+        c4b_batch *b = nullptr;
+        int rc = c4b_batch_create(e, model, scoring, 1, pair, 0, &b);
+        if (rc) return rc;
+        rc = c4b_batch_run(b, C4B_IMPOSSIBLY_LOW_SCORE);
+        if (!rc) rc = c4b_batch_fetch(b, result, nullptr, 0);
+        c4b_batch_destroy(b);
+        return rc;
+    }
+    if (mode == 1)
+        return c4b_find_path_batch(e, model, scoring, 1, pair, C4B_IMPOSSIBLY_LOW_SCORE, result, ops,
+                                   ops_capacity);
+    if (mode == 2) {
+        const int64_t cap = (int64_t)pair->query_length + pair->target_length + 8;
+        std::vector<int32_t> tmp(2 * (size_t)cap);
+        int rc = c4b_find_path_batch(e, model, scoring, 1, pair, C4B_IMPOSSIBLY_LOW_SCORE, result,
+                                     tmp.data(), cap);
+        if (!rc) result->n_ops = 0;
+        return rc;
+    }
+    set_error("c4b_viterbi_calculate: unknown mode");
+    return -1;
+}
+
+}  // extern "C"

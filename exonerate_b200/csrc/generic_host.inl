@@ -1,0 +1,339 @@
+// generic_host.inl -- host side of the table-driven path (included by c4b200.cu
+// after DevBuf / the ops packing kernels are defined).
+namespace c4b {
+
+struct GenericBatch {
+    cudaStream_t stream = nullptr;
+    int64_t *launches = nullptr;
+    int n = 0;
+    bool want_path = false;
+    bool use_region = false;
+    GenTables tables;
+    int64_t cells = 0;
+    int sm_count = 0, grid = 0, cmax = 1;
+    std::vector<c4b_pair> host_pairs;
+    std::vector<GenPair> h_full;
+    DevBuf<GenTables> d_tables;
+    DevBuf<uint8_t> d_seq;
+    DevBuf<int32_t> d_ints;  // splice arrays + blocked lists
+    DevBuf<GenPair> d_full, d_box;
+    DevBuf<GenOut> d_out_a, d_out_b;
+    DevBuf<GenJob> d_jobs;
+    DevBuf<int32_t> d_ring;
+    size_t ring_stride = 0;
+    DevBuf<int> d_cursor;
+    DevBuf<uint8_t> d_tb;
+    DevBuf<c4b_result> d_results;
+    DevBuf<int32_t> d_ops_slots, d_ops_packed;
+    DevBuf<int64_t> d_new_off;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    double fill_ms = -1;
+    ~GenericBatch() {
+        d_tables.release(); d_seq.release(); d_ints.release(); d_full.release(); d_box.release();
+        d_out_a.release(); d_out_b.release(); d_jobs.release(); d_ring.release(); d_cursor.release();
+        d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
+        d_new_off.release();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+    }
+};
+
+static bool model_needs_splice(const c4b_model &m) {
+    for (int k = 0; k < m.n_calcs; ++k)
+        if (m.calcs[k].kind == C4B_CALC_SPLICE_PRE || m.calcs[k].kind == C4B_CALC_SPLICE_POST) return true;
+    return false;
+}
+
+static int check_model(const c4b_model &m) {
+    if (m.n_states < 2 || m.n_states > C4B_MAX_STATES || m.n_transitions < 1 ||
+        m.n_transitions > C4B_MAX_TRANSITIONS || m.n_calcs < 0 || m.n_calcs > C4B_MAX_CALCS ||
+        m.n_shadow_slots < 0 || m.n_shadow_slots > C4B_MAX_SHADOW_SLOTS) {
+        set_error("model tables out of range");
+        return -1;
+    }
+    for (int k = 0; k < m.n_transitions; ++k) {
+        const c4b_transition &t = m.transitions[k];
+        if (t.input < 0 || t.input >= m.n_states || t.output < 0 || t.output >= m.n_states ||
+            t.advance_query < 0 || t.advance_target < 0 || t.calc >= m.n_calcs ||
+            t.advance_query > m.max_query_advance || t.advance_target > m.max_target_advance) {
+            set_error("transition " + std::to_string(k) + " is malformed");
+            return -1;
+        }
+        if (t.calc >= 0) {
+            const c4b_calc &c = m.calcs[t.calc];
+            if (c.kind < 0 || c.kind >= C4B_CALC_KIND_TOTAL) {
+                // the reference would fall back to a host callback here; we must not
+                set_error("calc kind of transition " + std::to_string(k) + " has no device form");
+                return -1;
+            }
+            // a calc that reads a shadow slot must not leave a state that stamps the
+            // same slot (then stamp-on-copy == stamp-on-source, DESIGN.md "shadows")
+            if (c.kind >= C4B_CALC_SPLICE_POST && m.shadow_start[t.input][c.param[2]] != 0) {
+                set_error("shadow read from its own source state is not supported");
+                return -1;
+            }
+        }
+    }
+    return 0;
+}
+
+int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
+                         const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
+                         GenericBatch **out) {
+    if (check_model(*model)) return -1;
+    GenericBatch *g = new GenericBatch();
+    g->stream = stream;
+    g->launches = launch_counter;
+    g->n = n;
+    g->want_path = want_path;
+    g->tables.model = *model;
+    g->tables.scoring = *scoring;
+    g->host_pairs.assign(pairs, pairs + n);
+    const c4b_model &m = *model;
+    const bool splice = model_needs_splice(m);
+    // REGION-then-box is only self-consistent for ANYWHERE starts (see tests/test_oracle_golden.py)
+    g->use_region = want_path && m.start_scope == C4B_SCOPE_ANYWHERE && m.end_scope == C4B_SCOPE_ANYWHERE;
+    g->cmax = 1 + m.n_shadow_slots + (g->use_region ? 2 : 0);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete g; set_error("no device"); return -1; }
+    g->sm_count = prop.multiProcessorCount;
+
+    // ---- stage sequences (dedupe by host pointer), splice arrays, blocked lists
+    std::map<std::pair<const uint8_t *, int>, size_t> smap;
+    std::map<const int32_t *, size_t> imap;
+    size_t sbytes = 0, ints = 0;
+    int maxQ = 0;
+    std::vector<size_t> qo(n), to(n);
+    std::vector<size_t> sp(4 * (size_t)n, 0), bq(n, 0), bt(n, 0);
+    auto place_seq = [&](const uint8_t *p, int len) {
+        auto key = std::make_pair(p, len);
+        auto it = smap.find(key);
+        if (it != smap.end()) return it->second;
+        const size_t off = sbytes;
+        smap[key] = off;
+        sbytes += align_up((size_t)len + 4, 16);  // +4: codon reads stay in-bounds
+        return off;
+    };
+    auto place_ints = [&](const int32_t *p, size_t len) {
+        auto it = imap.find(p);
+        if (it != imap.end()) return it->second;
+        const size_t off = ints;
+        imap[p] = off;
+        ints += align_up(len, 4);
+        return off;
+    };
+    std::map<const int32_t *, size_t> ilen;
+    for (int p = 0; p < n; ++p) {
+        const c4b_pair &pp = pairs[p];
+        if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
+            pp.query_start + pp.query_length > pp.query_len ||
+            pp.target_start + pp.target_length > pp.target_len) {
+            set_error("pair " + std::to_string(p) + ": region outside the sequences");
+            delete g;
+            return -1;
+        }
+        qo[p] = place_seq(pp.query, pp.query_len);
+        to[p] = place_seq(pp.target, pp.target_len);
+        if (splice)
+            for (int k = 0; k < 4; ++k) {
+                if (!pp.splice[k]) {
+                    set_error("model has splice calcs but pair " + std::to_string(p) + " has no splice arrays");
+                    delete g;
+                    return -1;
+                }
+                sp[4 * p + k] = place_ints(pp.splice[k], (size_t)pp.target_len);
+                ilen[pp.splice[k]] = (size_t)pp.target_len;
+            }
+        if (pp.n_blocked) {
+            bq[p] = place_ints(pp.blocked_query_pos, (size_t)pp.n_blocked);
+            bt[p] = place_ints(pp.blocked_target_pos, (size_t)pp.n_blocked);
+            ilen[pp.blocked_query_pos] = ilen[pp.blocked_target_pos] = (size_t)pp.n_blocked;
+        }
+        maxQ = std::max(maxQ, pp.query_length);
+        g->cells += (int64_t)pp.query_length * pp.target_length;
+    }
+    int rc = 0;
+    rc |= g->d_tables.alloc(1);
+    rc |= g->d_seq.alloc(sbytes + 64);
+    rc |= g->d_ints.alloc(ints + 4);
+    rc |= g->d_full.alloc(n);
+    rc |= g->d_box.alloc(n);
+    rc |= g->d_out_a.alloc(n);
+    rc |= g->d_out_b.alloc(n);
+    rc |= g->d_results.alloc(n);
+    rc |= g->d_cursor.alloc(1);
+    g->grid = std::max(1, std::min(n, g->sm_count * 4));
+    const int depth = m.max_target_advance + m.max_query_advance + 1;
+    g->ring_stride = align_up((size_t)depth * (maxQ + 1) * m.n_states * g->cmax, 4);
+    rc |= g->d_ring.alloc(g->ring_stride * g->grid);
+    if (rc) { delete g; return -1; }
+    std::vector<uint8_t> hs(sbytes + 64, 0);
+    for (auto &kv : smap) memcpy(hs.data() + kv.second, kv.first.first, (size_t)kv.first.second);
+    std::vector<int32_t> hi(ints + 4, 0);
+    for (auto &kv : imap) memcpy(hi.data() + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t));
+    g->h_full.resize(n);
+    for (int p = 0; p < n; ++p) {
+        const c4b_pair &pp = pairs[p];
+        GenPair &G = g->h_full[p];
+        G.q = g->d_seq.p + qo[p];
+        G.t = g->d_seq.p + to[p];
+        for (int k = 0; k < 4; ++k) G.splice[k] = splice ? g->d_ints.p + sp[4 * p + k] : nullptr;
+        G.n_blocked = pp.n_blocked;
+        G.blk_q = pp.n_blocked ? g->d_ints.p + bq[p] : nullptr;
+        G.blk_t = pp.n_blocked ? g->d_ints.p + bt[p] : nullptr;
+        G.q_start = pp.query_start; G.t_start = pp.target_start;
+        G.Q = pp.query_length; G.T = pp.target_length;
+        G.blk_dq = 0; G.blk_dt = 0;
+        G.tb = nullptr;
+        G.out_index = p;
+    }
+    if (cudaMemcpyAsync(g->d_tables.p, &g->tables, sizeof(GenTables), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->d_ints.p, hi.data(), (ints + 4) * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->d_full.p, g->h_full.data(), n * sizeof(GenPair), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+        set_error("staging the generic batch failed");
+        delete g;
+        return -1;
+    }
+    cudaEventCreate(&g->ev_a);
+    cudaEventCreate(&g->ev_b);
+    *out = g;
+    return 0;
+}
+
+static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode) {
+    if (!count) return 0;
+    C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
+    const int grid = std::min(g->grid, count);
+    generic_fill_kernel<<<grid, kGenThreads, 0, g->stream>>>(pairs, count, outs, g->d_tables.p, mode,
+                                                            g->d_ring.p, g->ring_stride, g->d_cursor.p);
+    C4B_CUDA(cudaGetLastError());
+    (*g->launches)++;
+    return 0;
+}
+
+int generic_batch_run(GenericBatch *g, c4b_score threshold) {
+    cudaStream_t st = g->stream;
+    const int n = g->n;
+    const int S = g->tables.model.n_states;
+    if (!n) return 0;
+    C4B_CUDA(cudaEventRecord(g->ev_a, st));
+    if (!g->want_path) {
+        if (generic_launch_fill(g, g->d_full.p, n, g->d_out_a.p, GEN_SCORE)) return -1;
+        C4B_CUDA(cudaEventRecord(g->ev_b, st));
+        generic_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(g->d_full.p, g->d_out_a.p, n, g->d_results.p);
+        (*g->launches)++;
+        C4B_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // 1) where is the alignment?  (FIND_REGION shadows)
+    std::vector<GenPair> box = g->h_full;
+    std::vector<GenOut> reg(n);
+    if (g->use_region) {
+        if (generic_launch_fill(g, g->d_full.p, n, g->d_out_a.p, GEN_REGION)) return -1;
+        C4B_CUDA(cudaMemcpyAsync(reg.data(), g->d_out_a.p, n * sizeof(GenOut), cudaMemcpyDeviceToHost, st));
+        C4B_CUDA(cudaStreamSynchronize(st));
+        for (int p = 0; p < n; ++p) {
+            GenPair &B = box[p];
+            const GenOut &o = reg[p];
+            if (o.flags || o.score < threshold) { B.Q = 0; B.T = 0; continue; }
+            B.blk_dq += o.start_i; B.blk_dt += o.start_j;
+            B.q_start += o.start_i; B.t_start += o.start_j;
+            B.Q = o.end_i - o.start_i; B.T = o.end_j - o.start_j;
+        }
+    }
+    // 2) PATH fill inside the boxes, chunked to the traceback arena
+    size_t free_b = 0, total_b = 0;
+    C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = free_b > (3ull << 30) ? (free_b - (2ull << 30)) / 2 : (256ull << 20);
+    std::vector<size_t> tb_off(n);
+    std::vector<Chunk> chunks;
+    std::vector<GenJob> jobs(n);
+    size_t cur = 0, arena = 0;
+    int64_t ops_cursor = 0;
+    int begin = 0;
+    for (int p = 0; p < n; ++p) {
+        const size_t need = align_up((size_t)(box[p].Q + 1) * (box[p].T + 1) * S, 16);
+        if (need > budget) {
+            set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget");
+            return -1;
+        }
+        if (cur + need > budget) { chunks.push_back({begin, p}); begin = p; cur = 0; }
+        tb_off[p] = cur;
+        cur += need;
+        arena = std::max(arena, cur);
+        GenJob &J = jobs[p];
+        J.pair = p; J.result = p; J.expect = g->use_region ? 1 : 0; J.score_slot = p;
+        J.ops_cap = (int32_t)std::min<int64_t>((int64_t)box[p].Q + box[p].T + 4, INT32_MAX);
+        J.ops_off = ops_cursor; J.reserved = 0;
+        ops_cursor += J.ops_cap;
+    }
+    if (begin < n) chunks.push_back({begin, n});
+    g->d_tb.release(); g->d_jobs.release(); g->d_ops_slots.release(); g->d_ops_packed.release();
+    g->d_new_off.release();
+    if (g->d_tb.alloc(arena + 16) || g->d_jobs.alloc(n) || g->d_ops_slots.alloc(2 * (size_t)ops_cursor + 2) ||
+        g->d_ops_packed.alloc(2 * (size_t)ops_cursor + 2) || g->d_new_off.alloc((size_t)n + 1))
+        return -1;
+    for (int p = 0; p < n; ++p) box[p].tb = g->d_tb.p + tb_off[p];
+    C4B_CUDA(cudaMemcpyAsync(g->d_box.p, box.data(), n * sizeof(GenPair), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(g->d_jobs.p, jobs.data(), n * sizeof(GenJob), cudaMemcpyHostToDevice, st));
+    for (const Chunk &c : chunks) {
+        const int cnt = c.end - c.begin;
+        if (generic_launch_fill(g, g->d_box.p + c.begin, cnt, g->d_out_b.p, GEN_PATH)) return -1;
+        generic_traceback_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(g->d_box.p, g->d_out_b.p, g->d_out_a.p,
+                                                                g->d_jobs.p + c.begin, cnt, g->d_tables.p,
+                                                                threshold, g->d_results.p, g->d_ops_slots.p);
+        (*g->launches)++;
+        C4B_CUDA(cudaGetLastError());
+    }
+    C4B_CUDA(cudaEventRecord(g->ev_b, st));
+    apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(g->d_results.p, n, threshold);
+    ops_scan_kernel<<<1, 1024, 0, st>>>(g->d_results.p, n, g->d_new_off.p, g->d_new_off.p + n);
+    ops_compact_kernel<<<n, 64, 0, st>>>(g->d_results.p, n, g->d_new_off.p, g->d_ops_slots.p, g->d_ops_packed.p);
+    (*g->launches) += 3;
+    C4B_CUDA(cudaGetLastError());
+    // host_pairs/box vectors die here; the copies above were from pageable memory
+    C4B_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity) {
+    cudaStream_t st = g->stream;
+    const int n = g->n;
+    if (!n) return 0;
+    int64_t total = 0;
+    C4B_CUDA(cudaMemcpyAsync(results, g->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
+    if (g->want_path)
+        C4B_CUDA(cudaMemcpyAsync(&total, g->d_new_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < n; ++k)
+        if (results[k].status >= 2) {
+            set_error("internal: lattice " + std::to_string(k) + " failed with status " +
+                      std::to_string(results[k].status));
+            return -1;
+        }
+    if (!g->want_path) return 0;
+    if (total > ops_capacity) {
+        set_error("ops buffer too small: need capacity " + std::to_string(total));
+        return -3;
+    }
+    if (total)
+        C4B_CUDA(cudaMemcpy(ops, g->d_ops_packed.p, 2 * (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int64_t generic_batch_cells(const GenericBatch *g) { return g->cells; }
+
+double generic_batch_fill_ms(GenericBatch *g) {
+    float f = 0;
+    cudaStreamSynchronize(g->stream);
+    if (cudaEventElapsedTime(&f, g->ev_a, g->ev_b) != cudaSuccess) return -1;
+    return f;
+}
+
+void generic_batch_destroy(GenericBatch *g) { delete g; }
+
+}  // namespace c4b

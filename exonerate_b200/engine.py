@@ -1,0 +1,224 @@
+"""ctypes binding of libc4b200.so -- the reference-side stub a maintainer would
+write, used by the tests and bench.py.
+
+The names mirror the reference's Optimal API (src/c4/optimal.h:49-65):
+Optimal.find_score / Optimal.find_path, batched.  There is NO fallback: if the
+CUDA library is missing or no device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libc4b200.so")
+
+EXPORTS = [
+    "c4b_abi_version", "c4b_last_error", "c4b_engine_create", "c4b_engine_destroy",
+    "c4b_engine_set_stream", "c4b_engine_kernel_launches", "c4b_find_score_batch",
+    "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
+    "c4b_batch_cells", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
+    "c4b_viterbi_calculate",
+]
+
+_lib = None
+
+
+class C4BError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fails loudly when it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise C4BError("libc4b200.so is not built (run __graft_entry__.build()); "
+                       "there is no CPU fallback for the C4 fill")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.c4b_abi_version.restype = C.c_int
+    lib.c4b_last_error.restype = C.c_char_p
+    lib.c4b_engine_create.argtypes = [C.c_int, P(C.c_void_p)]
+    lib.c4b_engine_destroy.argtypes = [C.c_void_p]
+    lib.c4b_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.c4b_engine_kernel_launches.argtypes = [C.c_void_p]
+    lib.c4b_engine_kernel_launches.restype = C.c_int64
+    lib.c4b_find_score_batch.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), C.c_int32,
+                                         P(abi.Pair), C.c_void_p]
+    lib.c4b_find_path_batch.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), C.c_int32, P(abi.Pair),
+                                        C.c_int32, P(abi.Result), C.c_void_p, C.c_int64]
+    lib.c4b_batch_create.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), C.c_int32, P(abi.Pair),
+                                     C.c_int, P(C.c_void_p)]
+    lib.c4b_batch_run.argtypes = [C.c_void_p, C.c_int32]
+    lib.c4b_batch_fetch.argtypes = [C.c_void_p, P(abi.Result), C.c_void_p, C.c_int64]
+    lib.c4b_batch_cells.argtypes = [C.c_void_p]
+    lib.c4b_batch_cells.restype = C.c_int64
+    lib.c4b_batch_last_fill_ms.argtypes = [C.c_void_p]
+    lib.c4b_batch_last_fill_ms.restype = C.c_double
+    lib.c4b_batch_kernel_name.argtypes = [C.c_void_p]
+    lib.c4b_batch_kernel_name.restype = C.c_char_p
+    lib.c4b_batch_destroy.argtypes = [C.c_void_p]
+    lib.c4b_viterbi_calculate.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), P(abi.Pair), C.c_int,
+                                          P(abi.Result), C.c_void_p, C.c_int64]
+    if lib.c4b_abi_version() != abi.ABI_VERSION:
+        raise C4BError("libc4b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise C4BError("%s failed (rc=%d): %s" % (what, rc, lib.c4b_last_error().decode()))
+
+
+class PairSet:
+    """n query x target lattices as a contiguous c4b_pair array (host buffers)."""
+
+    def __init__(self, queries, targets, splice=None, blocked=None, regions=None):
+        assert len(queries) == len(targets)
+        n = len(queries)
+        self.n = n
+        self._keep = []
+        self.array = (abi.Pair * max(n, 1))()
+        cache = {}
+
+        def buf(s):
+            key = id(s)
+            if key not in cache:
+                if isinstance(s, np.ndarray):  # used in place (must be contiguous uint8)
+                    assert s.dtype == np.uint8 and s.flags["C_CONTIGUOUS"]
+                    cache[key] = s
+                else:
+                    raw = s.encode() if isinstance(s, str) else bytes(s)
+                    cache[key] = np.frombuffer(raw, dtype=np.uint8).copy()
+                self._keep.append(cache[key])
+            return cache[key]
+
+        for k in range(n):
+            q, t = buf(queries[k]), buf(targets[k])
+            p = self.array[k]
+            p.query, p.target = q.ctypes.data, t.ctypes.data
+            p.query_len, p.target_len = len(q), len(t)
+            reg = regions[k] if regions else (0, 0, len(q), len(t))
+            p.query_start, p.target_start, p.query_length, p.target_length = reg
+            if splice and splice[k] is not None:
+                arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in splice[k]]
+                self._keep.append(arrs)
+                for i, a in enumerate(arrs):
+                    p.splice[i] = a.ctypes.data
+            if blocked and blocked[k]:
+                pts = sorted(set((tj, qi) for qi, tj in blocked[k]))
+                bq = np.array([qi for tj, qi in pts], dtype=np.int32)
+                bt = np.array([tj for tj, qi in pts], dtype=np.int32)
+                self._keep.append((bq, bt))
+                p.blocked_query_pos, p.blocked_target_pos, p.n_blocked = bq.ctypes.data, bt.ctypes.data, len(pts)
+        self.cells = sum(int(self.array[k].query_length) * int(self.array[k].target_length) for k in range(n))
+        self.h2d_bytes = sum(a.nbytes for a in cache.values())
+
+
+def results_to_list(results, ops, n):
+    out = []
+    for k in range(n):
+        r = results[k]
+        o = int(r.ops_offset)
+        out.append({"score": r.score,
+                    "region": [r.query_start, r.target_start, r.query_end - r.query_start,
+                               r.target_end - r.target_start],
+                    "ops": [(int(ops[2 * (o + i)]), int(ops[2 * (o + i) + 1])) for i in range(r.n_ops)],
+                    "status": r.status})
+    return out
+
+
+class Batch:
+    """A staged (HBM-resident) batch: create once, run many times, fetch."""
+
+    def __init__(self, engine, model, scoring, pairs, want_path=True):
+        self.engine, self.lib = engine, engine.lib
+        self.pairs, self.want_path = pairs, want_path
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.c4b_batch_create(engine.h, C.byref(model), C.byref(scoring), pairs.n,
+                                                   pairs.array, int(want_path), C.byref(self.h)),
+               "c4b_batch_create")
+
+    def run(self, threshold=abi.IMPOSSIBLY_LOW_SCORE):
+        _check(self.lib, self.lib.c4b_batch_run(self.h, threshold), "c4b_batch_run")
+
+    def fetch(self, ops_capacity=None):
+        n = self.pairs.n
+        results = (abi.Result * max(n, 1))()
+        if ops_capacity is None:
+            ops_capacity = sum(int(self.pairs.array[k].query_length) + int(self.pairs.array[k].target_length) + 4
+                               for k in range(n)) if self.want_path else 0
+        ops = np.zeros(2 * max(ops_capacity, 1), dtype=np.int32)
+        _check(self.lib, self.lib.c4b_batch_fetch(self.h, results, ops.ctypes.data, ops_capacity),
+               "c4b_batch_fetch")
+        return results, ops
+
+    @property
+    def cells(self):
+        return self.lib.c4b_batch_cells(self.h)
+
+    @property
+    def kernel_name(self):
+        return self.lib.c4b_batch_kernel_name(self.h).decode()
+
+    def last_fill_ms(self):
+        return self.lib.c4b_batch_last_fill_ms(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.c4b_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.c4b_engine_create(device, C.byref(self.h)), "c4b_engine_create")
+
+    def kernel_launches(self):
+        return self.lib.c4b_engine_kernel_launches(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.c4b_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Optimal:
+    """Optimal_create / Optimal_find_score / Optimal_find_path over batches
+    (src/c4/optimal.h:49-65)."""
+
+    def __init__(self, engine, model, scoring):
+        self.engine, self.model, self.scoring = engine, model, scoring
+
+    def find_score(self, pairs):
+        lib = self.engine.lib
+        scores = np.zeros(max(pairs.n, 1), dtype=np.int32)
+        _check(lib, lib.c4b_find_score_batch(self.engine.h, C.byref(self.model), C.byref(self.scoring),
+                                             pairs.n, pairs.array, scores.ctypes.data), "c4b_find_score_batch")
+        return [int(x) for x in scores[:pairs.n]]
+
+    def find_path(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None):
+        lib = self.engine.lib
+        n = pairs.n
+        results = (abi.Result * max(n, 1))()
+        if ops_capacity is None:
+            ops_capacity = sum(int(pairs.array[k].query_length) + int(pairs.array[k].target_length) + 4
+                               for k in range(n))
+        ops = np.zeros(2 * max(ops_capacity, 1), dtype=np.int32)
+        _check(lib, lib.c4b_find_path_batch(self.engine.h, C.byref(self.model), C.byref(self.scoring), n,
+                                            pairs.array, threshold, results, ops.ctypes.data, ops_capacity),
+               "c4b_find_path_batch")
+        return results_to_list(results, ops, n)

@@ -1,0 +1,61 @@
+"""CPU tier: the C-ABI library builds, loads and exports every symbol that
+include/c4b200.h declares; no compute call is made (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import helpers
+from exonerate_b200 import abi, engine
+
+
+def declared_symbols():
+    text = open(os.path.join(helpers.ROOT, "include", "c4b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(c4b_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(engine.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return C.CDLL(engine.LIB_PATH)
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libc4b200.so does not export %s" % s
+    assert sorted(engine.EXPORTS) == syms
+
+
+def test_abi_version(lib):
+    lib.c4b_abi_version.restype = C.c_int
+    assert lib.c4b_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_sizes_match_header():
+    # sizes the C compiler gives the same declarations (LP64)
+    assert C.sizeof(abi.Calc) == 24
+    assert C.sizeof(abi.Transition) == 24
+    assert C.sizeof(abi.Model) == 40 + 32 * 4 + 64 * 24 + 32 * 24
+    assert C.sizeof(abi.Scoring) == 2 * 576 * 4 + 3 * 256 + 4096 + 8
+    assert C.sizeof(abi.Pair) == 16 + 24 + 32 + 16 + 8
+    assert C.sizeof(abi.Result) == 40
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the engine must refuse to start, loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib.c4b_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.c4b_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    assert lib.c4b_engine_create(0, C.byref(h)) != 0
+    assert b"no CPU fallback" in lib.c4b_last_error()
+    with pytest.raises(engine.C4BError):
+        engine.Engine(0)

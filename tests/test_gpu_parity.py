@@ -1,0 +1,263 @@
+"""GPU tier: the CUDA path (through the C ABI) against the oracle and the
+committed golden vectors.  Bit-exact: scores, alignment regions, op lists and
+the vulgar / cigar strings built from them."""
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+from exonerate_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+AFFINE = ["affine_local_dna", "affine_global_dna", "affine_bestfit_dna", "affine_overlap_dna",
+          "affine_local_protein", "affine_global_protein", "affine_bestfit_protein",
+          "affine_overlap_protein"]
+GENERIC = ["ungapped_dna", "est2genome", "protein2genome", "coding2coding"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from exonerate_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def splice_for(name, case):
+    if name not in ("est2genome", "protein2genome"):
+        return None
+    z = np.load(helpers.GOLDEN + "/splice_%s.npz" % name)
+    return [z["%s_%d" % (case["name"], ty)] for ty in range(4)]
+
+
+def strands(name):
+    q = "." if name.endswith("protein") or name == "protein2genome" else "+"
+    t = "." if name.endswith("protein") else "+"
+    return q, t
+
+
+@pytest.mark.parametrize("name", AFFINE + GENERIC)
+def test_golden_vectors(eng, name, params, scoring):
+    """Every golden case of the reference, one batch per model."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    model, _ = helpers.load_model(name, params)
+    cases = helpers.load_cases(name)
+    pairs = PairSet([c["q"] for c in cases], [c["t"] for c in cases],
+                    splice=[splice_for(name, c) for c in cases])
+    b = Batch(eng, model, scoring, pairs, want_path=True)
+    assert b.kernel_name == ("affine_systolic" if name in AFFINE else "generic_wavefront")
+    b.close()
+    opt = Optimal(eng, model, scoring)
+    scores = opt.find_score(pairs)
+    paths = opt.find_path(pairs)
+    for c, s, r in zip(cases, scores, paths):
+        ref = c["path"]
+        assert s == c["score"], c["name"]
+        assert r["score"] == ref["score"], c["name"]
+        assert r["region"] == ref["region"], c["name"]
+        assert r["ops"] == [tuple(o) for o in ref["ops"]], c["name"]
+        assert helpers.report_line("vulgar", model, "qy", "tg", *strands(name), r) == ref["vulgar"]
+        assert helpers.report_line("cigar", model, "qy", "tg", *strands(name), r) == ref["cigar"]
+
+
+def oracle_path(model, scoring, q, t):
+    return helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t), abi.MODE_FIND_PATH,
+                                  max_ops=len(q) + len(t) + 8)
+
+
+@pytest.mark.parametrize("name", ["affine_local_dna", "affine_global_dna", "affine_bestfit_dna",
+                                  "affine_overlap_dna"])
+def test_random_dna_vs_oracle(eng, name, params, scoring):
+    """Seeded random lattices incl. ragged sizes around the strip widths
+    (R*32 rows) and multi-sweep queries."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model(name, params)
+    rng = random.Random(11)
+    shapes = [(1, 1), (1, 40), (40, 1), (7, 9), (31, 33), (32, 32), (255, 300), (256, 257), (257, 90),
+              (511, 600), (512, 512), (513, 700), (1000, 1000), (1023, 1100), (1024, 1500),
+              (1025, 1200), (2100, 2300)]
+    qs, ts = [], []
+    for k, (ql, tl) in enumerate(shapes):
+        q, t = helpers.dna_pair(9000 + k, ql, tl, rate=rng.choice([0.05, 0.15, 0.3]))
+        qs.append(q)
+        ts.append(t)
+    # unrelated noise and N-rich inputs
+    qs.append(helpers.rand_dna(rng, 400)); ts.append(helpers.rand_dna(rng, 900))
+    qs.append(helpers.rand_dna(rng, 300, "ACGTN")); ts.append(helpers.rand_dna(rng, 500, "ACGTNRY"))
+    pairs = PairSet(qs, ts)
+    opt = Optimal(eng, model, scoring)
+    scores = opt.find_score(pairs)
+    paths = opt.find_path(pairs)
+    for k in range(pairs.n):
+        want = oracle_path(model, scoring, qs[k], ts[k])
+        assert scores[k] == want["score"], (k, len(qs[k]), len(ts[k]))
+        assert paths[k]["score"] == want["score"], k
+        assert paths[k]["region"] == want["region"], (k, len(qs[k]), len(ts[k]))
+        assert paths[k]["ops"] == want["ops"], (k, len(qs[k]), len(ts[k]))
+
+
+def test_small_batches_each_strip_width(eng, params, scoring):
+    """R = 8 / 16 / 32 kernel instantiations (chosen from the longest query)."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    for maxq in (100, 400, 900):
+        qs, ts = [], []
+        for k in range(24):
+            q, t = helpers.dna_pair(maxq * 100 + k, max(1, maxq - 13 * k % maxq), 150 + 37 * k)
+            qs.append(q)
+            ts.append(t)
+        pairs = PairSet(qs, ts)
+        paths = opt.find_path(pairs)
+        for k in range(pairs.n):
+            want = oracle_path(model, scoring, qs[k], ts[k])
+            assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"]
+            assert paths[k]["ops"] == want["ops"]
+
+
+def test_banded_two_pass_route(eng, params, scoring):
+    """Long targets take score pass -> band refill -> traceback; the result must
+    equal the full-lattice traceback of the oracle."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    qs, ts = [], []
+    for k, (ql, tl) in enumerate([(60, 5000), (200, 8000), (333, 20000), (40, 3000), (1000, 12000)]):
+        q, t = helpers.dna_pair(7000 + k, ql, tl)
+        qs.append(q)
+        ts.append(t)
+    # a target with two equally good copies: END tie-break (first in scan order)
+    q = helpers.rand_dna(random.Random(5), 80)
+    qs.append(q)
+    ts.append(helpers.rand_dna(random.Random(6), 1000) + q + helpers.rand_dna(random.Random(7), 2500) + q
+              + helpers.rand_dna(random.Random(8), 700))
+    pairs = PairSet(qs, ts)
+    opt = Optimal(eng, model, scoring)
+    paths = opt.find_path(pairs)
+    for k in range(pairs.n):
+        want = oracle_path(model, scoring, qs[k], ts[k])
+        assert paths[k]["score"] == want["score"], k
+        assert paths[k]["region"] == want["region"], k
+        assert paths[k]["ops"] == want["ops"], k
+
+
+def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_protein", params)
+    qs, ts = [], []
+    for k, (ql, tl) in enumerate([(30, 60), (200, 400), (500, 500), (700, 1500)]):
+        q, t = helpers.protein_pair(600 + k, ql, tl)
+        qs.append(q)
+        ts.append(t)
+    pairs = PairSet(qs, ts)
+    opt = Optimal(eng, model, scoring)
+    paths = opt.find_path(pairs)
+    for k in range(pairs.n):
+        want = oracle_path(model, scoring, qs[k], ts[k])
+        assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"]
+        assert paths[k]["ops"] == want["ops"]
+
+
+def test_regions_sub_lattices(eng, params, scoring):
+    """A c4b_pair may address a Region of the sequences (src/c4/region.h)."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    q, t = helpers.dna_pair(42, 300, 900)
+    regions = [(0, 0, 300, 900), (10, 100, 200, 500), (150, 0, 150, 900), (0, 450, 300, 450)]
+    pairs = PairSet([q] * 4, [t] * 4, regions=regions)
+    opt = Optimal(eng, model, scoring)
+    paths = opt.find_path(pairs)
+    for k, reg in enumerate(regions):
+        want = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, region=reg), abi.MODE_FIND_PATH)
+        assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"]
+        assert paths[k]["ops"] == want["ops"]
+
+
+def blocked_points(model, alignments):
+    pts = []
+    for a in alignments:
+        qp, tp = a["region"][0], a["region"][1]
+        for tid, length in a["ops"]:
+            tr = model.transitions[tid]
+            for _ in range(length):
+                if tr.label == abi.LABEL_MATCH and (qp, tp) not in pts:
+                    pts.append((qp, tp))
+                qp += tr.advance_query
+                tp += tr.advance_target
+    return pts
+
+
+def test_subopt_blocking(eng, params, scoring):
+    """SubOpt_Index blocked cells (generic path): the reference's own series."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    n = 0
+    for case in helpers.load_cases("affine_local_dna"):
+        series = case.get("subopt_series")
+        if not series:
+            continue
+        done = []
+        for ref in series:
+            pairs = PairSet([case["q"]], [case["t"]], blocked=[blocked_points(model, done)])
+            r = opt.find_path(pairs)[0]
+            assert r["score"] == ref["score"] and r["region"] == ref["region"]
+            assert r["ops"] == [tuple(o) for o in ref["ops"]]
+            done.append(ref)
+            n += 1
+    assert n >= 6
+
+
+def test_threshold_and_errors(eng, params, scoring):
+    from exonerate_b200 import C4BError, Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    q, t = helpers.dna_pair(1, 50, 80)
+    r = opt.find_path(PairSet([q], [t]), threshold=10 ** 6)[0]
+    assert r["status"] == 1 and r["ops"] == []      # Optimal_find_path returns NULL
+    with pytest.raises(C4BError):                   # symbol outside the matrix alphabet
+        opt.find_path(PairSet(["ACGT-ACGT"], ["ACGTACGT"]))
+    with pytest.raises(C4BError):                   # ops buffer too small is an error, not truncation
+        opt.find_path(PairSet([q], [t]), ops_capacity=1)
+    assert opt.find_path(PairSet([], [])) == []     # empty batch
+
+
+@pytest.mark.parametrize("ql,tl", [(1000, 100000)])
+def test_full_size_properties(eng, params, scoring, ql, tl):
+    """BASELINE.json metric shape (1 kbp x 100 kbp): size-independent checks --
+    the path re-scores to the DP score (Alignment_is_valid), stays inside the
+    lattice, the score equals score-only mode; one lattice also against the
+    oracle's full fill."""
+    import ctypes as C
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    qs, ts = [], []
+    for k in range(6):
+        q, t = helpers.dna_pair(31000 + k, ql, tl)
+        qs.append(q)
+        ts.append(t)
+    pairs = PairSet(qs, ts)
+    opt = Optimal(eng, model, scoring)
+    scores = opt.find_score(pairs)
+    paths = opt.find_path(pairs)
+    lib = helpers.oracle()
+    for k in range(pairs.n):
+        r = paths[k]
+        assert r["score"] == scores[k] > 2000
+        qs_, ts_, qlen, tlen = r["region"]
+        assert 0 <= qs_ and qs_ + qlen <= ql and 0 <= ts_ and ts_ + tlen <= tl
+        res = abi.Result()
+        res.score, res.query_start, res.target_start = r["score"], qs_, ts_
+        res.n_ops = len(r["ops"])
+        ops = np.array([x for op in r["ops"] for x in op], dtype=np.int32)
+        pb = helpers.PairBuf(qs[k], ts[k])
+        assert lib.c4o_rescore_path(C.byref(model), C.byref(scoring), C.byref(pb.pair), C.byref(res),
+                                    ops.ctypes.data) == r["score"]
+        aq = sum(model.transitions[t_].advance_query * n for t_, n in r["ops"])
+        at = sum(model.transitions[t_].advance_target * n for t_, n in r["ops"])
+        assert (aq, at) == (qlen, tlen)
+    want = helpers.oracle_find_path(model, scoring, helpers.PairBuf(qs[0], ts[0]),
+                                    region_threshold_cells=0, max_ops=ql + tl)
+    assert paths[0]["score"] == want["score"] and paths[0]["region"] == want["region"]
+    assert paths[0]["ops"] == want["ops"]
