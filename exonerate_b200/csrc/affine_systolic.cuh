@@ -30,17 +30,25 @@
 namespace c4b {
 
 enum { END_ANYWHERE = 0, END_RESTRICTED = 1 };
+
+// prmt.b32 with the full 4-bit selector (bit 3 = replicate the sign of the
+// selected byte); __byte_perm masks the selector to 3 bits and cannot do this.
+__device__ __forceinline__ int prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel) {
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
 enum { SCORE_PRMT = 0, SCORE_SMEM = 1 };
 
 // score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code))
-//              SCORE_SMEM -> int32[25*24] (row 24 = "no symbol" row)
+//              SCORE_SMEM -> int32[25*25] (row 24 = pad rows, column 24 = "no symbol")
 template <int R, bool TB, int ENDMODE, int SM>
 __global__ void __launch_bounds__(32)
 affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                    const AffModel mdl, const void *__restrict__ score_table) {
     constexpr int WPL = R / 8;  // traceback words per lane per step
     __shared__ uint2 xtab[25];
-    __shared__ int32_t subm[SM == SCORE_SMEM ? 25 * 24 : 1];
+    __shared__ int32_t subm[SM == SCORE_SMEM ? 25 * 25 : 1];
 
     const int lane = threadIdx.x;
     const AffPair P = pairs[blockIdx.x];
@@ -49,7 +57,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     if (SM == SCORE_PRMT) {
         if (lane < 25) xtab[lane] = reinterpret_cast<const uint2 *>(score_table)[lane];
     } else {
-        for (int k = lane; k < 25 * 24; k += 32)
+        for (int k = lane; k < 25 * 25; k += 32)
             subm[k] = reinterpret_cast<const int32_t *>(score_table)[k];
     }
     __syncwarp();
@@ -85,7 +93,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 sel[r] = (uint32_t)c * 0x1111u | 0x8880u;  // byte c, sign-extended
             } else {
                 c = (i >= 1 && i <= Q) ? P.q[i - 1] : 24;
-                sel[r] = (uint32_t)c * 24u;
+                sel[r] = (uint32_t)c * 25u;
             }
         }
         int Mp[R], Dp[R];
@@ -141,7 +149,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     int sc;
-                    if (SM == SCORE_PRMT) sc = (int)__byte_perm(X.x, X.y, sel[r]);
+                    if (SM == SCORE_PRMT) sc = prmt_sx(X.x, X.y, sel[r]);
                     else sc = subcol[sel[r]];
                     int sv = sv_col;
                     if (r == 0) {

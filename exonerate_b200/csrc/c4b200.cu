@@ -499,8 +499,24 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     // ---- stage sequences: pinned bounce buffer -> HBM, then encode in place
     uint8_t *h_seq = nullptr;
     C4B_CUDA(cudaMallocHost(&h_seq, qbytes + tbytes + 64));
-    for (auto &kv : qmap) memcpy(h_seq + kv.second, kv.first.first, (size_t)kv.first.second);
-    for (auto &kv : tmap) memcpy(h_seq + qbytes + kv.second, kv.first.first, (size_t)kv.first.second);
+    // alignment gaps between sequences are encoded too: fill them with a symbol
+    // of the alphabet so only real sequence bytes can raise the "bad symbol" flag
+    uint8_t qfill = 0, tfill = 0;
+    for (int c = 255; c >= 0; --c) {
+        if (lut[c] != 0xFF) qfill = (uint8_t)c;
+        if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
+    }
+    for (auto &kv : qmap) {
+        const size_t len = (size_t)kv.first.second, slot = align_up(len, 16) + 16;
+        memcpy(h_seq + kv.second, kv.first.first, len);
+        memset(h_seq + kv.second + len, qfill, slot - len);
+    }
+    for (auto &kv : tmap) {
+        const size_t len = (size_t)kv.first.second, slot = align_up(len, 16) + 16;
+        memcpy(h_seq + qbytes + kv.second, kv.first.first, len);
+        memset(h_seq + qbytes + kv.second + len, tfill, slot - len);
+    }
+    memset(h_seq + qbytes + tbytes, tfill, 64);
     cudaStream_t st = e->stream;
     C4B_CUDA(cudaMemcpyAsync(b->d_seq.p, h_seq, qbytes + tbytes, cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, st));
