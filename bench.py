@@ -236,15 +236,17 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    score_buf = torch.zeros(n, dtype=torch.int32, device="cuda")
-    gathered = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+    gathered = [torch.zeros((n, 10), dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
 
     # ---- device-resident arm: inputs staged in HBM before the timed region ----
     batch = Batch(eng, model, scoring, pairs, want_path=True)
+    batch.run()
+    dev_results = torch.as_tensor(batch.device_results(), device="cuda")  # c4b_result[n] in HBM, zero-copy
+
     def step_resident():
         batch.run()
-        if world > 1:  # per-pair best scores gathered over NCCL (north_star)
-            dist.all_gather(gathered, score_buf)
+        if world > 1:  # per-pair result records gathered over NCCL/NVLink (north_star)
+            dist.all_gather(gathered, dev_results)
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -267,22 +269,24 @@ def ours(args):
         fill_ms.append(batch.last_fill_ms())
     stop.set()
     sampler.join(timeout=3)
-    results, ops = batch.fetch()
+    results, ops = batch.fetch(ops_capacity=n * 4096)
     n_ops_total = sum(results[k].n_ops for k in range(n))
     batch.close()
 
     # ---- end-to-end arm: host buffers in, host results out, every step ----
-    for _ in range(min(args.warmup, 1)):
-        opt.find_path(pairs)
+    out = ((abi.Result * n)(), np.empty(2 * n * 4096, dtype=np.int32))  # host result buffers, reused
+    host_scores = torch.zeros((n, 10), dtype=torch.int32, device="cuda")
+    for _ in range(min(args.warmup, 2)):
+        opt.find_path_raw(pairs, out=out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        got = opt.find_path(pairs)
+        got, _ = opt.find_path_raw(pairs, out=out)
         if world > 1:
-            dist.all_gather(gathered, score_buf)
+            dist.all_gather(gathered, host_scores)
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    assert all(got[k]["score"] == results[k].score for k in range(n))
+    assert all(got[k].score == results[k].score and got[k].n_ops == results[k].n_ops for k in range(n))
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -340,7 +344,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=10000, help="pairs per GPU per step (BASELINE: 10k)")
     ap.add_argument("--qlen", type=int, default=1000)
     ap.add_argument("--tlen", type=int, default=100000)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fill-timing", action="store_true", help="read the fill-kernel events every step")

@@ -40,6 +40,20 @@ __device__ __forceinline__ int prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel) {
 }
 enum { SCORE_PRMT = 0, SCORE_SMEM = 1 };
 
+// M + gap_open.  Written as a multiply-add by a run-time 1 so that it issues on
+// the FMA pipe (IMAD) and leaves the ALU/DPX pipe, the binding one, to the
+// max-plus instructions (profiles/: pipe_alu 65-83 %, pipe_fma 16 % before).
+__device__ __forceinline__ int add_open(int m, int one, int open) {
+#ifdef C4B_PLAIN_ADD
+    (void)one;
+    return m + open;
+#else
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(m), "r"(one), "r"(open));
+    return d;
+#endif
+}
+
 // score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code))
 //              SCORE_SMEM -> int32[25*25] (row 24 = pad rows, column 24 = "no symbol")
 template <int R, bool TB, int ENDMODE, int SM>
@@ -62,7 +76,8 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     }
     __syncwarp();
 
-    const int openD = mdl.openD, extD = mdl.extD, openI = mdl.openI, extI = mdl.extI;
+    const int open = mdl.openD, extD = mdl.extD, extI = mdl.extI;  // openD == openI (checked)
+    const int one = mdl.one;
     // where may START be entered / END be left (src/c4/layout.c:21-88)
     const int ss = mdl.start_scope, es = mdl.end_scope;
     const bool start_any = (ss == C4B_SCOPE_ANYWHERE);
@@ -140,9 +155,12 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 else subcol = subm + code;
                 // START candidate value per cell (T5); NEG2 where START is out of scope
                 const int sv_col = (start_any || (j == 0 && start_col0)) ? 0 : NEG2;
+                // "G" = M + gap_open everywhere: the open penalty is paid once per cell
+                // (it feeds both D of the next column and I of the next row) and the
+                // substitution table holds s - gap_open, so diagG + s' == M_diag + s.
                 int upM = topM, upI = topI, diag = topMprev;
                 int cm = INT32_MIN;   // column maximum over my rows (END_ANYWHERE)
-                int capt = INT32_MIN; // M at lattice row Q (END_RESTRICTED)
+                int capt = INT32_MIN; // G at lattice row Q (END_RESTRICTED)
                 uint32_t w[WPL > 0 ? WPL : 1];
 #pragma unroll
                 for (int k = 0; k < WPL; ++k) w[k] = 0;
@@ -159,18 +177,18 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                     const int mp = Mp[r];
                     int Iv, Dv, Mv;
                     if (!TB) {
-                        Iv = __viaddmax_s32(upI, extI, upM + openI);
-                        Dv = __viaddmax_s32(Dp[r], extD, mp + openD);
+                        Iv = __viaddmax_s32(upI, extI, upM);
+                        Dv = __viaddmax_s32(Dp[r], extD, mp);
                         Mv = __vimax3_s32(__viaddmax_s32(diag, sc, sv), Dv, Iv);
                     } else {
                         // I: T1 extend first, T3 open replaces only if strictly greater
-                        const int ia = upI + extI, ib = upM + openI;
-                        const bool pI = ib > ia;
-                        Iv = max(ia, ib);
+                        const int ia = upI + extI;
+                        const bool pI = upM > ia;
+                        Iv = max(ia, upM);
                         // D: T0 extend first, T2 open
-                        const int da = Dp[r] + extD, db = mp + openD;
-                        const bool pD = db > da;
-                        Dv = max(da, db);
+                        const int da = Dp[r] + extD;
+                        const bool pD = mp > da;
+                        Dv = max(da, mp);
                         // M: T4 match, T5 start, T6 from D, T7 from I
                         int cur = diag + sc;
                         int dir = 0;
@@ -181,13 +199,14 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                         const uint32_t nib = (uint32_t)pI | ((uint32_t)pD << 1) | ((uint32_t)dir << 2);
                         w[r / 8] |= nib << (4 * (r % 8));
                     }
+                    const int Gv = add_open(Mv, one, open);
                     diag = mp;
-                    Mp[r] = Mv;
+                    Mp[r] = Gv;
                     Dp[r] = Dv;
-                    upM = Mv;
+                    upM = Gv;
                     upI = Iv;
-                    if (ENDMODE == END_ANYWHERE) cm = max(cm, Mv);
-                    else if (r == rQ) capt = Mv;
+                    if (ENDMODE == END_ANYWHERE) cm = max(cm, Gv);
+                    else if (r == rQ) capt = Gv;
                 }
                 botM = upM;
                 botI = upI;
@@ -252,7 +271,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     }
     if (lane == 0) {
         AffOut o;
-        o.best = best;
+        o.best = (best == INT32_MIN) ? best : best - open;  // tracked as G = M + open
         o.end_i = best_i;
         o.end_j = best_j;
         o.flags = (best == INT32_MIN) ? 1 : 0;

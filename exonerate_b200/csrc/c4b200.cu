@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "affine_systolic.cuh"
@@ -27,6 +28,10 @@ struct c4b_engine {
     bool own_stream = true;
     int sm_count = 0;
     int64_t launches = 0;
+    // pinned bounce buffer for host->device staging, grow-only, reused by every batch
+    uint8_t *h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    cudaEvent_t stage_free = nullptr;  // last H2D that read h_stage
 };
 
 namespace {
@@ -39,18 +44,25 @@ struct Chunk {
     int begin, end;  // range in the ordered lattice list
 };
 
+// Device buffers come from the stream-ordered pool of the device (cudaMallocAsync
+// with an unbounded release threshold, set in c4b_engine_create): after the first
+// batch, allocation and free are bookkeeping, not driver calls that serialise.
+static thread_local cudaStream_t tl_pool_stream = nullptr;
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t stream = nullptr;
     int alloc(size_t count) {
         n = count;
         if (!count) return 0;
-        C4B_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        stream = tl_pool_stream;
+        C4B_CUDA(cudaMallocAsync(&p, count * sizeof(T), stream));
         return 0;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
     }
 };
@@ -92,6 +104,9 @@ bool analyze_affine(const c4b_model &m, AffModel *am, int *match_kind) {
     am->openI = m.calcs[t[3].calc].param[0];
     // the pad-row argument of the systolic kernel needs strictly negative gaps
     if (am->extD >= 0 || am->extI >= 0 || am->openD >= 0 || am->openI >= 0) return false;
+    // the kernel carries M + open (one shared open penalty, as Affine_create builds it)
+    if (am->openD != am->openI) return false;
+    am->one = 1;
     am->start_scope = m.start_scope;
     am->end_scope = m.end_scope;
     am->tDD = 0; am->tII = 1; am->tMD = 2; am->tMI = 3; am->tMM = 4;
@@ -367,6 +382,10 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     b->q_bytes = qbytes;
     b->t_bytes = tbytes;
     b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
+    if (const char *env = getenv("C4B_AFFINE_R")) {  // tuning override: rows per lane
+        const int r = atoi(env);
+        if (r == 8 || r == 16 || r == 32) b->R = r;
+    }
 
     // ---- scoring tables
     int n_used = 0, cls_of[24], code_of[8];
@@ -377,7 +396,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         for (int c = 0; c < 24; ++c) {
             const int v = matrix[a * 24 + c];
             max_sub = std::max(max_sub, v);
-            if (used[a] && (v < -127 || v > 127)) fits8 = false;
+            if (used[a] && (v - b->aff.openD < -127 || v - b->aff.openD > 127)) fits8 = false;
         }
         if (used[a]) {
             if (n_used < 7) code_of[n_used] = a;
@@ -394,8 +413,10 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         table.assign(25 * 8, 0);
         for (int tc = 0; tc < 25; ++tc) {
             int8_t *x = reinterpret_cast<int8_t *>(&table[tc * 8]);
-            for (int k = 0; k < n_used; ++k) x[k] = (tc < 24) ? (int8_t)matrix[code_of[k] * 24 + tc] : 0;
-            x[kPadClass] = -100;
+            // entries are s - gap_open (the kernel carries M + gap_open)
+            for (int k = 0; k < n_used; ++k)
+                x[k] = (tc < 24) ? (int8_t)(matrix[code_of[k] * 24 + tc] - b->aff.openD) : 0;
+            x[kPadClass] = (int8_t)(-100 - b->aff.openD);
         }
         for (int c = 0; c < 256; ++c)
             if (index[c] < 24 && cls_of[index[c]] >= 0) lut[c] = (uint8_t)cls_of[index[c]];
@@ -403,7 +424,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         std::vector<int32_t> t32(25 * 25, 0);
         for (int a = 0; a < 25; ++a)
             for (int c = 0; c < 25; ++c)
-                t32[a * 25 + c] = (a < 24 && c < 24) ? matrix[a * 24 + c] : (a == 24 ? -100 : 0);
+                t32[a * 25 + c] = ((a < 24 && c < 24) ? matrix[a * 24 + c] : (a == 24 ? -100 : 0)) - b->aff.openD;
         table.resize(t32.size() * 4);
         memcpy(table.data(), t32.data(), table.size());
         for (int c = 0; c < 256; ++c)
@@ -496,9 +517,21 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         }
     if (b->d_top.alloc(top_elems)) return -1;
 
-    // ---- stage sequences: pinned bounce buffer -> HBM, then encode in place
-    uint8_t *h_seq = nullptr;
-    C4B_CUDA(cudaMallocHost(&h_seq, qbytes + tbytes + 64));
+    // ---- stage sequences: pinned bounce buffer -> HBM, then encode in place.
+    // The bounce buffer belongs to the engine (grow-only); worker threads fill it
+    // slice by slice and each slice's H2D is issued as soon as it is complete, so
+    // the host copy and the DMA overlap.
+    cudaStream_t st = e->stream;
+    const size_t stage_bytes = qbytes + tbytes + 64;
+    if (e->stage_free) C4B_CUDA(cudaEventSynchronize(e->stage_free));  // previous batch done reading
+    if (e->h_stage_cap < stage_bytes) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr;
+        e->h_stage_cap = 0;
+        C4B_CUDA(cudaMallocHost(&e->h_stage, stage_bytes + stage_bytes / 8));
+        e->h_stage_cap = stage_bytes + stage_bytes / 8;
+    }
+    uint8_t *h_seq = e->h_stage;
     // alignment gaps between sequences are encoded too: fill them with a symbol
     // of the alphabet so only real sequence bytes can raise the "bad symbol" flag
     uint8_t qfill = 0, tfill = 0;
@@ -506,19 +539,48 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (lut[c] != 0xFF) qfill = (uint8_t)c;
         if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
     }
-    for (auto &kv : qmap) {
-        const size_t len = (size_t)kv.first.second, slot = align_up(len, 16) + 16;
-        memcpy(h_seq + kv.second, kv.first.first, len);
-        memset(h_seq + kv.second + len, qfill, slot - len);
-    }
-    for (auto &kv : tmap) {
-        const size_t len = (size_t)kv.first.second, slot = align_up(len, 16) + 16;
-        memcpy(h_seq + qbytes + kv.second, kv.first.first, len);
-        memset(h_seq + qbytes + kv.second + len, tfill, slot - len);
-    }
+    struct CopyJob { size_t dst; const uint8_t *src; size_t len, slot; uint8_t fill; };
+    std::vector<CopyJob> jobs;
+    jobs.reserve(qmap.size() + tmap.size());
+    for (auto &kv : qmap)
+        jobs.push_back({kv.second, kv.first.first, (size_t)kv.first.second,
+                        align_up((size_t)kv.first.second, 16) + 16, qfill});
+    for (auto &kv : tmap)
+        jobs.push_back({qbytes + kv.second, kv.first.first, (size_t)kv.first.second,
+                        align_up((size_t)kv.first.second, 16) + 16, tfill});
+    std::sort(jobs.begin(), jobs.end(), [](const CopyJob &x, const CopyJob &y) { return x.dst < y.dst; });
     memset(h_seq + qbytes + tbytes, tfill, 64);
-    cudaStream_t st = e->stream;
-    C4B_CUDA(cudaMemcpyAsync(b->d_seq.p, h_seq, qbytes + tbytes, cudaMemcpyHostToDevice, st));
+    {
+        const size_t slice_target = std::max<size_t>(stage_bytes / 8, 32u << 20);
+        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        size_t j0 = 0;
+        while (j0 < jobs.size()) {
+            size_t j1 = j0, bytes = 0;
+            while (j1 < jobs.size() && bytes < slice_target) bytes += jobs[j1++].slot;
+            const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
+            auto work = [&](unsigned t) {
+                for (size_t k = j0 + t; k < j1; k += nt) {
+                    const CopyJob &c = jobs[k];
+                    memcpy(h_seq + c.dst, c.src, c.len);
+                    memset(h_seq + c.dst + c.len, c.fill, c.slot - c.len);
+                }
+            };
+            if (nt <= 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th) x.join();
+            }
+            const size_t lo = jobs[j0].dst;
+            const size_t hi = (j1 < jobs.size()) ? jobs[j1].dst : qbytes + tbytes + 64;
+            C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + lo, h_seq + lo, hi - lo, cudaMemcpyHostToDevice, st));
+            j0 = j1;
+        }
+    }
+    if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
+    C4B_CUDA(cudaEventRecord(e->stage_free, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_score_table.p, table.data(), table.size(), cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), st));
@@ -600,7 +662,6 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
             C4B_CUDA(cudaMemcpyAsync(b->d_jobs_direct.p, h_jd.data(), nd * sizeof(TbJob), cudaMemcpyHostToDevice, st));
     }
     C4B_CUDA(cudaStreamSynchronize(st));
-    cudaFreeHost(h_seq);
     int bad = 0;
     C4B_CUDA(cudaMemcpy(&bad, b->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) {
@@ -712,6 +773,13 @@ int c4b_engine_create(int device, c4b_engine **out) {
     c4b_engine *e = new c4b_engine();
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    {   // keep freed device memory cached in the stream-ordered pool
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete e;
@@ -723,6 +791,9 @@ int c4b_engine_create(int device, c4b_engine **out) {
 
 void c4b_engine_destroy(c4b_engine *e) {
     if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->stage_free) cudaEventDestroy(e->stage_free);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -743,6 +814,7 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
         return -1;
     }
     C4B_CUDA(cudaSetDevice(e->device));
+    tl_pool_stream = e->stream;
     c4b_batch *b = new c4b_batch();
     b->e = e;
     b->n = n;
@@ -778,6 +850,7 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
 
 int c4b_batch_run(c4b_batch *b, c4b_score threshold) {
     C4B_CUDA(cudaSetDevice(b->e->device));
+    tl_pool_stream = b->e->stream;
     b->ran = true;
     if (b->n == 0) return 0;
     if (b->affine) return affine_run(b, threshold);
@@ -792,6 +865,12 @@ int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops
     if (b->n == 0) return 0;
     if (b->affine) return affine_fetch(b, results, ops, ops_capacity);
     return generic_batch_fetch(b->generic, results, ops, ops_capacity);
+}
+
+const void *c4b_batch_device_results(const c4b_batch *b) {
+    if (!b->ran || b->n == 0) return nullptr;
+    if (b->affine) return b->want_path ? b->d_results.p : nullptr;  // score-only is in slot order
+    return generic_batch_device_results(b->generic);
 }
 
 int64_t c4b_batch_cells(const c4b_batch *b) { return b->cells; }

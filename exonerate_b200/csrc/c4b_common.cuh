@@ -49,6 +49,7 @@ struct AffModel {
     int32_t openD, extD, openI, extI; // penalties on the delete / insert chains
     int32_t start_scope, end_scope;
     int32_t score_mode;               // 0 = PRMT classes, 1 = smem matrix rows
+    int32_t one;                      // run-time 1 (see add_open)
     // transition ids of the closed model, in template order
     int32_t tDD, tII, tMD, tMI, tMM, tSM, tDM, tIM, tME;
 };

@@ -326,6 +326,7 @@ int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int6
 }
 
 int64_t generic_batch_cells(const GenericBatch *g) { return g->cells; }
+const void *generic_batch_device_results(const GenericBatch *g) { return g->d_results.p; }
 
 double generic_batch_fill_ms(GenericBatch *g) {
     float f = 0;

@@ -351,6 +351,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
 int generic_batch_run(GenericBatch *g, c4b_score threshold);
 int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity);
 int64_t generic_batch_cells(const GenericBatch *g);
+const void *generic_batch_device_results(const GenericBatch *g);
 double generic_batch_fill_ms(GenericBatch *g);
 void generic_batch_destroy(GenericBatch *g);
 

@@ -13,13 +13,13 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libc4b200.so")
+LIB_PATH = os.environ.get("C4B_LIB", os.path.join(_HERE, "libc4b200.so"))  # override: A/B kernel builds
 
 EXPORTS = [
     "c4b_abi_version", "c4b_last_error", "c4b_engine_create", "c4b_engine_destroy",
     "c4b_engine_set_stream", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
-    "c4b_batch_cells", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
+    "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
     "c4b_viterbi_calculate",
 ]
 
@@ -55,6 +55,8 @@ def load_library():
                                      C.c_int, P(C.c_void_p)]
     lib.c4b_batch_run.argtypes = [C.c_void_p, C.c_int32]
     lib.c4b_batch_fetch.argtypes = [C.c_void_p, P(abi.Result), C.c_void_p, C.c_int64]
+    lib.c4b_batch_device_results.argtypes = [C.c_void_p]
+    lib.c4b_batch_device_results.restype = C.c_void_p
     lib.c4b_batch_cells.argtypes = [C.c_void_p]
     lib.c4b_batch_cells.restype = C.c_int64
     lib.c4b_batch_last_fill_ms.argtypes = [C.c_void_p]
@@ -169,6 +171,21 @@ class Batch:
     def last_fill_ms(self):
         return self.lib.c4b_batch_last_fill_ms(self.h)
 
+    def device_results(self):
+        """The c4b_result[n] array in HBM as an object exposing
+        __cuda_array_interface__ (int32 [n, 10]); e.g. torch.as_tensor(x, device="cuda")."""
+        ptr = self.lib.c4b_batch_device_results(self.h)
+        if not ptr:
+            raise C4BError("no device results (run the batch first; score-only batches have none)")
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.pairs.n, 10), "typestr": "<i4", "data": (ptr, False),
+                                      "version": 3, "strides": None}
+        v._owner = self
+        return v
+
     def close(self):
         if self.h:
             self.lib.c4b_batch_destroy(self.h)
@@ -210,15 +227,25 @@ class Optimal:
                                              pairs.n, pairs.array, scores.ctypes.data), "c4b_find_score_batch")
         return [int(x) for x in scores[:pairs.n]]
 
-    def find_path(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None):
+    def find_path_raw(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None, out=None):
+        """c4b_find_path_batch as is: (c4b_result array, int32 ops array).
+        `out` = (results, ops) buffers to reuse between calls."""
         lib = self.engine.lib
         n = pairs.n
-        results = (abi.Result * max(n, 1))()
-        if ops_capacity is None:
-            ops_capacity = sum(int(pairs.array[k].query_length) + int(pairs.array[k].target_length) + 4
-                               for k in range(n))
-        ops = np.zeros(2 * max(ops_capacity, 1), dtype=np.int32)
+        if out is not None:
+            results, ops = out
+            ops_capacity = len(ops) // 2
+        else:
+            results = (abi.Result * max(n, 1))()
+            if ops_capacity is None:
+                ops_capacity = sum(int(pairs.array[k].query_length) + int(pairs.array[k].target_length) + 4
+                                   for k in range(n))
+            ops = np.empty(2 * max(ops_capacity, 1), dtype=np.int32)
         _check(lib, lib.c4b_find_path_batch(self.engine.h, C.byref(self.model), C.byref(self.scoring), n,
                                             pairs.array, threshold, results, ops.ctypes.data, ops_capacity),
                "c4b_find_path_batch")
-        return results_to_list(results, ops, n)
+        return results, ops
+
+    def find_path(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None):
+        results, ops = self.find_path_raw(pairs, threshold, ops_capacity)
+        return results_to_list(results, ops, pairs.n)

@@ -223,6 +223,10 @@ int c4b_batch_run(c4b_batch *b, c4b_score threshold);
 /* Wait, then copy results (and ops when want_path) to the host. */
 int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops,
                     int64_t ops_capacity);
+/* Device pointer to the c4b_result[n] array of the last run (pair order), valid
+ * until the batch is destroyed; for device-side consumers such as an NCCL
+ * gather of the per-pair records.  NULL for score-only batches before a run. */
+const void *c4b_batch_device_results(const c4b_batch *b);
 /* Lattice cells (sum of query_length*target_length) of the batch. */
 int64_t c4b_batch_cells(const c4b_batch *b);
 /* Device time of the dominant fill kernel of the last run, ms (CUDA events on
