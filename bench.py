@@ -102,46 +102,45 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------
-# CPU arms
+# CPU arms: the reference's own implementation of the path on host cores
 # ----------------------------------------------------------------------------
-def _ref_worker(args):
-    """One host process: the unmodified reference (compiled models) on a few pairs."""
-    qs, ts = args
-    from oracle import refdrv
-    box = {}
+def _cpu_worker(kind, conn):
+    """One host process = one single-threaded reference instance.  Receives
+    lists of (query, target) strings, answers (seconds, scores)."""
+    def serve(align):
+        while True:
+            task = conn.recv()
+            if task is None:
+                return 0
+            t0 = time.perf_counter()
+            scores = [align(q, t) for q, t in task]
+            conn.send((time.perf_counter() - t0, scores))
 
-    def fn(lib):
-        m = refdrv.RefModel(lib, "affine:local", 0, 0, compiled=True)
-        t0 = time.perf_counter()
-        scores = []
-        for q, t in zip(qs, ts):
-            p = m.pair(q, t)
-            r = p.path(max_ops=1 << 15)
-            scores.append(r["score"])
-            p.close()
-        box["t"] = time.perf_counter() - t0
-        box["scores"] = scores
-        m.close()
-        return 0
+    if kind == "reference":
+        # the UNMODIFIED reference (compiled models), one long session per process
+        from oracle import refdrv
 
-    refdrv.session(fn)
-    return box["t"], box["scores"]
+        def fn(lib):
+            m = refdrv.RefModel(lib, "affine:local", 0, 0, compiled=True)
 
+            def align(q, t):
+                p = m.pair(q, t)
+                r = p.path(max_ops=1 << 15)
+                p.close()
+                return r["score"]
+            return serve(align)
+        refdrv.session(fn)
+    else:
+        # the oracle port (only where the reference binary did not travel)
+        import helpers
+        params = helpers.load_params()
+        scoring = helpers.load_scoring(params)
+        model, _ = helpers.load_model("affine_local_dna", params)
 
-def _port_worker(args):
-    qs, ts = args
-    import helpers
-    from exonerate_b200 import abi
-    params = helpers.load_params()
-    scoring = helpers.load_scoring(params)
-    model, _ = helpers.load_model("affine_local_dna", params)
-    t0 = time.perf_counter()
-    scores = []
-    for q, t in zip(qs, ts):
-        r = helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t), region_threshold_cells=0,
-                                     max_ops=len(q) + len(t) + 8)
-        scores.append(r["score"])
-    return time.perf_counter() - t0, scores
+        def align(q, t):
+            return helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t), region_threshold_cells=0,
+                                            max_ops=len(q) + len(t) + 8)["score"]
+        serve(align)
 
 
 def cpu_arm_available():
@@ -149,53 +148,72 @@ def cpu_arm_available():
     return "reference" if refdrv.available() else "port"
 
 
-def run_cpu_sample(kind, queries, targets, procs):
-    """Times the reference CPU implementation on the given pairs using `procs`
-    host processes (the reference itself is single-threaded)."""
-    import multiprocessing as mp
-    n = len(queries)
-    qs = [bytes(queries[k]).decode() for k in range(n)]
-    ts = [bytes(targets[k]).decode() for k in range(n)]
-    chunks = [(qs[i::procs], ts[i::procs]) for i in range(procs) if qs[i::procs]]
-    worker = _ref_worker if kind == "reference" else _port_worker
-    t0 = time.perf_counter()
-    if len(chunks) == 1:
-        res = [worker(chunks[0])]
-    else:
-        with mp.get_context("spawn").Pool(len(chunks)) as pool:
-            res = pool.map(worker, chunks)
-    wall = time.perf_counter() - t0
-    return wall, res
+class CpuPool:
+    """`procs` persistent reference processes (the reference has no threading)."""
+
+    def __init__(self, kind, procs):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.kind, self.workers = kind, []
+        for _ in range(procs):
+            parent, child = ctx.Pipe()
+            pr = ctx.Process(target=_cpu_worker, args=(kind, child), daemon=True)
+            pr.start()
+            self.workers.append((pr, parent))
+
+    def run(self, queries, targets):
+        """Wall time for all pairs, dealt round-robin to the processes."""
+        n, w = len(queries), len(self.workers)
+        tasks = [[] for _ in range(w)]
+        for k in range(n):
+            tasks[k % w].append((bytes(queries[k]).decode(), bytes(targets[k]).decode()))
+        t0 = time.perf_counter()
+        used = [(c, t) for (_, c), t in zip(self.workers, tasks) if t]
+        for c, t in used:
+            c.send(t)
+        res = [c.recv() for c, _ in used]
+        wall = time.perf_counter() - t0
+        scores = [None] * n
+        for wi, (_, sc) in enumerate(res):
+            for j, s in enumerate(sc):
+                scores[wi + j * w] = s
+        return wall, scores
+
+    def close(self):
+        for pr, c in self.workers:
+            try:
+                c.send(None)
+            except (BrokenPipeError, OSError):
+                pass
+        for pr, _ in self.workers:
+            pr.join(timeout=5)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return 0  # only rank 0 runs the CPU arm under torchrun
     kind = cpu_arm_available()
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
+    procs = max(1, min(os.cpu_count() or 1, 64))
     n = procs  # one pair per host process per step: a bounded sample of the workload
-    queries, targets = make_batch(12345, n, args.qlen, args.tlen)
+    queries, targets = make_batch(1000, n, args.qlen, args.tlen)  # same generator/seed as rank 0 of our arm
     cells = n * args.qlen * args.tlen
+    pool = CpuPool(kind, procs)
     for _ in range(args.warmup):
-        run_cpu_sample(kind, queries[:min(n, procs)], targets[:min(n, procs)], procs) if args.warmup_full else None
-    times = []
-    for _ in range(args.steps):
-        wall, _ = run_cpu_sample(kind, queries, targets, procs)
-        times.append(wall)
+        pool.run(queries, targets)
+    times = [pool.run(queries, targets)[0] for _ in range(args.steps)]
+    pool.close()
     t = float(np.mean(times))
     gcups = cells / t / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": "affine:local --exhaustive, %d bp x %d bp DNA pairs" % (args.qlen, args.tlen),
-                       "pairs_per_step": n, "model": None},
+                       "pairs_per_step": n},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": procs, "kind": kind,
                              "sample": "%d pairs of %d x %d per step, one per host process" % (n, args.qlen, args.tlen)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    del line["config"]["model"]
     print(json.dumps(line))
     return 0
 
@@ -322,8 +340,9 @@ def ours(args):
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_arm_available()
             k = max(1, args.cpu_pairs)
-            wall, res = run_cpu_sample(kind, queries[:k], targets[:k], 1)
-            cpu_scores = [s for _, sc in res for s in sc]
+            pool = CpuPool(kind, 1)
+            wall, cpu_scores = pool.run(queries[:k], targets[:k])
+            pool.close()
             assert cpu_scores == [results[i].score for i in range(k)], "CPU baseline disagrees with the GPU scores"
             line["cpu_baseline"] = {"value": k * args.qlen * args.tlen / wall / 1e9, "unit": "GCUPS", "cores": 1,
                                     "kind": kind,
@@ -348,7 +367,6 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fill-timing", action="store_true", help="read the fill-kernel events every step")
-    ap.add_argument("--warmup-full", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -132,8 +132,28 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         uint32_t *tbp = nullptr;
         if (TB) tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * WPL;
 
+        // END_ANYWHERE: the column maximum of a step is examined at the top of the
+        // NEXT step, when the column's values sit in their loop-carried registers
+        // (checking right after the row loop made ptxas copy all 2R registers on
+        // the common no-update path, +1 instruction per cell).
+        int pend_cm = INT32_MIN, pend_j = 0;
+        auto settle_pending = [&]() {
+            if (pend_cm > best || (pend_cm == best && pend_j < best_j)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && Mp[r] == pend_cm) { bi = row0 + r; found = true; }
+                best = pend_cm;
+                best_j = pend_j;
+                best_i = bi;
+            }
+            pend_cm = INT32_MIN;
+        };
+
         for (int s = 0; s < nsteps; ++s) {
             const int j = s - lane;
+            if (ENDMODE == END_ANYWHERE) settle_pending();
             int code;
             if (lane == 0) {
                 code = code0;
@@ -158,51 +178,63 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 // "G" = M + gap_open everywhere: the open penalty is paid once per cell
                 // (it feeds both D of the next column and I of the next row) and the
                 // substitution table holds s - gap_open, so diagG + s' == M_diag + s.
-                int upM = topM, upI = topI, diag = topMprev;
                 int cm = INT32_MIN;   // column maximum over my rows (END_ANYWHERE)
                 int capt = INT32_MIN; // G at lattice row Q (END_RESTRICTED)
                 uint32_t w[WPL > 0 ? WPL : 1];
 #pragma unroll
                 for (int k = 0; k < WPL; ++k) w[k] = 0;
+                // Phase A, rows BOTTOM-UP, all independent: D of this column and the
+                // (match | D) candidate of M.  Going upwards lets every result overwrite
+                // the register of the previous column's value it replaces (row r needs
+                // the old M of row r-1 as its diagonal, which is still untouched), so the
+                // loop-carried arrays are updated in place with no register copies.
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
+                for (int r = R - 1; r >= 0; --r) {
                     int sc;
                     if (SM == SCORE_PRMT) sc = prmt_sx(X.x, X.y, sel[r]);
                     else sc = subcol[sel[r]];
+                    const int diag = (r == 0) ? topMprev : Mp[r - 1];
+                    if (!TB) {
+                        Dp[r] = __viaddmax_s32(Dp[r], extD, Mp[r]);
+                        Mp[r] = __viaddmax_s32(diag, sc, Dp[r]);   // max(match, D); START and I follow
+                    } else {
+                        // D: T0 extend first, T2 open replaces only if strictly greater
+                        const int da = Dp[r] + extD;
+                        const bool pD = Mp[r] > da;
+                        Dp[r] = max(da, Mp[r]);
+                        Mp[r] = diag + sc;                         // T4 candidate only
+                        w[r / 8] |= ((uint32_t)pD << 1) << (4 * (r % 8));
+                    }
+                }
+                // Phase B, rows TOP-DOWN: the vertical chain I -> M -> G.
+                int upM = topM, upI = topI;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
                     int sv = sv_col;
                     if (r == 0) {
                         // lattice row 0: START scope QUERY/EDGE allows it; corner always
                         if (first_row_lane && (start_row0 || j == 0)) sv = 0;
                     }
-                    const int mp = Mp[r];
-                    int Iv, Dv, Mv;
+                    int Iv, Mv;
                     if (!TB) {
                         Iv = __viaddmax_s32(upI, extI, upM);
-                        Dv = __viaddmax_s32(Dp[r], extD, mp);
-                        Mv = __vimax3_s32(__viaddmax_s32(diag, sc, sv), Dv, Iv);
+                        Mv = __vimax3_s32(Mp[r], sv, Iv);
                     } else {
                         // I: T1 extend first, T3 open replaces only if strictly greater
                         const int ia = upI + extI;
                         const bool pI = upM > ia;
                         Iv = max(ia, upM);
-                        // D: T0 extend first, T2 open
-                        const int da = Dp[r] + extD;
-                        const bool pD = mp > da;
-                        Dv = max(da, mp);
                         // M: T4 match, T5 start, T6 from D, T7 from I
-                        int cur = diag + sc;
+                        int cur = Mp[r];
                         int dir = 0;
                         if (cur < sv) { cur = sv; dir = 1; }
-                        if (cur < Dv) { cur = Dv; dir = 2; }
+                        if (cur < Dp[r]) { cur = Dp[r]; dir = 2; }
                         if (cur < Iv) { cur = Iv; dir = 3; }
                         Mv = cur;
-                        const uint32_t nib = (uint32_t)pI | ((uint32_t)pD << 1) | ((uint32_t)dir << 2);
-                        w[r / 8] |= nib << (4 * (r % 8));
+                        w[r / 8] |= ((uint32_t)pI | ((uint32_t)dir << 2)) << (4 * (r % 8));
                     }
                     const int Gv = add_open(Mv, one, open);
-                    diag = mp;
                     Mp[r] = Gv;
-                    Dp[r] = Dv;
                     upM = Gv;
                     upI = Iv;
                     if (ENDMODE == END_ANYWHERE) cm = max(cm, Gv);
@@ -219,16 +251,8 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 if (write_top) top_out[j] = make_int2(botM, botI);
                 // ---- END bookkeeping ----
                 if (ENDMODE == END_ANYWHERE) {
-                    if (cm > best || (cm == best && j < best_j)) {
-                        int bi = 0;
-                        bool found = false;
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (!found && Mp[r] == cm) { bi = row0 + r; found = true; }
-                        best = cm;
-                        best_j = j;
-                        best_i = bi;
-                    }
+                    pend_cm = cm;
+                    pend_j = j;
                 } else {
                     const bool corner_only = (es == C4B_SCOPE_CORNER);
                     if (j == T && end_colT) {
@@ -259,6 +283,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 in_code = nC;
             }
         }
+        if (ENDMODE == END_ANYWHERE) settle_pending();
     }
     // lexicographic warp reduction: max score, then min j, then min i
 #pragma unroll
