@@ -210,15 +210,18 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 int upM = topM, upI = topI;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    int sv = sv_col;
-                    if (r == 0) {
+                    // START candidate (T5): identically 0 for a local model (the
+                    // END_ANYWHERE instantiation is only used when START is ANYWHERE too)
+                    int sv = (ENDMODE == END_ANYWHERE) ? 0 : sv_col;
+                    if (ENDMODE != END_ANYWHERE && r == 0) {
                         // lattice row 0: START scope QUERY/EDGE allows it; corner always
                         if (first_row_lane && (start_row0 || j == 0)) sv = 0;
                     }
                     int Iv, Mv;
                     if (!TB) {
                         Iv = __viaddmax_s32(upI, extI, upM);
-                        Mv = __vimax3_s32(Mp[r], sv, Iv);
+                        if (ENDMODE == END_ANYWHERE) Mv = __vimax_s32_relu(Mp[r], Iv);  // full-rate VIMNMX.RELU
+                        else Mv = __vimax3_s32(Mp[r], sv, Iv);
                     } else {
                         // I: T1 extend first, T3 open replaces only if strictly greater
                         const int ia = upI + extI;

@@ -104,6 +104,9 @@ bool analyze_affine(const c4b_model &m, AffModel *am, int *match_kind) {
     am->openI = m.calcs[t[3].calc].param[0];
     // the pad-row argument of the systolic kernel needs strictly negative gaps
     if (am->extD >= 0 || am->extI >= 0 || am->openD >= 0 || am->openI >= 0) return false;
+    // the local instantiation assumes START and END are both ANYWHERE (Affine_create
+    // always configures the two scopes alike, src/model/affine.c:189-190)
+    if ((m.start_scope == C4B_SCOPE_ANYWHERE) != (m.end_scope == C4B_SCOPE_ANYWHERE)) return false;
     // the kernel carries M + open (one shared open penalty, as Affine_create builds it)
     if (am->openD != am->openI) return false;
     am->one = 1;
