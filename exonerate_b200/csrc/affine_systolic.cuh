@@ -17,7 +17,7 @@
 // itself: the bottom cell of a lane's strip reaches the next lane through ONE
 // warp shuffle per value per step, the target symbol rides the same shuffle,
 // and no cell value ever touches shared memory or HBM.  Queries longer than
-// 32*R-1 are swept in strips; the strip hand-off row {M,I}[T+1] lives in L2.
+// 32*R-1 are swept in strips; the strip hand-off row {G,I}[T+1] lives in L2.
 // int32 max-plus on the DPX pipe (VIADDMNMX / VIMNMX3 / VIMNMX.RELU); the
 // substitution score is one PRMT on a byte-packed column of the matrix.
 //
@@ -25,11 +25,14 @@
 // D (1 bit) and I (1 bit): 4 bits/cell, R/2 bytes per lane per step, written as
 // one coalesced vector store in the skewed order the warp produces them.
 #pragma once
+#include <type_traits>
+
 #include "c4b_common.cuh"
 
 namespace c4b {
 
 enum { END_ANYWHERE = 0, END_RESTRICTED = 1 };
+enum { SCORE_PRMT = 0, SCORE_SMEM = 1 };
 
 // prmt.b32 with the full 4-bit selector (bit 3 = replicate the sign of the
 // selected byte); __byte_perm masks the selector to 3 bits and cannot do this.
@@ -38,29 +41,25 @@ __device__ __forceinline__ int prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
     return d;
 }
-enum { SCORE_PRMT = 0, SCORE_SMEM = 1 };
 
 // M + gap_open.  Written as a multiply-add by a run-time 1 so that it issues on
 // the FMA pipe (IMAD) and leaves the ALU/DPX pipe, the binding one, to the
-// max-plus instructions (profiles/: pipe_alu 65-83 %, pipe_fma 16 % before).
+// max-plus instructions (profiles/: pipe_alu 86 %, pipe_fma 12 %).
 __device__ __forceinline__ int add_open(int m, int one, int open) {
-#ifdef C4B_PLAIN_ADD
-    (void)one;
-    return m + open;
-#else
     int d;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(m), "r"(one), "r"(open));
     return d;
-#endif
 }
 
-// score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code))
+// score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code) - open)
 //              SCORE_SMEM -> int32[25*25] (row 24 = pad rows, column 24 = "no symbol")
+// ENDMODE END_ANYWHERE is only instantiated for START=END=ANYWHERE (local) models.
 template <int R, bool TB, int ENDMODE, int SM>
 __global__ void __launch_bounds__(32)
 affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                    const AffModel mdl, const void *__restrict__ score_table) {
     constexpr int WPL = R / 8;  // traceback words per lane per step
+    constexpr bool LOCAL = (ENDMODE == END_ANYWHERE);
     __shared__ uint2 xtab[25];
     __shared__ int32_t subm[SM == SCORE_SMEM ? 25 * 25 : 1];
 
@@ -85,32 +84,35 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     const bool start_col0 = start_any || ss == C4B_SCOPE_EDGE || ss == C4B_SCOPE_TARGET;
     const bool end_rowQ = (es == C4B_SCOPE_EDGE || es == C4B_SCOPE_QUERY);
     const bool end_colT = (es == C4B_SCOPE_EDGE || es == C4B_SCOPE_TARGET);
+    const bool corner_only = (es == C4B_SCOPE_CORNER);
 
     const int rows_per_sweep = 32 * R;
     const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     const int nsteps = T + 1 + 31;
 
     // first strict maximum of END in (target outer, query inner) order
-    // (viterbi.c:778-791) == lexicographic max of (score, -j, -i)
+    // (viterbi.c:778-791) == lexicographic max of (score, -j, -i); tracked on
+    // G = M + open and converted at the end
     int best = INT32_MIN, best_j = 0, best_i = 0;
 
     for (int sweep = 0; sweep < nsweeps; ++sweep) {
         const int row0 = sweep * rows_per_sweep + lane * R;  // lattice row of r = 0
         const bool first_row_lane = (sweep == 0 && lane == 0);
+        const bool later_sweep = (sweep > 0);
         // per-row query operand: PRMT selector or matrix row offset
         uint32_t sel[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = row0 + r;  // lattice row; consumes query symbol i-1
-            int c;
             if (SM == SCORE_PRMT) {
-                c = (i >= 1 && i <= Q) ? P.q[i - 1] : kPadClass;
+                const int c = (i >= 1 && i <= Q) ? P.q[i - 1] : kPadClass;
                 sel[r] = (uint32_t)c * 0x1111u | 0x8880u;  // byte c, sign-extended
             } else {
-                c = (i >= 1 && i <= Q) ? P.q[i - 1] : 24;
+                const int c = (i >= 1 && i <= Q) ? P.q[i - 1] : 24;
                 sel[r] = (uint32_t)c * 25u;
             }
         }
+        // loop-carried state: G = M + open and D of the previous column, per row
         int Mp[R], Dp[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -120,7 +122,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         // END at the last lattice row: which of my registers holds row Q
         const int rQ = (Q >= row0 && Q < row0 + R) ? (Q - row0) : -1;
 
-        const int2 *top_in = (sweep & 1) ? P.top0 : P.top1;   // written by sweep-1
+        const int2 *top_in = (sweep & 1) ? P.top0 : P.top1;  // written by sweep-1
         int2 *top_out = (sweep & 1) ? P.top1 : P.top0;
         const bool write_top = (sweep + 1 < nsweeps) && (lane == 31);
 
@@ -128,7 +130,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         int in_code = kTargetNone;                      // column code handed down
         int code0 = kTargetNone;                        // lane 0: column 0 has no symbol
         int2 top0v = make_int2(NEG2, NEG2);
-        if (lane == 0 && sweep > 0) top0v = top_in[0];
+        if (later_sweep) top0v = top_in[0];             // uniform load, lane 0 uses it
         uint32_t *tbp = nullptr;
         if (TB) tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * WPL;
 
@@ -151,24 +153,28 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
             pend_cm = INT32_MIN;
         };
 
-        for (int s = 0; s < nsteps; ++s) {
+        // One step of the wavefront.  ALL = std::true_type in the steady state, where
+        // every lane has a column in [0, T] and the activity test (and its divergence
+        // bookkeeping) disappears from the instruction stream.
+        auto step = [&](const int s, auto ALL) {
+            constexpr bool all_active = decltype(ALL)::value;
             const int j = s - lane;
-            if (ENDMODE == END_ANYWHERE) settle_pending();
-            int code;
-            if (lane == 0) {
-                code = code0;
-                if (sweep > 0) {
-                    topM = top0v.x;
-                    topI = top0v.y;
-                }
-                // prefetch column s+1 for the next step
-                code0 = (s + 1 <= T) ? (int)P.t[s] : kTargetNone;
-                if (sweep > 0 && s + 1 <= T) top0v = top_in[s + 1];
+            if (LOCAL) settle_pending();
+            // the column symbol / hand-off row are fetched with warp-uniform addresses
+            // (one broadcast transaction, no divergent branch); only lane 0 consumes them
+            int code = (lane == 0) ? code0 : in_code;
+            if (later_sweep && lane == 0) {
+                topM = top0v.x;
+                topI = top0v.y;
+            }
+            if (s + 1 <= T) {
+                code0 = (int)P.t[s];
+                if (later_sweep) top0v = top_in[s + 1];
             } else {
-                code = in_code;
+                code0 = kTargetNone;
             }
             int botM = NEG2, botI = NEG2;
-            if (j >= 0 && j <= T) {
+            if (all_active || (j >= 0 && j <= T)) {
                 uint2 X = make_uint2(0, 0);
                 const int32_t *subcol = nullptr;
                 if (SM == SCORE_PRMT) X = xtab[code];
@@ -210,17 +216,16 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 int upM = topM, upI = topI;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    // START candidate (T5): identically 0 for a local model (the
-                    // END_ANYWHERE instantiation is only used when START is ANYWHERE too)
-                    int sv = (ENDMODE == END_ANYWHERE) ? 0 : sv_col;
-                    if (ENDMODE != END_ANYWHERE && r == 0) {
+                    // START candidate (T5): identically 0 for a local model
+                    int sv = LOCAL ? 0 : sv_col;
+                    if (!LOCAL && r == 0) {
                         // lattice row 0: START scope QUERY/EDGE allows it; corner always
                         if (first_row_lane && (start_row0 || j == 0)) sv = 0;
                     }
                     int Iv, Mv;
                     if (!TB) {
                         Iv = __viaddmax_s32(upI, extI, upM);
-                        if (ENDMODE == END_ANYWHERE) Mv = __vimax_s32_relu(Mp[r], Iv);  // full-rate VIMNMX.RELU
+                        if (LOCAL) Mv = __vimax_s32_relu(Mp[r], Iv);  // full-rate VIMNMX.RELU
                         else Mv = __vimax3_s32(Mp[r], sv, Iv);
                     } else {
                         // I: T1 extend first, T3 open replaces only if strictly greater
@@ -240,7 +245,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                     Mp[r] = Gv;
                     upM = Gv;
                     upI = Iv;
-                    if (ENDMODE == END_ANYWHERE) cm = max(cm, Gv);
+                    if (LOCAL) cm = max(cm, Gv);
                     else if (r == rQ) capt = Gv;
                 }
                 botM = upM;
@@ -253,24 +258,21 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 }
                 if (write_top) top_out[j] = make_int2(botM, botI);
                 // ---- END bookkeeping ----
-                if (ENDMODE == END_ANYWHERE) {
+                if (LOCAL) {
                     pend_cm = cm;
                     pend_j = j;
-                } else {
-                    const bool corner_only = (es == C4B_SCOPE_CORNER);
-                    if (j == T && end_colT) {
-                        // whole last column is an END edge: rows in increasing order
+                } else if (j == T && end_colT) {
+                    // whole last column is an END edge: rows in increasing order
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int i = row0 + r;
-                            if (i <= Q && (Mp[r] > best || (Mp[r] == best && j < best_j))) {
-                                best = Mp[r]; best_j = j; best_i = i;
-                            }
+                    for (int r = 0; r < R; ++r) {
+                        const int i = row0 + r;
+                        if (i <= Q && (Mp[r] > best || (Mp[r] == best && j < best_j))) {
+                            best = Mp[r]; best_j = j; best_i = i;
                         }
-                    } else if (rQ >= 0 && (end_rowQ || (corner_only && j == T))) {
-                        if (capt > best || (capt == best && j < best_j)) {
-                            best = capt; best_j = j; best_i = Q;
-                        }
+                    }
+                } else if (rQ >= 0 && (end_rowQ || (corner_only && j == T))) {
+                    if (capt > best || (capt == best && j < best_j)) {
+                        best = capt; best_j = j; best_i = Q;
                     }
                 }
             }
@@ -280,13 +282,21 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
             const int nI = __shfl_up_sync(0xffffffffu, botI, 1);
             const int nC = __shfl_up_sync(0xffffffffu, code, 1);
             if (lane > 0) {
-                // topMprev for lane>0 is updated inside the active block from topM
                 topM = nM;
                 topI = nI;
                 in_code = nC;
             }
-        }
-        if (ENDMODE == END_ANYWHERE) settle_pending();
+        };
+
+        // fill (lanes switch on one by one), steady state, drain
+        const int fill_end = min(31, nsteps);
+        const int steady_end = max(fill_end, min(T + 1, nsteps));
+        int s = 0;
+        for (; s < fill_end; ++s) step(s, std::false_type{});
+        for (; s < steady_end; ++s) step(s, std::true_type{});
+        for (; s < nsteps; ++s) step(s, std::false_type{});
+        if (LOCAL) settle_pending();
+        __syncwarp();
     }
     // lexicographic warp reduction: max score, then min j, then min i
 #pragma unroll
