@@ -94,6 +94,16 @@ def summarise_clocks(lines):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(cells):
+    """ncu-measured DRAM bytes of the dominant kernel, scaled to this launch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        rec = json.load(open(path))["affine_fill_kernel<32,0,0,0>"]
+        return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / rec["cells"] * cells
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -236,9 +246,10 @@ def ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from exonerate_b200.models import host_model
     params = helpers.load_params()
-    scoring = helpers.load_scoring(params)
-    model, _ = helpers.load_model("affine_local_dna", params)
+    scoring = helpers.load_scoring(params)   # the reference's Submat tables (tests/golden/scoring.json)
+    model, _ = host_model("affine:local")    # closed by the host C layer (csrc/host)
     n = args.pairs
     queries, targets = make_batch(1000 + rank, n, args.qlen, args.tlen)
     pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)])
@@ -327,7 +338,7 @@ def ours(args):
                        "l2": "inputs (%d MB per GPU) exceed the 126 MB L2" % (pairs.h2d_bytes >> 20),
                        "kernel": "affine_systolic (score pass + banded traceback pass)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": measured_traffic(cells),
                          "note": "B_alg=20 B/cell (SURVEY 8d, reference row layout); the kernel keeps rows "
                                  "in registers and writes 0.5 B/cell only inside the traceback band, so "
                                  "frac>1 is expected; see DESIGN.md. peak " + peak_src,
