@@ -122,6 +122,12 @@ C4_Model *Model_Type_get_model(const char *name, Alphabet_Type query_type, Alpha
 int c4b_host_model(const char *name, int query_is_protein, int target_is_protein, const C4_Params *params,
                    c4b_model *out, char **description);
 
+/* ---- splice-site score arrays (src/sequence/splice.c) ---------------------- */
+/* SplicePredictor_predict_array_int over the whole sequence; type = C4B_SPLICE_* */
+void c4b_host_splice_array(int type, const uint8_t *seq, int32_t len, int force_gtag, int32_t *out);
+/* all four site types, C4B_SPLICE_* order, out[4*len] (feeds c4b_pair.splice[]) */
+void c4b_host_splice_arrays(const uint8_t *seq, int32_t len, int force_gtag, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ def load_host_library():
         lib.c4b_host_model.restype = C.c_int
         lib.C4_Params_default.argtypes = [C.POINTER(Params)]
         lib.C4_host_error.restype = C.c_char_p
+        lib.c4b_host_splice_arrays.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -61,3 +62,15 @@ def host_model(name, query_is_protein=False, target_is_protein=False, params=Non
     if rc != 0:
         raise RuntimeError("model %r: %s" % (name, lib.C4_host_error().decode()))
     return m, text
+
+
+def splice_arrays(target, force_gtag=False):
+    """The four per-position splice-site score arrays of a genomic sequence
+    (SplicePredictor_predict_array_int): list of int32 numpy arrays in
+    C4B_SPLICE_* order, ready for PairSet(splice=...)."""
+    import numpy as np
+    raw = target.encode() if isinstance(target, str) else bytes(target)
+    seq = np.frombuffer(raw, dtype=np.uint8)
+    out = np.zeros((4, len(seq)), dtype=np.int32)
+    load_host_library().c4b_host_splice_arrays(seq.ctypes.data, len(seq), int(force_gtag), out.ctypes.data)
+    return [out[k] for k in range(4)]

@@ -90,3 +90,19 @@ def test_host_tables_drive_the_oracle(params, scoring):
     kat = [c for c in helpers.load_cases("affine_local_protein") if c["name"] == "kat"][0]
     r = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(kat["q"], kat["t"]), abi.MODE_FIND_PATH)
     assert r["score"] == 32 and r["ops"] == [tuple(o) for o in kat["path"]["ops"]]
+
+
+@pytest.mark.parametrize("name", ["est2genome", "protein2genome"])
+def test_splice_arrays_match_reference(name):
+    """Host splice predictor == SplicePredictor_predict_array_int of the reference
+    (float32 PSSM log-odds, windowed sums clipped at the ends, rounding)."""
+    import numpy as np
+    from exonerate_b200.models import splice_arrays
+    z = np.load(helpers.GOLDEN + "/splice_%s.npz" % name)
+    n = 0
+    for case in helpers.load_cases(name):
+        mine = splice_arrays(case["t"])
+        for ty in range(4):
+            assert (mine[ty] == z["%s_%d" % (case["name"], ty)]).all(), (case["name"], ty)
+            n += 1
+    assert n >= 4
