@@ -1,0 +1,449 @@
+/* viterbi_b200.c -- the reference-side binding of libc4b200.so.
+ *
+ * A drop-in replacement for the reference's src/c4/viterbi.c: same public
+ * functions (src/c4/viterbi.h:122-159), but the lattice fill and the traceback
+ * run on the GPU through the C ABI of include/c4b200.h.  It is linked INTO THE
+ * UNMODIFIED REFERENCE in place of viterbi.o (the substitution point the
+ * reference's own build provides, src/program/Makefile.am:18,76-86); nothing in
+ * src/model, src/hub, optimal.c or alignment.c changes.  See INTEGRATION.md.
+ *
+ * Our own code; it includes the reference's headers because it implements the
+ * reference's interface.  Built only where /root/reference exists
+ * (integration/Makefile) into integration/_build/exonerate_b200.
+ */
+#include <string.h>
+#include <stdlib.h>
+
+#include "viterbi.h"
+#include "ungapped.h"
+#include "affine.h"
+#include "intron.h"
+#include "frameshift.h"
+#include "match.h"
+#include "splice.h"
+#include "c4b200.h"
+
+/* ---- options (viterbi.c:27-38): -D/--dpmemory is accepted and ignored -------- */
+Viterbi_ArgumentSet *Viterbi_ArgumentSet_create(Argument *arg){
+    register ArgumentSet *as;
+    static Viterbi_ArgumentSet vas = {32};
+    if(arg){
+        as = ArgumentSet_create("Viterbi algorithm options");
+        ArgumentSet_add_option(as, 'D', "dpmemory", "Mb",
+           "Maximum memory to use for DP tracebacks (Mb) [unused: GPU engine]",
+           "32", Argument_parse_int, &vas.traceback_memory_limit);
+        Argument_absorb_ArgumentSet(arg, as);
+        }
+    return &vas;
+    }
+
+/* ---- engine + per-Viterbi tables --------------------------------------------- */
+static c4b_engine *engine = NULL;
+
+static c4b_engine *get_engine(void){
+    if(!engine){
+        register const gchar *dev = g_getenv("EXONERATE_B200_DEVICE");
+        if(c4b_engine_create(dev?atoi(dev):0, &engine))
+            g_error("libc4b200: %s", c4b_last_error());
+        }
+    return engine;
+    }
+
+typedef struct B200_Tables {
+    Viterbi *viterbi;
+    c4b_model model;
+    struct B200_Tables *next;
+} B200_Tables;
+static B200_Tables *tables_list = NULL;
+
+typedef struct { /* what one FIND_PATH call leaves behind for create_Alignment */
+    c4b_result result;
+    gint32 *ops;
+} B200_Path;
+
+/* Map one C4_Calc of the reference to a device calc kind by its calc_macro
+ * (the text the reference's own code generator pastes; every calc of every
+ * compiled model has one).  Unknown => g_error: there is no host fallback. */
+static void classify_calc(C4_Model *model, C4_Calc *calc, c4b_calc *out){
+    register gchar *m = calc->calc_macro;
+    register Affine_ArgumentSet *aas = Affine_ArgumentSet_create(NULL);
+    register Frameshift_ArgumentSet *fas = Frameshift_ArgumentSet_create(NULL);
+    register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
+    memset(out, 0, sizeof(c4b_calc));
+    out->protect = calc->protect;
+    if(!m)
+        g_error("libc4b200: calc [%s] of model [%s] has no macro to classify",
+                calc->name, model->name);
+    if(strstr(m, "split_score_func")){
+        out->kind = strstr(m, "curr_intron_start >= 1")
+                  ? C4B_CALC_PHASE1_POST : C4B_CALC_PHASE2_POST;
+    } else if(strstr(m, "SplicePrediction_get")){
+        if(strstr(m, "sps->ss5_forward")) out->param[1] = C4B_SPLICE_5_FORWARD;
+        else if(strstr(m, "sps->ss3_forward")) out->param[1] = C4B_SPLICE_3_FORWARD;
+        else if(strstr(m, "sps->ss5_reverse")) out->param[1] = C4B_SPLICE_5_REVERSE;
+        else if(strstr(m, "sps->ss3_reverse")) out->param[1] = C4B_SPLICE_3_REVERSE;
+        else g_error("libc4b200: unknown splice site in calc [%s]", calc->name);
+        if(strstr(m, "query_data"))
+            g_error("libc4b200: query introns have no device form [%s]", calc->name);
+        if(strstr(m, "intron_open_penalty")){
+            out->kind = C4B_CALC_SPLICE_PRE;
+            out->param[0] = ias->intron_open_penalty;
+        } else {
+            out->kind = C4B_CALC_SPLICE_POST;
+            }
+    } else if(strstr(m, "Submat_lookup")){
+        register gboolean tq = strstr(m, "Sequence_get_symbol(ud->query, %QP+1)")?TRUE:FALSE,
+                          tt = strstr(m, "Sequence_get_symbol(ud->target, %TP+1)")?TRUE:FALSE;
+        if(strstr(m, "dna_submat")) out->kind = C4B_CALC_MATCH_DNA;
+        else if(tq && tt) out->kind = C4B_CALC_MATCH_3_3;
+        else if(tt) out->kind = C4B_CALC_MATCH_1_3;
+        else if(tq) out->kind = C4B_CALC_MATCH_3_1;
+        else out->kind = C4B_CALC_MATCH_PROTEIN;
+    } else if(strstr(m, "aas->codon_gap_open)")){
+        out->kind = C4B_CALC_CONST; out->param[0] = aas->codon_gap_open;
+    } else if(strstr(m, "aas->codon_gap_extend)")){
+        out->kind = C4B_CALC_CONST; out->param[0] = aas->codon_gap_extend;
+    } else if(strstr(m, "aas->gap_open)")){
+        out->kind = C4B_CALC_CONST; out->param[0] = aas->gap_open;
+    } else if(strstr(m, "aas->gap_extend)")){
+        out->kind = C4B_CALC_CONST; out->param[0] = aas->gap_extend;
+    } else if(strstr(m, "frameshift_penalty")){
+        out->kind = C4B_CALC_CONST; out->param[0] = fas->frameshift_penalty;
+    } else {
+        g_error("libc4b200: calc [%s] of model [%s] has no device form",
+                calc->name, model->name);
+        }
+    return;
+    }
+
+/* closed C4_Model -> c4b_model */
+static void flatten_model(C4_Model *model, c4b_model *out){
+    register gint i, j;
+    register C4_Transition *t;
+    register C4_Shadow *shadow;
+    register C4_State *state;
+    g_assert(!model->is_open);
+    memset(out, 0, sizeof(c4b_model));
+    if((model->state_list->len > C4B_MAX_STATES)
+    || (model->transition_list->len > C4B_MAX_TRANSITIONS)
+    || (model->calc_list->len > C4B_MAX_CALCS)
+    || (model->total_shadow_designations > C4B_MAX_SHADOW_SLOTS))
+        g_error("libc4b200: model [%s] exceeds the engine's table sizes",
+                model->name);
+    if(model->start_state->cell_start_func || model->end_state->cell_end_func)
+        g_error("libc4b200: model [%s] uses cell callbacks (BSDP derived model);"
+                " only --exhaustive models have a device form", model->name);
+    out->n_states = model->state_list->len;
+    out->n_transitions = model->transition_list->len;
+    out->n_calcs = model->calc_list->len;
+    out->n_shadow_slots = model->total_shadow_designations;
+    out->start_state = model->start_state->state->id;
+    out->end_state = model->end_state->state->id;
+    out->start_scope = model->start_state->scope;
+    out->end_scope = model->end_state->scope;
+    out->max_query_advance = model->max_query_advance;
+    out->max_target_advance = model->max_target_advance;
+    for(i = 0; i < model->calc_list->len; i++)
+        classify_calc(model, model->calc_list->pdata[i], &out->calcs[i]);
+    for(i = 0; i < model->transition_list->len; i++){
+        t = model->transition_list->pdata[i]; /* closed order = tie-break contract */
+        out->transitions[i].input = t->input->id;
+        out->transitions[i].output = t->output->id;
+        out->transitions[i].advance_query = t->advance_query;
+        out->transitions[i].advance_target = t->advance_target;
+        out->transitions[i].calc = t->calc?t->calc->id:-1;
+        out->transitions[i].label = t->label;
+        if(t->calc && (out->calcs[t->calc->id].kind >= C4B_CALC_SPLICE_POST)){
+            g_assert(t->dst_shadow_list->len == 1);
+            shadow = t->dst_shadow_list->pdata[0];
+            out->calcs[t->calc->id].param[2] = shadow->designation;
+            }
+        }
+    for(i = 0; i < model->shadow_list->len; i++){
+        shadow = model->shadow_list->pdata[i];
+        for(j = 0; j < shadow->src_state_list->len; j++){
+            state = shadow->src_state_list->pdata[j];
+            out->shadow_start[state->id][shadow->designation]
+                = strstr(shadow->start_macro, "%TP")?1:2;
+            }
+        }
+    return;
+    }
+
+static c4b_model *tables_for(Viterbi *viterbi){
+    register B200_Tables *bt;
+    for(bt = tables_list; bt; bt = bt->next)
+        if(bt->viterbi == viterbi)
+            return &bt->model;
+    bt = g_new0(B200_Tables, 1);
+    bt->viterbi = viterbi;
+    flatten_model(viterbi->model, &bt->model);
+    bt->next = tables_list;
+    tables_list = bt;
+    return &bt->model;
+    }
+
+/* ---- Viterbi objects (viterbi.c:58-104) ----------------------------------------- */
+Viterbi *Viterbi_create(C4_Model *model, gchar *name,
+                        Viterbi_Mode mode, gboolean use_continuation,
+                        gboolean use_codegen){
+    register Viterbi *viterbi = g_new0(Viterbi, 1);
+    viterbi->vas = Viterbi_ArgumentSet_create(NULL);
+    viterbi->name = Codegen_clean_path_component(name);
+    if(use_continuation){ /* kept for API fidelity; never run (no reduced space) */
+        viterbi->model = C4_Model_copy(model);
+        C4_Model_configure_start_state(viterbi->model, C4_Scope_CORNER,
+             viterbi->model->start_state->cell_start_func,
+             viterbi->model->start_state->cell_start_macro);
+        C4_Model_configure_end_state(viterbi->model, C4_Scope_CORNER,
+             viterbi->model->end_state->cell_end_func,
+             viterbi->model->end_state->cell_end_macro);
+    } else {
+        viterbi->model = C4_Model_share(model);
+        }
+    viterbi->func = NULL; /* there is no generated C: the tables ARE the compiled model */
+    viterbi->mode = mode;
+    viterbi->use_continuation = use_continuation;
+    viterbi->cell_size = 1 + viterbi->model->total_shadow_designations;
+    viterbi->layout = Layout_create(viterbi->model);
+    return viterbi;
+    }
+
+void Viterbi_destroy(Viterbi *viterbi){
+    register B200_Tables *bt, *prev = NULL;
+    for(bt = tables_list; bt; prev = bt, bt = bt->next)
+        if(bt->viterbi == viterbi){
+            if(prev) prev->next = bt->next; else tables_list = bt->next;
+            g_free(bt);
+            break;
+            }
+    C4_Model_destroy(viterbi->model);
+    Layout_destroy(viterbi->layout);
+    g_free(viterbi->name);
+    g_free(viterbi);
+    return;
+    }
+
+/* The device keeps 4 bit/cell in a band; --dpmemory never forces the
+ * region / checkpoint machinery (viterbi.c:128-150). */
+gboolean Viterbi_use_reduced_space(Viterbi *viterbi, Region *region){
+    return FALSE;
+    }
+
+Viterbi_Data *Viterbi_Data_create(Viterbi *viterbi, Region *region){
+    register Viterbi_Data *vd = g_new0(Viterbi_Data, 1);
+    if(viterbi->mode == Viterbi_Mode_FIND_REGION)
+        vd->alignment_region = Region_copy(region);
+    return vd;
+    }
+
+void Viterbi_Data_destroy(Viterbi_Data *vd){
+    register B200_Path *path = (B200_Path*)vd->traceback;
+    if(vd->alignment_region)
+        Region_destroy(vd->alignment_region);
+    if(path){
+        g_free(path->ops);
+        g_free(path);
+        }
+    g_free(vd);
+    return;
+    }
+
+void Viterbi_Data_set_continuation(Viterbi_Data *vd,
+              C4_State *first_state, C4_Score *first_cell,
+              C4_State *final_state, C4_Score *final_cell){
+    g_error("libc4b200: continuation DP is not used by the GPU engine");
+    }
+
+void Viterbi_Data_clear_continuation(Viterbi_Data *vd){
+    return;
+    }
+
+GPtrArray *Viterbi_Checkpoint_traceback(Viterbi *viterbi,
+        Viterbi_Data *vd, Region *region,
+        C4_State *first_state, C4_Score *final_cell){
+    g_error("libc4b200: checkpoint traceback is not used by the GPU engine");
+    return NULL;
+    }
+
+void Viterbi_SubAlignment_destroy(Viterbi_SubAlignment *vsa){
+    Region_destroy(vsa->region);
+    g_free(vsa->final_cell);
+    g_free(vsa);
+    return;
+    }
+
+Codegen *Viterbi_make_Codegen(Viterbi *viterbi){
+    g_error("libc4b200: nothing to generate for [%s]", viterbi->name);
+    return NULL;
+    }
+
+/* ---- the call: Viterbi_calculate (viterbi.c:846-865) ----------------------------- */
+static void fill_scoring(Ungapped_Data *ud, c4b_scoring *sc){
+    register gint i, j;
+    register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
+    register Translate *t = ud->mas->translate;
+    memset(sc, 0, sizeof(c4b_scoring));
+    for(i = 0; i < SUBMAT_ALPHABETSIZE; i++)
+        for(j = 0; j < SUBMAT_ALPHABETSIZE; j++){
+            sc->dna_matrix[i*C4B_SUBMAT_N+j] = ud->mas->dna_submat->matrix[i][j];
+            sc->protein_matrix[i*C4B_SUBMAT_N+j]
+                = ud->mas->protein_submat->matrix[i][j];
+            }
+    for(i = 0; i < 256; i++){
+        sc->dna_index[i] = ud->mas->dna_submat->index[i];
+        sc->protein_index[i] = ud->mas->protein_submat->index[i];
+        sc->nt2d[i] = t->nt2d[i];
+        }
+    for(i = 0; i < 4096; i++)
+        sc->codon_aa[i] = t->aa[t->trans[i]];
+    sc->min_intron = ias->min_intron;
+    sc->max_intron = ias->max_intron;
+    return;
+    }
+
+static gboolean model_has_splice(c4b_model *m){
+    register gint i;
+    for(i = 0; i < m->n_calcs; i++)
+        if((m->calcs[i].kind == C4B_CALC_SPLICE_PRE)
+        || (m->calcs[i].kind == C4B_CALC_SPLICE_POST))
+            return TRUE;
+    return FALSE;
+    }
+
+C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
+                           Viterbi_Data *vd, gpointer user_data,
+                           SubOpt *subopt){
+    register Ungapped_Data *ud = user_data; /* every shipped *_Data inherits it */
+    register c4b_model *tables = tables_for(viterbi);
+    register SubOpt_Index *soi = NULL;
+    register SubOpt_Index_Row *soir;
+    register gchar *qseq, *tseq;
+    register gint i, j, n_blocked = 0, mode = 0;
+    register gint32 *bq = NULL, *bt = NULL, *splice = NULL;
+    register gint64 ops_capacity;
+    register B200_Path *path = NULL;
+    register Intron_ArgumentSet *ias;
+    c4b_scoring scoring;
+    c4b_pair pair;
+    c4b_result result;
+    g_assert(Region_is_valid(region));
+    if(vd->continuation || (viterbi->mode == Viterbi_Mode_FIND_CHECKPOINTS))
+        g_error("libc4b200: continuation / checkpoint modes are not used");
+    switch(viterbi->mode){
+        case Viterbi_Mode_FIND_SCORE:  mode = 0; break;
+        case Viterbi_Mode_FIND_PATH:   mode = 1; break;
+        case Viterbi_Mode_FIND_REGION: mode = 2; break;
+        default: g_error("libc4b200: bad mode"); break;
+        }
+    /* sequences are virtual in the reference (revcomp/subseq views): flatten */
+    qseq = g_new(gchar, ud->query->len+4);
+    tseq = g_new(gchar, ud->target->len+4);
+    Sequence_strncpy(ud->query, 0, ud->query->len, qseq);
+    Sequence_strncpy(ud->target, 0, ud->target->len, tseq);
+    memset(&pair, 0, sizeof(pair));
+    pair.query = (const uint8_t*)qseq;
+    pair.target = (const uint8_t*)tseq;
+    pair.query_len = ud->query->len;
+    pair.target_len = ud->target->len;
+    pair.query_start = region->query_start;
+    pair.target_start = region->target_start;
+    pair.query_length = region->query_length;
+    pair.target_length = region->target_length;
+    fill_scoring(ud, &scoring);
+    if(model_has_splice(tables)){ /* what intron_init_func prepares (intron.c:259-293) */
+        ias = Intron_ArgumentSet_create(NULL);
+        splice = g_new(gint32, 4*(ud->target->len+1));
+        SplicePredictor_predict_array_int(ias->sps->ss5_forward, tseq,
+            ud->target->len, 0, ud->target->len, splice);
+        SplicePredictor_predict_array_int(ias->sps->ss3_forward, tseq,
+            ud->target->len, 0, ud->target->len, splice+ud->target->len);
+        SplicePredictor_predict_array_int(ias->sps->ss5_reverse, tseq,
+            ud->target->len, 0, ud->target->len, splice+2*ud->target->len);
+        SplicePredictor_predict_array_int(ias->sps->ss3_reverse, tseq,
+            ud->target->len, 0, ud->target->len, splice+3*ud->target->len);
+        for(i = 0; i < 4; i++)
+            pair.splice[i] = splice + i*ud->target->len;
+        }
+    if(subopt)
+        soi = SubOpt_Index_create(subopt, region);
+    if(soi){ /* rows are sorted by target_pos, positions by query_pos (subopt.c:250-338) */
+        for(i = 0; i < soi->row_list->len; i++){
+            soir = soi->row_list->pdata[i];
+            if(soir != soi->blank_row)
+                n_blocked += soir->total;
+            }
+        bq = g_new(gint32, n_blocked+1);
+        bt = g_new(gint32, n_blocked+1);
+        n_blocked = 0;
+        for(i = 0; i < soi->row_list->len; i++){
+            soir = soi->row_list->pdata[i];
+            if(soir == soi->blank_row)
+                continue;
+            for(j = 0; j < soir->total; j++){
+                bq[n_blocked] = soir->query_pos[j];
+                bt[n_blocked++] = soir->target_pos;
+                }
+            }
+        pair.blocked_query_pos = bq;
+        pair.blocked_target_pos = bt;
+        pair.n_blocked = n_blocked;
+        }
+    ops_capacity = (gint64)region->query_length + region->target_length + 8;
+    if(mode == 1){
+        path = g_new0(B200_Path, 1);
+        path->ops = g_new(gint32, 2*ops_capacity);
+        }
+    if(c4b_viterbi_calculate(get_engine(), tables, &scoring, &pair, mode,
+                             &result, path?path->ops:NULL, ops_capacity))
+        g_error("libc4b200: %s", c4b_last_error());
+    /* what a Viterbi_DP_Func leaves in vd (viterbi.c:464-478,633-653) */
+    vd->curr_query_end = result.query_end - region->query_start;
+    vd->curr_target_end = result.target_end - region->target_start;
+    vd->curr_query_start = result.query_start - region->query_start;
+    vd->curr_target_start = result.target_start - region->target_start;
+    if(vd->alignment_region){
+        vd->alignment_region->query_start = result.query_start;
+        vd->alignment_region->target_start = result.target_start;
+        vd->alignment_region->query_length = result.query_end - result.query_start;
+        vd->alignment_region->target_length = result.target_end - result.target_start;
+        }
+    if(path){
+        path->result = result;
+        if(vd->traceback){
+            g_free(((B200_Path*)vd->traceback)->ops);
+            g_free(vd->traceback);
+            }
+        vd->traceback = (C4_Transition****)path;
+        }
+    if(soi)
+        SubOpt_Index_destroy(soi);
+    g_free(bq);
+    g_free(bt);
+    g_free(splice);
+    g_free(qseq);
+    g_free(tseq);
+    return result.score;
+    }
+
+/* Viterbi_Data_create_Alignment (viterbi.c:342-392): the walk already happened
+ * on the device; replay the (transition, length) list into an Alignment. */
+Alignment *Viterbi_Data_create_Alignment(Viterbi_Data *vd,
+                  C4_Model *model, C4_Score score, Region *region){
+    register B200_Path *path = (B200_Path*)vd->traceback;
+    register Alignment *alignment;
+    register Region *alignment_region;
+    register gint i;
+    g_assert(path);
+    alignment_region = Region_create(path->result.query_start,
+        path->result.target_start,
+        path->result.query_end - path->result.query_start,
+        path->result.target_end - path->result.target_start);
+    alignment = Alignment_create(model, alignment_region, score);
+    for(i = 0; i < path->result.n_ops; i++)
+        Alignment_add(alignment,
+            model->transition_list->pdata[path->ops[2*(path->result.ops_offset+i)]],
+            path->ops[2*(path->result.ops_offset+i)+1]);
+    Region_destroy(alignment_region);
+    return alignment;
+    }

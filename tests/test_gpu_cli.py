@@ -1,0 +1,35 @@
+"""GPU tier: the exonerate CLI itself, bit for bit.
+
+integration/_build/exonerate_b200 is the UNMODIFIED reference (hub, models,
+alignment printers, FASTA I/O ...) with OUR viterbi.o replacement linked in place
+of the reference's, so every lattice fill and traceback of an
+`--exhaustive` run happens in libc4b200.so.  Its stdout must equal, byte for
+byte, what the reference's own binary (compiled models) printed for the same
+command lines: scores, coordinates, strands, cigar and vulgar strings, --ryo
+percent identity, sub-optimal series (--subopt yes), reverse-complement passes.
+
+The binary exists only where the reference was present at build time; it
+travels to the GPU box with the snapshot.  Skipped (not failed) if absent."""
+import json
+import os
+import subprocess
+
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(helpers.GOLDEN, "cli")
+BIN = os.path.join(helpers.ROOT, "integration", "_build", "exonerate_b200")
+COMMANDS = json.load(open(os.path.join(CLI, "commands.json")))
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")
+@pytest.mark.parametrize("name", sorted(COMMANDS))
+def test_cli_output_identical_to_reference(name):
+    want = open(os.path.join(CLI, name + ".out")).read()
+    got = subprocess.run([BIN] + COMMANDS[name], cwd=CLI, capture_output=True, text=True, timeout=600)
+    assert got.returncode == 0, got.stderr[-2000:]
+    assert got.stdout == want
+    assert len(want.splitlines()) >= 2
