@@ -14,6 +14,7 @@
 #include "affine_systolic.cuh"
 #include "affine_traceback.cuh"
 #include "generic_wavefront.cuh"
+#include "e2g_systolic.cuh"
 
 namespace c4b {
 static thread_local std::string g_error;
@@ -200,6 +201,7 @@ __global__ void ops_compact_kernel(c4b_result *results, int n, const int64_t *ne
 }  // namespace
 
 #include "generic_host.inl"
+#include "e2g_host.inl"
 
 // =============================================================================
 struct c4b_batch {
@@ -238,6 +240,9 @@ struct c4b_batch {
     // ---- generic path ----
     GenericBatch *generic = nullptr;
 
+    // ---- est2genome systolic path ----
+    E2gBatch *e2g = nullptr;
+
     ~c4b_batch() {
         d_seq.release(); d_lut.release(); d_score_table.release(); d_bad.release();
         d_full.release(); d_band.release(); d_direct.release();
@@ -251,6 +256,7 @@ struct c4b_batch {
             if (ev.b) cudaEventDestroy(ev.b);
         }
         if (generic) generic_batch_destroy(generic);
+        delete e2g;
     }
 };
 
@@ -836,6 +842,15 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
         b->affine = true;
         rc = affine_create(b, pairs, match_kind);
     } else {
+        rc = getenv("C4B_NO_E2G") ? 1
+                                  : e2g_batch_create(e->stream, &e->launches, model, scoring, n, pairs,
+                                                     want_path != 0, &b->e2g);
+        if (rc == 0) {
+            b->kernel_name = "e2g_systolic";
+            b->cells = b->e2g->cells;
+        }
+    }
+    if (rc == 1) {  // neither specialised template applies: table-driven wavefront
         rc = generic_batch_create(e->stream, &e->launches, model, scoring, n, pairs, want_path != 0,
                                   &b->generic);
         if (!rc) {
@@ -857,6 +872,7 @@ int c4b_batch_run(c4b_batch *b, c4b_score threshold) {
     b->ran = true;
     if (b->n == 0) return 0;
     if (b->affine) return affine_run(b, threshold);
+    if (b->e2g) return e2g_batch_run(b->e2g, threshold);
     return generic_batch_run(b->generic, threshold);
 }
 
@@ -867,12 +883,14 @@ int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops
     }
     if (b->n == 0) return 0;
     if (b->affine) return affine_fetch(b, results, ops, ops_capacity);
+    if (b->e2g) return e2g_batch_fetch(b->e2g, results, ops, ops_capacity);
     return generic_batch_fetch(b->generic, results, ops, ops_capacity);
 }
 
 const void *c4b_batch_device_results(const c4b_batch *b) {
     if (!b->ran || b->n == 0) return nullptr;
     if (b->affine) return b->want_path ? b->d_results.p : nullptr;  // score-only is in slot order
+    if (b->e2g) return b->want_path ? b->e2g->d_results.p : nullptr;
     return generic_batch_device_results(b->generic);
 }
 
@@ -880,6 +898,7 @@ int64_t c4b_batch_cells(const c4b_batch *b) { return b->cells; }
 
 double c4b_batch_last_fill_ms(c4b_batch *b) {
     if (!b->ran || b->n == 0) return -1.0;
+    if (b->e2g) return e2g_batch_fill_ms(b->e2g);
     if (!b->affine) return generic_batch_fill_ms(b->generic);
     cudaStreamSynchronize(b->e->stream);
     double ms = 0;

@@ -1,0 +1,395 @@
+// e2g_host.inl -- host side of the est2genome systolic path (included by
+// c4b200.cu after DevBuf / the ops packing kernels are defined).
+namespace c4b {
+
+// Is the closed model the est2genome template of SURVEY.md §8a?  Every transition
+// is checked (state roles are derived from the tables, the ORDER is required).
+static bool analyze_est2genome(const c4b_model &m, const c4b_scoring &sc, E2gModel *em) {
+    if (m.n_states != 10 || m.n_transitions != 24 || m.n_shadow_slots != 1) return false;
+    if (m.max_query_advance != 1 || m.max_target_advance != 2) return false;
+    if (m.start_scope != C4B_SCOPE_ANYWHERE || m.end_scope != C4B_SCOPE_ANYWHERE) return false;
+    const c4b_transition *t = m.transitions;
+    const int S = m.start_state, E = m.end_state;
+    const int MR = t[6].input, MF = t[11].input, IR = t[7].output, DR = t[8].output;
+    const int IF = t[12].output, DF = t[13].output, NR = t[0].output, NF = t[3].output;
+    enum { cNONE, cMATCH, cOPEN, cEXT, cPRE, cPOST };
+    struct Want { int in, out, aq, at, calc, site; };
+    const Want want[24] = {
+        {MR, NR, 0, 2, cPRE, C4B_SPLICE_3_REVERSE}, {NR, NR, 0, 1, cNONE, 0}, {NR, MR, 0, 2, cPOST, C4B_SPLICE_5_REVERSE},
+        {MF, NF, 0, 2, cPRE, C4B_SPLICE_5_FORWARD}, {NF, NF, 0, 1, cNONE, 0}, {NF, MF, 0, 2, cPOST, C4B_SPLICE_3_FORWARD},
+        {MR, MR, 1, 1, cMATCH, 0}, {MR, IR, 1, 0, cOPEN, 0}, {MR, DR, 0, 1, cOPEN, 0}, {IR, IR, 1, 0, cEXT, 0},
+        {DR, DR, 0, 1, cEXT, 0}, {MF, MF, 1, 1, cMATCH, 0}, {MF, IF, 1, 0, cOPEN, 0}, {MF, DF, 0, 1, cOPEN, 0},
+        {IF, IF, 1, 0, cEXT, 0}, {DF, DF, 0, 1, cEXT, 0}, {IR, MR, 0, 0, cNONE, 0}, {DR, MR, 0, 0, cNONE, 0},
+        {S, MR, 0, 0, cNONE, 0}, {IF, MF, 0, 0, cNONE, 0}, {DF, MF, 0, 0, cNONE, 0}, {S, MF, 0, 0, cNONE, 0},
+        {MR, E, 0, 0, cNONE, 0}, {MF, E, 0, 0, cNONE, 0}};
+    int open = 0, ext = 0, intron_open = 0;
+    bool have_open = false, have_ext = false, have_pre = false;
+    for (int k = 0; k < 24; ++k) {
+        const Want &w = want[k];
+        if (t[k].input != w.in || t[k].output != w.out || t[k].advance_query != w.aq ||
+            t[k].advance_target != w.at)
+            return false;
+        if (w.calc == cNONE) {
+            if (t[k].calc >= 0) return false;
+            continue;
+        }
+        if (t[k].calc < 0) return false;
+        const c4b_calc &c = m.calcs[t[k].calc];
+        switch (w.calc) {
+        case cMATCH:
+            if (c.kind != C4B_CALC_MATCH_DNA || c.protect != 0 || t[k].label != C4B_LABEL_MATCH) return false;
+            break;
+        case cOPEN:
+            if (c.kind != C4B_CALC_CONST || c.protect != 0) return false;
+            if (have_open && c.param[0] != open) return false;
+            open = c.param[0]; have_open = true;
+            break;
+        case cEXT:
+            if (c.kind != C4B_CALC_CONST || c.protect != 0) return false;
+            if (have_ext && c.param[0] != ext) return false;
+            ext = c.param[0]; have_ext = true;
+            break;
+        case cPRE:
+            if (c.kind != C4B_CALC_SPLICE_PRE || c.param[1] != w.site || c.protect != C4B_PROTECT_UNDERFLOW) return false;
+            if (have_pre && c.param[0] != intron_open) return false;
+            intron_open = c.param[0]; have_pre = true;
+            break;
+        case cPOST:
+            if (c.kind != C4B_CALC_SPLICE_POST || c.param[1] != w.site || c.param[2] != 0 ||
+                c.protect != C4B_PROTECT_UNDERFLOW)
+                return false;
+            break;
+        }
+    }
+    // the one shadow slot is stamped with the target position when leaving a match state
+    for (int s = 0; s < m.n_states; ++s) {
+        const int want_stamp = (s == MF || s == MR) ? 1 : 0;
+        if (m.shadow_start[s][0] != want_stamp) return false;
+    }
+    if (open >= 0 || ext >= 0) return false;
+    em->open = open; em->ext = ext; em->intron_open = intron_open;
+    em->min_intron = sc.min_intron; em->max_intron = sc.max_intron; em->one = 1;
+    // x = 0 forward, 1 reverse
+    em->tNopen[0] = 3; em->tNloop[0] = 4; em->tNclose[0] = 5; em->tMatch[0] = 11; em->tIopen[0] = 12;
+    em->tDopen[0] = 13; em->tIext[0] = 14; em->tDext[0] = 15; em->tI2M[0] = 19; em->tD2M[0] = 20;
+    em->tS2M[0] = 21; em->tM2E[0] = 23;
+    em->tNopen[1] = 0; em->tNloop[1] = 1; em->tNclose[1] = 2; em->tMatch[1] = 6; em->tIopen[1] = 7;
+    em->tDopen[1] = 8; em->tIext[1] = 9; em->tDext[1] = 10; em->tI2M[1] = 16; em->tD2M[1] = 17;
+    em->tS2M[1] = 18; em->tM2E[1] = 22;
+    return true;
+}
+
+struct E2gBatch {
+    cudaStream_t stream = nullptr;
+    int64_t *launches = nullptr;
+    int n = 0, warps = 1;
+    bool want_path = false;
+    E2gModel mdl;
+    int64_t cells = 0;
+    std::vector<int> order;           // pair indices, cost-descending
+    std::vector<Chunk> chunks;
+    DevBuf<uint8_t> d_seq;
+    DevBuf<uint32_t> d_sp;
+    DevBuf<uint8_t> d_lut;
+    DevBuf<uint2> d_xtab;
+    DevBuf<int> d_bad;
+    DevBuf<E2gPair> d_pairs;
+    DevBuf<E2gOut> d_outs;
+    DevBuf<E2gJob> d_jobs;
+    DevBuf<int32_t> d_qorg, d_torg;
+    DevBuf<uint16_t> d_tb;
+    DevBuf<c4b_result> d_results;
+    DevBuf<int32_t> d_ops_slots, d_ops_packed;
+    DevBuf<int64_t> d_new_off;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    ~E2gBatch() {
+        d_seq.release(); d_sp.release(); d_lut.release(); d_xtab.release(); d_bad.release();
+        d_pairs.release(); d_outs.release(); d_jobs.release(); d_qorg.release(); d_torg.release();
+        d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
+        d_new_off.release();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+    }
+};
+
+// returns 0 ok, 1 "not eligible, use the generic path", <0 error
+static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
+                            const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
+                            E2gBatch **out) {
+    E2gModel mdl;
+    if (!analyze_est2genome(*model, *scoring, &mdl)) return 1;
+    int maxQ = 0;
+    bool used[24] = {false};
+    for (int p = 0; p < n; ++p) {
+        const c4b_pair &pp = pairs[p];
+        if (pp.n_blocked) return 1;
+        if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
+            pp.query_start + pp.query_length > pp.query_len || pp.target_start + pp.target_length > pp.target_len) {
+            set_error("pair " + std::to_string(p) + ": region outside the sequences");
+            return -1;
+        }
+        for (int k = 0; k < 4; ++k)
+            if (!pp.splice[k]) {
+                set_error("est2genome pair " + std::to_string(p) + " has no splice arrays");
+                return -1;
+            }
+        maxQ = std::max(maxQ, pp.query_length);
+        for (int k = 0; k < pp.query_length; ++k) {
+            const int c = scoring->dna_index[pp.query[pp.query_start + k]];
+            if (c >= 24) {
+                set_error("query " + std::to_string(p) + ": symbol outside the substitution matrix");
+                return -1;
+            }
+            used[c] = true;
+        }
+    }
+    if (maxQ + 1 > kE2gMaxWarps * 32 * kE2gR) return 1;
+    // PRMT classes of the query alphabet; s - open must fit int8
+    int n_used = 0, cls_of[24], code_of[8];
+    for (int a = 0; a < 24; ++a) {
+        cls_of[a] = -1;
+        if (!used[a]) continue;
+        if (n_used >= 7) return 1;
+        for (int c = 0; c < 24; ++c) {
+            const int v = scoring->dna_matrix[a * 24 + c] - mdl.open;
+            if (v < -127 || v > 127) return 1;
+        }
+        code_of[n_used] = a;
+        cls_of[a] = n_used++;
+    }
+    // splice scores must fit int8 (they do for the built-in frequency tables)
+    for (int p = 0; p < n; ++p)
+        for (int k = 0; k < 4; ++k) {
+            const int32_t *a = pairs[p].splice[k] + pairs[p].target_start;
+            for (int j = 0; j < pairs[p].target_length; ++j)
+                if (a[j] < -127 || a[j] > 127) return 1;
+        }
+
+    E2gBatch *b = new E2gBatch();
+    b->stream = stream; b->launches = launch_counter; b->n = n; b->want_path = want_path; b->mdl = mdl;
+    b->warps = std::max(1, (maxQ + 1 + 32 * kE2gR - 1) / (32 * kE2gR));
+    // ---- staging: region slices of query / target, packed splice words ---------------
+    std::vector<size_t> qoff(n), toff(n);
+    size_t qbytes = 0, tbytes = 0;
+    std::map<std::pair<const uint8_t *, int>, size_t> qmap, tmap;
+    for (int p = 0; p < n; ++p) {
+        const c4b_pair &pp = pairs[p];
+        auto qk = std::make_pair(pp.query + pp.query_start, pp.query_length);
+        auto tk = std::make_pair(pp.target + pp.target_start, pp.target_length);
+        auto qi = qmap.find(qk);
+        if (qi == qmap.end()) { qmap[qk] = qbytes; qoff[p] = qbytes; qbytes += align_up((size_t)pp.query_length, 16) + 16; }
+        else qoff[p] = qi->second;
+        auto ti = tmap.find(tk);
+        if (ti == tmap.end()) { tmap[tk] = tbytes; toff[p] = tbytes; tbytes += align_up((size_t)pp.target_length, 16) + 16; }
+        else toff[p] = ti->second;
+        b->cells += (int64_t)pp.query_length * pp.target_length;
+    }
+    std::vector<uint8_t> lut(512, 0xFF);
+    for (int c = 0; c < 256; ++c) {
+        const int idx = scoring->dna_index[c];
+        if (idx < 24 && cls_of[idx] >= 0) lut[c] = (uint8_t)cls_of[idx];
+        if (idx < 24) lut[256 + c] = (uint8_t)idx;
+    }
+    uint8_t qfill = 0, tfill = 0;
+    for (int c = 255; c >= 0; --c) {
+        if (lut[c] != 0xFF) qfill = (uint8_t)c;
+        if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
+    }
+    std::vector<uint8_t> hseq(qbytes + tbytes + 64, tfill);
+    memset(hseq.data(), qfill, qbytes);
+    for (auto &kv : qmap) memcpy(hseq.data() + kv.second, kv.first.first, (size_t)kv.first.second);
+    for (auto &kv : tmap) memcpy(hseq.data() + qbytes + kv.second, kv.first.first, (size_t)kv.first.second);
+    std::vector<uint32_t> hsp(tbytes + 16, 0);  // one word per staged target byte slot
+    {
+        std::map<std::pair<const uint8_t *, int>, int> owner;  // target slice -> a pair that carries its splice arrays
+        for (int p = 0; p < n; ++p) owner[std::make_pair(pairs[p].target + pairs[p].target_start, pairs[p].target_length)] = p;
+        for (auto &kv : tmap) {
+            const c4b_pair &pp = pairs[owner[kv.first]];
+            for (int j = 0; j < pp.target_length; ++j) {
+                uint32_t w = 0;
+                for (int k = 0; k < 4; ++k)
+                    w |= (uint32_t)(uint8_t)(int8_t)pp.splice[k][pp.target_start + j] << (8 * k);
+                hsp[kv.second + j] = w;
+            }
+        }
+    }
+    std::vector<uint2> xt(25);
+    for (int tc = 0; tc < 25; ++tc) {
+        int8_t x[8] = {0};
+        for (int k = 0; k < n_used; ++k) x[k] = (tc < 24) ? (int8_t)(scoring->dna_matrix[code_of[k] * 24 + tc] - mdl.open) : 0;
+        x[kPadClass] = (int8_t)(-100 - mdl.open);
+        memcpy(&xt[tc], x, 8);
+    }
+    // ---- traceback arena + chunks ------------------------------------------------------
+    b->order.resize(n);
+    for (int p = 0; p < n; ++p) b->order[p] = p;
+    std::sort(b->order.begin(), b->order.end(), [&](int a, int c) {
+        const int64_t ca = (int64_t)pairs[a].query_length * pairs[a].target_length;
+        const int64_t cc = (int64_t)pairs[c].query_length * pairs[c].target_length;
+        return ca != cc ? ca > cc : a < c;
+    });
+    size_t free_b = 0, total_b = 0;
+    C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fixed = qbytes + tbytes * 5 + (1ull << 30);
+    const size_t budget_hw = (free_b > fixed + (1ull << 30) ? (free_b - fixed) / 2 : (256ull << 20)) / 2;
+    std::vector<size_t> tb_off(n, 0);
+    size_t arena = 0;
+    int64_t ops_cursor = 0;
+    std::vector<E2gJob> jobs(n);
+    if (want_path) {
+        size_t cur = 0;
+        int begin = 0;
+        for (int k = 0; k < n; ++k) {
+            const c4b_pair &pp = pairs[b->order[k]];
+            const size_t hw = align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 8);
+            if (hw > budget_hw) {
+                set_error("traceback of pair " + std::to_string(b->order[k]) + " exceeds the device memory budget");
+                delete b;
+                return -1;
+            }
+            if (cur + hw > budget_hw) { b->chunks.push_back({begin, k}); begin = k; cur = 0; }
+            tb_off[k] = cur;
+            cur += hw;
+            arena = std::max(arena, cur);
+            E2gJob &J = jobs[k];
+            J.pair = k; J.result = b->order[k]; J.q_origin = pp.query_start; J.t_origin = pp.target_start;
+            J.ops_cap = (int32_t)std::min<int64_t>((int64_t)pp.query_length + pp.target_length + 4, INT32_MAX);
+            J.ops_off = ops_cursor; J.reserved = 0;
+            ops_cursor += J.ops_cap;
+        }
+        if (begin < n) b->chunks.push_back({begin, n});
+    } else {
+        b->chunks.push_back({0, n});
+    }
+    int rc = 0;
+    rc |= b->d_seq.alloc(qbytes + tbytes + 64);
+    rc |= b->d_sp.alloc(tbytes + 16);
+    rc |= b->d_lut.alloc(512);
+    rc |= b->d_xtab.alloc(25);
+    rc |= b->d_bad.alloc(1);
+    rc |= b->d_pairs.alloc(n);
+    rc |= b->d_outs.alloc(n);
+    rc |= b->d_results.alloc(n);
+    rc |= b->d_qorg.alloc(n);
+    rc |= b->d_torg.alloc(n);
+    if (want_path) {
+        rc |= b->d_jobs.alloc(n);
+        rc |= b->d_tb.alloc(arena + 16);
+        rc |= b->d_ops_slots.alloc(2 * (size_t)ops_cursor + 2);
+        rc |= b->d_ops_packed.alloc(2 * (size_t)ops_cursor + 2);
+        rc |= b->d_new_off.alloc((size_t)n + 1);
+    }
+    if (rc) { delete b; return -1; }
+    std::vector<E2gPair> hp(n);
+    std::vector<int32_t> hq(n), ht(n);
+    for (int k = 0; k < n; ++k) {
+        const int p = b->order[k];
+        E2gPair &e = hp[k];
+        e.q = b->d_seq.p + qoff[p];
+        e.t = b->d_seq.p + qbytes + toff[p];
+        e.sp = b->d_sp.p + toff[p];
+        e.Q = pairs[p].query_length;
+        e.T = pairs[p].target_length;
+        e.tb = want_path ? b->d_tb.p + tb_off[k] : nullptr;
+        e.out_index = k;
+        hq[k] = pairs[p].query_start;
+        ht[k] = pairs[p].target_start;
+    }
+    bool ok = true;
+    ok &= cudaMemcpyAsync(b->d_seq.p, hseq.data(), qbytes + tbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_sp.p, hsp.data(), (tbytes + 16) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_xtab.p, xt.data(), 25 * sizeof(uint2), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_pairs.p, hp.data(), n * sizeof(E2gPair), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_qorg.p, hq.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_torg.p, ht.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    if (want_path)
+        ok &= cudaMemcpyAsync(b->d_jobs.p, jobs.data(), n * sizeof(E2gJob), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    if (qbytes) encode_kernel<<<(unsigned)((qbytes / 16 + 255) / 256 + 1), 256, 0, stream>>>(b->d_seq.p, qbytes, b->d_lut.p, b->d_bad.p);
+    if (tbytes) encode_kernel<<<(unsigned)((tbytes / 16 + 255) / 256 + 1), 256, 0, stream>>>(b->d_seq.p + qbytes, tbytes, b->d_lut.p + 256, b->d_bad.p);
+    (*launch_counter) += 2;
+    ok &= cudaStreamSynchronize(stream) == cudaSuccess;
+    int bad = 0;
+    ok &= cudaMemcpy(&bad, b->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok || bad) {
+        set_error(bad ? "a sequence holds a symbol outside the substitution matrix alphabet"
+                      : "staging the est2genome batch failed");
+        delete b;
+        return -1;
+    }
+    cudaEventCreate(&b->ev_a);
+    cudaEventCreate(&b->ev_b);
+    *out = b;
+    return 0;
+}
+
+static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
+    cudaStream_t st = b->stream;
+    const int n = b->n;
+    const int threads = 32 * b->warps;
+    C4B_CUDA(cudaEventRecord(b->ev_a, st));
+    if (!b->want_path) {
+        e2g_fill_kernel<false><<<n, threads, 0, st>>>(b->d_pairs.p, b->d_outs.p, b->mdl, b->d_xtab.p);
+        C4B_CUDA(cudaGetLastError());
+        C4B_CUDA(cudaEventRecord(b->ev_b, st));
+        e2g_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs.p, b->d_outs.p, b->d_qorg.p,
+                                                                 b->d_torg.p, n, b->d_results.p);
+        (*b->launches) += 2;
+        C4B_CUDA(cudaGetLastError());
+        return 0;
+    }
+    for (const Chunk &c : b->chunks) {
+        const int cnt = c.end - c.begin;
+        e2g_fill_kernel<true><<<cnt, threads, 0, st>>>(b->d_pairs.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p);
+        C4B_CUDA(cudaGetLastError());
+        e2g_traceback_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs.p, b->d_outs.p, b->d_jobs.p + c.begin, cnt,
+                                                            b->mdl, threshold, b->d_results.p, b->d_ops_slots.p);
+        C4B_CUDA(cudaGetLastError());
+        (*b->launches) += 2;
+    }
+    C4B_CUDA(cudaEventRecord(b->ev_b, st));
+    apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_results.p, n, threshold);
+    ops_scan_kernel<<<1, 1024, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_new_off.p + n);
+    ops_compact_kernel<<<n, 64, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_ops_slots.p, b->d_ops_packed.p);
+    (*b->launches) += 3;
+    C4B_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int e2g_batch_fetch(E2gBatch *b, c4b_result *results, int32_t *ops, int64_t ops_capacity) {
+    cudaStream_t st = b->stream;
+    const int n = b->n;
+    if (!b->want_path) {
+        std::vector<c4b_result> tmp(n);
+        C4B_CUDA(cudaMemcpyAsync(tmp.data(), b->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
+        C4B_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < n; ++k) results[b->order[k]] = tmp[k];
+        return 0;
+    }
+    int64_t total = 0;
+    C4B_CUDA(cudaMemcpyAsync(results, b->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaMemcpyAsync(&total, b->d_new_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < n; ++k)
+        if (results[k].status >= 2) {
+            set_error("internal: est2genome traceback of pair " + std::to_string(k) + " failed with status " +
+                      std::to_string(results[k].status));
+            return -1;
+        }
+    if (total > ops_capacity) {
+        set_error("ops buffer too small: need capacity " + std::to_string(total));
+        return -3;
+    }
+    if (total) C4B_CUDA(cudaMemcpy(ops, b->d_ops_packed.p, 2 * (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static double e2g_batch_fill_ms(E2gBatch *b) {
+    float f = 0;
+    cudaStreamSynchronize(b->stream);
+    if (cudaEventElapsedTime(&f, b->ev_a, b->ev_b) != cudaSuccess) return -1;
+    return f;
+}
+
+}  // namespace c4b

@@ -345,3 +345,29 @@ def protein_pair(seed, qlen, tlen, rate=0.2):
     off = rng.randrange(0, tlen - len(core) + 1)
     t = rand_dna(rng, off, PROTEIN_ALPHABET) + core + rand_dna(rng, tlen - len(core) - off, PROTEIN_ALPHABET)
     return q, t
+
+
+def gene_pair(seed, qlen, tlen, n_exons=5, rate=0.02, reverse=False):
+    """cDNA query of n_exons exons; target = the exons (lightly mutated) separated
+    by GT..AG introns (CT..AC for a reverse-strand gene) planted in random flank."""
+    rng = random.Random(seed)
+    n_exons = max(1, min(n_exons, qlen // 8 or 1))
+    cuts = sorted(rng.sample(range(1, qlen), n_exons - 1)) if n_exons > 1 else []
+    exons = [e for e in (("x" * qlen)[a:b] for a, b in zip([0] + cuts, cuts + [qlen]))]
+    q = rand_dna(rng, qlen)
+    pos, parts = 0, []
+    for e in exons:
+        parts.append(q[pos:pos + len(e)])
+        pos += len(e)
+    spare = max(0, tlen * 3 // 4 - qlen)
+    intron = max(35, spare // max(1, n_exons - 1))
+    donor, acceptor = ("CT", "AC") if reverse else ("GT", "AG")
+    body = ""
+    for k, e in enumerate(parts):
+        body += mutate(rng, e, rate)
+        if k + 1 < len(parts):
+            body += donor + rand_dna(rng, max(1, intron - 4)) + acceptor
+    if len(body) >= tlen:
+        return q, body[:tlen]
+    left = rng.randrange(0, tlen - len(body) + 1)
+    return q, rand_dna(rng, left) + body + rand_dna(rng, tlen - len(body) - left)

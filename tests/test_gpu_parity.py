@@ -47,7 +47,9 @@ def test_golden_vectors(eng, name, params, scoring):
     pairs = PairSet([c["q"] for c in cases], [c["t"] for c in cases],
                     splice=[splice_for(name, c) for c in cases])
     b = Batch(eng, model, scoring, pairs, want_path=True)
-    assert b.kernel_name == ("affine_systolic" if name in AFFINE else "generic_wavefront")
+    want_kernel = "affine_systolic" if name in AFFINE else \
+        "e2g_systolic" if name == "est2genome" else "generic_wavefront"
+    assert b.kernel_name == want_kernel
     b.close()
     opt = Optimal(eng, model, scoring)
     scores = opt.find_score(pairs)
@@ -261,3 +263,80 @@ def test_full_size_properties(eng, params, scoring, ql, tl):
                                     region_threshold_cells=0, max_ops=ql + tl)
     assert paths[0]["score"] == want["score"] and paths[0]["region"] == want["region"]
     assert paths[0]["ops"] == want["ops"]
+
+
+def e2g_oracle(model, scoring, q, t, sp, region=None):
+    return helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, splice=sp, region=region),
+                                  abi.MODE_FIND_PATH, max_ops=len(q) + len(t) + 8)
+
+
+E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257, 2500), (511, 1200),
+              (513, 3000), (600, 5000), (1000, 6000), (1300, 2500), (2047, 2400)]
+
+
+def test_est2genome_systolic_vs_oracle(eng, params, scoring):
+    """The hand-specialised est2genome kernel (1..8 strips of 256 rows, pipelined
+    through shared memory) against the oracle: forward and reverse-strand genes,
+    ragged sizes around the strip height, unrelated and N-rich inputs; one mixed
+    batch (idle strips for short queries) and per-shape batches (every strip count)."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    model, _ = helpers.load_model("est2genome", params)
+    rng = random.Random(3)
+    qs, ts = [], []
+    for k, (ql, tl) in enumerate(E2G_SHAPES):
+        q, t = helpers.gene_pair(4000 + k, ql, tl, n_exons=1 + k % 5, rate=rng.choice([0.0, 0.02, 0.1]),
+                                 reverse=bool(k & 1))
+        qs.append(q)
+        ts.append(t)
+    qs.append(helpers.rand_dna(rng, 300)); ts.append(helpers.rand_dna(rng, 1500))
+    qs.append(helpers.rand_dna(rng, 200, "ACGTN")); ts.append(helpers.rand_dna(rng, 800, "ACGTNRY"))
+    sp = [splice_arrays(t) for t in ts]
+    want = [e2g_oracle(model, scoring, q, t, s_) for q, t, s_ in zip(qs, ts, sp)]
+    assert any(any(model.transitions[t_].advance_target == 2 for t_, _ in w["ops"]) for w in want)
+    opt = Optimal(eng, model, scoring)
+
+    def check(idx):
+        pairs = PairSet([qs[k] for k in idx], [ts[k] for k in idx], splice=[sp[k] for k in idx])
+        b = Batch(eng, model, scoring, pairs, want_path=True)
+        assert b.kernel_name == "e2g_systolic"
+        b.close()
+        scores = opt.find_score(pairs)
+        paths = opt.find_path(pairs)
+        for n, k in enumerate(idx):
+            shape = (len(qs[k]), len(ts[k]))
+            assert scores[n] == want[k]["score"], shape
+            assert paths[n]["score"] == want[k]["score"], shape
+            assert paths[n]["region"] == want[k]["region"], shape
+            assert paths[n]["ops"] == want[k]["ops"], shape
+
+    check(list(range(len(qs))))
+    for k in range(len(E2G_SHAPES)):
+        check([k])
+
+
+def test_est2genome_regions_threshold_and_fallback(eng, params, scoring):
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    model, _ = helpers.load_model("est2genome", params)
+    opt = Optimal(eng, model, scoring)
+    q, t = helpers.gene_pair(77, 400, 3000)
+    sp = splice_arrays(t)
+    regions = [(0, 0, 400, 3000), (10, 100, 300, 2500), (200, 0, 200, 3000), (0, 1500, 400, 1500)]
+    paths = opt.find_path(PairSet([q] * 4, [t] * 4, splice=[sp] * 4, regions=regions))
+    for k, reg in enumerate(regions):
+        want = e2g_oracle(model, scoring, q, t, sp, region=reg)
+        assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"], reg
+        assert paths[k]["ops"] == want["ops"], reg
+    r = opt.find_path(PairSet([q], [t], splice=[sp]), threshold=10 ** 6)[0]
+    assert r["status"] == 1 and r["ops"] == []
+    # queries beyond 8 strips take the table-driven kernel, same answers
+    q2, t2 = helpers.gene_pair(78, 2100, 2600)
+    sp2 = splice_arrays(t2)
+    pairs = PairSet([q2], [t2], splice=[sp2])
+    b = Batch(eng, model, scoring, pairs, want_path=True)
+    assert b.kernel_name == "generic_wavefront"
+    b.close()
+    want = e2g_oracle(model, scoring, q2, t2, sp2)
+    got = opt.find_path(pairs)[0]
+    assert got["score"] == want["score"] and got["ops"] == want["ops"]
