@@ -1,0 +1,202 @@
+// affine_packed16.cuh -- score pass of the affine:local lattice fill with TWO
+// lattices per warp, one in each 16-bit half of every register (DPX S16x2).
+//
+// Same recurrence, same closed-model order and the same END rule as
+// affine_fill_kernel<R, false, END_ANYWHERE, SCORE_PRMT> (affine_systolic.cuh;
+// reference: generated optimal:affine:local find score / find region,
+// src/c4/viterbi.c:1638-1727, semantics viterbi.c:655-837), and bit-identical
+// results: the int32 max-plus values of a LOCAL lattice are bounded,
+//     0 <= M <= max_sub * min(Q, T),    D, I >= 2 * gap_open + gap_extend,
+// so when max_sub * (min(Q,T) + 1) fits 15 bits no 16-bit add can wrap and the
+// halfword arithmetic IS the int32 arithmetic.  The host (affine_create) sends a
+// lattice here only when that bound, Q + 1 <= 32 R (one sweep) and <= 4 query
+// symbol classes hold; everything else takes the int32 kernel.
+//
+// Mapping: one CTA = one warp = lattices 2b (low halves) and 2b+1 (high halves).
+// VIADDMNMX.S16x2 / VIMNMX.S16x2.RELU / VIMNMX3.S16x2 each advance both lattices,
+// and ONE prmt builds both sign-extended substitution scores: the 8-byte pool is
+// {column of A's target symbol (4 classes), column of B's target symbol}, the
+// per-row selector picks (class_A, sign, 4 + class_B, sign).
+//
+// Padding is by input conditioning: rows below a query select "sign of a pool
+// byte" for both bytes (score' = 0 or -1, i.e. s = gap_open or gap_open - 1 < 0)
+// and columns right of a target use the "no symbol" column (score' = 0).  Every
+// move into or inside the padding is strictly negative, so a padded cell with
+// value v > 0 descends from a real cell with value > v that precedes it in the
+// reference's scan order (target outer, query inner): padding can never be the
+// first maximum (viterbi.c:778-791), and real cells never read padded ones.
+#pragma once
+#include "affine_systolic.cuh"
+
+namespace c4b {
+
+constexpr uint32_t kNeg16x2 = 0xC000C000u;  // -16384 | -16384: "not reachable"
+constexpr uint32_t kMin16x2 = 0x80008000u;  // -32768 | -32768
+
+__device__ __forceinline__ uint32_t pack16(int v) {
+    return ((uint32_t)v & 0xFFFFu) * 0x10001u;
+}
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
+
+template <int R>
+__global__ void __launch_bounds__(32, 12)
+affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
+                     const AffModel mdl, const void *__restrict__ score_table) {
+    __shared__ uint32_t xt4[25];
+    const int lane = threadIdx.x;
+    const int ia = 2 * blockIdx.x, ib = min(ia + 1, n - 1);
+    const AffPair PA = pairs[ia], PB = pairs[ib];
+    const int QA = PA.Q, TA = PA.T, QB = PB.Q, TB_ = PB.T;
+    const int T = max(TA, TB_);
+    if (lane < 25) xt4[lane] = reinterpret_cast<const uint2 *>(score_table)[lane].x;  // classes 0..3
+    __syncwarp();
+
+    const int open = mdl.openD;
+    const uint32_t open2 = pack16(open), extD2 = pack16(mdl.extD), extI2 = pack16(mdl.extI);
+    const int nsteps = T + 1 + 31;
+    const int row0 = lane * R;
+
+    uint32_t sel[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = row0 + r;  // lattice row; consumes query symbol i-1
+        uint32_t sa = 0x88u, sb = 0xCCu;  // padding: sign of pool byte 0 / byte 4
+        if (i >= 1 && i <= QA) { const uint32_t c = PA.q[i - 1]; sa = c | ((c | 8u) << 4); }
+        if (i >= 1 && i <= QB) { const uint32_t c = 4u + PB.q[i - 1]; sb = c | ((c | 8u) << 4); }
+        sel[r] = sa | (sb << 8);
+    }
+    uint32_t Mp[R], Dp[R];  // G = M + open and D of the previous column, both lattices
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        Mp[r] = kNeg16x2;
+        Dp[r] = kNeg16x2;
+    }
+    uint32_t topM = kNeg16x2, topI = kNeg16x2, topMprev = kNeg16x2;
+    uint32_t in_code = kTargetNone | (kTargetNone << 8), code0 = in_code;
+
+    // per lattice: first strict maximum of END in (target outer, query inner) order
+    uint32_t best2 = kMin16x2;
+    int bjA = 0, biA = 0, bjB = 0, biB = 0;
+    uint32_t pend = kMin16x2;
+    int pend_j = 0;
+    auto settle_pending = [&]() {
+        const uint32_t nb = __vimax3_s16x2(best2, pend, pend);
+        if (nb != best2) {  // some half improved strictly (columns arrive in increasing j)
+            if (lo16(pend) > lo16(best2)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) & 0xFFFFu) == 0) { bi = row0 + r; found = true; }
+                biA = bi;
+                bjA = pend_j;
+            }
+            if (hi16(pend) > hi16(best2)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) >> 16) == 0) { bi = row0 + r; found = true; }
+                biB = bi;
+                bjB = pend_j;
+            }
+            best2 = nb;
+        }
+        pend = kMin16x2;
+    };
+
+    auto step = [&](const int s, auto ALL) {
+        constexpr bool all_active = decltype(ALL)::value;
+        const int j = s - lane;
+        settle_pending();
+        const uint32_t code = (lane == 0) ? code0 : in_code;
+        {   // column s+1 of both lattices (uniform addresses, lane 0 consumes them)
+            const uint32_t ca = (s + 1 <= TA) ? (uint32_t)PA.t[s] : (uint32_t)kTargetNone;
+            const uint32_t cb = (s + 1 <= TB_) ? (uint32_t)PB.t[s] : (uint32_t)kTargetNone;
+            code0 = ca | (cb << 8);
+        }
+        uint32_t botM = kNeg16x2, botI = kNeg16x2;
+        if (all_active || (j >= 0 && j <= T)) {
+            const uint32_t Xa = xt4[code & 0xFFu], Xb = xt4[code >> 8];
+            uint32_t cm = kMin16x2;
+            // phase A, bottom-up, rows independent: D of this column, max(match, D)
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                uint32_t sc;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(Xa), "r"(Xb), "r"(sel[r]));
+                const uint32_t diag = (r == 0) ? topMprev : Mp[r - 1];
+                Dp[r] = __viaddmax_s16x2(Dp[r], extD2, Mp[r]);
+                Mp[r] = __viaddmax_s16x2(diag, sc, Dp[r]);
+            }
+            // phase B, top-down: the vertical chain I -> M -> G
+            uint32_t upM = topM, upI = topI;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t Iv = __viaddmax_s16x2(upI, extI2, upM);
+                const uint32_t Mv = __vimax_s16x2_relu(Mp[r], Iv);       // START's 0 is the RELU
+                const uint32_t Gv = __viaddmax_s16x2(Mv, open2, kMin16x2);  // M + open per half
+                Mp[r] = Gv;
+                upM = Gv;
+                upI = Iv;
+                if (r & 1) cm = __vimax3_s16x2(cm, Gv, Mp[r - 1]);
+            }
+            botM = upM;
+            botI = upI;
+            topMprev = topM;
+            pend = cm;
+            pend_j = j;
+        }
+        const uint32_t nM = __shfl_up_sync(0xffffffffu, botM, 1);
+        const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
+        const uint32_t nC = __shfl_up_sync(0xffffffffu, code, 1);
+        if (lane > 0) {
+            topM = nM;
+            topI = nI;
+            in_code = nC;
+        }
+    };
+
+    const int fill_end = min(31, nsteps);
+    const int steady_end = max(fill_end, min(T + 1, nsteps));
+    int s = 0;
+    for (; s < fill_end; ++s) step(s, std::false_type{});
+    for (; s < steady_end; ++s) step(s, std::true_type{});
+    for (; s < nsteps; ++s) step(s, std::false_type{});
+    settle_pending();
+    __syncwarp();
+
+    // lexicographic warp reduction per lattice: max score, then min j, then min i
+    int bA = lo16(best2), bB = hi16(best2);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bA, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjA, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biA, off);
+            if ((ob > bA) || (ob == bA && (oj < bjA || (oj == bjA && oi < biA)))) { bA = ob; bjA = oj; biA = oi; }
+        }
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bB, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjB, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biB, off);
+            if ((ob > bB) || (ob == bB && (oj < bjB || (oj == bjB && oi < biB)))) { bB = ob; bjB = oj; biB = oi; }
+        }
+    }
+    if (lane == 0) {
+        AffOut o;
+        o.best = bA - open;  // tracked as G = M + open
+        o.end_i = biA;
+        o.end_j = bjA;
+        o.flags = 0;
+        outs[PA.out_index] = o;
+        if (ia + 1 < n) {
+            o.best = bB - open;
+            o.end_i = biB;
+            o.end_j = bjB;
+            outs[PB.out_index] = o;
+        }
+    }
+}
+
+}  // namespace c4b

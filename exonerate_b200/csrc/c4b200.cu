@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "affine_systolic.cuh"
+#include "affine_packed16.cuh"
 #include "affine_traceback.cuh"
 #include "generic_wavefront.cuh"
 #include "e2g_systolic.cuh"
@@ -218,6 +219,7 @@ struct c4b_batch {
     // ---- affine path ----
     AffModel aff;
     int R = 32, score_mode = SCORE_PRMT, max_sub = 0, gap_min = 0;
+    int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
     DevBuf<uint8_t> d_seq;
@@ -298,6 +300,29 @@ int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, boo
     case 8: launch_fill_r<8>(b, pairs, outs, count, tb); break;
     case 16: launch_fill_r<16>(b, pairs, outs, count, tb); break;
     default: launch_fill_r<32>(b, pairs, outs, count, tb); break;
+    }
+    C4B_CUDA(cudaGetLastError());
+    C4B_CUDA(cudaEventRecord(ev.b, b->e->stream));
+    b->e->launches++;
+    return 0;
+}
+
+// score pass of the first `count` lattices of d_full, two per warp (affine_packed16.cuh)
+int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count) {
+    if (!count) return 0;
+    if ((size_t)b->fill_events_used >= b->fill_events.size()) {
+        EventPair ev;
+        C4B_CUDA(cudaEventCreate(&ev.a));
+        C4B_CUDA(cudaEventCreate(&ev.b));
+        b->fill_events.push_back(ev);
+    }
+    EventPair &ev = b->fill_events[b->fill_events_used++];
+    C4B_CUDA(cudaEventRecord(ev.a, b->e->stream));
+    const int blocks = (count + 1) / 2;
+    switch (b->R) {
+    case 8: affine_fill16_kernel<8><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    case 16: affine_fill16_kernel<16><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    default: affine_fill16_kernel<32><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
     }
     C4B_CUDA(cudaGetLastError());
     C4B_CUDA(cudaEventRecord(ev.b, b->e->stream));
@@ -463,6 +488,21 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     };
     std::sort(b->score_list.begin(), b->score_list.end(), by_cost);
     std::sort(b->direct_list.begin(), b->direct_list.end(), by_cost);
+    // Packed 16-bit score pass (affine_packed16.cuh): exact whenever no halfword add
+    // can wrap.  Eligible lattices go first in score_list, still cost-descending.
+    {
+        const char *env = getenv("C4B_AFFINE_PACK16");
+        const bool allow = !(env && atoi(env) == 0);
+        const bool model_ok = allow && local && b->score_mode == SCORE_PRMT && n_used <= 4 && max_sub > 0 &&
+                              b->aff.openD < 0 && b->aff.openD > -1000 && b->aff.extD < 0 && b->aff.extD > -1000 &&
+                              b->aff.extI < 0 && b->aff.extI > -1000;
+        auto fits16 = [&](int p) {
+            const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
+            return model_ok && Q + 1 <= 32 * b->R && (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
+        };
+        auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
+        b->n16 = (int)(mid - b->score_list.begin());
+    }
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
 
     // ---- traceback arena, chunked to a memory budget
@@ -687,7 +727,8 @@ int affine_run(c4b_batch *b, c4b_score threshold) {
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
     b->fill_events_used = 0;
     // pass 1: score + END cell over the full lattices, nothing written per cell
-    if (launch_fill(b, b->d_full.p, b->d_out1.p, ns, false)) return -1;
+    if (launch_fill16(b, b->d_full.p, b->d_out1.p, b->n16)) return -1;
+    if (launch_fill(b, b->d_full.p + b->n16, b->d_out1.p, ns - b->n16, false)) return -1;
     if (!b->want_path) {
         if (ns) {
             // results are indexed by ordered slot here; the host un-permutes on fetch

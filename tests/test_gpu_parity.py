@@ -144,6 +144,53 @@ def test_banded_two_pass_route(eng, params, scoring):
         assert paths[k]["ops"] == want["ops"], k
 
 
+def test_packed16_score_pass(eng, params, scoring, monkeypatch):
+    """affine_fill16_kernel (two lattices per warp in 16-bit halves) is the score
+    pass of ACGT-only local batches: ragged partners, odd counts, identical and
+    unrelated sequences, every strip width, against the oracle; and against the
+    int32 kernel (C4B_AFFINE_PACK16=0) on the same batch."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    rng = random.Random(77)
+    for maxq in (30, 250, 500, 1023):
+        qs, ts = [], []
+        shapes = [(maxq, 700), (1, 1), (maxq, 40), (max(1, maxq // 3), 2500), (max(1, maxq - 1), 33)]
+        shapes += [(rng.randrange(1, maxq + 1), rng.randrange(1, 1800)) for _ in range(8)]
+        for k, (ql, tl) in enumerate(shapes):
+            q, t = helpers.dna_pair(maxq * 131 + k, ql, tl, rate=rng.choice([0.0, 0.1, 0.3]))
+            qs.append(q)
+            ts.append(t)
+        same = helpers.rand_dna(rng, maxq)          # the largest reachable score for this Q
+        qs.append(same); ts.append(same)
+        qs.append("A" * min(maxq, 200)); ts.append("C" * 300)   # best score 0 -> END at (0,0)
+        pairs = PairSet(qs, ts)
+        assert pairs.n % 2 == 1
+        scores = opt.find_score(pairs)
+        paths = opt.find_path(pairs)
+        monkeypatch.setenv("C4B_AFFINE_PACK16", "0")
+        scores32 = opt.find_score(pairs)
+        paths32 = opt.find_path(pairs)
+        monkeypatch.delenv("C4B_AFFINE_PACK16")
+        assert scores == scores32 and paths == paths32
+        for k in range(pairs.n):
+            want = oracle_path(model, scoring, qs[k], ts[k])
+            assert scores[k] == want["score"], (maxq, k)
+            assert paths[k]["region"] == want["region"] and paths[k]["ops"] == want["ops"], (maxq, k)
+    # metric shape: the END cell (score, query_end, target_end) of both kernels agrees
+    qs, ts = [], []
+    for k in range(5):
+        q, t = helpers.dna_pair(52000 + k, 1000, 100000 - 1000 * k)
+        qs.append(q)
+        ts.append(t)
+    pairs = PairSet(qs, ts)
+    got = opt.find_path(pairs)
+    monkeypatch.setenv("C4B_AFFINE_PACK16", "0")
+    want = opt.find_path(pairs)
+    monkeypatch.delenv("C4B_AFFINE_PACK16")
+    assert got == want and all(r["score"] > 2000 for r in got)
+
+
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
     from exonerate_b200 import Optimal, PairSet
     model, _ = helpers.load_model("affine_local_protein", params)

@@ -22,6 +22,10 @@ __global__ void k(int *out, int a0, int b0, int c0) {
             if (OP == 6) acc[i] = __viaddmax_s16x2(acc[i], b, c);            // packed 16-bit
             if (OP == 7) acc[i] = __vimax3_s16x2(acc[i], b, c + i);
             if (OP == 8) acc[i] = __vimax_s32_relu(acc[i] , c + i);
+            if (OP == 10) acc[i] = __vimax_s16x2_relu(acc[i], c + i);        // VIMNMX.S16x2.RELU
+            if (OP == 11) acc[i] = __vmaxs2(acc[i], c + i);             // VIMNMX.S16x2
+            if (OP == 12) acc[i] = __viaddmax_u16x2(acc[i], b, c);           // VIADDMNMX.U16x2
+            if (OP == 13) acc[i] = __vimax3_s16x2_relu(acc[i], b, c + i);    // VIMNMX3.S16x2.RELU
             if (OP == 9) { asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(acc[i]) : "r"(a0), "r"(b)); acc[i] = max(acc[i], c); } // IMAD+VIMNMX
         }
         b ^= it;
@@ -57,5 +61,7 @@ int main() {
     run<0>("VIADDMNMX", 1); run<1>("VIMNMX3", 1); run<2>("VIMNMX", 1); run<3>("IADD", 1);
     run<4>("IMAD", 1); run<5>("PRMT", 1); run<6>("VIADDMNMX.16x2", 1); run<7>("VIMNMX3.16x2", 1);
     run<8>("VIMNMX.RELU", 1); run<9>("IMAD+VIMNMX pair", 2);
+    run<10>("VIMNMX.S16x2.RELU", 1); run<11>("VIMNMX.S16x2", 1); run<12>("VIADDMNMX.U16x2", 1);
+    run<13>("VIMNMX3.S16x2.RELU", 1);
     return 0;
 }
