@@ -25,6 +25,29 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "GCUPS affine:local find_path (score+region+ops, bit-exact), 1 kbp x 100 kbp DNA batch"
 B_ALG = 20  # algorithmic bytes per lattice cell, SURVEY.md 8d: 4 B x 5 states x C=1
 
+# The default run is BASELINE.json's metric configuration (affine:local).  --model
+# est2genome runs north_star's second target workload (configs[2]) the same way.
+WORKLOADS = {
+    "affine:local": {
+        "metric": METRIC, "b_alg": B_ALG, "pairs": 10000, "cpu_pairs": 2,
+        "workload": "affine:local --exhaustive, %d bp x %d bp DNA pairs",
+        "kernel": "affine_fill16 (score pass, two lattices per warp in 16-bit halves) + affine_systolic "
+                  "(banded traceback pass, int32)",
+        "traffic_key": "affine_fill16_kernel<32>",
+        "note": "B_alg=20 B/cell (SURVEY 8d, reference row layout); the kernel keeps rows in registers and "
+                "writes 0.5 B/cell only inside the traceback band, so frac>1 is expected; see DESIGN.md. peak ",
+    },
+    "est2genome": {
+        "metric": "GCUPS est2genome find_path (score+region+ops, bit-exact), 1 kbp cDNA x 100 kbp genomic batch",
+        "b_alg": 80, "pairs": 1000, "cpu_pairs": 1,
+        "workload": "est2genome --exhaustive, %d bp cDNA x %d bp genomic pairs (5 exons, GT..AG introns)",
+        "kernel": "e2g_systolic (one fill with 13-bit traceback records + walk)",
+        "traffic_key": "e2g_fill_kernel<1>",
+        "note": "B_alg=80 B/cell (SURVEY 8d: 4 B x 10 states x C=2, reference row layout); the kernel keeps "
+                "rows in registers and writes a 2 B/cell traceback record; see DESIGN.md. peak ",
+    },
+}
+
 
 # ----------------------------------------------------------------------------
 # synthetic workload: random target, mutated query planted in it
@@ -52,6 +75,32 @@ def make_batch(seed, n, qlen, tlen, rate=0.15):
         core = core[:tlen]
         off = int(rng.integers(0, tlen - len(core) + 1))
         targets[k, off:off + len(core)] = core
+    return queries, targets
+
+
+def make_batch_e2g(seed, n, qlen, tlen, n_exons=5, rate=0.02):
+    """cDNA of n_exons exons; genomic = random sequence with
+    the (lightly mutated) exons planted in order, separated by GT...AG introns."""
+    rng = np.random.default_rng(seed)
+    exon = qlen // n_exons
+    qlen = exon * n_exons
+    intron = max(40, (tlen * 3 // 4 - qlen) // max(1, n_exons - 1))
+    body_len = qlen + (n_exons - 1) * (intron + 4)
+    queries = ACGT[rng.integers(0, 4, size=(n, qlen), dtype=np.uint8)]
+    targets = ACGT[rng.integers(0, 4, size=(n, max(tlen, body_len)), dtype=np.uint8)]
+    for k in range(n):
+        off = int(rng.integers(0, targets.shape[1] - body_len + 1))
+        pos = off
+        for e in range(n_exons):
+            ex = queries[k, e * exon:(e + 1) * exon].copy()
+            sub = rng.random(exon) < rate
+            ex[sub] = ACGT[rng.integers(0, 4, size=int(sub.sum()))]
+            targets[k, pos:pos + exon] = ex
+            pos += exon
+            if e + 1 < n_exons:
+                targets[k, pos:pos + 2] = np.frombuffer(b"GT", dtype=np.uint8)
+                targets[k, pos + 2 + intron:pos + 4 + intron] = np.frombuffer(b"AG", dtype=np.uint8)
+                pos += intron + 4
     return queries, targets
 
 
@@ -94,11 +143,11 @@ def summarise_clocks(lines):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_traffic(cells):
+def measured_traffic(cells, key):
     """ncu-measured DRAM bytes of the dominant kernel, scaled to this launch."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        rec = json.load(open(path))["affine_fill_kernel<32,0,0,0>"]
+        rec = json.load(open(path))[key]
         return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / rec["cells"] * cells
     except (OSError, KeyError, ValueError):
         return None
@@ -114,7 +163,7 @@ def measured_peak():
 # ----------------------------------------------------------------------------
 # CPU arms: the reference's own implementation of the path on host cores
 # ----------------------------------------------------------------------------
-def _cpu_worker(kind, conn):
+def _cpu_worker(kind, conn, model_name="affine:local"):
     """One host process = one single-threaded reference instance.  Receives
     lists of (query, target) strings, answers (seconds, scores)."""
     def serve(align):
@@ -131,7 +180,7 @@ def _cpu_worker(kind, conn):
         from oracle import refdrv
 
         def fn(lib):
-            m = refdrv.RefModel(lib, "affine:local", 0, 0, compiled=True)
+            m = refdrv.RefModel(lib, model_name, 0, 0, compiled=True)
 
             def align(q, t):
                 p = m.pair(q, t)
@@ -145,11 +194,15 @@ def _cpu_worker(kind, conn):
         import helpers
         params = helpers.load_params()
         scoring = helpers.load_scoring(params)
-        model, _ = helpers.load_model("affine_local_dna", params)
+        model, _ = helpers.load_model("affine_local_dna" if model_name == "affine:local" else model_name, params)
 
         def align(q, t):
-            return helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t), region_threshold_cells=0,
-                                            max_ops=len(q) + len(t) + 8)["score"]
+            sp = None
+            if model_name == "est2genome":
+                from exonerate_b200.models import splice_arrays
+                sp = splice_arrays(t)
+            return helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t, splice=sp),
+                                            region_threshold_cells=0, max_ops=len(q) + len(t) + 8)["score"]
         serve(align)
 
 
@@ -161,13 +214,13 @@ def cpu_arm_available():
 class CpuPool:
     """`procs` persistent reference processes (the reference has no threading)."""
 
-    def __init__(self, kind, procs):
+    def __init__(self, kind, procs, model_name="affine:local"):
         import multiprocessing as mp
         ctx = mp.get_context("spawn")
         self.kind, self.workers = kind, []
         for _ in range(procs):
             parent, child = ctx.Pipe()
-            pr = ctx.Process(target=_cpu_worker, args=(kind, child), daemon=True)
+            pr = ctx.Process(target=_cpu_worker, args=(kind, child, model_name), daemon=True)
             pr.start()
             self.workers.append((pr, parent))
 
@@ -205,21 +258,22 @@ def reference_arm(args):
         return 0  # only rank 0 runs the CPU arm under torchrun
     kind = cpu_arm_available()
     procs = max(1, min(os.cpu_count() or 1, 64))
+    W = WORKLOADS[args.model]
     n = procs  # one pair per host process per step: a bounded sample of the workload
-    queries, targets = make_batch(1000, n, args.qlen, args.tlen)  # same generator/seed as rank 0 of our arm
-    cells = n * args.qlen * args.tlen
-    pool = CpuPool(kind, procs)
+    gen = make_batch if args.model == "affine:local" else make_batch_e2g
+    queries, targets = gen(1000, n, args.qlen, args.tlen)  # same generator/seed as rank 0 of our arm
+    cells = n * queries.shape[1] * targets.shape[1]
+    pool = CpuPool(kind, procs, args.model)
     for _ in range(args.warmup):
         pool.run(queries, targets)
     times = [pool.run(queries, targets)[0] for _ in range(args.steps)]
     pool.close()
     t = float(np.mean(times))
     gcups = cells / t / 1e9
-    line = {"impl": "reference", "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": W["metric"], "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "affine:local --exhaustive, %d bp x %d bp DNA pairs" % (args.qlen, args.tlen),
-                       "pairs_per_step": n},
+            "config": {"workload": W["workload"] % (args.qlen, args.tlen), "pairs_per_step": n},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": procs, "kind": kind,
                              "sample": "%d pairs of %d x %d per step, one per host process" % (n, args.qlen, args.tlen)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,10 +303,17 @@ def ours(args):
     from exonerate_b200.models import host_model
     params = helpers.load_params()
     scoring = helpers.load_scoring(params)   # the reference's Submat tables (tests/golden/scoring.json)
-    model, _ = host_model("affine:local")    # closed by the host C layer (csrc/host)
-    n = args.pairs
-    queries, targets = make_batch(1000 + rank, n, args.qlen, args.tlen)
-    pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)])
+    W = WORKLOADS[args.model]
+    model, _ = host_model(args.model)        # closed by the host C layer (csrc/host)
+    n = args.pairs or W["pairs"]
+    if args.model == "affine:local":
+        queries, targets = make_batch(1000 + rank, n, args.qlen, args.tlen)
+        splice = None
+    else:
+        from exonerate_b200.models import splice_arrays
+        queries, targets = make_batch_e2g(1000 + rank, n, args.qlen, args.tlen)
+        splice = [splice_arrays(targets[k]) for k in range(n)]   # host C splice predictor (csrc/host/splice.c)
+    pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)], splice=splice)
     cells = pairs.cells
 
     eng = Engine(local)
@@ -331,21 +392,18 @@ def ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         kfill = float(np.mean(fill_ms))
-        achieved = cells * B_ALG / (kfill * 1e-3) / 1e9
+        achieved = cells * W["b_alg"] / (kfill * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "metric": W["metric"], "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "affine:local --exhaustive, %d bp x %d bp DNA pairs" % (args.qlen, args.tlen),
+            "config": {"workload": W["workload"] % (queries.shape[1], targets.shape[1]),
                        "pairs_per_gpu": n, "cells_per_step": total_cells, "seed": 1000,
                        "l2": "inputs (%d MB per GPU) exceed the 126 MB L2" % (pairs.h2d_bytes >> 20),
-                       "kernel": "affine_systolic (score pass + banded traceback pass)"},
+                       "kernel": W["kernel"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(cells),
-                         "note": "B_alg=20 B/cell (SURVEY 8d, reference row layout); the kernel keeps rows "
-                                 "in registers and writes 0.5 B/cell only inside the traceback band, so "
-                                 "frac>1 is expected; see DESIGN.md. peak " + peak_src,
-                         "fill_kernel_ms": kfill},
+                         "frac": achieved / peak, "traffic": measured_traffic(cells, W["traffic_key"]),
+                         "note": W["note"] + peak_src, "fill_kernel_ms": kfill},
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": pairs.h2d_bytes * world,
                     "d2h_bytes_per_step": (n * 40 + n_ops_total * 8) * world},
             "gpu_launches": int(launches),
@@ -353,12 +411,12 @@ def ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_arm_available()
-            k = max(1, args.cpu_pairs)
-            pool = CpuPool(kind, 1)
+            k = max(1, args.cpu_pairs or W["cpu_pairs"])
+            pool = CpuPool(kind, 1, args.model)
             wall, cpu_scores = pool.run(queries[:k], targets[:k])
             pool.close()
             assert cpu_scores == [results[i].score for i in range(k)], "CPU baseline disagrees with the GPU scores"
-            line["cpu_baseline"] = {"value": k * args.qlen * args.tlen / wall / 1e9, "unit": "GCUPS", "cores": 1,
+            line["cpu_baseline"] = {"value": k * queries.shape[1] * targets.shape[1] / wall / 1e9, "unit": "GCUPS", "cores": 1,
                                     "kind": kind,
                                     "sample": "first %d pair(s) of the batch, single-threaded, %.1f s" % (k, wall)}
         print(json.dumps(line))
@@ -374,11 +432,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=10000, help="pairs per GPU per step (BASELINE: 10k)")
+    ap.add_argument("--model", default="affine:local", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0,
+                    help="pairs per GPU per step (default: 10k affine:local, 1k est2genome -- BASELINE configs)")
     ap.add_argument("--qlen", type=int, default=1000)
     ap.add_argument("--tlen", type=int, default=100000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-pairs", type=int, default=2)
+    ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fill-timing", action="store_true", help="read the fill-kernel events every step")
     args = ap.parse_args()

@@ -53,7 +53,15 @@ affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ out
     __syncwarp();
 
     const int open = mdl.openD;
-    const uint32_t open2 = pack16(open), extD2 = pack16(mdl.extD), extI2 = pack16(mdl.extI);
+    const uint32_t extD2 = pack16(mdl.extD), extI2 = pack16(mdl.extI);
+    // M + open per half without a DPX slot: after the RELU both halves are in
+    // [0, 32767], so adding K = {open, open + 0x8000} as ONE 32-bit integer never
+    // carries between the halves (low half <= 0x7FFF + 0x7FFF), and flipping bit 15
+    // afterwards takes the 0x8000 out again modulo 2^16.  The add is an IMAD by a
+    // run-time 1 (FMA pipe), the flip one LOP3; VIADDMNMX.S16x2 costs twice that
+    // on the binding ALU pipe (tools/ubench/dpx_rates.cu).
+    const uint32_t openK = (((uint32_t)open & 0xFFFFu) << 16) | (((uint32_t)open + 0x8000u) & 0xFFFFu);
+    const int one = mdl.one;
     const int nsteps = T + 1 + 31;
     const int row0 = lane * R;
 
@@ -135,7 +143,7 @@ affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ out
             for (int r = 0; r < R; ++r) {
                 const uint32_t Iv = __viaddmax_s16x2(upI, extI2, upM);
                 const uint32_t Mv = __vimax_s16x2_relu(Mp[r], Iv);       // START's 0 is the RELU
-                const uint32_t Gv = __viaddmax_s16x2(Mv, open2, kMin16x2);  // M + open per half
+                const uint32_t Gv = (uint32_t)add_open((int)Mv, one, (int)openK) ^ 0x8000u;  // M + open per half
                 Mp[r] = Gv;
                 upM = Gv;
                 upI = Iv;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -34,6 +35,11 @@ struct c4b_engine {
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0;
     cudaEvent_t stage_free = nullptr;  // last H2D that read h_stage
+    // staging pipeline of the affine path: sequence slices are copied and encoded on
+    // copy_stream while the score pass of the lattices that are already resident
+    // runs on the aux streams (concurrent launches fill each other's tails)
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -120,9 +126,12 @@ bool analyze_affine(const c4b_model &m, AffModel *am, int *match_kind) {
     return true;
 }
 
-__global__ void encode_kernel(uint8_t *buf, size_t n, const uint8_t *__restrict__ lut, int *bad) {
-    // raw symbol bytes -> matrix codes, 16 bytes per thread; 0xFF marks a symbol
-    // outside the substitution matrix alphabet (src/sequence/submat.c:26-55)
+__global__ void encode_kernel(uint8_t *buf, size_t n, const uint8_t *__restrict__ lut, int *bad,
+                              const uint32_t safe = 0xFFu) {
+    // raw symbol bytes -> matrix codes, 16 bytes per thread; a symbol outside the
+    // substitution matrix alphabet (LUT entry 0xFF; the reference reads out of
+    // bounds there, src/sequence/submat.c:26-55) raises *bad and is stored as
+    // `safe`, so a fill that was queued before the host saw the flag stays in bounds
     const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t base = v * 16;
     if (base >= n) return;
@@ -135,8 +144,8 @@ __global__ void encode_kernel(uint8_t *buf, size_t n, const uint8_t *__restrict_
             uint32_t o = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const uint32_t c = lut[(a[k] >> (8 * b)) & 255u];
-                any_bad |= (c == 0xFFu);
+                uint32_t c = lut[(a[k] >> (8 * b)) & 255u];
+                if (c == 0xFFu) { any_bad = true; c = safe; }
                 o |= c << (8 * b);
             }
             a[k] = o;
@@ -145,8 +154,8 @@ __global__ void encode_kernel(uint8_t *buf, size_t n, const uint8_t *__restrict_
         if (any_bad) atomicOr(bad, 1);
     } else {
         for (size_t k = base; k < n; ++k) {
-            const uint8_t c = lut[buf[k]];
-            if (c == 0xFF) atomicOr(bad, 1);
+            uint8_t c = lut[buf[k]];
+            if (c == 0xFF) { atomicOr(bad, 1); c = (uint8_t)safe; }
             buf[k] = c;
         }
     }
@@ -238,6 +247,14 @@ struct c4b_batch {
     size_t q_bytes = 0, t_bytes = 0;
     std::vector<EventPair> fill_events;
     int fill_events_used = 0;
+    // score pass (pass 1) launch groups: a contiguous range of score_list that becomes
+    // runnable when staging slice `slice` is resident
+    struct P1Group { int begin, end, slice; cudaEvent_t done; };
+    std::vector<P1Group> groups;
+    std::vector<cudaEvent_t> slice_events;
+    cudaEvent_t ev_base = nullptr, ev_p1a = nullptr, ev_p1b = nullptr;
+    bool pass1_inflight = false;  // launched by affine_create while staging was still running
+    bool bad_checked = false;
 
     // ---- generic path ----
     GenericBatch *generic = nullptr;
@@ -246,6 +263,11 @@ struct c4b_batch {
     E2gBatch *e2g = nullptr;
 
     ~c4b_batch() {
+        if (e && affine) {  // frees are ordered on e->stream: drain the side streams first
+            if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+            for (cudaStream_t a : e->aux)
+                if (a) cudaStreamSynchronize(a);
+        }
         d_seq.release(); d_lut.release(); d_score_table.release(); d_bad.release();
         d_full.release(); d_band.release(); d_direct.release();
         d_out1.release(); d_out2.release(); d_outd.release();
@@ -257,6 +279,12 @@ struct c4b_batch {
             if (ev.a) cudaEventDestroy(ev.a);
             if (ev.b) cudaEventDestroy(ev.b);
         }
+        for (auto &g : groups)
+            if (g.done) cudaEventDestroy(g.done);
+        for (auto ev : slice_events)
+            if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : {ev_base, ev_p1a, ev_p1b})
+            if (ev) cudaEventDestroy(ev);
         if (generic) generic_batch_destroy(generic);
         delete e2g;
     }
@@ -265,68 +293,77 @@ struct c4b_batch {
 namespace {
 
 template <int R, bool TB, int ENDMODE>
-void launch_fill_sm(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count) {
+void launch_fill_sm(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
     if (b->score_mode == SCORE_PRMT)
-        affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, 32, 0, b->e->stream>>>(
-            pairs, outs, b->aff, b->d_score_table.p);
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, 32, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
     else
-        affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM><<<count, 32, 0, b->e->stream>>>(
-            pairs, outs, b->aff, b->d_score_table.p);
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM><<<count, 32, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
 }
 
 template <int R>
-void launch_fill_r(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb) {
+void launch_fill_r(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb, cudaStream_t s) {
     const bool any = (b->aff.end_scope == C4B_SCOPE_ANYWHERE);
     if (tb) {
-        if (any) launch_fill_sm<R, true, END_ANYWHERE>(b, pairs, outs, count);
-        else launch_fill_sm<R, true, END_RESTRICTED>(b, pairs, outs, count);
+        if (any) launch_fill_sm<R, true, END_ANYWHERE>(b, pairs, outs, count, s);
+        else launch_fill_sm<R, true, END_RESTRICTED>(b, pairs, outs, count, s);
     } else {
-        if (any) launch_fill_sm<R, false, END_ANYWHERE>(b, pairs, outs, count);
-        else launch_fill_sm<R, false, END_RESTRICTED>(b, pairs, outs, count);
+        if (any) launch_fill_sm<R, false, END_ANYWHERE>(b, pairs, outs, count, s);
+        else launch_fill_sm<R, false, END_RESTRICTED>(b, pairs, outs, count, s);
     }
 }
 
-int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb) {
+// timed = bracket the launch with an event pair on its stream (c4b_batch_last_fill_ms)
+int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb, cudaStream_t s,
+                bool timed) {
     if (!count) return 0;
-    if ((size_t)b->fill_events_used >= b->fill_events.size()) {
-        EventPair ev;
-        C4B_CUDA(cudaEventCreate(&ev.a));
-        C4B_CUDA(cudaEventCreate(&ev.b));
-        b->fill_events.push_back(ev);
+    EventPair *ev = nullptr;
+    if (timed) {
+        if ((size_t)b->fill_events_used >= b->fill_events.size()) {
+            EventPair nev;
+            C4B_CUDA(cudaEventCreate(&nev.a));
+            C4B_CUDA(cudaEventCreate(&nev.b));
+            b->fill_events.push_back(nev);
+        }
+        ev = &b->fill_events[b->fill_events_used++];
+        C4B_CUDA(cudaEventRecord(ev->a, s));
     }
-    EventPair &ev = b->fill_events[b->fill_events_used++];
-    C4B_CUDA(cudaEventRecord(ev.a, b->e->stream));
     switch (b->R) {
-    case 8: launch_fill_r<8>(b, pairs, outs, count, tb); break;
-    case 16: launch_fill_r<16>(b, pairs, outs, count, tb); break;
-    default: launch_fill_r<32>(b, pairs, outs, count, tb); break;
+    case 8: launch_fill_r<8>(b, pairs, outs, count, tb, s); break;
+    case 16: launch_fill_r<16>(b, pairs, outs, count, tb, s); break;
+    default: launch_fill_r<32>(b, pairs, outs, count, tb, s); break;
     }
     C4B_CUDA(cudaGetLastError());
-    C4B_CUDA(cudaEventRecord(ev.b, b->e->stream));
+    if (timed) C4B_CUDA(cudaEventRecord(ev->b, s));
     b->e->launches++;
     return 0;
 }
 
 // score pass of the first `count` lattices of d_full, two per warp (affine_packed16.cuh)
-int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count) {
+int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
     if (!count) return 0;
-    if ((size_t)b->fill_events_used >= b->fill_events.size()) {
-        EventPair ev;
-        C4B_CUDA(cudaEventCreate(&ev.a));
-        C4B_CUDA(cudaEventCreate(&ev.b));
-        b->fill_events.push_back(ev);
-    }
-    EventPair &ev = b->fill_events[b->fill_events_used++];
-    C4B_CUDA(cudaEventRecord(ev.a, b->e->stream));
     const int blocks = (count + 1) / 2;
     switch (b->R) {
-    case 8: affine_fill16_kernel<8><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
-    case 16: affine_fill16_kernel<16><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
-    default: affine_fill16_kernel<32><<<blocks, 32, 0, b->e->stream>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    case 8: affine_fill16_kernel<8><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    case 16: affine_fill16_kernel<16><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    default: affine_fill16_kernel<32><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
     }
     C4B_CUDA(cudaGetLastError());
-    C4B_CUDA(cudaEventRecord(ev.b, b->e->stream));
     b->e->launches++;
+    return 0;
+}
+
+// Pass 1 (score + END cell, nothing written per cell) of one launch group, on an aux
+// stream, as soon as the group's sequences are resident.
+int launch_pass1_group(c4b_batch *b, int g) {
+    c4b_batch::P1Group &G = b->groups[g];
+    cudaStream_t s = b->e->aux[g % 4];
+    C4B_CUDA(cudaStreamWaitEvent(s, b->ev_base, 0));
+    C4B_CUDA(cudaStreamWaitEvent(s, b->slice_events[G.slice], 0));
+    const int a16 = G.begin, b16 = std::min(G.end, b->n16);
+    const int a32 = std::max(G.begin, b->n16), b32 = G.end;
+    if (b16 > a16 && launch_fill16(b, b->d_full.p + a16, b->d_out1.p, b16 - a16, s)) return -1;
+    if (b32 > a32 && launch_fill(b, b->d_full.p + a32, b->d_out1.p, b32 - a32, false, s, false)) return -1;
+    C4B_CUDA(cudaEventRecord(G.done, s));
     return 0;
 }
 
@@ -365,56 +402,39 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     const c4b_scoring &sc = b->scoring;
     const int32_t *matrix = (match_kind == C4B_CALC_MATCH_DNA) ? sc.dna_matrix : sc.protein_matrix;
     const uint8_t *index = (match_kind == C4B_CALC_MATCH_DNA) ? sc.dna_index : sc.protein_index;
+    typedef std::pair<const uint8_t *, int> SeqKey;
 
-    // ---- sequence placement (dedupe identical host buffers), lattice geometry
-    std::map<std::pair<const uint8_t *, int>, size_t> qmap, tmap;
-    std::vector<size_t> qoff(n), toff(n);
-    size_t qbytes = 0, tbytes = 0;
+    // ---- validation, alphabet use, lattice geometry
     int maxQ = 0;
     bool used[24] = {false};
-    for (int p = 0; p < n; ++p) {
-        const c4b_pair &pp = pairs[p];
-        if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
-            pp.query_start + pp.query_length > pp.query_len ||
-            pp.target_start + pp.target_length > pp.target_len) {
-            set_error("pair " + std::to_string(p) + ": region outside the sequences");
-            return -1;
-        }
-        if (pp.n_blocked) {
-            set_error("affine systolic path does not take SubOpt blocked cells");
-            return -2;
-        }
-        auto qk = std::make_pair(pp.query + pp.query_start, pp.query_length);
-        auto it = qmap.find(qk);
-        if (it == qmap.end()) {
-            qmap[qk] = qbytes;
-            qoff[p] = qbytes;
-            qbytes += align_up((size_t)pp.query_length, 16) + 16;
-            for (int k = 0; k < pp.query_length; ++k) {
-                const int c = index[qk.first[k]];
-                if (c >= 24) {
-                    set_error("query " + std::to_string(p) + ": symbol outside the substitution matrix");
-                    return -1;
-                }
-                used[c] = true;
+    {
+        std::set<SeqKey> seen;
+        for (int p = 0; p < n; ++p) {
+            const c4b_pair &pp = pairs[p];
+            if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
+                pp.query_start + pp.query_length > pp.query_len ||
+                pp.target_start + pp.target_length > pp.target_len) {
+                set_error("pair " + std::to_string(p) + ": region outside the sequences");
+                return -1;
             }
-        } else {
-            qoff[p] = it->second;
+            if (pp.n_blocked) {
+                set_error("affine systolic path does not take SubOpt blocked cells");
+                return -2;
+            }
+            const SeqKey qk(pp.query + pp.query_start, pp.query_length);
+            if (seen.insert(qk).second)
+                for (int k = 0; k < pp.query_length; ++k) {
+                    const int c = index[qk.first[k]];
+                    if (c >= 24) {
+                        set_error("query " + std::to_string(p) + ": symbol outside the substitution matrix");
+                        return -1;
+                    }
+                    used[c] = true;
+                }
+            maxQ = std::max(maxQ, pp.query_length);
+            b->cells += (int64_t)pp.query_length * pp.target_length;
         }
-        auto tk = std::make_pair(pp.target + pp.target_start, pp.target_length);
-        auto jt = tmap.find(tk);
-        if (jt == tmap.end()) {
-            tmap[tk] = tbytes;
-            toff[p] = tbytes;
-            tbytes += align_up((size_t)pp.target_length, 16) + 16;
-        } else {
-            toff[p] = jt->second;
-        }
-        maxQ = std::max(maxQ, pp.query_length);
-        b->cells += (int64_t)pp.query_length * pp.target_length;
     }
-    b->q_bytes = qbytes;
-    b->t_bytes = tbytes;
     b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
     if (const char *env = getenv("C4B_AFFINE_R")) {  // tuning override: rows per lane
         const int r = atoi(env);
@@ -505,6 +525,93 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     }
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
 
+    // ---- sequence placement: every distinct host buffer once (dedupe by pointer +
+    // length), IN LAUNCH ORDER (score_list, then direct_list), so that the lattices
+    // at the head of the launch order are the first to be resident
+    std::map<SeqKey, size_t> qmap, tmap;
+    std::vector<size_t> qoff(n), toff(n);
+    size_t qbytes = 0, tbytes = 0;
+    struct CopyJob { size_t dst; const uint8_t *src; size_t len, slot; uint8_t fill; };
+    std::vector<CopyJob> qjobs, tjobs;
+    auto place = [&](int p) {
+        const c4b_pair &pp = pairs[p];
+        const SeqKey qk(pp.query + pp.query_start, pp.query_length);
+        auto it = qmap.find(qk);
+        if (it == qmap.end()) {
+            qmap[qk] = qbytes;
+            qoff[p] = qbytes;
+            const size_t slot = align_up((size_t)pp.query_length, 16) + 16;
+            qjobs.push_back({qbytes, qk.first, (size_t)qk.second, slot, 0});
+            qbytes += slot;
+        } else {
+            qoff[p] = it->second;
+        }
+        const SeqKey tk(pp.target + pp.target_start, pp.target_length);
+        auto jt = tmap.find(tk);
+        if (jt == tmap.end()) {
+            tmap[tk] = tbytes;
+            toff[p] = tbytes;
+            const size_t slot = align_up((size_t)pp.target_length, 16) + 16;
+            tjobs.push_back({tbytes, tk.first, (size_t)tk.second, slot, 0});
+            tbytes += slot;
+        } else {
+            toff[p] = jt->second;
+        }
+    };
+    for (int k = 0; k < ns; ++k) place(b->score_list[k]);
+    for (int k = 0; k < nd; ++k) place(b->direct_list[k]);
+    b->q_bytes = qbytes;
+    b->t_bytes = tbytes;
+    // alignment gaps between sequences are encoded too: fill them with a symbol
+    // of the alphabet so only real sequence bytes can raise the "bad symbol" flag
+    uint8_t qfill = 0, tfill = 0;
+    for (int c = 255; c >= 0; --c) {
+        if (lut[c] != 0xFF) qfill = (uint8_t)c;
+        if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
+    }
+    std::vector<CopyJob> jobs;
+    jobs.reserve(qjobs.size() + tjobs.size());
+    for (CopyJob j : qjobs) { j.fill = qfill; jobs.push_back(j); }
+    for (CopyJob j : tjobs) { j.dst += qbytes; j.fill = tfill; jobs.push_back(j); }  // already in dst order
+    // staging slices: [jobs j0, j1) -> device bytes [lo, hi)
+    struct Slice { size_t j0, j1, lo, hi; };
+    std::vector<Slice> slices;
+    const size_t stage_bytes = qbytes + tbytes + 64;
+    {
+        const size_t slice_target = std::max<size_t>(stage_bytes / 8, 32u << 20);
+        size_t j0 = 0;
+        while (j0 < jobs.size()) {
+            size_t j1 = j0, bytes = 0;
+            while (j1 < jobs.size() && bytes < slice_target) bytes += jobs[j1++].slot;
+            slices.push_back({j0, j1, jobs[j0].dst, (j1 < jobs.size()) ? jobs[j1].dst : stage_bytes});
+            j0 = j1;
+        }
+        if (slices.empty()) slices.push_back({0, 0, 0, stage_bytes});
+    }
+    auto slice_of = [&](size_t dst) {
+        int lo = 0, hi = (int)slices.size() - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (dst < slices[mid].hi) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    // pass-1 launch groups: maximal runs of score_list with the same (running max)
+    // resident slice; boundaries even, because the packed kernel pairs neighbours
+    {
+        int begin = 0, cur = 0;
+        for (int k = 0; k < ns; ++k) {
+            const int p = b->score_list[k];
+            const int ready = std::max(slice_of(qoff[p]), slice_of(qbytes + toff[p]));
+            if (ready > cur && (k & 1) == 0 && k - begin >= 256) {
+                b->groups.push_back({begin, k, cur, nullptr});
+                begin = k;
+            }
+            cur = std::max(cur, ready);
+        }
+        if (begin < ns) b->groups.push_back({begin, ns, cur, nullptr});
+    }
+
     // ---- traceback arena, chunked to a memory budget
     size_t free_b = 0, total_b = 0;
     C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -541,8 +648,8 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (chunkify(b->direct_list, tb_off_d, b->direct_chunks, false)) return -1;
     }
 
-    // ---- device allocations
-    if (b->d_seq.alloc(qbytes + tbytes + 64)) return -1;
+    // ---- device allocations (stream-ordered on the engine stream)
+    if (b->d_seq.alloc(stage_bytes)) return -1;
     if (b->d_lut.alloc(512)) return -1;
     if (b->d_score_table.alloc(table.size())) return -1;
     if (b->d_bad.alloc(1)) return -1;
@@ -566,85 +673,11 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         }
     if (b->d_top.alloc(top_elems)) return -1;
 
-    // ---- stage sequences: pinned bounce buffer -> HBM, then encode in place.
-    // The bounce buffer belongs to the engine (grow-only); worker threads fill it
-    // slice by slice and each slice's H2D is issued as soon as it is complete, so
-    // the host copy and the DMA overlap.
+    // ---- tables, lattice descriptors and traceback jobs go up first (small)
     cudaStream_t st = e->stream;
-    const size_t stage_bytes = qbytes + tbytes + 64;
-    if (e->stage_free) C4B_CUDA(cudaEventSynchronize(e->stage_free));  // previous batch done reading
-    if (e->h_stage_cap < stage_bytes) {
-        if (e->h_stage) cudaFreeHost(e->h_stage);
-        e->h_stage = nullptr;
-        e->h_stage_cap = 0;
-        C4B_CUDA(cudaMallocHost(&e->h_stage, stage_bytes + stage_bytes / 8));
-        e->h_stage_cap = stage_bytes + stage_bytes / 8;
-    }
-    uint8_t *h_seq = e->h_stage;
-    // alignment gaps between sequences are encoded too: fill them with a symbol
-    // of the alphabet so only real sequence bytes can raise the "bad symbol" flag
-    uint8_t qfill = 0, tfill = 0;
-    for (int c = 255; c >= 0; --c) {
-        if (lut[c] != 0xFF) qfill = (uint8_t)c;
-        if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
-    }
-    struct CopyJob { size_t dst; const uint8_t *src; size_t len, slot; uint8_t fill; };
-    std::vector<CopyJob> jobs;
-    jobs.reserve(qmap.size() + tmap.size());
-    for (auto &kv : qmap)
-        jobs.push_back({kv.second, kv.first.first, (size_t)kv.first.second,
-                        align_up((size_t)kv.first.second, 16) + 16, qfill});
-    for (auto &kv : tmap)
-        jobs.push_back({qbytes + kv.second, kv.first.first, (size_t)kv.first.second,
-                        align_up((size_t)kv.first.second, 16) + 16, tfill});
-    std::sort(jobs.begin(), jobs.end(), [](const CopyJob &x, const CopyJob &y) { return x.dst < y.dst; });
-    memset(h_seq + qbytes + tbytes, tfill, 64);
-    {
-        const size_t slice_target = std::max<size_t>(stage_bytes / 8, 32u << 20);
-        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-        size_t j0 = 0;
-        while (j0 < jobs.size()) {
-            size_t j1 = j0, bytes = 0;
-            while (j1 < jobs.size() && bytes < slice_target) bytes += jobs[j1++].slot;
-            const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
-            auto work = [&](unsigned t) {
-                for (size_t k = j0 + t; k < j1; k += nt) {
-                    const CopyJob &c = jobs[k];
-                    memcpy(h_seq + c.dst, c.src, c.len);
-                    memset(h_seq + c.dst + c.len, c.fill, c.slot - c.len);
-                }
-            };
-            if (nt <= 1) {
-                work(0);
-            } else {
-                std::vector<std::thread> th;
-                for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-                work(0);
-                for (auto &x : th) x.join();
-            }
-            const size_t lo = jobs[j0].dst;
-            const size_t hi = (j1 < jobs.size()) ? jobs[j1].dst : qbytes + tbytes + 64;
-            C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + lo, h_seq + lo, hi - lo, cudaMemcpyHostToDevice, st));
-            j0 = j1;
-        }
-    }
-    if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
-    C4B_CUDA(cudaEventRecord(e->stage_free, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_score_table.p, table.data(), table.size(), cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), st));
-    if (qbytes) {
-        encode_kernel<<<(unsigned)((qbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(b->d_seq.p, qbytes, b->d_lut.p, b->d_bad.p);
-        e->launches++;
-    }
-    if (tbytes) {
-        encode_kernel<<<(unsigned)((tbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(b->d_seq.p + qbytes, tbytes,
-                                                                                b->d_lut.p + 256, b->d_bad.p);
-        e->launches++;
-    }
-    C4B_CUDA(cudaGetLastError());
-
-    // ---- lattice descriptors and traceback jobs
     std::vector<AffPair> h_full(ns), h_direct(nd);
     std::vector<int32_t> h_qorg(ns), h_torg(ns);
     std::vector<TbJob> h_jb(ns), h_jd(nd);
@@ -695,9 +728,6 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (b->d_ops_slots.alloc(2 * (size_t)ops_cursor + 2)) return -1;
         if (b->d_ops_packed.alloc(2 * (size_t)ops_cursor + 2)) return -1;
     }
-    // score-only results are indexed by original pair: remap out_index for them
-    if (!b->want_path)
-        for (int k = 0; k < ns; ++k) h_full[k].out_index = k;
     if (ns) {
         C4B_CUDA(cudaMemcpyAsync(b->d_full.p, h_full.data(), ns * sizeof(AffPair), cudaMemcpyHostToDevice, st));
         C4B_CUDA(cudaMemcpyAsync(b->d_qorg.p, h_qorg.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -710,14 +740,97 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (b->want_path)
             C4B_CUDA(cudaMemcpyAsync(b->d_jobs_direct.p, h_jd.data(), nd * sizeof(TbJob), cudaMemcpyHostToDevice, st));
     }
-    C4B_CUDA(cudaStreamSynchronize(st));
+    // the pageable sources above are consumed before cudaMemcpyAsync returns
+    for (cudaEvent_t *ev : {&b->ev_base, &b->ev_p1a, &b->ev_p1b}) C4B_CUDA(cudaEventCreate(ev));
+    for (auto &g : b->groups) C4B_CUDA(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    b->slice_events.assign(slices.size(), nullptr);
+    for (auto &ev : b->slice_events) C4B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    C4B_CUDA(cudaEventRecord(b->ev_p1a, st));
+    C4B_CUDA(cudaEventRecord(b->ev_base, st));  // allocations + tables + descriptors are in place
+
+    // ---- stage sequences: pinned bounce buffer -> HBM -> encode in place, slice by
+    // slice on the copy stream.  Worker threads fill the bounce buffer (grow-only,
+    // owned by the engine); as soon as a slice is issued, the score pass of every
+    // launch group whose sequences it completes is queued on an aux stream, so host
+    // copy, DMA and the fill overlap.
+    cudaStream_t cs = e->copy_stream;
+    C4B_CUDA(cudaStreamWaitEvent(cs, b->ev_base, 0));
+    if (e->stage_free) C4B_CUDA(cudaEventSynchronize(e->stage_free));  // previous batch done reading
+    if (e->h_stage_cap < stage_bytes) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr;
+        e->h_stage_cap = 0;
+        C4B_CUDA(cudaMallocHost(&e->h_stage, stage_bytes + stage_bytes / 8));
+        e->h_stage_cap = stage_bytes + stage_bytes / 8;
+    }
+    uint8_t *h_seq = e->h_stage;
+    memset(h_seq + qbytes + tbytes, tfill, 64);
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    size_t next_group = 0;
+    for (size_t si = 0; si < slices.size(); ++si) {
+        const Slice &S = slices[si];
+        const size_t bytes = S.hi - S.lo;
+        const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
+        auto work = [&](unsigned t) {
+            for (size_t k = S.j0 + t; k < S.j1; k += nt) {
+                const CopyJob &c = jobs[k];
+                memcpy(h_seq + c.dst, c.src, c.len);
+                memset(h_seq + c.dst + c.len, c.fill, c.slot - c.len);
+            }
+        };
+        if (nt <= 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+        }
+        C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + S.lo, h_seq + S.lo, bytes, cudaMemcpyHostToDevice, cs));
+        // encode [lo, hi): the part inside the query region with the query LUT, the rest
+        // with the target LUT (slots are multiples of 16 bytes, so is every boundary)
+        const size_t qhi = std::min(S.hi, qbytes);
+        if (S.lo < qhi) {
+            encode_kernel<<<(unsigned)(((qhi - S.lo) / 16 + 255) / 256 + 1), 256, 0, cs>>>(
+                b->d_seq.p + S.lo, qhi - S.lo, b->d_lut.p, b->d_bad.p, 0u);
+            e->launches++;
+        }
+        const size_t tlo = std::max(S.lo, qbytes);
+        if (tlo < S.hi) {
+            encode_kernel<<<(unsigned)(((S.hi - tlo) / 16 + 255) / 256 + 1), 256, 0, cs>>>(
+                b->d_seq.p + tlo, S.hi - tlo, b->d_lut.p + 256, b->d_bad.p, (uint32_t)kTargetNone);
+            e->launches++;
+        }
+        C4B_CUDA(cudaGetLastError());
+        C4B_CUDA(cudaEventRecord(b->slice_events[si], cs));
+        while (next_group < b->groups.size() && b->groups[next_group].slice <= (int)si) {
+            if (launch_pass1_group(b, (int)next_group)) return -1;
+            ++next_group;
+        }
+    }
+    while (next_group < b->groups.size()) {
+        if (launch_pass1_group(b, (int)next_group)) return -1;
+        ++next_group;
+    }
+    b->pass1_inflight = true;
+    if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
+    C4B_CUDA(cudaEventRecord(e->stage_free, cs));
+    b->kernel_name = "affine_systolic";
+    return 0;
+}
+
+// The encode kernels flag symbols outside the matrix alphabet; the host looks at
+// the flag once, at the first synchronisation point of the batch.
+int affine_check_symbols(c4b_batch *b) {
+    if (b->bad_checked) return 0;
     int bad = 0;
+    C4B_CUDA(cudaStreamSynchronize(b->e->copy_stream));
     C4B_CUDA(cudaMemcpy(&bad, b->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) {
         set_error("a sequence holds a symbol outside the substitution matrix alphabet");
         return -1;
     }
-    b->kernel_name = "affine_systolic";
+    b->bad_checked = true;
     return 0;
 }
 
@@ -726,9 +839,19 @@ int affine_run(c4b_batch *b, c4b_score threshold) {
     cudaStream_t st = e->stream;
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
     b->fill_events_used = 0;
-    // pass 1: score + END cell over the full lattices, nothing written per cell
-    if (launch_fill16(b, b->d_full.p, b->d_out1.p, b->n16)) return -1;
-    if (launch_fill(b, b->d_full.p + b->n16, b->d_out1.p, ns - b->n16, false)) return -1;
+    // pass 1: score + END cell over the full lattices, nothing written per cell.
+    // The first run of a batch finds it already queued by affine_create (it started
+    // while the sequences were still being staged); later runs queue it again.
+    if (!b->pass1_inflight) {
+        C4B_CUDA(cudaEventRecord(b->ev_p1a, st));
+        C4B_CUDA(cudaEventRecord(b->ev_base, st));
+        for (int g = 0; g < (int)b->groups.size(); ++g)
+            if (launch_pass1_group(b, g)) return -1;
+    }
+    b->pass1_inflight = false;
+    for (auto &g : b->groups) C4B_CUDA(cudaStreamWaitEvent(st, g.done, 0));
+    C4B_CUDA(cudaStreamWaitEvent(st, b->slice_events.back(), 0));  // direct lattices read every slice
+    C4B_CUDA(cudaEventRecord(b->ev_p1b, st));
     if (!b->want_path) {
         if (ns) {
             // results are indexed by ordered slot here; the host un-permutes on fetch
@@ -748,13 +871,13 @@ int affine_run(c4b_batch *b, c4b_score threshold) {
     // pass 2: refill only the band with the traceback record, then walk it
     for (const Chunk &c : b->band_chunks) {
         const int cnt = c.end - c.begin;
-        if (launch_fill(b, b->d_band.p + c.begin, b->d_out2.p, cnt, true)) return -1;
+        if (launch_fill(b, b->d_band.p + c.begin, b->d_out2.p, cnt, true, st, true)) return -1;
         if (launch_traceback(b, b->d_band.p, b->d_out2.p, b->d_out1.p, b->d_band_j0.p,
                              b->d_jobs_band.p + c.begin, cnt)) return -1;
     }
     for (const Chunk &c : b->direct_chunks) {
         const int cnt = c.end - c.begin;
-        if (launch_fill(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, true)) return -1;
+        if (launch_fill(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, true, st, true)) return -1;
         if (launch_traceback(b, b->d_direct.p, b->d_outd.p, nullptr, nullptr,
                              b->d_jobs_direct.p + c.begin, cnt)) return -1;
     }
@@ -771,6 +894,7 @@ int affine_run(c4b_batch *b, c4b_score threshold) {
 int affine_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops_capacity) {
     cudaStream_t st = b->e->stream;
     const int n = b->n;
+    if (affine_check_symbols(b)) return -1;
     if (!b->want_path) {
         std::vector<c4b_result> tmp(n);
         C4B_CUDA(cudaMemcpyAsync(tmp.data(), b->d_results.p, n * sizeof(c4b_result), cudaMemcpyDeviceToHost, st));
@@ -830,7 +954,10 @@ int c4b_engine_create(int device, c4b_engine **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
-    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (cudaStream_t &a : e->aux) ok = ok && cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
         set_error("cudaStreamCreate failed");
         delete e;
         return -1;
@@ -844,6 +971,9 @@ void c4b_engine_destroy(c4b_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->stage_free) cudaEventDestroy(e->stage_free);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (cudaStream_t a : e->aux)
+        if (a) cudaStreamDestroy(a);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -943,6 +1073,10 @@ double c4b_batch_last_fill_ms(c4b_batch *b) {
     if (!b->affine) return generic_batch_fill_ms(b->generic);
     cudaStreamSynchronize(b->e->stream);
     double ms = 0;
+    {
+        float f = 0;  // pass 1: fork to the aux streams .. join, measured on the engine stream
+        if (cudaEventElapsedTime(&f, b->ev_p1a, b->ev_p1b) == cudaSuccess) ms += f;
+    }
     for (int k = 0; k < b->fill_events_used; ++k) {
         float f = 0;
         if (cudaEventElapsedTime(&f, b->fill_events[k].a, b->fill_events[k].b) == cudaSuccess) ms += f;

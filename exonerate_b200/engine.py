@@ -119,7 +119,11 @@ class PairSet:
                 self._keep.append((bq, bt))
                 p.blocked_query_pos, p.blocked_target_pos, p.n_blocked = bq.ctypes.data, bt.ctypes.data, len(pts)
         self.cells = sum(int(self.array[k].query_length) * int(self.array[k].target_length) for k in range(n))
+        # bytes the engine copies to the device: every distinct sequence once, plus one
+        # packed 4 x int8 splice word per target position where splice arrays are given
         self.h2d_bytes = sum(a.nbytes for a in cache.values())
+        if splice:
+            self.h2d_bytes += 4 * sum(int(self.array[k].target_length) for k in range(n) if splice[k] is not None)
 
 
 def results_to_list(results, ops, n):
