@@ -53,15 +53,7 @@ affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ out
     __syncwarp();
 
     const int open = mdl.openD;
-    const uint32_t extD2 = pack16(mdl.extD), extI2 = pack16(mdl.extI);
-    // M + open per half without a DPX slot: after the RELU both halves are in
-    // [0, 32767], so adding K = {open, open + 0x8000} as ONE 32-bit integer never
-    // carries between the halves (low half <= 0x7FFF + 0x7FFF), and flipping bit 15
-    // afterwards takes the 0x8000 out again modulo 2^16.  The add is an IMAD by a
-    // run-time 1 (FMA pipe), the flip one LOP3; VIADDMNMX.S16x2 costs twice that
-    // on the binding ALU pipe (tools/ubench/dpx_rates.cu).
-    const uint32_t openK = (((uint32_t)open & 0xFFFFu) << 16) | (((uint32_t)open + 0x8000u) & 0xFFFFu);
-    const int one = mdl.one;
+    const uint32_t open2 = pack16(open), extD2 = pack16(mdl.extD), extI2 = pack16(mdl.extI);
     const int nsteps = T + 1 + 31;
     const int row0 = lane * R;
 
@@ -143,7 +135,7 @@ affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ out
             for (int r = 0; r < R; ++r) {
                 const uint32_t Iv = __viaddmax_s16x2(upI, extI2, upM);
                 const uint32_t Mv = __vimax_s16x2_relu(Mp[r], Iv);       // START's 0 is the RELU
-                const uint32_t Gv = (uint32_t)add_open((int)Mv, one, (int)openK) ^ 0x8000u;  // M + open per half
+                const uint32_t Gv = __viaddmax_s16x2(Mv, open2, kMin16x2);  // M + open per half
                 Mp[r] = Gv;
                 upM = Gv;
                 upI = Iv;
@@ -200,6 +192,196 @@ affine_fill16_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ out
         outs[PA.out_index] = o;
         if (ia + 1 < n) {
             o.best = bB - open;
+            o.end_i = biB;
+            o.end_j = bjB;
+            outs[PB.out_index] = o;
+        }
+    }
+}
+
+
+// -----------------------------------------------------------------------------
+// affine_fill16u_kernel: the same two-lattices-per-warp score pass, re-balanced
+// over the SM's pipes (measured with tools/ubench/dpx_rates.cu on B200: the
+// three-input DPX forms VIADDMNMX / VIMNMX3 and PRMT issue every ~2.4 cycles per
+// scheduler on the ALU pipe, two-input VIMNMX every ~1.1, IMAD every ~2.2 on the
+// FMA pipe).  Two changes against affine_fill16_kernel:
+//
+//  1. OFFSET-BINARY halves: every halfword holds value + kBias16 and is compared
+//     UNSIGNED.  All stored values are >= kBias16 - 16000 > |any penalty| and the
+//     score' entries are >= 0 (host-checked: s >= gap_open), so "+ penalty" and
+//     "+ score'" on both halves is ONE 32-bit integer add with no carry or borrow
+//     across the halves -- an IMAD by a run-time 1 on the FMA pipe -- and the max
+//     is the cheap two-input VIMNMX.U16x2.  START's 0 is max(., kBias16).
+//  2. SHORT VERTICAL CHAIN: with G~ = max(match, D, START) + open (independent of the
+//     row above),  I(r+1) = max(I(r) + ext, M(r) + open)
+//                         = max(I(r) + ext, G~(r), I(r) + open) = max(I(r) + ext, G~(r))
+//     because open <= ext (host-checked).  The only loop-carried dependency down the
+//     rows is ONE VIADDMNMX.U16x2 per row; G = max(G~, I + open) is off the chain.
+// Per packed row: ALU 10.5 cycles (PRMT, VIMNMX, VIMNMX3, VIADDMNMX, VIMNMX, half a
+// VIMNMX3), FMA 8.6 (4 IMAD), against 14.1 ALU cycles of the signed kernel.
+constexpr uint32_t kBias16 = 0x4000u;
+constexpr uint32_t kBias16x2 = 0x40004000u;   // START / RELU floor: true 0
+constexpr uint32_t kNegU16x2 = 0x01800180u;   // true -16000: "not reachable"
+
+__device__ __forceinline__ uint32_t imad_add(uint32_t a, int one, uint32_t k) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"((uint32_t)one), "r"(k));
+    return d;
+}
+
+template <int R>
+__global__ void __launch_bounds__(32, 12)
+affine_fill16u_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
+                      const AffModel mdl, const void *__restrict__ score_table) {
+    __shared__ uint32_t xt4[25];
+    const int lane = threadIdx.x;
+    const int ia = 2 * blockIdx.x, ib = min(ia + 1, n - 1);
+    const AffPair PA = pairs[ia], PB = pairs[ib];
+    const int QA = PA.Q, TA = PA.T, QB = PB.Q, TB_ = PB.T;
+    const int T = max(TA, TB_);
+    if (lane < 25) xt4[lane] = reinterpret_cast<const uint2 *>(score_table)[lane].x;  // classes 0..3, all >= 0
+    __syncwarp();
+
+    const int open = mdl.openD, one = mdl.one;
+    // x + {p, p} for a penalty p < 0 and halves >= |p|: one 32-bit add of p * 0x10001
+    const uint32_t openK = (uint32_t)(open * 0x10001), extDK = (uint32_t)(mdl.extD * 0x10001);
+    const uint32_t extI2 = pack16(mdl.extI);  // per-half operand of VIADDMNMX.U16x2 (wraps per half)
+    const int nsteps = T + 1 + 31;
+    const int row0 = lane * R;
+
+    uint32_t sel[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = row0 + r;
+        uint32_t sa = 0x88u, sb = 0xCCu;  // padding: sign of a (non-negative) pool byte = 0
+        if (i >= 1 && i <= QA) { const uint32_t c = PA.q[i - 1]; sa = c | ((c | 8u) << 4); }
+        if (i >= 1 && i <= QB) { const uint32_t c = 4u + PB.q[i - 1]; sb = c | ((c | 8u) << 4); }
+        sel[r] = sa | (sb << 8);
+    }
+    uint32_t Mp[R], Dp[R];  // G = M + open and D of the previous column (offset binary)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        Mp[r] = kNegU16x2;
+        Dp[r] = kNegU16x2;
+    }
+    uint32_t topM = kNegU16x2, topI = kNegU16x2, topMprev = kNegU16x2;
+    uint32_t in_code = kTargetNone | (kTargetNone << 8), code0 = in_code;
+
+    uint32_t best2 = 0u;  // below every stored value
+    int bjA = 0, biA = 0, bjB = 0, biB = 0;
+    uint32_t pend = 0u;
+    int pend_j = 0;
+    auto settle_pending = [&]() {
+        const uint32_t nb = __vmaxu2(best2, pend);
+        if (nb != best2) {  // some half improved strictly (columns arrive in increasing j)
+            if ((pend & 0xFFFFu) > (best2 & 0xFFFFu)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) & 0xFFFFu) == 0) { bi = row0 + r; found = true; }
+                biA = bi;
+                bjA = pend_j;
+            }
+            if ((pend >> 16) > (best2 >> 16)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) >> 16) == 0) { bi = row0 + r; found = true; }
+                biB = bi;
+                bjB = pend_j;
+            }
+            best2 = nb;
+        }
+        pend = 0u;
+    };
+
+    auto step = [&](const int s, auto ALL) {
+        constexpr bool all_active = decltype(ALL)::value;
+        const int j = s - lane;
+        settle_pending();
+        const uint32_t code = (lane == 0) ? code0 : in_code;
+        {
+            const uint32_t ca = (s + 1 <= TA) ? (uint32_t)PA.t[s] : (uint32_t)kTargetNone;
+            const uint32_t cb = (s + 1 <= TB_) ? (uint32_t)PB.t[s] : (uint32_t)kTargetNone;
+            code0 = ca | (cb << 8);
+        }
+        uint32_t botM = kNegU16x2, botI = kNegU16x2;
+        if (all_active || (j >= 0 && j <= T)) {
+            const uint32_t Xa = xt4[code & 0xFFu], Xb = xt4[code >> 8];
+            uint32_t cm = 0u;
+            // phase A, bottom-up, rows independent: D, then G~ = max(match, D, START) + open
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                uint32_t sc;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(Xa), "r"(Xb), "r"(sel[r]));
+                const uint32_t diag = (r == 0) ? topMprev : Mp[r - 1];
+                Dp[r] = __vmaxu2(imad_add(Dp[r], one, extDK), Mp[r]);
+                const uint32_t x = __vimax3_u16x2(imad_add(diag, one, sc), Dp[r], kBias16x2);
+                Mp[r] = imad_add(x, one, openK);
+            }
+            // phase B, top-down: I chain (one op per row), G = max(G~, I + open) off the chain
+            uint32_t Iv = __viaddmax_u16x2(topI, extI2, topM);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t gt = Mp[r];
+                const uint32_t Gv = __vmaxu2(gt, imad_add(Iv, one, openK));
+                Mp[r] = Gv;
+                if (r & 1) cm = __vimax3_u16x2(cm, Gv, Mp[r - 1]);
+                if (r + 1 < R) Iv = __viaddmax_u16x2(Iv, extI2, gt);
+            }
+            botM = Mp[R - 1];
+            botI = Iv;
+            topMprev = topM;
+            pend = cm;
+            pend_j = j;
+        }
+        const uint32_t nM = __shfl_up_sync(0xffffffffu, botM, 1);
+        const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
+        const uint32_t nC = __shfl_up_sync(0xffffffffu, code, 1);
+        if (lane > 0) {
+            topM = nM;
+            topI = nI;
+            in_code = nC;
+        }
+    };
+
+    const int fill_end = min(31, nsteps);
+    const int steady_end = max(fill_end, min(T + 1, nsteps));
+    int s = 0;
+    for (; s < fill_end; ++s) step(s, std::false_type{});
+    for (; s < steady_end; ++s) step(s, std::true_type{});
+    for (; s < nsteps; ++s) step(s, std::false_type{});
+    settle_pending();
+    __syncwarp();
+
+    int bA = (int)(best2 & 0xFFFFu), bB = (int)(best2 >> 16);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bA, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjA, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biA, off);
+            if ((ob > bA) || (ob == bA && (oj < bjA || (oj == bjA && oi < biA)))) { bA = ob; bjA = oj; biA = oi; }
+        }
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bB, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjB, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biB, off);
+            if ((ob > bB) || (ob == bB && (oj < bjB || (oj == bjB && oi < biB)))) { bB = ob; bjB = oj; biB = oi; }
+        }
+    }
+    if (lane == 0) {
+        AffOut o;
+        o.best = bA - (int)kBias16 - open;  // tracked as G = M + open, offset binary
+        o.end_i = biA;
+        o.end_j = bjA;
+        o.flags = 0;
+        outs[PA.out_index] = o;
+        if (ia + 1 < n) {
+            o.best = bB - (int)kBias16 - open;
             o.end_i = biB;
             o.end_j = bjB;
             outs[PB.out_index] = o;

@@ -5,6 +5,7 @@
 // choose the fill variant, run it, trace back, hand an operation list to the
 // caller.  No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <map>
 #include <set>
@@ -229,6 +230,7 @@ struct c4b_batch {
     AffModel aff;
     int R = 32, score_mode = SCORE_PRMT, max_sub = 0, gap_min = 0;
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
+    bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
     DevBuf<uint8_t> d_seq;
@@ -342,11 +344,25 @@ int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, boo
 int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
     if (!count) return 0;
     const int blocks = (count + 1) / 2;
-    switch (b->R) {
-    case 8: affine_fill16_kernel<8><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
-    case 16: affine_fill16_kernel<16><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
-    default: affine_fill16_kernel<32><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    auto go = [&](auto kernel) -> int {
+        kernel<<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
+        return 0;
+    };
+    int rc;
+    if (b->p16_unsigned) {
+        switch (b->R) {
+        case 8: rc = go(affine_fill16u_kernel<8>); break;
+        case 16: rc = go(affine_fill16u_kernel<16>); break;
+        default: rc = go(affine_fill16u_kernel<32>); break;
+        }
+    } else {
+        switch (b->R) {
+        case 8: rc = go(affine_fill16_kernel<8>); break;
+        case 16: rc = go(affine_fill16_kernel<16>); break;
+        default: rc = go(affine_fill16_kernel<32>); break;
+        }
     }
+    if (rc) return rc;
     C4B_CUDA(cudaGetLastError());
     b->e->launches++;
     return 0;
@@ -409,6 +425,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     bool used[24] = {false};
     {
         std::set<SeqKey> seen;
+        std::vector<SeqKey> distinct_q;
         for (int p = 0; p < n; ++p) {
             const c4b_pair &pp = pairs[p];
             if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
@@ -422,18 +439,40 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                 return -2;
             }
             const SeqKey qk(pp.query + pp.query_start, pp.query_length);
-            if (seen.insert(qk).second)
-                for (int k = 0; k < pp.query_length; ++k) {
-                    const int c = index[qk.first[k]];
-                    if (c >= 24) {
-                        set_error("query " + std::to_string(p) + ": symbol outside the substitution matrix");
-                        return -1;
-                    }
-                    used[c] = true;
-                }
+            if (seen.insert(qk).second) distinct_q.push_back(qk);
             maxQ = std::max(maxQ, pp.query_length);
             b->cells += (int64_t)pp.query_length * pp.target_length;
         }
+        // which matrix rows do the queries use (decides PRMT classes / packed16); the
+        // scan is the only per-byte host work before staging starts, so it is threaded
+        size_t qtotal = 0;
+        for (const SeqKey &k : distinct_q) qtotal += (size_t)k.second;
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(
+            std::min(8u, std::max(1u, std::thread::hardware_concurrency())), qtotal >> 20));
+        std::vector<std::array<bool, 256>> seen_byte(nt);
+        auto scan = [&](unsigned t) {
+            std::array<bool, 256> &sb = seen_byte[t];
+            sb.fill(false);
+            for (size_t k = t; k < distinct_q.size(); k += nt) {
+                const uint8_t *q = distinct_q[k].first;
+                for (int i = 0; i < distinct_q[k].second; ++i) sb[q[i]] = true;
+            }
+        };
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; ++t) th.emplace_back(scan, t);
+            scan(0);
+            for (auto &x : th) x.join();
+        }
+        for (unsigned t = 0; t < nt; ++t)
+            for (int c = 0; c < 256; ++c)
+                if (seen_byte[t][c]) {
+                    if (index[c] >= 24) {
+                        set_error("a query holds a symbol outside the substitution matrix");
+                        return -1;
+                    }
+                    used[index[c]] = true;
+                }
     }
     b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
     if (const char *env = getenv("C4B_AFFINE_R")) {  // tuning override: rows per lane
@@ -522,6 +561,13 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         };
         auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
         b->n16 = (int)(mid - b->score_list.begin());
+        // the offset-binary variant adds score' = s - open as an unsigned halfword and
+        // shortens the I chain with open <= extend
+        bool nonneg = true;
+        for (int a = 0; a < 24; ++a)
+            for (int c = 0; c < 24 && used[a]; ++c) nonneg = nonneg && matrix[a * 24 + c] >= b->aff.openD;
+        const char *v = getenv("C4B_P16_VARIANT");
+        b->p16_unsigned = nonneg && b->aff.openI <= b->aff.extI && !(v && v[0] == 's');
     }
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
 
@@ -578,13 +624,17 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     std::vector<Slice> slices;
     const size_t stage_bytes = qbytes + tbytes + 64;
     {
-        const size_t slice_target = std::max<size_t>(stage_bytes / 8, 32u << 20);
-        size_t j0 = 0;
+        // slice sizes grow geometrically (1/64, 1/32, 1/16 of the batch, then 1/8 each):
+        // the fill starts after the first small slice, later slices amortise the launch
+        size_t unit = std::max<size_t>(stage_bytes / 64, 4u << 20), cap = std::max<size_t>(stage_bytes / 8, 32u << 20);
+        if (const char *env = getenv("C4B_STAGE_SLICE_KB")) unit = cap = std::max(1, atoi(env)) * (size_t)1024;
+        size_t j0 = 0, slice_target = unit;
         while (j0 < jobs.size()) {
             size_t j1 = j0, bytes = 0;
             while (j1 < jobs.size() && bytes < slice_target) bytes += jobs[j1++].slot;
             slices.push_back({j0, j1, jobs[j0].dst, (j1 < jobs.size()) ? jobs[j1].dst : stage_bytes});
             j0 = j1;
+            slice_target = std::min(cap, slice_target * 2);
         }
         if (slices.empty()) slices.push_back({0, 0, 0, stage_bytes});
     }
@@ -599,11 +649,12 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     // pass-1 launch groups: maximal runs of score_list with the same (running max)
     // resident slice; boundaries even, because the packed kernel pairs neighbours
     {
-        int begin = 0, cur = 0;
+        int begin = 0, cur = 0, min_group = 256;
+        if (const char *env = getenv("C4B_P1_MIN_GROUP")) min_group = std::max(2, atoi(env));
         for (int k = 0; k < ns; ++k) {
             const int p = b->score_list[k];
             const int ready = std::max(slice_of(qoff[p]), slice_of(qbytes + toff[p]));
-            if (ready > cur && (k & 1) == 0 && k - begin >= 256) {
+            if (ready > cur && (k & 1) == 0 && k - begin >= min_group) {
                 b->groups.push_back({begin, k, cur, nullptr});
                 begin = k;
             }

@@ -145,8 +145,8 @@ def test_banded_two_pass_route(eng, params, scoring):
 
 
 def test_packed16_score_pass(eng, params, scoring, monkeypatch):
-    """affine_fill16_kernel (two lattices per warp in 16-bit halves) is the score
-    pass of ACGT-only local batches: ragged partners, odd counts, identical and
+    """affine_fill16u_kernel / affine_fill16_kernel (two lattices per warp in 16-bit
+    halves, offset-binary and signed variants) are the score pass of ACGT-only local batches: ragged partners, odd counts, identical and
     unrelated sequences, every strip width, against the oracle; and against the
     int32 kernel (C4B_AFFINE_PACK16=0) on the same batch."""
     from exonerate_b200 import Optimal, PairSet
@@ -173,6 +173,9 @@ def test_packed16_score_pass(eng, params, scoring, monkeypatch):
         paths32 = opt.find_path(pairs)
         monkeypatch.delenv("C4B_AFFINE_PACK16")
         assert scores == scores32 and paths == paths32
+        monkeypatch.setenv("C4B_P16_VARIANT", "s")      # signed-halfword variant of the packed kernel
+        assert opt.find_score(pairs) == scores and opt.find_path(pairs) == paths
+        monkeypatch.delenv("C4B_P16_VARIANT")
         for k in range(pairs.n):
             want = oracle_path(model, scoring, qs[k], ts[k])
             assert scores[k] == want["score"], (maxq, k)
@@ -189,6 +192,38 @@ def test_packed16_score_pass(eng, params, scoring, monkeypatch):
     want = opt.find_path(pairs)
     monkeypatch.delenv("C4B_AFFINE_PACK16")
     assert got == want and all(r["score"] > 2000 for r in got)
+
+
+def test_staging_pipeline_many_slices(eng, params, scoring, monkeypatch):
+    """The staging pipeline (sequence slices copied + encoded on the copy stream,
+    score-pass launch groups on the aux streams as their slice lands) with tiny
+    slices and groups, so that a small batch crosses many of them; shared targets,
+    regions and a mixed (packed16 + int32 + direct) batch.  Same answers as with one
+    slice, and as the oracle."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    rng = random.Random(99)
+    qs, ts = [], []
+    shared_t = helpers.rand_dna(rng, 6000)
+    for k in range(40):
+        ql = rng.choice([20, 150, 400, 1000, 1300])       # 1300 > one sweep: int32 kernel
+        tl = rng.choice([300, 2500, 9000])
+        q, t = helpers.dna_pair(88000 + k, ql, tl)
+        qs.append(q)
+        ts.append(shared_t if k % 7 == 0 else t)
+    pairs = PairSet(qs, ts)
+    want_scores, want_paths = opt.find_score(pairs), opt.find_path(pairs)
+    monkeypatch.setenv("C4B_STAGE_SLICE_KB", "8")
+    monkeypatch.setenv("C4B_P1_MIN_GROUP", "2")
+    got_scores, got_paths = opt.find_score(pairs), opt.find_path(pairs)
+    monkeypatch.delenv("C4B_STAGE_SLICE_KB")
+    monkeypatch.delenv("C4B_P1_MIN_GROUP")
+    assert got_scores == want_scores and got_paths == want_paths
+    for k in range(0, pairs.n, 3):
+        want = oracle_path(model, scoring, qs[k], ts[k])
+        assert got_scores[k] == want["score"], k
+        assert got_paths[k]["region"] == want["region"] and got_paths[k]["ops"] == want["ops"], k
 
 
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
