@@ -18,6 +18,7 @@
 #include "affine_traceback.cuh"
 #include "generic_wavefront.cuh"
 #include "e2g_systolic.cuh"
+#include "e2g_packed16.cuh"
 
 namespace c4b {
 static thread_local std::string g_error;
@@ -1068,7 +1069,7 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
                                   : e2g_batch_create(e->stream, &e->launches, model, scoring, n, pairs,
                                                      want_path != 0, &b->e2g);
         if (rc == 0) {
-            b->kernel_name = "e2g_systolic";
+            b->kernel_name = b->e2g->packed ? "e2g_packed16" : "e2g_systolic";
             b->cells = b->e2g->cells;
         }
     }

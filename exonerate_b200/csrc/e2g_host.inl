@@ -94,6 +94,9 @@ struct E2gBatch {
     DevBuf<uint2> d_xtab;
     DevBuf<int> d_bad;
     DevBuf<E2gPair> d_pairs;
+    bool packed = false;              // e2g_packed16.cuh: both strands per register, one warp per lattice
+    DevBuf<E2pPair> d_pairs16;
+    DevBuf<uint2> d_top;              // sweep hand-off rows (packed path, queries longer than 511)
     DevBuf<E2gOut> d_outs;
     DevBuf<E2gJob> d_jobs;
     DevBuf<int32_t> d_qorg, d_torg;
@@ -104,7 +107,7 @@ struct E2gBatch {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     ~E2gBatch() {
         d_seq.release(); d_sp.release(); d_lut.release(); d_xtab.release(); d_bad.release();
-        d_pairs.release(); d_outs.release(); d_jobs.release(); d_qorg.release(); d_torg.release();
+        d_pairs.release(); d_pairs16.release(); d_top.release(); d_outs.release(); d_jobs.release(); d_qorg.release(); d_torg.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
         d_new_off.release();
         if (ev_a) cudaEventDestroy(ev_a);
@@ -143,7 +146,8 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
             used[c] = true;
         }
     }
-    if (maxQ + 1 > kE2gMaxWarps * 32 * kE2gR) return 1;
+    int maxT = 0;
+    for (int p = 0; p < n; ++p) maxT = std::max(maxT, pairs[p].target_length);
     // PRMT classes of the query alphabet; s - open must fit int8
     int n_used = 0, cls_of[24], code_of[8];
     for (int a = 0; a < 24; ++a) {
@@ -165,8 +169,24 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
                 if (a[j] < -127 || a[j] > 127) return 1;
         }
 
+    // packed 16-bit path (e2g_packed16.cuh): exact when every reachable value fits a
+    // signed halfword and the intron-length upper bound can never fire
+    bool packed = false;
+    {
+        int max_sub = 0;
+        for (int a = 0; a < 24; ++a)
+            for (int c = 0; c < 24 && used[a]; ++c) max_sub = std::max(max_sub, scoring->dna_matrix[a * 24 + c]);
+        const char *env = getenv("C4B_E2G_PACK16");
+        const int64_t top_score = (int64_t)max_sub * (std::min(maxQ, maxT) + 1) + 400;
+        packed = !(env && atoi(env) == 0) && top_score <= 30000 && mdl.open > -1000 && mdl.ext > -1000 &&
+                 mdl.intron_open > -4000 && mdl.intron_open < 1000 && mdl.min_intron - 2 <= 32000 &&
+                 (int64_t)mdl.max_intron >= (int64_t)maxT + 2;
+    }
+    if (!packed && maxQ + 1 > kE2gMaxWarps * 32 * kE2gR) return 1;
+
     E2gBatch *b = new E2gBatch();
     b->stream = stream; b->launches = launch_counter; b->n = n; b->want_path = want_path; b->mdl = mdl;
+    b->packed = packed;
     b->warps = std::max(1, (maxQ + 1 + 32 * kE2gR - 1) / (32 * kE2gR));
     // ---- staging: region slices of query / target, packed splice words ---------------
     std::vector<size_t> qoff(n), toff(n);
@@ -241,7 +261,9 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         int begin = 0;
         for (int k = 0; k < n; ++k) {
             const c4b_pair &pp = pairs[b->order[k]];
-            const size_t hw = align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 8);
+            const size_t sweeps = ((size_t)pp.query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+            const size_t hw = packed ? align_up(sweeps * (pp.target_length + 32) * 32 * kE2pR, 16)
+                                     : align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 16);
             if (hw > budget_hw) {
                 set_error("traceback of pair " + std::to_string(b->order[k]) + " exceeds the device memory budget");
                 delete b;
@@ -268,6 +290,17 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     rc |= b->d_xtab.alloc(25);
     rc |= b->d_bad.alloc(1);
     rc |= b->d_pairs.alloc(n);
+    std::vector<size_t> top_off(n, (size_t)-1);
+    size_t top_elems = 0;
+    if (packed) {
+        for (int p = 0; p < n; ++p)
+            if (pairs[p].query_length + 1 > 32 * kE2pR) {
+                top_off[p] = top_elems;
+                top_elems += 2 * ((size_t)pairs[p].target_length + 1);
+            }
+        rc |= b->d_pairs16.alloc(n);
+        rc |= b->d_top.alloc(top_elems);
+    }
     rc |= b->d_outs.alloc(n);
     rc |= b->d_results.alloc(n);
     rc |= b->d_qorg.alloc(n);
@@ -296,6 +329,22 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         ht[k] = pairs[p].target_start;
     }
     bool ok = true;
+    std::vector<E2pPair> hp16(packed ? n : 0);
+    if (packed) {
+        for (int k = 0; k < n; ++k) {
+            const int p = b->order[k];
+            E2pPair &e = hp16[k];
+            e.q = hp[k].q; e.t = hp[k].t; e.sp = hp[k].sp; e.Q = hp[k].Q; e.T = hp[k].T;
+            e.tb = hp[k].tb;
+            e.top0 = e.top1 = nullptr;
+            if (top_off[p] != (size_t)-1) {
+                e.top0 = b->d_top.p + top_off[p];
+                e.top1 = e.top0 + (pairs[p].target_length + 1);
+            }
+            e.out_index = k;
+        }
+        ok &= cudaMemcpyAsync(b->d_pairs16.p, hp16.data(), n * sizeof(E2pPair), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    }
     ok &= cudaMemcpyAsync(b->d_seq.p, hseq.data(), qbytes + tbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(b->d_sp.p, hsp.data(), (tbytes + 16) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, stream) == cudaSuccess;
@@ -329,6 +378,35 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
     const int n = b->n;
     const int threads = 32 * b->warps;
     C4B_CUDA(cudaEventRecord(b->ev_a, st));
+    if (b->packed) {
+        if (!b->want_path) {
+            e2g_fill16_kernel<false><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p);
+            C4B_CUDA(cudaGetLastError());
+            C4B_CUDA(cudaEventRecord(b->ev_b, st));
+            e2g16_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_qorg.p,
+                                                                       b->d_torg.p, n, b->d_results.p);
+            (*b->launches) += 2;
+            C4B_CUDA(cudaGetLastError());
+            return 0;
+        }
+        for (const Chunk &c : b->chunks) {
+            const int cnt = c.end - c.begin;
+            e2g_fill16_kernel<true><<<cnt, 32, 0, st>>>(b->d_pairs16.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p);
+            C4B_CUDA(cudaGetLastError());
+            e2g16_traceback_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p + c.begin,
+                                                                  cnt, b->mdl, threshold, b->d_results.p,
+                                                                  b->d_ops_slots.p);
+            C4B_CUDA(cudaGetLastError());
+            (*b->launches) += 2;
+        }
+        C4B_CUDA(cudaEventRecord(b->ev_b, st));
+        apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_results.p, n, threshold);
+        ops_scan_kernel<<<1, 1024, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_new_off.p + n);
+        ops_compact_kernel<<<n, 64, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_ops_slots.p, b->d_ops_packed.p);
+        (*b->launches) += 3;
+        C4B_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (!b->want_path) {
         e2g_fill_kernel<false><<<n, threads, 0, st>>>(b->d_pairs.p, b->d_outs.p, b->mdl, b->d_xtab.p);
         C4B_CUDA(cudaGetLastError());

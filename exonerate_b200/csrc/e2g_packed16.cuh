@@ -1,0 +1,362 @@
+// e2g_packed16.cuh -- est2genome lattice fill with BOTH STRANDS of the model in one
+// register: forward-strand states in the low 16 bits, reverse-strand states in the
+// high 16 bits (DPX S16x2), one warp per lattice.
+//
+// Same closed model, candidate order and END rule as e2g_fill_kernel
+// (e2g_systolic.cuh; reference: generated optimal:est2genome DP functions,
+// src/c4/viterbi.c:1638-1727 over src/model/est2genome.c:57-93 +
+// src/model/intron.c:588-697).  The forward and the reverse half of the model are
+// the same automaton with different splice-site columns, so every max-plus
+// instruction advances both.  Bit-identical to the int32 kernel whenever no
+// halfword add can wrap: all reachable values lie in
+//     [2 gap_open + intron_open - 300,  max_sub * min(Q, T)],
+// and the host sends a batch here only when that fits 15 bits (e2g16_eligible).
+//
+// What changed against the int32 kernel, and why it is ~8x fewer instructions:
+//  * two strands per instruction (S16x2);
+//  * the two-column delay lines (intron open / close advance the target by 2) are
+//    PING-PONG register arrays indexed by the parity of the step: the value of
+//    column j overwrites column j-2 in place, no register shifting;
+//  * the intron-start shadow (viterbi.c:413-422; read only by the length test of
+//    intron.c:138-161) is carried as a saturating 16-bit AGE = j - start: "open"
+//    sets 2, "loop" adds 1, the close candidate of column j is valid iff
+//    age(j-2) + 2 >= min_intron (the host guarantees max_intron >= T + 2, so the
+//    upper test can never fire; saturation at 32767 keeps the lower one exact);
+//  * which candidate won comes for free from VIMNMX.S16x2's predicate outputs
+//    (__vibmax_s16x2), stored as raw "earlier candidate held" bits.
+// Mapping: lane l owns 16 consecutive rows, lanes are skewed by one column, strips
+// of 512 rows are swept one after the other with the hand-off row {G, I} in L2 --
+// exactly the scheme of affine_systolic.cuh.
+//
+// Traceback record, one halfword per cell: per strand 7 bits (forward at bit 0,
+// reverse at bit 7) + bit 14 = "END prefers the forward strand":
+//   bit0 close >= match   bit1 M held against I   bit2 .. against D   bit3 .. against START
+//   bit4 N: open held against loop   bit5 I: open held against extend   bit6 D: likewise
+#pragma once
+#include "affine_packed16.cuh"
+#include "e2g_systolic.cuh"
+
+namespace c4b {
+
+constexpr int kE2pR = 16;  // rows per lane -> 512 rows per sweep
+
+struct E2pPair {
+    const uint8_t *q;    // query classes (PRMT) per position
+    const uint8_t *t;    // target column codes per position
+    const uint32_t *sp;  // per target position: int8 x4 {ss5_fwd, ss3_fwd, ss5_rev, ss3_rev}
+    int32_t Q, T;
+    uint16_t *tb;        // [sweep][step][lane][16] halfwords, or null
+    uint2 *top0, *top1;  // sweep hand-off rows {G, I}[T+1], ping-pong; null when one sweep
+    int64_t out_index;
+};
+
+template <bool TB>
+__global__ void __launch_bounds__(32)
+e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, const E2gModel mdl,
+                  const uint2 *__restrict__ score_table) {
+    constexpr int R = kE2pR;
+    __shared__ uint2 xtab[25];
+    const int lane = threadIdx.x;
+    const E2pPair P = pairs[blockIdx.x];
+    const int Q = P.Q, T = P.T;
+    if (lane < 25) xtab[lane] = score_table[lane];
+    __syncwarp();
+
+    const uint32_t open2 = pack16(mdl.open), ext2 = pack16(mdl.ext);
+    const uint32_t preK = pack16(mdl.intron_open - mdl.open);  // N opens from G = M + open
+    const uint32_t thr2 = pack16(max(0, mdl.min_intron - 2));
+    const int rows_per_sweep = 32 * R;
+    const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    const int nsteps = T + 1 + 31;
+
+    // first strict maximum of END per strand, tracked on G = M + open
+    int bestF = INT32_MIN, bjF = 0, biF = 0, bestR = INT32_MIN, bjR = 0, biR = 0;
+    uint32_t best2 = kMin16x2;
+
+    for (int sweep = 0; sweep < nsweeps; ++sweep) {
+        const int row0 = sweep * rows_per_sweep + lane * R;
+        const bool first_row_lane = (sweep == 0 && lane == 0);
+        const bool later_sweep = (sweep > 0);
+        const int nvalid = min(R, max(0, Q - row0 + 1));  // rows r < nvalid are lattice rows <= Q
+        uint32_t sel[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + r;
+            const uint32_t c = (i >= 1 && i <= Q) ? (uint32_t)P.q[i - 1] : (uint32_t)kPadClass;
+            const uint32_t s = c | ((c | 8u) << 4);  // byte c, sign-extended
+            sel[r] = s | (s << 8);                   // the same score in both halves
+        }
+        // ping-pong by step parity: [p] holds the column two steps back and is overwritten
+        uint32_t G[2][R], N[2][R], A[2][R], Dp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            G[0][r] = G[1][r] = N[0][r] = N[1][r] = Dp[r] = kNeg16x2;
+            A[0][r] = A[1][r] = 0u;
+        }
+        const uint2 *top_in = (sweep & 1) ? P.top0 : P.top1;  // written by sweep-1
+        uint2 *top_out = (sweep & 1) ? P.top1 : P.top0;
+        const bool write_top = (sweep + 1 < nsweeps) && (lane == 31);
+        uint32_t topG = kNeg16x2, topI = kNeg16x2, topGprev = kNeg16x2;
+        int in_code = kTargetNone, code0 = kTargetNone;
+        uint32_t in_sp = 0u, sp0 = 0u;
+        uint2 top0v = make_uint2(kNeg16x2, kNeg16x2);
+        if (later_sweep) top0v = top_in[0];
+        uint4 *tbp = nullptr;
+        if (TB) tbp = reinterpret_cast<uint4 *>(P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R);
+
+        auto step = [&](const int s, auto PAR) {
+            constexpr int p = decltype(PAR)::value, o = p ^ 1;
+            const int j = s - lane;
+            const int code = (lane == 0) ? code0 : in_code;
+            const uint32_t spw = (lane == 0) ? sp0 : in_sp;  // splice word of column j-2
+            if (later_sweep && lane == 0) { topG = top0v.x; topI = top0v.y; }
+            if (s + 1 <= T) {
+                code0 = (int)P.t[s];
+                sp0 = (s >= 1) ? P.sp[s - 1] : 0u;   // source column (s+1)-2
+                if (later_sweep) top0v = top_in[s + 1];
+            } else {
+                code0 = kTargetNone;
+                sp0 = 0u;
+            }
+            uint32_t botG = kNeg16x2, botI = kNeg16x2;
+            if (j >= 0 && j <= T) {
+                const uint2 X = xtab[code];
+                // forward opens at a 5' site and closes at a 3' site, reverse 3' then 5'
+                uint32_t pre2, post2;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pre2) : "r"(spw), "r"(0u), "r"(0xB380u));
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(post2) : "r"(spw), "r"(0u), "r"(0xA291u));
+                pre2 = __vadd2(pre2, preK);
+                uint32_t rec[TB ? R : 1];
+                // ---- phase A: everything that depends on previous columns only ----------
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    uint32_t sc;
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(X.x), "r"(X.y), "r"(sel[r]));
+                    // N: open (T3/T0) first, loop (T4/T1) replaces only if strictly greater
+                    bool oh, ol;
+                    const uint32_t nv = __vadd2(G[p][r], pre2);
+                    const uint32_t Nn = __vibmax_s16x2(nv, N[o][r], &oh, &ol);
+                    uint32_t An = __viaddmin_u16x2(A[o][r], 0x00010001u, 0x7FFF7FFFu);
+                    if (ol) An = (An & 0xFFFF0000u) | 0x00000002u;
+                    if (oh) An = (An & 0x0000FFFFu) | 0x00020000u;
+                    // close candidate (T5/T2) from column j-2, valid iff its intron is long enough
+                    bool vh, vl;
+                    (void)__vibmax_u16x2(A[p][r], thr2, &vh, &vl);
+                    uint32_t c5 = __vadd2(N[p][r], post2);
+                    if (!vl) c5 = (c5 & 0xFFFF0000u) | 0x0000C000u;
+                    if (!vh) c5 = (c5 & 0x0000FFFFu) | 0xC0000000u;
+                    const uint32_t diag = (r == 0) ? topGprev : G[o][r - 1];
+                    uint32_t xc, Dn;
+                    if (!TB) {
+                        xc = __viaddmax_s16x2(diag, sc, c5);               // max(close, match)
+                        Dn = __viaddmax_s16x2(Dp[r], ext2, G[o][r]);       // max(open, extend)
+                    } else {
+                        bool ch, cl, dh, dl;
+                        xc = __vibmax_s16x2(c5, __vadd2(diag, sc), &ch, &cl);       // close first (T5, T11)
+                        Dn = __vibmax_s16x2(G[o][r], __vadd2(Dp[r], ext2), &dh, &dl);  // open first (T13, T15)
+                        rec[r] = (cl ? 0x0001u : 0u) | (ch ? 0x0080u : 0u) | (ol ? 0x0010u : 0u) | (oh ? 0x0800u : 0u) |
+                                 (dl ? 0x0040u : 0u) | (dh ? 0x2000u : 0u);
+                    }
+                    N[p][r] = Nn;
+                    A[p][r] = An;
+                    Dp[r] = Dn;
+                    G[p][r] = xc;  // until phase B turns it into G of this column
+                }
+                // ---- phase B: the vertical chain I -> M -> G, top-down ---------------------
+                uint32_t upG = topG, upI = topI, cm = kMin16x2;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    uint32_t Iv, Mv;
+                    if (!TB) {
+                        Iv = __viaddmax_s16x2(upI, ext2, upG);
+                        Mv = __vimax3_s16x2_relu(G[p][r], Iv, Dp[r]);
+                    } else {
+                        bool ih, il, ah, al, bh, bl, sh, sl;
+                        Iv = __vibmax_s16x2(upG, __vadd2(upI, ext2), &ih, &il);   // open first (T12, T14)
+                        Mv = __vibmax_s16x2(G[p][r], Iv, &ah, &al);               // then I (T19/T16)
+                        Mv = __vibmax_s16x2(Mv, Dp[r], &bh, &bl);                 // then D (T20/T17)
+                        Mv = __vibmax_s16x2(Mv, 0u, &sh, &sl);                    // then START (T21/T18)
+                        // END: reverse strand first (T22), forward (T23) only if strictly greater
+                        const bool endf = lo16(Mv) > hi16(Mv);
+                        rec[r] |= (al ? 0x0002u : 0u) | (ah ? 0x0100u : 0u) | (bl ? 0x0004u : 0u) | (bh ? 0x0200u : 0u) |
+                                  (sl ? 0x0008u : 0u) | (sh ? 0x0400u : 0u) | (il ? 0x0020u : 0u) | (ih ? 0x1000u : 0u) |
+                                  (endf ? 0x4000u : 0u);
+                    }
+                    const uint32_t Gv = __vadd2(Mv, open2);
+                    G[p][r] = Gv;
+                    upG = Gv;
+                    upI = Iv;
+                    if (r & 1) cm = __vimax3_s16x2(cm, Gv, G[p][r - 1]);
+                }
+                botG = upG;
+                botI = upI;
+                topGprev = topG;
+                if (TB) {
+                    tbp[0] = make_uint4(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16), rec[4] | (rec[5] << 16),
+                                        rec[6] | (rec[7] << 16));
+                    tbp[1] = make_uint4(rec[8] | (rec[9] << 16), rec[10] | (rec[11] << 16),
+                                        rec[12] | (rec[13] << 16), rec[14] | (rec[15] << 16));
+                }
+                if (write_top) top_out[j] = make_uint2(botG, botI);
+                // ---- END bookkeeping: cm covers padding rows too, so it only TRIGGERS the exact
+                // search (first sweep: strictly greater; later sweeps: a tie at a smaller j wins)
+                bool trig;
+                {
+                    bool gh, gl;
+                    if (later_sweep) {
+                        (void)__vibmax_s16x2(cm, best2, &gh, &gl);   // cm >= best
+                        trig = gh || gl;
+                    } else {
+                        (void)__vibmax_s16x2(best2, cm, &gh, &gl);   // best >= cm
+                        trig = !(gh && gl);
+                    }
+                }
+                if (trig) {
+                    int vF = INT32_MIN, iF = 0, vR = INT32_MIN, iR = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nvalid) {
+                            const int f = lo16(G[p][r]), rv = hi16(G[p][r]);
+                            if (f > vF) { vF = f; iF = r; }
+                            if (rv > vR) { vR = rv; iR = r; }
+                        }
+                    if (vF > bestF || (vF == bestF && j < bjF)) { bestF = vF; bjF = j; biF = row0 + iF; }
+                    if (vR > bestR || (vR == bestR && j < bjR)) { bestR = vR; bjR = j; biR = row0 + iR; }
+                    best2 = ((uint32_t)max(bestF, -32768) & 0xFFFFu) | ((uint32_t)max(bestR, -32768) << 16);
+                }
+            }
+            if (first_row_lane) { topG = kNeg16x2; topI = kNeg16x2; }
+            if (TB) tbp += 2 * 32;
+            const uint32_t nG = __shfl_up_sync(0xffffffffu, botG, 1);
+            const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
+            const int nC = __shfl_up_sync(0xffffffffu, code, 1);
+            const uint32_t nS = __shfl_up_sync(0xffffffffu, spw, 1);
+            if (lane > 0) {
+                topG = nG;
+                topI = nI;
+                in_code = nC;
+                in_sp = nS;
+            }
+        };
+
+        int s = 0;
+        for (; s + 1 < nsteps; s += 2) {
+            step(s, std::integral_constant<int, 0>{});
+            step(s + 1, std::integral_constant<int, 1>{});
+        }
+        if (s < nsteps) step(s, std::integral_constant<int, 0>{});
+        __syncwarp();
+    }
+
+    // per strand: lexicographic warp reduction (max score, min j, min i)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bestF, off), oj = __shfl_xor_sync(0xffffffffu, bjF, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biF, off);
+            if (ob > bestF || (ob == bestF && (oj < bjF || (oj == bjF && oi < biF)))) { bestF = ob; bjF = oj; biF = oi; }
+        }
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bestR, off), oj = __shfl_xor_sync(0xffffffffu, bjR, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biR, off);
+            if (ob > bestR || (ob == bestR && (oj < bjR || (oj == bjR && oi < biR)))) { bestR = ob; bjR = oj; biR = oi; }
+        }
+    }
+    if (lane == 0) {
+        // the first cell (target outer, query inner) that reaches the overall maximum; in that
+        // cell the reverse strand is tried first and the forward one must be strictly greater
+        bool fwd;
+        if (bestF != bestR) fwd = bestF > bestR;
+        else if (bjF != bjR) fwd = bjF < bjR;
+        else if (biF != biR) fwd = biF < biR;
+        else fwd = false;
+        E2gOut o;
+        o.best = (fwd ? bestF : bestR) - mdl.open;
+        o.end_i = fwd ? biF : biR;
+        o.end_j = fwd ? bjF : bjR;
+        o.end_forward = fwd ? 1 : 0;
+        outs[P.out_index] = o;
+    }
+}
+
+// Viterbi_Data_create_Alignment (viterbi.c:342-392) over the 15-bit records.
+__global__ void e2g16_traceback_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
+                                       const E2gJob *__restrict__ jobs, int n, const E2gModel mdl, int threshold,
+                                       c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const E2gJob J = jobs[g];
+    const E2pPair P = pairs[J.pair];
+    const E2gOut o = outs[P.out_index];
+    const int nsteps = P.T + 1 + 31;
+    c4b_result res;
+    res.score = o.best; res.status = 0; res.reserved = 0; res.n_ops = 0; res.ops_offset = J.ops_off;
+    int i = o.end_i, j = o.end_j;
+    res.query_end = J.q_origin + i;
+    res.target_end = J.t_origin + j;
+    int32_t *out = ops + 2 * J.ops_off;
+    int n_runs = 0, last_t = -1;
+    bool overflow = false;
+    auto emit = [&](int t) {
+        if (t == last_t) out[2 * (n_runs - 1) + 1] += 1;
+        else if (n_runs < J.ops_cap) { out[2 * n_runs] = t; out[2 * n_runs + 1] = 1; ++n_runs; last_t = t; }
+        else overflow = true;
+    };
+    auto record = [&](int ci, int cj) -> uint32_t {
+        const int w = ci / (32 * kE2pR), ln = (ci / kE2pR) & 31, r = ci % kE2pR;
+        return P.tb[(((size_t)w * nsteps + (cj + ln)) * 32 + ln) * kE2pR + r];
+    };
+    if (o.best < threshold) {
+        res.status = 1;
+    } else {
+        const int x = o.end_forward ? 0 : 1;  // 0 = forward fields (bits 0..6), 1 = reverse (bits 7..13)
+        int state = 0;                         // 0 M, 1 I, 2 D, 3 N
+        emit(mdl.tM2E[x]);
+        for (;;) {
+            const uint32_t f = (record(i, j) >> (7 * x)) & 127u;
+            if (state == 0) {
+                if (!(f & 8u)) { emit(mdl.tS2M[x]); break; }
+                else if (!(f & 4u)) { emit(mdl.tD2M[x]); state = 2; }
+                else if (!(f & 2u)) { emit(mdl.tI2M[x]); state = 1; }
+                else if (f & 1u) { emit(mdl.tNclose[x]); j -= 2; state = 3; }
+                else { emit(mdl.tMatch[x]); --i; --j; }
+            } else if (state == 1) {
+                if (f & 32u) { emit(mdl.tIopen[x]); state = 0; } else emit(mdl.tIext[x]);
+                --i;
+            } else if (state == 2) {
+                if (f & 64u) { emit(mdl.tDopen[x]); state = 0; } else emit(mdl.tDext[x]);
+                --j;
+            } else {
+                if (f & 16u) { emit(mdl.tNopen[x]); j -= 2; state = 0; }
+                else { emit(mdl.tNloop[x]); --j; }
+            }
+            if (i < 0 || j < 0 || overflow) { res.status = 4; break; }
+        }
+        for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
+            const int t0 = out[2 * a], l0 = out[2 * a + 1];
+            out[2 * a] = out[2 * b]; out[2 * a + 1] = out[2 * b + 1];
+            out[2 * b] = t0; out[2 * b + 1] = l0;
+        }
+    }
+    res.n_ops = (res.status == 0) ? n_runs : 0;
+    res.query_start = J.q_origin + max(i, 0);
+    res.target_start = J.t_origin + max(j, 0);
+    results[J.result] = res;
+}
+
+__global__ void e2g16_score_results_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
+                                           const int32_t *__restrict__ q_origin,
+                                           const int32_t *__restrict__ t_origin, int n,
+                                           c4b_result *__restrict__ results) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const E2gOut o = outs[pairs[p].out_index];
+    c4b_result r;
+    r.score = o.best;
+    r.query_start = q_origin[p]; r.target_start = t_origin[p];
+    r.query_end = q_origin[p] + o.end_i; r.target_end = t_origin[p] + o.end_j;
+    r.n_ops = 0; r.ops_offset = 0; r.status = 0; r.reserved = 0;
+    results[pairs[p].out_index] = r;
+}
+
+}  // namespace c4b

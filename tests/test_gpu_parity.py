@@ -48,7 +48,7 @@ def test_golden_vectors(eng, name, params, scoring):
                     splice=[splice_for(name, c) for c in cases])
     b = Batch(eng, model, scoring, pairs, want_path=True)
     want_kernel = "affine_systolic" if name in AFFINE else \
-        "e2g_systolic" if name == "est2genome" else "generic_wavefront"
+        "e2g_packed16" if name == "est2genome" else "generic_wavefront"
     assert b.kernel_name == want_kernel
     b.close()
     opt = Optimal(eng, model, scoring)
@@ -356,9 +356,12 @@ E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257
               (513, 3000), (600, 5000), (1000, 6000), (1300, 2500), (2047, 2400)]
 
 
-def test_est2genome_systolic_vs_oracle(eng, params, scoring):
-    """The hand-specialised est2genome kernel (1..8 strips of 256 rows, pipelined
-    through shared memory) against the oracle: forward and reverse-strand genes,
+@pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_systolic"])
+def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel):
+    """The hand-specialised est2genome kernels -- e2g_packed16 (both strands per
+    register, one warp per lattice, 512-row sweeps) and the int32 e2g_systolic
+    (1..8 strips of 256 rows, pipelined through shared memory; C4B_E2G_PACK16=0)
+    -- against the oracle: forward and reverse-strand genes,
     ragged sizes around the strip height, unrelated and N-rich inputs; one mixed
     batch (idle strips for short queries) and per-shape batches (every strip count)."""
     from exonerate_b200 import Batch, Optimal, PairSet
@@ -377,11 +380,13 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring):
     want = [e2g_oracle(model, scoring, q, t, s_) for q, t, s_ in zip(qs, ts, sp)]
     assert any(any(model.transitions[t_].advance_target == 2 for t_, _ in w["ops"]) for w in want)
     opt = Optimal(eng, model, scoring)
+    if kernel == "e2g_systolic":
+        monkeypatch.setenv("C4B_E2G_PACK16", "0")
 
     def check(idx):
         pairs = PairSet([qs[k] for k in idx], [ts[k] for k in idx], splice=[sp[k] for k in idx])
         b = Batch(eng, model, scoring, pairs, want_path=True)
-        assert b.kernel_name == "e2g_systolic"
+        assert b.kernel_name == kernel
         b.close()
         scores = opt.find_score(pairs)
         paths = opt.find_path(pairs)
@@ -397,7 +402,7 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring):
         check([k])
 
 
-def test_est2genome_regions_threshold_and_fallback(eng, params, scoring):
+def test_est2genome_regions_threshold_and_fallback(eng, params, scoring, monkeypatch):
     from exonerate_b200 import Batch, Optimal, PairSet
     from exonerate_b200.models import splice_arrays
     model, _ = helpers.load_model("est2genome", params)
@@ -412,13 +417,18 @@ def test_est2genome_regions_threshold_and_fallback(eng, params, scoring):
         assert paths[k]["ops"] == want["ops"], reg
     r = opt.find_path(PairSet([q], [t], splice=[sp]), threshold=10 ** 6)[0]
     assert r["status"] == 1 and r["ops"] == []
-    # queries beyond 8 strips take the table-driven kernel, same answers
+    # a query of five 512-row sweeps on the packed kernel; without it, queries beyond 8
+    # strips take the table-driven kernel: same answers
     q2, t2 = helpers.gene_pair(78, 2100, 2600)
     sp2 = splice_arrays(t2)
     pairs = PairSet([q2], [t2], splice=[sp2])
-    b = Batch(eng, model, scoring, pairs, want_path=True)
-    assert b.kernel_name == "generic_wavefront"
-    b.close()
     want = e2g_oracle(model, scoring, q2, t2, sp2)
-    got = opt.find_path(pairs)[0]
-    assert got["score"] == want["score"] and got["ops"] == want["ops"]
+    for env, name in ((None, "e2g_packed16"), ("0", "generic_wavefront")):
+        if env is not None:
+            monkeypatch.setenv("C4B_E2G_PACK16", env)
+        b = Batch(eng, model, scoring, pairs, want_path=True)
+        assert b.kernel_name == name
+        b.close()
+        got = opt.find_path(pairs)[0]
+        assert got["score"] == want["score"] and got["ops"] == want["ops"], name
+        assert opt.find_score(pairs)[0] == want["score"], name
