@@ -82,7 +82,7 @@ static bool analyze_est2genome(const c4b_model &m, const c4b_scoring &sc, E2gMod
 struct E2gBatch {
     cudaStream_t stream = nullptr;
     int64_t *launches = nullptr;
-    int n = 0, warps = 1;
+    int n = 0, warps = 1, max_target = 0;
     bool want_path = false;
     E2gModel mdl;
     int64_t cells = 0;
@@ -97,6 +97,12 @@ struct E2gBatch {
     bool packed = false;              // e2g_packed16.cuh: both strands per register, one warp per lattice
     DevBuf<E2pPair> d_pairs16;
     DevBuf<uint2> d_top;              // sweep hand-off rows (packed path, queries longer than 511)
+    bool windowed = false;            // find_path by checkpoints + window refills (e2g_packed16.cuh)
+    DevBuf<uint32_t> d_ck;
+    DevBuf<E2pWalk> d_walk;
+    DevBuf<int32_t> d_active, d_count;
+    DevBuf<uint16_t> d_win;
+    size_t win_stride = 0;
     DevBuf<E2gOut> d_outs;
     DevBuf<E2gJob> d_jobs;
     DevBuf<int32_t> d_qorg, d_torg;
@@ -107,7 +113,8 @@ struct E2gBatch {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     ~E2gBatch() {
         d_seq.release(); d_sp.release(); d_lut.release(); d_xtab.release(); d_bad.release();
-        d_pairs.release(); d_pairs16.release(); d_top.release(); d_outs.release(); d_jobs.release(); d_qorg.release(); d_torg.release();
+        d_pairs.release(); d_pairs16.release(); d_top.release(); d_ck.release(); d_walk.release(); d_active.release();
+        d_count.release(); d_win.release(); d_outs.release(); d_jobs.release(); d_qorg.release(); d_torg.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
         d_new_off.release();
         if (ev_a) cudaEventDestroy(ev_a);
@@ -187,6 +194,7 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     E2gBatch *b = new E2gBatch();
     b->stream = stream; b->launches = launch_counter; b->n = n; b->want_path = want_path; b->mdl = mdl;
     b->packed = packed;
+    b->max_target = maxT;
     b->warps = std::max(1, (maxQ + 1 + 32 * kE2gR - 1) / (32 * kE2gR));
     // ---- staging: region slices of query / target, packed splice words ---------------
     std::vector<size_t> qoff(n), toff(n);
@@ -256,14 +264,32 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     size_t arena = 0;
     int64_t ops_cursor = 0;
     std::vector<E2gJob> jobs(n);
+    // windowed traceback: per lattice checkpoints + one window of records, all resident
+    std::vector<size_t> ck_off(n, 0);
+    size_t ck_words = 0;
+    if (packed && want_path) {
+        const char *env = getenv("C4B_E2G_WINDOWS");
+        size_t max_sweeps = 1;
+        for (int p = 0; p < n; ++p) {
+            const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+            const size_t nwin = (size_t)pairs[p].target_length / kE2pWin + 1;
+            max_sweeps = std::max(max_sweeps, sweeps);
+            ck_off[p] = ck_words;
+            ck_words += (nwin - 1) * sweeps * 32 * kE2pR * kE2pCkWords;
+        }
+        b->win_stride = max_sweeps * kE2pWinSteps * 32 * kE2pR;
+        const size_t need = ck_words * 4 + (size_t)n * b->win_stride * 2;
+        b->windowed = !(env && atoi(env) == 0) && need / 2 < budget_hw;
+    }
     if (want_path) {
         size_t cur = 0;
         int begin = 0;
         for (int k = 0; k < n; ++k) {
             const c4b_pair &pp = pairs[b->order[k]];
             const size_t sweeps = ((size_t)pp.query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
-            const size_t hw = packed ? align_up(sweeps * (pp.target_length + 32) * 32 * kE2pR, 16)
-                                     : align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 16);
+            const size_t hw = b->windowed ? 0
+                              : packed ? align_up(sweeps * (pp.target_length + 32) * 32 * kE2pR, 16)
+                                       : align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 16);
             if (hw > budget_hw) {
                 set_error("traceback of pair " + std::to_string(b->order[k]) + " exceeds the device memory budget");
                 delete b;
@@ -295,11 +321,19 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     if (packed) {
         for (int p = 0; p < n; ++p)
             if (pairs[p].query_length + 1 > 32 * kE2pR) {
+                const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
                 top_off[p] = top_elems;
-                top_elems += 2 * ((size_t)pairs[p].target_length + 1);
+                top_elems += (sweeps - 1) * ((size_t)pairs[p].target_length + 1);
             }
         rc |= b->d_pairs16.alloc(n);
         rc |= b->d_top.alloc(top_elems);
+        if (b->windowed) {
+            rc |= b->d_ck.alloc(ck_words + 8);
+            rc |= b->d_walk.alloc(n);
+            rc |= b->d_active.alloc(n);
+            rc |= b->d_count.alloc(1);
+            rc |= b->d_win.alloc((size_t)n * b->win_stride + 16);
+        }
     }
     rc |= b->d_outs.alloc(n);
     rc |= b->d_results.alloc(n);
@@ -336,11 +370,8 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
             E2pPair &e = hp16[k];
             e.q = hp[k].q; e.t = hp[k].t; e.sp = hp[k].sp; e.Q = hp[k].Q; e.T = hp[k].T;
             e.tb = hp[k].tb;
-            e.top0 = e.top1 = nullptr;
-            if (top_off[p] != (size_t)-1) {
-                e.top0 = b->d_top.p + top_off[p];
-                e.top1 = e.top0 + (pairs[p].target_length + 1);
-            }
+            e.top = (top_off[p] != (size_t)-1) ? b->d_top.p + top_off[p] : nullptr;
+            e.ck = b->windowed ? b->d_ck.p + ck_off[p] : nullptr;
             e.out_index = k;
         }
         ok &= cudaMemcpyAsync(b->d_pairs16.p, hp16.data(), n * sizeof(E2pPair), cudaMemcpyHostToDevice, stream) == cudaSuccess;
@@ -380,7 +411,8 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
     C4B_CUDA(cudaEventRecord(b->ev_a, st));
     if (b->packed) {
         if (!b->want_path) {
-            e2g_fill16_kernel<false><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p);
+            e2g_fill16_kernel<E2P_SCORE><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
+                                                           nullptr, nullptr, 0);
             C4B_CUDA(cudaGetLastError());
             C4B_CUDA(cudaEventRecord(b->ev_b, st));
             e2g16_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_qorg.p,
@@ -389,9 +421,53 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
             C4B_CUDA(cudaGetLastError());
             return 0;
         }
+        if (b->windowed) {
+            // pass 1: END cell + column checkpoints; then rounds of (refill the window under
+            // each traceback cursor, walk it) until every cursor has reached START
+            e2g_fill16_kernel<E2P_SCORE_CK><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
+                                                              nullptr, nullptr, nullptr, 0);
+            e2g16_walk_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n, b->mdl,
+                                                                   threshold, b->d_walk.p, b->d_ops_slots.p);
+            e2g16_walk_rejected_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n,
+                                                                       b->d_walk.p, b->d_results.p);
+            (*b->launches) += 3;
+            C4B_CUDA(cudaGetLastError());
+            int max_t = 0;
+            for (int k = 0; k < n; ++k) max_t = std::max(max_t, b->max_target);
+            const int round_cap = 4 * (max_t / kE2pWin + 1) + 16;
+            for (int round = 0;; ++round) {
+                int cnt = 0;
+                C4B_CUDA(cudaMemsetAsync(b->d_count.p, 0, sizeof(int32_t), st));
+                e2g16_active_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_walk.p, n, b->d_active.p, b->d_count.p);
+                C4B_CUDA(cudaMemcpyAsync(&cnt, b->d_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                C4B_CUDA(cudaStreamSynchronize(st));
+                (*b->launches) += 1;
+                if (cnt == 0) break;
+                if (round >= round_cap) {
+                    set_error("internal: est2genome windowed traceback did not terminate");
+                    return -1;
+                }
+                e2g_fill16_kernel<E2P_WINDOW_TB><<<cnt, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
+                                                                   b->d_active.p, b->d_walk.p, b->d_win.p,
+                                                                   b->win_stride);
+                e2g16_walk_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, b->d_active.p,
+                                                                 cnt, b->mdl, b->d_walk.p, b->d_win.p, b->win_stride,
+                                                                 b->d_results.p, b->d_ops_slots.p);
+                (*b->launches) += 2;
+                C4B_CUDA(cudaGetLastError());
+            }
+            C4B_CUDA(cudaEventRecord(b->ev_b, st));
+            apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_results.p, n, threshold);
+            ops_scan_kernel<<<1, 1024, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_new_off.p + n);
+            ops_compact_kernel<<<n, 64, 0, st>>>(b->d_results.p, n, b->d_new_off.p, b->d_ops_slots.p, b->d_ops_packed.p);
+            (*b->launches) += 3;
+            C4B_CUDA(cudaGetLastError());
+            return 0;
+        }
         for (const Chunk &c : b->chunks) {
             const int cnt = c.end - c.begin;
-            e2g_fill16_kernel<true><<<cnt, 32, 0, st>>>(b->d_pairs16.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p);
+            e2g_fill16_kernel<E2P_FULL_TB><<<cnt, 32, 0, st>>>(b->d_pairs16.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p,
+                                                             nullptr, nullptr, nullptr, 0);
             C4B_CUDA(cudaGetLastError());
             e2g16_traceback_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p + c.begin,
                                                                   cnt, b->mdl, threshold, b->d_results.p,

@@ -45,19 +45,46 @@ struct E2pPair {
     const uint8_t *t;    // target column codes per position
     const uint32_t *sp;  // per target position: int8 x4 {ss5_fwd, ss3_fwd, ss5_rev, ss3_rev}
     int32_t Q, T;
-    uint16_t *tb;        // [sweep][step][lane][16] halfwords, or null
-    uint2 *top0, *top1;  // sweep hand-off rows {G, I}[T+1], ping-pong; null when one sweep
+    uint16_t *tb;        // single-pass traceback: [sweep][step][lane][16] halfwords, or null
+    uint2 *top;          // sweep hand-off rows {G, I}: [sweep boundary][T+1]; null when one sweep
+    uint32_t *ck;        // column checkpoints [window-1][sweep][lane][row][7], or null
     int64_t out_index;
 };
 
-template <bool TB>
+// Windowed traceback (find_path on long targets): pass 1 is the score-only fill, which
+// also saves the complete column state {G, N, age (two columns each), D} of every row at
+// the last column of each window of kE2pWin columns.  The traceback then refills ONLY
+// the windows the path crosses, from the checkpoint to their left, with records -- and
+// an intron is crossed in one jump, because the checkpoint holds its age (= length so
+// far).  Record memory is 2 MB per lattice instead of 2 B per cell, so every lattice of
+// a batch is resident at once and the refilled area is a few per cent of the lattice.
+constexpr int kE2pWin = 1024;
+constexpr int kE2pWinSteps = kE2pWin + 31;
+constexpr int kE2pCkWords = 7;
+
+struct E2pWalk {       // traceback cursor of one lattice between rounds
+    int32_t i, j, state, x;      // state: 0 M, 1 I, 2 D, 3 N; x: 0 forward, 1 reverse
+    int32_t n_runs, last_t, status, done;
+};
+
+enum { E2P_SCORE = 0, E2P_FULL_TB = 1, E2P_SCORE_CK = 2, E2P_WINDOW_TB = 3 };
+
+// MODE: E2P_SCORE (END cell only), E2P_FULL_TB (records for the whole lattice),
+// E2P_SCORE_CK (END cell + column checkpoints), E2P_WINDOW_TB (records for one window
+// of one lattice, started from a checkpoint; active = list of lattices, walk = cursors).
+template <int MODE>
 __global__ void __launch_bounds__(32)
 e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, const E2gModel mdl,
-                  const uint2 *__restrict__ score_table) {
+                  const uint2 *__restrict__ score_table, const int32_t *__restrict__ active,
+                  const E2pWalk *__restrict__ walk, uint16_t *__restrict__ winbuf, size_t win_stride) {
     constexpr int R = kE2pR;
+    constexpr bool TB = (MODE == E2P_FULL_TB || MODE == E2P_WINDOW_TB);
+    constexpr bool WIN = (MODE == E2P_WINDOW_TB);
+    constexpr bool CK = (MODE == E2P_SCORE_CK);
     __shared__ uint2 xtab[25];
     const int lane = threadIdx.x;
-    const E2pPair P = pairs[blockIdx.x];
+    const int pidx = WIN ? active[blockIdx.x] : (int)blockIdx.x;
+    const E2pPair P = pairs[pidx];
     const int Q = P.Q, T = P.T;
     if (lane < 25) xtab[lane] = score_table[lane];
     __syncwarp();
@@ -66,8 +93,18 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
     const uint32_t preK = pack16(mdl.intron_open - mdl.open);  // N opens from G = M + open
     const uint32_t thr2 = pack16(max(0, mdl.min_intron - 2));
     const int rows_per_sweep = 32 * R;
-    const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     const int nsteps = T + 1 + 31;
+    // column range [c0, c1] and sweeps of this launch
+    int c0 = 0, c1 = T, nsweeps = all_sweeps;
+    if (WIN) {
+        const E2pWalk W = walk[pidx];
+        c0 = (W.j / kE2pWin) * kE2pWin;
+        c1 = W.j;                                   // the path never moves right or down
+        nsweeps = min(all_sweeps, W.i / rows_per_sweep + 1);
+    }
+    const uint32_t *ck_in = (WIN && c0 > 0) ? P.ck + (size_t)(c0 / kE2pWin - 1) * all_sweeps * 32 * R * kE2pCkWords
+                                            : nullptr;
 
     // first strict maximum of END per strand, tracked on G = M + open
     int bestF = INT32_MIN, bjF = 0, biF = 0, bestR = INT32_MIN, bjR = 0, biR = 0;
@@ -93,16 +130,41 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             G[0][r] = G[1][r] = N[0][r] = N[1][r] = Dp[r] = kNeg16x2;
             A[0][r] = A[1][r] = 0u;
         }
-        const uint2 *top_in = (sweep & 1) ? P.top0 : P.top1;  // written by sweep-1
-        uint2 *top_out = (sweep & 1) ? P.top1 : P.top0;
-        const bool write_top = (sweep + 1 < nsweeps) && (lane == 31);
+        if (WIN && ck_in) {
+            // columns c0-1 ("new") and c0-2 ("old") of my rows; my first step is c0 + lane,
+            // and the array indexed by a step's parity must hold the column two steps back
+            const uint32_t *c = ck_in + ((size_t)(sweep * 32 + lane) * R) * kE2pCkWords;
+            const int po = (c0 + lane) & 1;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t gn = c[r * kE2pCkWords + 0], go = c[r * kE2pCkWords + 1];
+                const uint32_t nn = c[r * kE2pCkWords + 2], no = c[r * kE2pCkWords + 3];
+                const uint32_t an = c[r * kE2pCkWords + 4], ao = c[r * kE2pCkWords + 5];
+                Dp[r] = c[r * kE2pCkWords + 6];
+                G[0][r] = po ? gn : go; G[1][r] = po ? go : gn;
+                N[0][r] = po ? nn : no; N[1][r] = po ? no : nn;
+                A[0][r] = po ? an : ao; A[1][r] = po ? ao : an;
+            }
+        }
+        const uint2 *top_in = later_sweep ? P.top + (size_t)(sweep - 1) * (T + 1) : nullptr;  // written by sweep-1
+        uint2 *top_out = (!WIN && sweep + 1 < all_sweeps) ? P.top + (size_t)sweep * (T + 1) : nullptr;
+        const bool write_top = (top_out != nullptr) && (lane == 31);
         uint32_t topG = kNeg16x2, topI = kNeg16x2, topGprev = kNeg16x2;
-        int in_code = kTargetNone, code0 = kTargetNone;
-        uint32_t in_sp = 0u, sp0 = 0u;
+        // lane 0's inputs for its first column c0: symbol, splice word of column c0-2, row above
+        int in_code = kTargetNone, code0 = (c0 >= 1) ? (int)P.t[c0 - 1] : kTargetNone;
+        uint32_t in_sp = 0u, sp0 = (c0 >= 2) ? P.sp[c0 - 2] : 0u;
         uint2 top0v = make_uint2(kNeg16x2, kNeg16x2);
-        if (later_sweep) top0v = top_in[0];
+        // diagonal input of my first row at column c0: G of the row above at column c0-1
+        if (WIN && ck_in && lane > 0)
+            topGprev = ck_in[((size_t)(sweep * 32 + lane - 1) * R + (R - 1)) * kE2pCkWords + 0];
+        if (later_sweep) {
+            top0v = top_in[c0];
+            if (c0 >= 1 && lane == 0) topGprev = top_in[c0 - 1].x;
+        }
         uint4 *tbp = nullptr;
-        if (TB) tbp = reinterpret_cast<uint4 *>(P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R);
+        if (MODE == E2P_FULL_TB) tbp = reinterpret_cast<uint4 *>(P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R);
+        if (WIN) tbp = reinterpret_cast<uint4 *>(winbuf + (size_t)blockIdx.x * win_stride +
+                                                 (((size_t)sweep * kE2pWinSteps) * 32 + lane) * R);
 
         auto step = [&](const int s, auto PAR) {
             constexpr int p = decltype(PAR)::value, o = p ^ 1;
@@ -119,7 +181,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 sp0 = 0u;
             }
             uint32_t botG = kNeg16x2, botI = kNeg16x2;
-            if (j >= 0 && j <= T) {
+            if (j >= c0 && j <= c1) {
                 const uint2 X = xtab[code];
                 // forward opens at a 5' site and closes at a 3' site, reverse 3' then 5'
                 uint32_t pre2, post2;
@@ -198,10 +260,21 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                                         rec[12] | (rec[13] << 16), rec[14] | (rec[15] << 16));
                 }
                 if (write_top) top_out[j] = make_uint2(botG, botI);
+                if (CK && ((j + 1) & (kE2pWin - 1)) == 0 && j < T) {
+                    // last column of a window: the state a later window refill starts from
+                    uint32_t *c = P.ck + ((size_t)(((j + 1) / kE2pWin - 1) * all_sweeps + sweep) * 32 + lane) * R * kE2pCkWords;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        c[r * kE2pCkWords + 0] = G[p][r]; c[r * kE2pCkWords + 1] = G[o][r];
+                        c[r * kE2pCkWords + 2] = N[p][r]; c[r * kE2pCkWords + 3] = N[o][r];
+                        c[r * kE2pCkWords + 4] = A[p][r]; c[r * kE2pCkWords + 5] = A[o][r];
+                        c[r * kE2pCkWords + 6] = Dp[r];
+                    }
+                }
                 // ---- END bookkeeping: cm covers padding rows too, so it only TRIGGERS the exact
                 // search (first sweep: strictly greater; later sweeps: a tie at a smaller j wins)
-                bool trig;
-                {
+                bool trig = false;
+                if (!WIN) {
                     bool gh, gl;
                     if (later_sweep) {
                         (void)__vibmax_s16x2(cm, best2, &gh, &gl);   // cm >= best
@@ -239,14 +312,18 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             }
         };
 
-        int s = 0;
-        for (; s + 1 < nsteps; s += 2) {
+        // steps c0 .. c1+31 (lane l works on column step - l); parity = step & 1
+        int s = c0;
+        const int s_end = c1 + 32;
+        if (s & 1) { step(s, std::integral_constant<int, 1>{}); ++s; }
+        for (; s + 1 < s_end; s += 2) {
             step(s, std::integral_constant<int, 0>{});
             step(s + 1, std::integral_constant<int, 1>{});
         }
-        if (s < nsteps) step(s, std::integral_constant<int, 0>{});
+        if (s < s_end) step(s, std::integral_constant<int, 0>{});
         __syncwarp();
     }
+    if (WIN) return;
 
     // per strand: lexicographic warp reduction (max score, min j, min i)
 #pragma unroll
@@ -341,6 +418,139 @@ __global__ void e2g16_traceback_kernel(const E2pPair *__restrict__ pairs, const 
     res.n_ops = (res.status == 0) ? n_runs : 0;
     res.query_start = J.q_origin + max(i, 0);
     res.target_start = J.t_origin + max(j, 0);
+    results[J.result] = res;
+}
+
+// ---- windowed traceback: cursors, window records, intron jumps -----------------------
+__global__ void e2g16_walk_init_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
+                                       const E2gJob *__restrict__ jobs, int n, const E2gModel mdl, int threshold,
+                                       E2pWalk *__restrict__ walk, int32_t *__restrict__ ops) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const E2gJob J = jobs[g];
+    const E2gOut o = outs[pairs[J.pair].out_index];
+    E2pWalk W;
+    W.i = o.end_i; W.j = o.end_j; W.state = 0; W.x = o.end_forward ? 0 : 1;
+    W.n_runs = 0; W.last_t = -1; W.status = 0; W.done = 0;
+    if (o.best < threshold) { W.status = 1; W.done = 1; }
+    else if (J.ops_cap >= 1) {
+        int32_t *out = ops + 2 * J.ops_off;
+        out[0] = mdl.tM2E[W.x]; out[1] = 1; W.n_runs = 1; W.last_t = mdl.tM2E[W.x];
+    } else { W.status = 4; W.done = 1; }
+    walk[J.pair] = W;
+}
+
+// which lattices still have a traceback in flight (order = job order)
+__global__ void e2g16_active_kernel(const E2pWalk *__restrict__ walk, int n, int32_t *__restrict__ active,
+                                    int32_t *__restrict__ count) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    if (!walk[g].done) active[atomicAdd(count, 1)] = g;
+}
+
+// Viterbi_Data_create_Alignment (viterbi.c:342-392) inside the window that was just
+// refilled; leaves the cursor at the first cell left of the window (or finishes).
+__global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
+                                  const E2gJob *__restrict__ jobs, const int32_t *__restrict__ active, int n_active,
+                                  const E2gModel mdl, E2pWalk *__restrict__ walk,
+                                  const uint16_t *__restrict__ winbuf, size_t win_stride,
+                                  c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_active) return;
+    const int pidx = active[slot];
+    const E2gJob J = jobs[pidx];   // jobs are indexed like pairs (J.pair == pidx)
+    const E2pPair P = pairs[pidx];
+    E2pWalk W = walk[pidx];
+    const int c0 = (W.j / kE2pWin) * kE2pWin;
+    const int all_sweeps = (P.Q + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+    const uint16_t *rec_base = winbuf + (size_t)slot * win_stride;
+    int32_t *out = ops + 2 * J.ops_off;
+    int i = W.i, j = W.j, state = W.state, n_runs = W.n_runs, last_t = W.last_t;
+    const int x = W.x;
+    bool overflow = false, finished = false;
+    auto emit = [&](int t, int cnt) {
+        if (cnt <= 0) return;
+        if (t == last_t) out[2 * (n_runs - 1) + 1] += cnt;
+        else if (n_runs < J.ops_cap) { out[2 * n_runs] = t; out[2 * n_runs + 1] = cnt; ++n_runs; last_t = t; }
+        else overflow = true;
+    };
+    auto record = [&](int ci, int cj) -> uint32_t {
+        const int w = ci / (32 * kE2pR), ln = (ci / kE2pR) & 31, r = ci % kE2pR;
+        return rec_base[(((size_t)w * kE2pWinSteps + (cj - c0 + ln)) * 32 + ln) * kE2pR + r];
+    };
+    while (j >= c0) {
+        const uint32_t f = (record(i, j) >> (7 * x)) & 127u;
+        if (state == 0) {
+            if (!(f & 8u)) { emit(mdl.tS2M[x], 1); finished = true; break; }
+            else if (!(f & 4u)) { emit(mdl.tD2M[x], 1); state = 2; }
+            else if (!(f & 2u)) { emit(mdl.tI2M[x], 1); state = 1; }
+            else if (f & 1u) { emit(mdl.tNclose[x], 1); j -= 2; state = 3; }
+            else { emit(mdl.tMatch[x], 1); --i; --j; }
+        } else if (state == 1) {
+            if (f & 32u) { emit(mdl.tIopen[x], 1); state = 0; } else emit(mdl.tIext[x], 1);
+            --i;
+        } else if (state == 2) {
+            if (f & 64u) { emit(mdl.tDopen[x], 1); state = 0; } else emit(mdl.tDext[x], 1);
+            --j;
+        } else {
+            if (f & 16u) { emit(mdl.tNopen[x], 1); j -= 2; state = 0; }
+            else { emit(mdl.tNloop[x], 1); --j; }
+        }
+        if (i < 0 || j < 0 || overflow) break;
+    }
+    if (!finished && !overflow && i >= 0 && j >= 0 && state == 3 && c0 > 0) {
+        // inside an intron at column j in {c0-1, c0-2}: the checkpoint left of this window
+        // holds the intron's age there = j - (column the intron was opened from)
+        const int w = i / (32 * kE2pR), ln = (i / kE2pR) & 31, r = i % kE2pR;
+        const uint32_t *c = P.ck + (((size_t)(c0 / kE2pWin - 1) * all_sweeps + w) * 32 + ln) * kE2pR * kE2pCkWords +
+                            (size_t)r * kE2pCkWords;
+        const uint32_t a2 = (j == c0 - 1) ? c[4] : c[5];
+        const int age = (int)((a2 >> (16 * x)) & 0xFFFFu);
+        if (age >= 2 && age < 0x7FFF && age <= j) {
+            emit(mdl.tNloop[x], age - 2);
+            emit(mdl.tNopen[x], 1);
+            j -= age;
+            state = 0;
+        }
+    }
+    if (finished || overflow || i < 0 || j < 0) {
+        c4b_result res;
+        const E2gOut o = outs[P.out_index];
+        res.score = o.best; res.reserved = 0; res.ops_offset = J.ops_off;
+        res.status = finished && !overflow ? 0 : 4;
+        res.query_end = J.q_origin + o.end_i;
+        res.target_end = J.t_origin + o.end_j;
+        if (res.status == 0)
+            for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
+                const int t0 = out[2 * a], l0 = out[2 * a + 1];
+                out[2 * a] = out[2 * b]; out[2 * a + 1] = out[2 * b + 1];
+                out[2 * b] = t0; out[2 * b + 1] = l0;
+            }
+        res.n_ops = (res.status == 0) ? n_runs : 0;
+        res.query_start = J.q_origin + max(i, 0);
+        res.target_start = J.t_origin + max(j, 0);
+        results[J.result] = res;
+        W.done = 1;
+        W.status = res.status;
+    }
+    W.i = i; W.j = j; W.state = state; W.n_runs = n_runs; W.last_t = last_t;
+    walk[pidx] = W;
+}
+
+// lattices whose score is below the threshold never enter the rounds
+__global__ void e2g16_walk_rejected_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
+                                           const E2gJob *__restrict__ jobs, int n, const E2pWalk *__restrict__ walk,
+                                           c4b_result *__restrict__ results) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const E2gJob J = jobs[g];
+    const E2pWalk W = walk[J.pair];
+    if (!(W.done && W.status != 0 && W.n_runs == 0)) return;
+    const E2gOut o = outs[pairs[J.pair].out_index];
+    c4b_result res;
+    res.score = o.best; res.status = W.status; res.reserved = 0; res.n_ops = 0; res.ops_offset = J.ops_off;
+    res.query_end = J.q_origin + o.end_i; res.target_end = J.t_origin + o.end_j;
+    res.query_start = J.q_origin + o.end_i; res.target_start = J.t_origin + o.end_j;
     results[J.result] = res;
 }
 

@@ -356,7 +356,7 @@ E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257
               (513, 3000), (600, 5000), (1000, 6000), (1300, 2500), (2047, 2400)]
 
 
-@pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_systolic"])
+@pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_packed16:full", "e2g_systolic"])
 def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel):
     """The hand-specialised est2genome kernels -- e2g_packed16 (both strands per
     register, one warp per lattice, 512-row sweeps) and the int32 e2g_systolic
@@ -382,6 +382,9 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel
     opt = Optimal(eng, model, scoring)
     if kernel == "e2g_systolic":
         monkeypatch.setenv("C4B_E2G_PACK16", "0")
+    if kernel.endswith(":full"):     # records for the whole lattice instead of checkpoints + windows
+        monkeypatch.setenv("C4B_E2G_WINDOWS", "0")
+        kernel = kernel.split(":")[0]
 
     def check(idx):
         pairs = PairSet([qs[k] for k in idx], [ts[k] for k in idx], splice=[sp[k] for k in idx])
@@ -400,6 +403,35 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel
     check(list(range(len(qs))))
     for k in range(len(E2G_SHAPES)):
         check([k])
+
+
+def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkeypatch):
+    """find_path on long targets: pass 1 saves column checkpoints every 1024 columns, the
+    traceback refills only the windows under the path and crosses introns in one jump
+    (the checkpoint holds the intron's age).  Introns of 3 .. 40 kbp (the 16-bit age
+    saturates at 32767: no jump, window-by-window walk), both strands; against the
+    full-lattice record pass and, for the smaller ones, the oracle."""
+    from exonerate_b200 import Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    model, _ = helpers.load_model("est2genome", params)
+    opt = Optimal(eng, model, scoring)
+    qs, ts = [], []
+    for k, (ql, tl, nex) in enumerate([(300, 12000, 3), (600, 30000, 4), (1000, 100000, 5), (900, 70000, 2),
+                                       (200, 90000, 2), (1000, 100000, 5), (520, 45000, 3)]):
+        q, t = helpers.gene_pair(6100 + k, ql, tl, n_exons=nex, rate=0.02, reverse=bool(k & 1))
+        qs.append(q)
+        ts.append(t)
+    sp = [splice_arrays(t) for t in ts]
+    pairs = PairSet(qs, ts, splice=sp)
+    got = opt.find_path(pairs)
+    monkeypatch.setenv("C4B_E2G_WINDOWS", "0")
+    want = opt.find_path(pairs)
+    monkeypatch.delenv("C4B_E2G_WINDOWS")
+    assert got == want
+    assert all(any(model.transitions[t_].advance_target == 2 for t_, _ in r["ops"]) for r in got)
+    for k in (0, 1):
+        ref = e2g_oracle(model, scoring, qs[k], ts[k], sp[k])
+        assert got[k]["score"] == ref["score"] and got[k]["region"] == ref["region"] and got[k]["ops"] == ref["ops"]
 
 
 def test_est2genome_regions_threshold_and_fallback(eng, params, scoring, monkeypatch):
