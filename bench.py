@@ -41,10 +41,12 @@ WORKLOADS = {
         "metric": "GCUPS est2genome find_path (score+region+ops, bit-exact), 1 kbp cDNA x 100 kbp genomic batch",
         "b_alg": 80, "pairs": 1000, "cpu_pairs": 1,
         "workload": "est2genome --exhaustive, %d bp cDNA x %d bp genomic pairs (5 exons, GT..AG introns)",
-        "kernel": "e2g_systolic (one fill with 13-bit traceback records + walk)",
-        "traffic_key": "e2g_fill_kernel<1>",
+        "kernel": "e2g_fill16 (both strands per register, score pass + column checkpoints) + window refills "
+                  "with 15-bit traceback records under the path + walk with intron jumps",
+        "traffic_key": "e2g_fill16_kernel<2>",
         "note": "B_alg=80 B/cell (SURVEY 8d: 4 B x 10 states x C=2, reference row layout); the kernel keeps "
-                "rows in registers and writes a 2 B/cell traceback record; see DESIGN.md. peak ",
+                "rows in registers, writes 28 B/row checkpoints every 1024 columns and 2 B/cell records only "
+                "inside the refilled windows, so frac>1 is expected; see DESIGN.md. peak ",
     },
 }
 

@@ -36,6 +36,12 @@ constexpr uint32_t kMin16x2 = 0x80008000u;  // -32768 | -32768
 __device__ __forceinline__ uint32_t pack16(int v) {
     return ((uint32_t)v & 0xFFFFu) * 0x10001u;
 }
+// 0xFFFF in every halfword whose sign bit is set, else 0 (one PRMT)
+__device__ __forceinline__ uint32_t sign_mask16x2(uint32_t v) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(0u), "r"(0xBB99u));
+    return d;
+}
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
 

@@ -6,6 +6,7 @@
 // caller.  No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <set>

@@ -79,6 +79,44 @@ static bool analyze_est2genome(const c4b_model &m, const c4b_scoring &sc, E2gMod
     return true;
 }
 
+// Grow-only pinned staging memory of this host thread (pinning is far too slow to
+// repeat per batch); `busy` is the last copy that read it.
+struct PinnedScratch {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t busy = nullptr;
+    uint8_t *get(size_t bytes) {
+        if (busy) cudaEventSynchronize(busy);
+        if (cap < bytes) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            if (cudaMallocHost(&p, bytes + bytes / 8) != cudaSuccess) return nullptr;
+            cap = bytes + bytes / 8;
+        }
+        return p;
+    }
+    void mark(cudaStream_t st) {
+        if (!busy) cudaEventCreateWithFlags(&busy, cudaEventDisableTiming);
+        cudaEventRecord(busy, st);
+    }
+};
+static thread_local PinnedScratch tl_e2g_scratch;
+
+template <typename F>
+static void parallel_for(int n, F f) {
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n));
+    if (nt <= 1) {
+        for (int k = 0; k < n; ++k) f(k);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t)
+        th.emplace_back([&, t] { for (int k = (int)t; k < n; k += (int)nt) f(k); });
+    for (int k = 0; k < n; k += (int)nt) f(k);
+    for (auto &x : th) x.join();
+}
+
 struct E2gBatch {
     cudaStream_t stream = nullptr;
     int64_t *launches = nullptr;
@@ -168,14 +206,6 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         code_of[n_used] = a;
         cls_of[a] = n_used++;
     }
-    // splice scores must fit int8 (they do for the built-in frequency tables)
-    for (int p = 0; p < n; ++p)
-        for (int k = 0; k < 4; ++k) {
-            const int32_t *a = pairs[p].splice[k] + pairs[p].target_start;
-            for (int j = 0; j < pairs[p].target_length; ++j)
-                if (a[j] < -127 || a[j] > 127) return 1;
-        }
-
     // packed 16-bit path (e2g_packed16.cuh): exact when every reachable value fits a
     // signed halfword and the intron-length upper bound can never fire
     bool packed = false;
@@ -223,22 +253,53 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         if (lut[c] != 0xFF) qfill = (uint8_t)c;
         if (lut[256 + c] != 0xFF) tfill = (uint8_t)c;
     }
-    std::vector<uint8_t> hseq(qbytes + tbytes + 64, tfill);
-    memset(hseq.data(), qfill, qbytes);
-    for (auto &kv : qmap) memcpy(hseq.data() + kv.second, kv.first.first, (size_t)kv.first.second);
-    for (auto &kv : tmap) memcpy(hseq.data() + qbytes + kv.second, kv.first.first, (size_t)kv.first.second);
-    std::vector<uint32_t> hsp(tbytes + 16, 0);  // one word per staged target byte slot
+    // staged through pinned memory, filled by worker threads: sequences, slot padding, and
+    // the four int32 splice arrays of every distinct target packed to one int8 x 4 word per
+    // position (a score outside int8 sends the batch to the table-driven kernel instead)
+    const size_t seq_bytes = align_up(qbytes + tbytes + 64, 256);
+    uint8_t *scratch = tl_e2g_scratch.get(seq_bytes + (tbytes + 16) * 4);
+    if (!scratch) {
+        set_error("pinned staging allocation failed");
+        delete b;
+        return -1;
+    }
+    uint8_t *hseq = scratch;
+    uint32_t *hsp = reinterpret_cast<uint32_t *>(scratch + seq_bytes);
     {
-        std::map<std::pair<const uint8_t *, int>, int> owner;  // target slice -> a pair that carries its splice arrays
-        for (int p = 0; p < n; ++p) owner[std::make_pair(pairs[p].target + pairs[p].target_start, pairs[p].target_length)] = p;
-        for (auto &kv : tmap) {
-            const c4b_pair &pp = pairs[owner[kv.first]];
-            for (int j = 0; j < pp.target_length; ++j) {
-                uint32_t w = 0;
-                for (int k = 0; k < 4; ++k)
-                    w |= (uint32_t)(uint8_t)(int8_t)pp.splice[k][pp.target_start + j] << (8 * k);
-                hsp[kv.second + j] = w;
+        typedef std::pair<const uint8_t *, int> SeqKey;
+        std::vector<std::pair<SeqKey, size_t>> qlist(qmap.begin(), qmap.end()), tlist(tmap.begin(), tmap.end());
+        std::map<SeqKey, int> owner;  // target slice -> a pair that carries its splice arrays
+        for (int p = 0; p < n; ++p) owner[SeqKey(pairs[p].target + pairs[p].target_start, pairs[p].target_length)] = p;
+        std::vector<const c4b_pair *> towner(tlist.size());
+        for (size_t k = 0; k < tlist.size(); ++k) towner[k] = &pairs[owner[tlist[k].first]];
+        for (auto &kv : qlist) {
+            const size_t len = (size_t)kv.first.second, slot = align_up(len, 16) + 16;
+            memcpy(hseq + kv.second, kv.first.first, len);
+            memset(hseq + kv.second + len, qfill, slot - len);
+        }
+        memset(hseq + qbytes + tbytes, tfill, 64);
+        std::atomic<bool> out_of_range(false);
+        parallel_for((int)tlist.size(), [&](int k) {
+            const size_t off = tlist[k].second, len = (size_t)tlist[k].first.second, slot = align_up(len, 16) + 16;
+            memcpy(hseq + qbytes + off, tlist[k].first.first, len);
+            memset(hseq + qbytes + off + len, tfill, slot - len);
+            const c4b_pair &pp = *towner[k];
+            const int32_t *s0 = pp.splice[0] + pp.target_start, *s1 = pp.splice[1] + pp.target_start;
+            const int32_t *s2 = pp.splice[2] + pp.target_start, *s3 = pp.splice[3] + pp.target_start;
+            uint32_t *dst = hsp + off;
+            bool bad = false;
+            for (size_t j = 0; j < len; ++j) {
+                const int32_t a = s0[j], c = s1[j], d = s2[j], e = s3[j];
+                bad |= (uint32_t)(a + 127) > 254u || (uint32_t)(c + 127) > 254u || (uint32_t)(d + 127) > 254u ||
+                       (uint32_t)(e + 127) > 254u;
+                dst[j] = (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)c << 8) | ((uint32_t)(uint8_t)d << 16) |
+                         ((uint32_t)(uint8_t)e << 24);
             }
+            if (bad) out_of_range = true;
+        });
+        if (out_of_range) {
+            delete b;
+            return 1;
         }
     }
     std::vector<uint2> xt(25);
@@ -376,8 +437,9 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         }
         ok &= cudaMemcpyAsync(b->d_pairs16.p, hp16.data(), n * sizeof(E2pPair), cudaMemcpyHostToDevice, stream) == cudaSuccess;
     }
-    ok &= cudaMemcpyAsync(b->d_seq.p, hseq.data(), qbytes + tbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    ok &= cudaMemcpyAsync(b->d_sp.p, hsp.data(), (tbytes + 16) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_seq.p, hseq, qbytes + tbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b->d_sp.p, hsp, (tbytes + 16) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    tl_e2g_scratch.mark(stream);
     ok &= cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(b->d_xtab.p, xt.data(), 25 * sizeof(uint2), cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), stream) == cudaSuccess;
@@ -432,9 +494,7 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
                                                                        b->d_walk.p, b->d_results.p);
             (*b->launches) += 3;
             C4B_CUDA(cudaGetLastError());
-            int max_t = 0;
-            for (int k = 0; k < n; ++k) max_t = std::max(max_t, b->max_target);
-            const int round_cap = 4 * (max_t / kE2pWin + 1) + 16;
+            const int round_cap = 4 * (b->max_target / kE2pWin + 1) + 16;
             for (int round = 0;; ++round) {
                 int cnt = 0;
                 C4B_CUDA(cudaMemsetAsync(b->d_count.p, 0, sizeof(int32_t), st));

@@ -21,7 +21,8 @@
 //    intron.c:138-161) is carried as a saturating 16-bit AGE = j - start: "open"
 //    sets 2, "loop" adds 1, the close candidate of column j is valid iff
 //    age(j-2) + 2 >= min_intron (the host guarantees max_intron >= T + 2, so the
-//    upper test can never fire; saturation at 32767 keeps the lower one exact);
+//    upper test can never fire; saturation keeps the lower one exact).  The age is
+//    stored relative to that threshold, so "invalid" is its sign bit;
 //  * which candidate won comes for free from VIMNMX.S16x2's predicate outputs
 //    (__vibmax_s16x2), stored as raw "earlier candidate held" bits.
 // Mapping: lane l owns 16 consecutive rows, lanes are skewed by one column, strips
@@ -91,7 +92,9 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
 
     const uint32_t open2 = pack16(mdl.open), ext2 = pack16(mdl.ext);
     const uint32_t preK = pack16(mdl.intron_open - mdl.open);  // N opens from G = M + open
-    const uint32_t thr2 = pack16(max(0, mdl.min_intron - 2));
+    // ages are stored relative to the validity threshold: a = (j - start) - (min_intron - 2)
+    const int age_thr = max(0, mdl.min_intron - 2);
+    const uint32_t openA = pack16(2 - age_thr);
     const int rows_per_sweep = 32 * R;
     const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     const int nsteps = T + 1 + 31;
@@ -194,19 +197,20 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 for (int r = 0; r < R; ++r) {
                     uint32_t sc;
                     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(X.x), "r"(X.y), "r"(sel[r]));
-                    // N: open (T3/T0) first, loop (T4/T1) replaces only if strictly greater
-                    bool oh, ol;
+                    // N: open (T3/T0) first, loop (T4/T1) replaces only if strictly greater.  The
+                    // per-strand choice is a halfword MASK (sign of open - loop, replicated by one
+                    // PRMT), so the age follows with one LOP3 and no predicates
                     const uint32_t nv = __vadd2(G[p][r], pre2);
-                    const uint32_t Nn = __vibmax_s16x2(nv, N[o][r], &oh, &ol);
-                    uint32_t An = __viaddmin_u16x2(A[o][r], 0x00010001u, 0x7FFF7FFFu);
-                    if (ol) An = (An & 0xFFFF0000u) | 0x00000002u;
-                    if (oh) An = (An & 0x0000FFFFu) | 0x00020000u;
-                    // close candidate (T5/T2) from column j-2, valid iff its intron is long enough
-                    bool vh, vl;
-                    (void)__vibmax_u16x2(A[p][r], thr2, &vh, &vl);
+                    const uint32_t lm = sign_mask16x2(__vsub2(nv, N[o][r]));  // 0xFFFF: loop replaces open
+                    const uint32_t Nn = __vmaxs2(nv, N[o][r]);
+                    uint32_t An = __viaddmin_s16x2(A[o][r], 0x00010001u, 0x7FFE7FFEu);   // age + 1, saturating
+                    An = (An & lm) | (openA & ~lm);
+                    // close candidate (T5/T2) from column j-2, valid iff its intron is long enough:
+                    // the age is kept relative to the threshold, invalid <=> negative
+                    const uint32_t vm = sign_mask16x2(A[p][r]);
                     uint32_t c5 = __vadd2(N[p][r], post2);
-                    if (!vl) c5 = (c5 & 0xFFFF0000u) | 0x0000C000u;
-                    if (!vh) c5 = (c5 & 0x0000FFFFu) | 0xC0000000u;
+                    c5 = (c5 & ~vm) | (kNeg16x2 & vm);
+                    const bool ol = !(lm & 1u), oh = !(lm >> 31);
                     const uint32_t diag = (r == 0) ? topGprev : G[o][r - 1];
                     uint32_t xc, Dn;
                     if (!TB) {
@@ -505,8 +509,9 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
         const uint32_t *c = P.ck + (((size_t)(c0 / kE2pWin - 1) * all_sweeps + w) * 32 + ln) * kE2pR * kE2pCkWords +
                             (size_t)r * kE2pCkWords;
         const uint32_t a2 = (j == c0 - 1) ? c[4] : c[5];
-        const int age = (int)((a2 >> (16 * x)) & 0xFFFFu);
-        if (age >= 2 && age < 0x7FFF && age <= j) {
+        const int rel = (int)(short)((a2 >> (16 * x)) & 0xFFFFu);   // stored relative to the threshold
+        const int age = rel + max(0, mdl.min_intron - 2);
+        if (rel < 0x7FFE && age >= 2 && age <= j) {
             emit(mdl.tNloop[x], age - 2);
             emit(mdl.tNopen[x], 1);
             j -= age;
