@@ -64,3 +64,19 @@ class Result(C.Structure):
     _fields_ = [("score", C.c_int32), ("query_start", C.c_int32), ("target_start", C.c_int32),
                 ("query_end", C.c_int32), ("target_end", C.c_int32), ("n_ops", C.c_int32),
                 ("ops_offset", C.c_int64), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
+# ---- HSP seeding / extension (c4b_hsp_extend_batch) -------------------------
+class HspParam(C.Structure):
+    _fields_ = [("match_kind", C.c_int32), ("seedlen", C.c_int32), ("dropoff", C.c_int32),
+                ("threshold", C.c_int32)]
+
+
+class HspSeed(C.Structure):
+    _fields_ = [("query_start", C.c_int32), ("target_start", C.c_int32)]
+
+
+class Hsp(C.Structure):
+    _fields_ = [("query_start", C.c_int32), ("target_start", C.c_int32), ("length", C.c_int32),
+                ("score", C.c_int32), ("cobs", C.c_int32), ("stored", C.c_int32),
+                ("target_end", C.c_int32), ("status", C.c_int32)]

@@ -8,6 +8,7 @@
 #include <array>
 #include <atomic>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <set>
 #include <string>
@@ -20,6 +21,7 @@
 #include "generic_wavefront.cuh"
 #include "e2g_systolic.cuh"
 #include "e2g_packed16.cuh"
+#include "hsp_extend.cuh"
 
 namespace c4b {
 static thread_local std::string g_error;
@@ -1195,6 +1197,96 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model, const c4b_scori
     }
     set_error("c4b_viterbi_calculate: unknown mode");
     return -1;
+}
+
+int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hsp_param *param,
+                         const uint8_t *query, int32_t query_len, const uint8_t *query_mask,
+                         const uint8_t *target, int32_t target_len, const uint8_t *target_mask,
+                         int32_t n_seeds, const c4b_hsp_seed *seeds, c4b_hsp *out) {
+    if (!e || !scoring || !param || !query || !target || query_len < 0 || target_len < 0 || n_seeds < 0 ||
+        (n_seeds && (!seeds || !out))) {
+        set_error("c4b_hsp_extend_batch: bad arguments");
+        return -1;
+    }
+    const int kind = param->match_kind;
+    if (kind != C4B_CALC_MATCH_DNA && kind != C4B_CALC_MATCH_PROTEIN && kind != C4B_CALC_MATCH_1_3) {
+        set_error("c4b_hsp_extend_batch: match kind has no device form");
+        return -1;
+    }
+    if (param->seedlen <= 0) {
+        set_error("c4b_hsp_extend_batch: seed length must be positive");
+        return -1;
+    }
+    if (n_seeds == 0) return 0;
+    const int tadv = (kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    for (int k = 0; k < n_seeds; ++k)   // HSP_check (hspset.c): the seed lies inside both sequences
+        if (seeds[k].query_start < 0 || seeds[k].target_start < 0 ||
+            (int64_t)seeds[k].query_start + param->seedlen > query_len ||
+            (int64_t)seeds[k].target_start + (int64_t)param->seedlen * tadv > target_len) {
+            set_error("seed " + std::to_string(k) + " outside the sequences");
+            return -1;
+        }
+    C4B_CUDA(cudaSetDevice(e->device));
+    tl_pool_stream = e->stream;
+    cudaStream_t st = e->stream;
+    const bool dna = (kind == C4B_CALC_MATCH_DNA);
+    DevBuf<uint8_t> d_q, d_t, d_qm, d_tm, d_qc, d_tc, d_qmo, d_tmo, d_tab;
+    DevBuf<int32_t> d_matrix;
+    DevBuf<int> d_bad;
+    DevBuf<c4b_hsp_seed> d_seeds;
+    DevBuf<c4b_hsp> d_out;
+    struct Releaser {
+        std::vector<std::function<void()>> f;
+        ~Releaser() { for (auto &x : f) x(); }
+    } rel;
+    auto own = [&](auto &buf) { rel.f.push_back([&buf] { buf.release(); }); };
+    own(d_q); own(d_t); own(d_qm); own(d_tm); own(d_qc); own(d_tc); own(d_qmo); own(d_tmo); own(d_tab);
+    own(d_matrix); own(d_bad); own(d_seeds); own(d_out);
+    const size_t ql = (size_t)query_len, tl = (size_t)target_len;
+    if (d_q.alloc(ql + 4) || d_t.alloc(tl + 4) || d_qc.alloc(ql + 4) || d_tc.alloc(tl + 4) ||
+        d_tab.alloc(256 * 3 + 4096) || d_matrix.alloc(24 * 24) || d_bad.alloc(1) || d_seeds.alloc(n_seeds) ||
+        d_out.alloc(n_seeds))
+        return -1;
+    if (query_mask && (d_qm.alloc(ql + 4) || d_qmo.alloc(ql + 4))) return -1;
+    if (target_mask && (d_tm.alloc(tl + 4) || d_tmo.alloc(tl + 4))) return -1;
+    // tables: [0,256) query index, [256,512) target index, [512,768) nt2d, [768,..) codon_aa
+    std::vector<uint8_t> tab(256 * 3 + 4096);
+    memcpy(&tab[0], dna ? scoring->dna_index : scoring->protein_index, 256);
+    memcpy(&tab[256], dna ? scoring->dna_index : scoring->protein_index, 256);
+    memcpy(&tab[512], scoring->nt2d, 256);
+    memcpy(&tab[768], scoring->codon_aa, 4096);
+    C4B_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(d_matrix.p, dna ? scoring->dna_matrix : scoring->protein_matrix, 24 * 24 * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(d_q.p, query, ql, cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(d_t.p, target, tl, cudaMemcpyHostToDevice, st));
+    if (query_mask) C4B_CUDA(cudaMemcpyAsync(d_qm.p, query_mask, ql, cudaMemcpyHostToDevice, st));
+    if (target_mask) C4B_CUDA(cudaMemcpyAsync(d_tm.p, target_mask, tl, cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_seeds * sizeof(c4b_hsp_seed), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+    if (query_len)
+        hsp_encode_kernel<<<(query_len + 255) / 256, 256, 0, st>>>(d_q.p, query_len, d_tab.p, d_tab.p + 512,
+                                                                   d_tab.p + 768, 0, d_qc.p, d_qm.p, d_qmo.p, d_bad.p);
+    if (target_len)
+        hsp_encode_kernel<<<(target_len + 255) / 256, 256, 0, st>>>(d_t.p, target_len, d_tab.p + 256, d_tab.p + 512,
+                                                                    d_tab.p + 768, tadv == 3, d_tc.p, d_tm.p,
+                                                                    d_tmo.p, d_bad.p);
+    HspArgs A;
+    A.qc = d_qc.p; A.tc = d_tc.p; A.qm = query_mask ? d_qmo.p : nullptr; A.tm = target_mask ? d_tmo.p : nullptr;
+    A.ql = query_len; A.tl = target_len; A.tadv = tadv;
+    A.seedlen = param->seedlen; A.dropoff = param->dropoff; A.threshold = param->threshold;
+    hsp_extend_kernel<<<(n_seeds + 127) / 128, 128, 0, st>>>(A, d_matrix.p, n_seeds, d_seeds.p, d_out.p);
+    e->launches += 3;
+    C4B_CUDA(cudaGetLastError());
+    int bad = 0;
+    C4B_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n_seeds * sizeof(c4b_hsp), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    C4B_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        set_error("a sequence holds a symbol outside the substitution matrix alphabet");
+        return -1;
+    }
+    return 0;
 }
 
 }  // extern "C"

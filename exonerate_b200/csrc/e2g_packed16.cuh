@@ -327,7 +327,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         if (s < s_end) step(s, std::integral_constant<int, 0>{});
         __syncwarp();
     }
-    if (WIN) return;
+    if constexpr (!WIN) {
 
     // per strand: lexicographic warp reduction (max score, min j, min i)
 #pragma unroll
@@ -357,6 +357,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         o.end_j = fwd ? bjF : bjR;
         o.end_forward = fwd ? 1 : 0;
         outs[P.out_index] = o;
+    }
     }
 }
 

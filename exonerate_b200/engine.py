@@ -20,7 +20,7 @@ EXPORTS = [
     "c4b_engine_set_stream", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
-    "c4b_viterbi_calculate",
+    "c4b_viterbi_calculate", "c4b_hsp_extend_batch",
 ]
 
 _lib = None
@@ -59,6 +59,10 @@ def load_library():
     lib.c4b_batch_device_results.restype = C.c_void_p
     lib.c4b_batch_cells.argtypes = [C.c_void_p]
     lib.c4b_batch_cells.restype = C.c_int64
+    lib.c4b_hsp_extend_batch.argtypes = [C.c_void_p, P(abi.Scoring), P(abi.HspParam), C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_void_p]
+    lib.c4b_hsp_extend_batch.restype = C.c_int
     lib.c4b_batch_last_fill_ms.argtypes = [C.c_void_p]
     lib.c4b_batch_last_fill_ms.restype = C.c_double
     lib.c4b_batch_kernel_name.argtypes = [C.c_void_p]
@@ -253,3 +257,56 @@ class Optimal:
     def find_path(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None):
         results, ops = self.find_path_raw(pairs, threshold, ops_capacity)
         return results_to_list(results, ops, pairs.n)
+
+
+class HSPset:
+    """HSPset_create / HSPset_seed_hsp / HSPset_finalise (src/comparison/hspset.h:205-229)
+    for one query x target comparison.  Seeds are collected; finalise() extends all of
+    them on the device in one c4b_hsp_extend_batch call and then replays the diagonal
+    horizon of HSPset_seed_hsp (hspset.c:933-972,991-996; seed_repeat 1, no hspfilter)
+    over the results in seed order, which reproduces hsp_list exactly."""
+
+    def __init__(self, engine, scoring, param, query, target, query_mask=None, target_mask=None):
+        self.engine, self.scoring, self.param = engine, scoring, param
+        self.q = np.frombuffer(query.encode() if isinstance(query, str) else bytes(query), dtype=np.uint8).copy()
+        self.t = np.frombuffer(target.encode() if isinstance(target, str) else bytes(target), dtype=np.uint8).copy()
+        self.qm = None if query_mask is None else np.ascontiguousarray(query_mask, dtype=np.uint8)
+        self.tm = None if target_mask is None else np.ascontiguousarray(target_mask, dtype=np.uint8)
+        self.seeds = []
+        self.hsp_list = None
+
+    def seed_hsp(self, query_start, target_start):
+        assert self.hsp_list is None, "HSPset already finalised"
+        self.seeds.append((int(query_start), int(target_start)))
+
+    def extend_all(self):
+        """per-seed device results (abi.Hsp array), before the horizon"""
+        lib = self.engine.lib
+        n = len(self.seeds)
+        sd = (abi.HspSeed * max(1, n))(*[abi.HspSeed(a, b) for a, b in self.seeds])
+        out = (abi.Hsp * max(1, n))()
+        _check(lib, lib.c4b_hsp_extend_batch(self.engine.h, C.byref(self.scoring), C.byref(self.param),
+                                             self.q.ctypes.data, len(self.q),
+                                             self.qm.ctypes.data if self.qm is not None else None,
+                                             self.t.ctypes.data, len(self.t),
+                                             self.tm.ctypes.data if self.tm is not None else None,
+                                             n, sd, out), "c4b_hsp_extend_batch")
+        return out
+
+    def finalise(self):
+        ext = self.extend_all()
+        tadv = 3 if self.param.match_kind == abi.CALC_MATCH_1_3 else 1
+        ql = len(self.q)
+        horizon = {}
+        self.hsp_list = []
+        for k, (qs, ts) in enumerate(self.seeds):
+            if ext[k].status != 0:   # the reference aborts here (hspset.c:740-743)
+                raise C4BError("Initial HSP score less than zero for seed (%d, %d)" % (qs, ts))
+            key = ((ts - qs * tadv + ql) % ql, ts % tadv)
+            if ts < horizon.get(key, 0):
+                continue
+            horizon[key] = ext[k].target_end
+            if ext[k].stored:
+                h = ext[k]
+                self.hsp_list.append([h.query_start, h.target_start, h.length, h.score, h.cobs])
+        return self.hsp_list

@@ -244,6 +244,44 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model,
                           int mode, c4b_result *result, int32_t *ops,
                           int64_t ops_capacity);
 
+/* ---- HSP seeding / extension ----------------------
+ * Replaces the per-seed work of HSPset_seed_hsp (src/comparison/hspset.c:933-997):
+ * HSP_trim_ends (:850-878), HSP_init (:725-745), HSP_extend with masking forbidden
+ * and then ignored (:747-812), the threshold test of HSP_store (:893-894) and
+ * HSP_find_cobs (:426-441), for EVERY seed of one query x target comparison in one
+ * launch.  The diagonal horizon (:951-972,991-996) is sequential state over the seed
+ * list; it only decides which seeds are looked at, so the caller (our hspset.c
+ * binding, exonerate_b200.engine.HSPset) replays it over these results in seed order.
+ * match_kind: C4B_CALC_MATCH_DNA (advance 1,1), C4B_CALC_MATCH_PROTEIN (1,1) or
+ * C4B_CALC_MATCH_1_3 (protein query vs translated DNA target, advance 1,3).
+ * query_mask / target_mask: one byte per position, non-zero = masked
+ * (Alphabet_is_masked, src/sequence/alphabet.h:87-88); NULL = nothing masked. */
+typedef struct {
+    int32_t match_kind;
+    int32_t seedlen;   /* HSP_Param.seedlen = wordlen / query advance (hspset.c:110-117) */
+    int32_t dropoff;   /* HSP_Param.dropoff */
+    int32_t threshold; /* HSP_Param.threshold */
+} c4b_hsp_param;
+
+typedef struct {
+    int32_t query_start, target_start;
+} c4b_hsp_seed;
+
+typedef struct {
+    int32_t query_start, target_start;
+    int32_t length;     /* match-state visits */
+    int32_t score;
+    int32_t cobs;       /* centre offset by score; valid when stored */
+    int32_t stored;     /* 1: score >= threshold (HSP_store keeps it); 0: dropped */
+    int32_t target_end; /* what the seed writes into horizon[0] (hspset.c:985,995) */
+    int32_t status;     /* 0 ok; 1 = "Initial HSP score less than zero" (g_error in the reference) */
+} c4b_hsp;
+
+int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hsp_param *param,
+                         const uint8_t *query, int32_t query_len, const uint8_t *query_mask,
+                         const uint8_t *target, int32_t target_len, const uint8_t *target_mask,
+                         int32_t n_seeds, const c4b_hsp_seed *seeds, c4b_hsp *out);
+
 #ifdef __cplusplus
 }
 #endif

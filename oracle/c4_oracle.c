@@ -395,3 +395,160 @@ int c4o_format_vulgar(const c4b_model *m, const int32_t *ops, int n_ops, char *b
      * block out (alignment.c:1696-1766). */
     return b.overflow ? -1 : b.len;
 }
+
+/* ======================================================================
+ * HSP seeding / extension -- restatement of src/comparison/hspset.c
+ * (TEST INFRASTRUCTURE: the checker of c4b_hsp_extend_batch)
+ * ====================================================================== */
+typedef struct {
+    const c4b_scoring *s;
+    const c4b_hsp_param *p;
+    const uint8_t *q, *t, *qm, *tm;
+    int ql, tl, qadv, tadv;
+} hsp_ctx;
+
+/* HSP_get_score -> Match.score_func (match.c:271-295,332-355) */
+static int hsp_score(const hsp_ctx *c, int qp, int tp) {
+    switch (c->p->match_kind) {
+    case C4B_CALC_MATCH_DNA: return submat(c->s->dna_matrix, c->s->dna_index, c->q[qp], c->t[tp]);
+    case C4B_CALC_MATCH_PROTEIN: return submat(c->s->protein_matrix, c->s->protein_index, c->q[qp], c->t[tp]);
+    default:
+        return submat(c->s->protein_matrix, c->s->protein_index, c->q[qp],
+                      translate(c->s, c->t[tp], c->t[tp + 1], c->t[tp + 2]));
+    }
+}
+/* Match_1_mask_func / Match_3_mask_func (match.c:178-183,212-220) */
+static int hsp_qmasked(const hsp_ctx *c, int qp) { return c->qm && c->qm[qp]; }
+static int hsp_tmasked(const hsp_ctx *c, int tp) {
+    int k;
+    if (!c->tm) return 0;
+    for (k = 0; k < c->tadv; ++k)
+        if (c->tm[tp + k]) return 1;
+    return 0;
+}
+
+/* HSP_extend, hspset.c:747-812 */
+static void hsp_extend(const hsp_ctx *c, c4b_hsp *h, int forbid_masked) {
+    int score, maxscore, qp, tp, extend, maxext;
+    maxscore = score = h->score;
+    qp = h->query_start - c->qadv;
+    tp = h->target_start - c->tadv;
+    for (extend = 1, maxext = 0; qp >= 0 && tp >= 0; extend++) {
+        if (forbid_masked && (hsp_qmasked(c, qp) || hsp_tmasked(c, tp))) break;
+        score += hsp_score(c, qp, tp);
+        if (maxscore <= score) {
+            maxscore = score;
+            maxext = extend;
+        } else {
+            if (score < 0) break;
+            if (maxscore - score >= c->p->dropoff) break;
+        }
+        qp -= c->qadv;
+        tp -= c->tadv;
+    }
+    qp = h->query_start + h->length * c->qadv;
+    tp = h->target_start + h->length * c->tadv;
+    h->query_start -= maxext * c->qadv;
+    h->target_start -= maxext * c->tadv;
+    h->length += maxext;
+    score = maxscore;
+    for (extend = 1, maxext = 0; qp + c->qadv <= c->ql && tp + c->tadv <= c->tl; extend++) {
+        if (forbid_masked && (hsp_qmasked(c, qp) || hsp_tmasked(c, tp))) break;
+        score += hsp_score(c, qp, tp);
+        if (maxscore <= score) {
+            maxscore = score;
+            maxext = extend;
+        } else {
+            if (score < 0) break;
+            if (maxscore - score >= c->p->dropoff) break;
+        }
+        qp += c->qadv;
+        tp += c->tadv;
+    }
+    h->score = maxscore;
+    h->length += maxext;
+}
+
+/* The per-seed part of HSPset_seed_hsp (hspset.c:974-996): trim, init, extend x2,
+ * threshold, cobs.  Same outputs as the device entry point. */
+void c4o_hsp_extend_one(const c4b_scoring *s, const c4b_hsp_param *p, const uint8_t *q, int ql,
+                        const uint8_t *qm, const uint8_t *t, int tl, const uint8_t *tm,
+                        c4b_hsp_seed seed, c4b_hsp *h) {
+    hsp_ctx c;
+    int i, qp, tp, score;
+    c.s = s; c.p = p; c.q = q; c.t = t; c.qm = qm; c.tm = tm; c.ql = ql; c.tl = tl;
+    c.qadv = 1;
+    c.tadv = (p->match_kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    memset(h, 0, sizeof(*h));
+    h->query_start = seed.query_start;
+    h->target_start = seed.target_start;
+    h->length = p->seedlen;
+    /* HSP_trim_ends, hspset.c:850-878 */
+    for (i = 0; i < h->length; i++) {
+        if (hsp_score(&c, h->query_start, h->target_start) > 0) break;
+        h->query_start += c.qadv;
+        h->target_start += c.tadv;
+    }
+    h->length -= i;
+    qp = h->query_start + h->length * c.qadv - c.qadv;
+    tp = h->target_start + h->length * c.tadv - c.tadv;
+    while (h->length > 0) {
+        if (hsp_score(&c, qp, tp) > 0) break;
+        h->length--;
+        qp -= c.qadv;
+        tp -= c.tadv;
+    }
+    /* HSP_init, hspset.c:725-745 */
+    qp = h->query_start;
+    tp = h->target_start;
+    for (i = 0; i < h->length; i++) {
+        h->score += hsp_score(&c, qp, tp);
+        qp += c.qadv;
+        tp += c.tadv;
+    }
+    if (h->score < 0) {
+        h->status = 1; /* g_error("Initial HSP score [%d] less than zero") */
+        h->target_end = h->target_start + h->length * c.tadv;
+        return;
+    }
+    /* mask_func is set for every Match_Strand (match.c:670,679): the masked pass always runs */
+    hsp_extend(&c, h, 1);
+    if (h->score >= p->threshold) hsp_extend(&c, h, 0);
+    h->target_end = h->target_start + h->length * c.tadv;
+    h->stored = h->score >= p->threshold; /* HSP_store, hspset.c:893-894 */
+    if (h->stored) {
+        /* HSP_find_cobs, hspset.c:426-441 */
+        qp = h->query_start;
+        tp = h->target_start;
+        score = 0;
+        for (i = 0; i < h->length; i++) {
+            score += hsp_score(&c, qp, tp);
+            if (score >= (h->score >> 1)) break;
+            qp += c.qadv;
+            tp += c.tadv;
+        }
+        h->cobs = i;
+    }
+}
+
+/* HSPset_seed_hsp over a seed list with the diagonal horizon (hspset.c:933-997,
+ * seed_repeat == 1, filter_threshold == 0), then HSPset_finalise: the stored HSPs in
+ * seed order.  `ext` are the per-seed results (from c4o_hsp_extend_one or from the
+ * device); returns the number of HSPs written to out. */
+int c4o_hspset_replay(const c4b_hsp_param *p, int ql, int n_seeds, const c4b_hsp_seed *seeds,
+                      const c4b_hsp *ext, c4b_hsp *out) {
+    const int qadv = 1, tadv = (p->match_kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    int *horizon = (int *)calloc((size_t)ql * qadv * tadv, sizeof(int));
+    int k, n = 0;
+    for (k = 0; k < n_seeds; ++k) {
+        const int qs = seeds[k].query_start, ts = seeds[k].target_start;
+        const int diag = ts * qadv - qs * tadv;
+        const int section = ((diag + ql) % ql + ql) % ql; /* (diag_pos + query->len) % query->len, C remainder kept non-negative by the reference's assert */
+        int *hz = &horizon[(section * qadv + qs % qadv) * tadv + ts % tadv];
+        if (ts < *hz) continue;
+        *hz = ext[k].target_end;
+        if (ext[k].stored) out[n++] = ext[k];
+    }
+    free(horizon);
+    return n;
+}

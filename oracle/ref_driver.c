@@ -387,3 +387,42 @@ void c4ref_splice_array(int type, const char *seq, int len, int *out) {
     }
     SplicePredictor_predict_array_int(sp, (gchar *)seq, (guint)len, 0, (guint)len, out);
 }
+
+/* ---- HSP seeding / extension (src/comparison/hspset.c:725-815, 933-997) ----------
+ * HSPset_seed_hsp for every (query_start, target_start) in list order, then
+ * HSPset_finalise; the pattern of src/comparison/hspset.test.c.  softmask_* selects
+ * a soft-masked Alphabet for that sequence (lower case = masked).
+ * out: 5 ints per stored HSP {query_start, target_start, length, score, cobs};
+ * params: {seedlen, dropoff, threshold, query_advance, target_advance, filter_threshold,
+ * seed_repeat}.  Returns the number of HSPs (or -1 when out is too small). */
+int c4ref_hspset(int match_type, const char *qseq, const char *tseq, int softmask_q, int softmask_t,
+                 const unsigned *seeds, int n_seeds, int *out, int max_out, int *params) {
+    Match *match = Match_find((Match_Type)match_type);
+    Alphabet *qa = Alphabet_create(match->query->alphabet->type, softmask_q ? TRUE : FALSE);
+    Alphabet *ta = Alphabet_create(match->target->alphabet->type, softmask_t ? TRUE : FALSE);
+    Sequence *query = Sequence_create("qy", NULL, (gchar *)qseq, 0, Sequence_Strand_UNKNOWN, qa);
+    Sequence *target = Sequence_create("tg", NULL, (gchar *)tseq, 0, Sequence_Strand_UNKNOWN, ta);
+    HSP_Param *hsp_param = HSP_Param_create(match, TRUE);
+    HSPset *hsp_set = HSPset_create(query, target, hsp_param);
+    int i, n;
+    params[0] = hsp_param->seedlen; params[1] = hsp_param->dropoff; params[2] = hsp_param->threshold;
+    params[3] = match->query->advance; params[4] = match->target->advance;
+    params[5] = hsp_param->has->filter_threshold; params[6] = hsp_param->seed_repeat;
+    for (i = 0; i < n_seeds; i++)
+        HSPset_seed_hsp(hsp_set, seeds[2 * i], seeds[2 * i + 1]);
+    HSPset_finalise(hsp_set);
+    n = hsp_set->hsp_list->len;
+    if (n > max_out) n = -1;
+    for (i = 0; i < n; i++) {
+        HSP *hsp = hsp_set->hsp_list->pdata[i];
+        out[5 * i + 0] = hsp->query_start; out[5 * i + 1] = hsp->target_start;
+        out[5 * i + 2] = hsp->length; out[5 * i + 3] = hsp->score; out[5 * i + 4] = hsp->cobs;
+    }
+    HSPset_destroy(hsp_set);
+    HSP_Param_destroy(hsp_param);
+    Sequence_destroy(query);
+    Sequence_destroy(target);
+    Alphabet_destroy(qa);
+    Alphabet_destroy(ta);
+    return n;
+}

@@ -250,6 +250,13 @@ def oracle():
                                          C.POINTER(abi.Result), C.c_void_p]
         lib.c4o_rescore_path.restype = C.c_int32
         lib.c4o_transition_is_valid.argtypes = [C.POINTER(abi.Model)] + [C.c_int] * 5
+        lib.c4o_hsp_extend_one.argtypes = [C.POINTER(abi.Scoring), C.POINTER(abi.HspParam), C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, abi.HspSeed,
+                                           C.POINTER(abi.Hsp)]
+        lib.c4o_hsp_extend_one.restype = None
+        lib.c4o_hspset_replay.argtypes = [C.POINTER(abi.HspParam), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+        lib.c4o_hspset_replay.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -371,3 +378,50 @@ def gene_pair(seed, qlen, tlen, n_exons=5, rate=0.02, reverse=False):
         return q, body[:tlen]
     left = rng.randrange(0, tlen - len(body) + 1)
     return q, rand_dna(rng, left) + body + rand_dna(rng, tlen - len(body) - left)
+
+
+# ---------------------------------------------------------------------------
+# HSP seeding / extension
+# ---------------------------------------------------------------------------
+HSP_MATCH_KIND = {"dna2dna": abi.CALC_MATCH_DNA, "protein2protein": abi.CALC_MATCH_PROTEIN,
+                  "protein2dna": abi.CALC_MATCH_1_3}
+
+
+def hsp_param(case):
+    p = case["params"]
+    return abi.HspParam(HSP_MATCH_KIND[case["match"]], p["seedlen"], p["dropoff"], p["threshold"])
+
+
+def softmask_bytes(seq, enabled):
+    """Alphabet_is_masked for a soft-masked alphabet: lower case (alphabet.h:87-88)."""
+    if not enabled:
+        return None
+    return np.array([1 if c.islower() else 0 for c in seq], dtype=np.uint8)
+
+
+def hsp_tuple(h):
+    return [h.query_start, h.target_start, h.length, h.score, h.cobs]
+
+
+def oracle_hsp_extend(scoring, param, q, t, seeds, qmask=None, tmask=None):
+    """per-seed results of the oracle (c4o_hsp_extend_one), as abi.Hsp array"""
+    lib = oracle()
+    qb = np.frombuffer(q.encode(), dtype=np.uint8).copy()
+    tb = np.frombuffer(t.encode(), dtype=np.uint8).copy()
+    out = (abi.Hsp * max(1, len(seeds)))()
+    for k, (qs, ts) in enumerate(seeds):
+        lib.c4o_hsp_extend_one(C.byref(scoring), C.byref(param), qb.ctypes.data, len(qb),
+                               qmask.ctypes.data if qmask is not None else None, tb.ctypes.data, len(tb),
+                               tmask.ctypes.data if tmask is not None else None, abi.HspSeed(qs, ts),
+                               C.byref(out[k]))
+    return out
+
+
+def hspset_replay(param, qlen, seeds, ext):
+    """HSPset_seed_hsp's diagonal horizon over per-seed results -> stored HSPs (seed order)"""
+    lib = oracle()
+    n = len(seeds)
+    sd = (abi.HspSeed * max(1, n))(*[abi.HspSeed(a, b) for a, b in seeds])
+    out = (abi.Hsp * max(1, n))()
+    cnt = lib.c4o_hspset_replay(C.byref(param), qlen, n, sd, ext, out)
+    return [hsp_tuple(out[k]) for k in range(cnt)]

@@ -464,3 +464,76 @@ def test_est2genome_regions_threshold_and_fallback(eng, params, scoring, monkeyp
         got = opt.find_path(pairs)[0]
         assert got["score"] == want["score"] and got["ops"] == want["ops"], name
         assert opt.find_score(pairs)[0] == want["score"], name
+
+
+# ---------------------------------------------------------------------------
+# HSP seeding / extension
+# ---------------------------------------------------------------------------
+def test_hsp_extend_golden_and_oracle(eng, scoring):
+    """c4b_hsp_extend_batch + the HSPset binding against the reference's own HSP lists
+    (tests/golden/hsp_cases.json: DNA, protein, protein vs translated DNA, soft-masked)
+    and, seed by seed, against the oracle."""
+    import json
+    from exonerate_b200 import HSPset
+    cases = json.load(open(helpers.GOLDEN + "/hsp_cases.json"))
+    total = 0
+    for case in cases:
+        param = helpers.hsp_param(case)
+        qm = helpers.softmask_bytes(case["q"], case["softmask_query"])
+        tm = helpers.softmask_bytes(case["t"], case["softmask_target"])
+        hs = HSPset(eng, scoring, param, case["q"], case["t"], qm, tm)
+        for qs, ts in case["seeds"]:
+            hs.seed_hsp(qs, ts)
+        ext = hs.extend_all()
+        want = helpers.oracle_hsp_extend(scoring, param, case["q"], case["t"], [tuple(s) for s in case["seeds"]], qm, tm)
+        for k in range(len(case["seeds"])):
+            for f, _ in abi.Hsp._fields_:
+                assert getattr(ext[k], f) == getattr(want[k], f), (case["name"], k, f)
+        assert hs.finalise() == case["hsps"], case["name"]
+        total += len(case["hsps"])
+    assert total >= 150
+
+
+def test_hsp_extend_large_random_vs_oracle(eng, scoring):
+    """100k seeds on a 20 kbp x 200 kbp comparison (every 12-mer match + noise), incl.
+    seeds whose trimmed score is negative (status 1: fatal in the reference) and masks."""
+    from exonerate_b200 import C4BError, HSPset
+    rng = random.Random(4242)
+    q, t = helpers.dna_pair(99001, 20000, 200000, rate=0.12)
+    t = t[:50000] + t[50000:50400].lower() + t[50400:]
+    param = abi.HspParam(abi.CALC_MATCH_DNA, 12, 30, 75)
+    tm = helpers.softmask_bytes(t, True)
+    index = {}
+    for i in range(len(q) - 11):
+        index.setdefault(q[i:i + 12], []).append(i)
+    seeds = []
+    for j in range(len(t) - 11):
+        for i in index.get(t[j:j + 12].upper(), ()):
+            seeds.append((i, j))
+    noise = [(rng.randrange(0, len(q) - 12), rng.randrange(0, len(t) - 12)) for _ in range(3000)]
+    hs = HSPset(eng, scoring, param, q, t, None, tm)
+    for s_ in seeds + noise:
+        hs.seed_hsp(*s_)
+    ext = hs.extend_all()
+    pick = list(range(0, len(seeds), max(1, len(seeds) // 400))) + list(range(len(seeds), len(seeds) + len(noise), 7))
+    want = helpers.oracle_hsp_extend(scoring, param, q, t, [(seeds + noise)[k] for k in pick], None, tm)
+    for n, k in enumerate(pick):
+        for f, _ in abi.Hsp._fields_:
+            assert getattr(ext[k], f) == getattr(want[n], f), (k, f)
+    assert any(ext[k].status == 1 for k in range(len(seeds), len(seeds) + len(noise)))
+    with pytest.raises(C4BError):
+        hs.finalise()
+    hs2 = HSPset(eng, scoring, param, q, t, None, tm)
+    for s_ in seeds:
+        hs2.seed_hsp(*s_)
+    got = hs2.finalise()
+    ext2 = helpers.oracle_hsp_extend(scoring, param, q, t, seeds, None, tm)
+    assert got == helpers.hspset_replay(param, len(q), seeds, ext2) and len(got) >= 1
+    with pytest.raises(C4BError):   # a seed outside the sequences / a foreign symbol are errors
+        h3 = HSPset(eng, scoring, param, q, t)
+        h3.seed_hsp(len(q) - 3, 0)
+        h3.finalise()
+    with pytest.raises(C4BError):
+        h4 = HSPset(eng, scoring, param, "ACGT-ACGTACGTACG", "ACGTACGTACGTACGT")
+        h4.seed_hsp(0, 0)
+        h4.finalise()
