@@ -54,8 +54,16 @@ __device__ __forceinline__ int add_open(int m, int one, int open) {
 // score_table: SCORE_PRMT -> uint2[25]  (bytes k=0..7 = s(class k, column code) - open)
 //              SCORE_SMEM -> int32[25*25] (row 24 = pad rows, column 24 = "no symbol")
 // ENDMODE END_ANYWHERE is only instantiated for START=END=ANYWHERE (local) models.
+// blockDim.x = 32 W: the W warps of a CTA take the sweeps (strips of 32 R rows) of ONE
+// lattice round-robin and run them concurrently as a pipeline -- sweep k+1 follows sweep
+// k at a distance of >= 32 columns, reading the hand-off row {G, I} the moment it is
+// published (a monotone counter in shared memory, no __syncthreads in the fill).  A
+// long query therefore occupies up to 8 schedulers instead of one.  W = 1 for batches
+// whose queries fit one sweep.
+constexpr int kAffMaxWarps = 8;
+
 template <int R, bool TB, int ENDMODE, int SM>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * kAffMaxWarps)
 affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                    const AffModel mdl, const void *__restrict__ score_table) {
     constexpr int WPL = R / 8;  // traceback words per lane per step
@@ -63,17 +71,23 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     __shared__ uint2 xtab[25];
     __shared__ int32_t subm[SM == SCORE_SMEM ? 25 * 25 : 1];
 
-    const int lane = threadIdx.x;
+    // published columns of the sweep each warp is (or was last) working on, as a
+    // monotone count: sweep * (T + 1) + columns whose bottom row is in the hand-off array
+    __shared__ volatile long long vprog[kAffMaxWarps];
+    __shared__ int red[kAffMaxWarps][3];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const AffPair P = pairs[blockIdx.x];
     const int Q = P.Q, T = P.T;
 
     if (SM == SCORE_PRMT) {
-        if (lane < 25) xtab[lane] = reinterpret_cast<const uint2 *>(score_table)[lane];
+        if (threadIdx.x < 25) xtab[threadIdx.x] = reinterpret_cast<const uint2 *>(score_table)[threadIdx.x];
     } else {
-        for (int k = lane; k < 25 * 25; k += 32)
+        for (int k = threadIdx.x; k < 25 * 25; k += blockDim.x)
             subm[k] = reinterpret_cast<const int32_t *>(score_table)[k];
     }
-    __syncwarp();
+    if (threadIdx.x < kAffMaxWarps) vprog[threadIdx.x] = 0;
+    __syncthreads();
 
     const int open = mdl.openD, extD = mdl.extD, extI = mdl.extI;  // openD == openI (checked)
     const int one = mdl.one;
@@ -95,7 +109,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     // G = M + open and converted at the end
     int best = INT32_MIN, best_j = 0, best_i = 0;
 
-    for (int sweep = 0; sweep < nsweeps; ++sweep) {
+    for (int sweep = warp; sweep < nsweeps; sweep += W) {
         const int row0 = sweep * rows_per_sweep + lane * R;  // lattice row of r = 0
         const bool first_row_lane = (sweep == 0 && lane == 0);
         const bool later_sweep = (sweep > 0);
@@ -129,8 +143,23 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         int topM = NEG2, topI = NEG2, topMprev = NEG2;  // row above my strip
         int in_code = kTargetNone;                      // column code handed down
         int code0 = kTargetNone;                        // lane 0: column 0 has no symbol
+        // hand-off from the sweep above, which another warp may still be producing
+        const bool piped = later_sweep && W > 1;
+        const int wp = (sweep - 1) % W;
+        const long long in_base = (long long)(sweep - 1) * (T + 1);
+        long long avail = 0;   // last value seen of the producer's counter
+        auto wait_column = [&](int col) {   // until column `col` of the sweep above is published
+            const long long need = in_base + col + 1;
+            if (avail < need) {
+                while ((avail = vprog[wp]) < need) __nanosleep(40);
+                __threadfence_block();
+            }
+        };
         int2 top0v = make_int2(NEG2, NEG2);
-        if (later_sweep) top0v = top_in[0];             // uniform load, lane 0 uses it
+        if (later_sweep) {
+            if (piped) wait_column(0);
+            top0v = __ldcg(top_in);                     // uniform load, lane 0 uses it
+        }
         uint32_t *tbp = nullptr;
         if (TB) tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * WPL;
 
@@ -169,7 +198,10 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
             }
             if (s + 1 <= T) {
                 code0 = (int)P.t[s];
-                if (later_sweep) top0v = top_in[s + 1];
+                if (later_sweep) {
+                    if (piped) wait_column(s + 1);
+                    top0v = __ldcg(top_in + s + 1);
+                }
             } else {
                 code0 = kTargetNone;
             }
@@ -256,7 +288,13 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                     else if (WPL == 2) *reinterpret_cast<uint2 *>(tbp) = make_uint2(w[0], w[1]);
                     else tbp[0] = w[0];
                 }
-                if (write_top) top_out[j] = make_int2(botM, botI);
+                if (write_top) {
+                    top_out[j] = make_int2(botM, botI);
+                    if (W > 1) {
+                        __threadfence_block();  // the row is written before the counter moves
+                        vprog[warp] = (long long)sweep * (T + 1) + j + 1;
+                    }
+                }
                 // ---- END bookkeeping ----
                 if (LOCAL) {
                     pend_cm = cm;
@@ -307,7 +345,18 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         const bool take = (ob > best) || (ob == best && (oj < best_j || (oj == best_j && oi < best_i)));
         if (take) { best = ob; best_j = oj; best_i = oi; }
     }
-    if (lane == 0) {
+    if (W > 1) {   // combine the warps' sweeps (idle warps carry INT32_MIN)
+        if (lane == 0) { red[warp][0] = best; red[warp][1] = best_j; red[warp][2] = best_i; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w < W; ++w) {
+                const int ob = red[w][0], oj = red[w][1], oi = red[w][2];
+                if ((ob > best) || (ob == best && (oj < best_j || (oj == best_j && oi < best_i)))) {
+                    best = ob; best_j = oj; best_i = oi;
+                }
+            }
+    }
+    if (threadIdx.x == 0) {
         AffOut o;
         o.best = (best == INT32_MIN) ? best : best - open;  // tracked as G = M + open
         o.end_i = best_i;

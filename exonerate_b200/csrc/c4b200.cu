@@ -233,6 +233,7 @@ struct c4b_batch {
     // ---- affine path ----
     AffModel aff;
     int R = 32, score_mode = SCORE_PRMT, max_sub = 0, gap_min = 0;
+    int fill_warps = 1;  // warps per lattice of the int32 fill (concurrent sweeps of long queries)
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
@@ -300,10 +301,11 @@ namespace {
 
 template <int R, bool TB, int ENDMODE>
 void launch_fill_sm(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
+    const int threads = 32 * b->fill_warps;  // warps per lattice = concurrent sweeps (affine_systolic.cuh)
     if (b->score_mode == SCORE_PRMT)
-        affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, 32, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
     else
-        affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM><<<count, 32, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+        affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
 }
 
 template <int R>
@@ -483,6 +485,8 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const int r = atoi(env);
         if (r == 8 || r == 16 || r == 32) b->R = r;
     }
+    b->fill_warps = std::max(1, std::min(kAffMaxWarps, (maxQ + 1 + 32 * b->R - 1) / (32 * b->R)));
+    if (const char *env = getenv("C4B_AFFINE_WARPS")) b->fill_warps = std::max(1, std::min(kAffMaxWarps, atoi(env)));
 
     // ---- scoring tables
     int n_used = 0, cls_of[24], code_of[8];

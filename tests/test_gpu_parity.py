@@ -226,6 +226,32 @@ def test_staging_pipeline_many_slices(eng, params, scoring, monkeypatch):
         assert got_paths[k]["region"] == want["region"] and got_paths[k]["ops"] == want["ops"], k
 
 
+def test_long_queries_pipelined_sweeps(eng, params, scoring, monkeypatch):
+    """Queries of many 1024-row sweeps: the warps of a CTA run the sweeps of one lattice
+    concurrently (hand-off row published through a shared-memory counter).  Same answers
+    with 1, 3 and 8 warps, and as the oracle; local and global scopes; ragged batch."""
+    from exonerate_b200 import Optimal, PairSet
+    for name in ("affine_local_dna", "affine_global_dna"):
+        model, _ = helpers.load_model(name, params)
+        opt = Optimal(eng, model, scoring)
+        qs, ts = [], []
+        for k, (ql, tl) in enumerate([(5000, 3000), (9000, 1200), (1025, 4000), (3000, 3000), (40, 500), (2049, 2049)]):
+            q, t = helpers.dna_pair(61000 + k, ql, tl, rate=0.1)
+            qs.append(q)
+            ts.append(t)
+        pairs = PairSet(qs, ts)
+        got = {}
+        for w in ("1", "3", "8"):
+            monkeypatch.setenv("C4B_AFFINE_WARPS", w)
+            got[w] = (opt.find_score(pairs), opt.find_path(pairs))
+        monkeypatch.delenv("C4B_AFFINE_WARPS")
+        assert got["1"] == got["3"] == got["8"]
+        for k in range(pairs.n):
+            want = oracle_path(model, scoring, qs[k], ts[k])
+            assert got["8"][0][k] == want["score"], (name, k)
+            assert got["8"][1][k]["region"] == want["region"] and got["8"][1][k]["ops"] == want["ops"], (name, k)
+
+
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
     from exonerate_b200 import Optimal, PairSet
     model, _ = helpers.load_model("affine_local_protein", params)
