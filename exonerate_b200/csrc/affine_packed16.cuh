@@ -395,4 +395,210 @@ affine_fill16u_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ ou
     }
 }
 
+
+// -----------------------------------------------------------------------------
+// affine_fill16tb_kernel: the TRACEBACK pass with two lattices per warp.  Used for
+// the banded refill of long targets and for the single pass of short ones (e.g.
+// 1 kbp x 1 kbp) when every lattice of the launch qualifies.
+//
+// Who won is not asked with compares: every halfword is  8 * value + 1024 + TAG
+// (unsigned), and the candidates of a max carry their rank in the closed-model order
+// as the tag, so "first assigns, later replace only if strictly greater"
+// (viterbi.c:766-775) IS the unsigned max, and the winner is read off the low bits:
+//   M = max( match|3 , START|2 , D|1 , I|0 )     (T4, T5, T6, T7)
+//   D = max( D<- + ext |4 , G<- |0 )              (T0 extend first, T2 open)
+//   I = max( I^  + ext |4 , G^  |0 )              (T1, T3)
+// Values are cleaned (& ~7) before they are used again.  Exact while
+// 8 * max_sub * (min(Q,T) + 1) + 2048 < 65536 (host-checked), score' >= 0 and
+// open <= ext (same vertical-chain identity as affine_fill16u_kernel; it preserves
+// the tag: if G = I + open then extend beats it strictly).
+// Record: one nibble per cell in the int32 kernel's layout ([sweep][step][lane][R/8]
+// words per lattice), TAG FORMAT: bits 0-1 M tag, bit 2 D extended, bit 3 I extended
+// (TbJob.reserved = 1 tells affine_traceback_kernel).
+constexpr uint32_t kTbBias = 1024u;
+constexpr uint32_t kTbNeg = (1024u - 800u) * 0x10001u;  // true -100: "not reachable"
+
+template <int R>
+__global__ void __launch_bounds__(32)
+affine_fill16tb_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
+                       const AffModel mdl, const void *__restrict__ score_table) {
+    constexpr int WPL = R / 8;
+    __shared__ uint32_t xt4[25];
+    const int lane = threadIdx.x;
+    const int ia = 2 * blockIdx.x, ib = min(ia + 1, n - 1);
+    const AffPair PA = pairs[ia], PB = pairs[ib];
+    const bool haveB = (ia + 1 < n);
+    const int QA = PA.Q, TA = PA.T, QB = PB.Q, TB_ = PB.T;
+    const int T = max(TA, TB_);
+    // bytes 0..3 = score' of classes 0..3 (>= 0); scaled by 8 after the PRMT (one IMAD)
+    if (lane < 25) xt4[lane] = reinterpret_cast<const uint2 *>(score_table)[lane].x;
+    __syncwarp();
+
+    const int open = mdl.openD, one = mdl.one;
+    const uint32_t open8 = (uint32_t)(8 * open * 0x10001);            // x + 8*open on both halves (x >= 96)
+    const uint32_t extD8t = (uint32_t)((8 * mdl.extD + 4 - 1) * 0x10001);  // from Dm = D|1 to (D + ext)|4
+    const uint32_t extI8t = pack16(8 * mdl.extI + 4);                  // per-half operand of VIADDMNMX.U16x2
+    const uint32_t start2 = (kTbBias + 2u) * 0x10001u;                 // START: value 0, tag 2
+    const int nstepsA = TA + 1 + 31, nstepsB = TB_ + 1 + 31, nsteps = T + 1 + 31;
+    const int row0 = lane * R;
+
+    uint32_t sel[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = row0 + r;
+        uint32_t sa = 0x88u, sb = 0xCCu;  // padding: sign of a (non-negative) pool byte = 0
+        if (i >= 1 && i <= QA) { const uint32_t c = PA.q[i - 1]; sa = c | ((c | 8u) << 4); }
+        if (i >= 1 && i <= QB) { const uint32_t c = 4u + PB.q[i - 1]; sb = c | ((c | 8u) << 4); }
+        sel[r] = sa | (sb << 8);
+    }
+    uint32_t Gp[R], Dm[R];  // clean G = M + open, and D|1, of the previous column
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        Gp[r] = kTbNeg;
+        Dm[r] = kTbNeg | 0x00010001u;
+    }
+    uint32_t topG = kTbNeg, topI = kTbNeg, topGprev = kTbNeg;
+    uint32_t in_code = kTargetNone | (kTargetNone << 8), code0 = in_code;
+    uint32_t *tbA = PA.tb + (size_t)lane * WPL, *tbB = PB.tb + (size_t)lane * WPL;
+
+    uint32_t best2 = 0u, pend = 0u;
+    int bjA = 0, biA = 0, bjB = 0, biB = 0, pend_j = 0;
+    auto settle_pending = [&]() {
+        const uint32_t nb = __vmaxu2(best2, pend);
+        if (nb != best2) {
+            if ((pend & 0xFFFFu) > (best2 & 0xFFFFu)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Gp[r] ^ pend) & 0xFFFFu) == 0) { bi = row0 + r; found = true; }
+                biA = bi;
+                bjA = pend_j;
+            }
+            if ((pend >> 16) > (best2 >> 16)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Gp[r] ^ pend) >> 16) == 0) { bi = row0 + r; found = true; }
+                biB = bi;
+                bjB = pend_j;
+            }
+            best2 = nb;
+        }
+        pend = 0u;
+    };
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int j = s - lane;
+        settle_pending();
+        const uint32_t code = (lane == 0) ? code0 : in_code;
+        {
+            const uint32_t ca = (s + 1 <= TA) ? (uint32_t)PA.t[s] : (uint32_t)kTargetNone;
+            const uint32_t cb = (s + 1 <= TB_) ? (uint32_t)PB.t[s] : (uint32_t)kTargetNone;
+            code0 = ca | (cb << 8);
+        }
+        uint32_t botG = kTbNeg, botI = kTbNeg;
+        if (j >= 0 && j <= T) {
+            const uint32_t Xa = xt4[code & 0xFFu], Xb = xt4[code >> 8];
+            uint32_t acc[R / 4];
+#pragma unroll
+            for (int k = 0; k < R / 4; ++k) acc[k] = 0u;
+            uint32_t Gt[R];  // G~ = max(match, START, D) + open, clean
+            // phase A (rows independent; bottom-up, so that row r still finds the previous
+            // column's G of row r-1 in place): D, then G~
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+                uint32_t sc;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(Xa), "r"(Xb), "r"(sel[r]));
+                const uint32_t diag = (r == 0) ? topGprev : Gp[r - 1];
+                // D: extend (tag 4) first, open (tag 0) replaces only if strictly greater
+                const uint32_t Dt = __vmaxu2(imad_add(Dm[r], one, extD8t), Gp[r]);
+                const uint32_t dm = (Dt & 0xFFF8FFF8u) | 0x00010001u;          // clean, M-level tag 1
+                // match candidate: 8 * (G_diag + score') + tag 3
+                const uint32_t x = imad_add(sc, 8, diag) + 0x00030003u;
+                const uint32_t mt = __vimax3_u16x2(x, start2, dm);            // T4, T5, T6
+                Gt[r] = imad_add(mt & 0xFFF8FFF8u, one, open8);
+                // record: M tag (bits 0-1, completed in phase B) and D's bit 2
+                acc[r / 4] |= ((mt & 0x00030003u) | (Dt & 0x00040004u)) << (4 * (r % 4));
+                Dm[r] = dm;
+                Gp[r] = mt;  // tagged max without I; phase B finishes it
+            }
+            // phase B: I chain (one dependent op per row); M = max(mt, I|0)
+            uint32_t It = __viaddmax_u16x2(topI, extI8t, topG);   // I of row 0: extend|4 vs open|0
+            uint32_t cm = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t ic = It & 0xFFF8FFF8u;                          // clean, M-level tag 0
+                const uint32_t mt = Gp[r];
+                // if I wins (strictly greater than every earlier candidate) the tag becomes 0
+                const uint32_t m2 = __vmaxu2(mt, ic);
+                const uint32_t Gv = __vmaxu2(Gt[r], imad_add(ic, one, open8));  // clean G of this cell
+                // fix the M tag where I won: (m2 & 3) replaces (mt & 3); plus I's bit 3
+                acc[r / 4] ^= (((mt ^ m2) & 0x00030003u) | ((It & 0x00040004u) << 1)) << (4 * (r % 4));
+                Gp[r] = Gv;
+                if (r & 1) cm = __vimax3_u16x2(cm, Gv, Gp[r - 1]);
+                if (r + 1 < R) It = __viaddmax_u16x2(ic, extI8t, Gt[r]);
+                else botI = ic;
+            }
+            botG = Gp[R - 1];
+            topGprev = topG;
+            pend = cm;
+            pend_j = j;
+            // nibbles: acc[k] = rows 4k..4k+3, lattice A in the low half, B in the high half
+            if (s < nstepsA && j <= TA) {
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) tbA[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x5410);
+            }
+            if (haveB && s < nstepsB && j <= TB_) {
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) tbB[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x7632);
+            }
+        }
+        tbA += 32 * WPL;
+        tbB += 32 * WPL;
+        const uint32_t nG = __shfl_up_sync(0xffffffffu, botG, 1);
+        const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
+        const uint32_t nC = __shfl_up_sync(0xffffffffu, code, 1);
+        if (lane > 0) {
+            topG = nG;
+            topI = nI;
+            in_code = nC;
+        }
+    }
+    settle_pending();
+    __syncwarp();
+
+    int bA = (int)(best2 & 0xFFFFu), bB = (int)(best2 >> 16);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bA, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjA, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biA, off);
+            if ((ob > bA) || (ob == bA && (oj < bjA || (oj == bjA && oi < biA)))) { bA = ob; bjA = oj; biA = oi; }
+        }
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bB, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjB, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biB, off);
+            if ((ob > bB) || (ob == bB && (oj < bjB || (oj == bjB && oi < biB)))) { bB = ob; bjB = oj; biB = oi; }
+        }
+    }
+    if (lane == 0) {
+        AffOut o;
+        o.best = (bA - (int)kTbBias) / 8 - open;  // tracked as clean 8 * (M + open) + bias
+        o.end_i = biA;
+        o.end_j = bjA;
+        o.flags = 0;
+        outs[PA.out_index] = o;
+        if (haveB) {
+            o.best = (bB - (int)kTbBias) / 8 - open;
+            o.end_i = biB;
+            o.end_j = bjB;
+            outs[PB.out_index] = o;
+        }
+    }
+}
+
 }  // namespace c4b

@@ -20,7 +20,7 @@ struct TbJob {
     int32_t score_slot; // slot of the score-only pass result, or -1
     int64_t ops_off;    // first (transition,length) pair of this job's ops slot
     int32_t ops_cap;    // capacity of the slot in pairs
-    int32_t reserved;
+    int32_t reserved;   // record format: 0 = affine_fill_kernel nibbles, 1 = tag format (affine_fill16tb_kernel)
 };
 
 // Longest target span an optimal local path ending at lattice row end_i can
@@ -110,7 +110,10 @@ __global__ void affine_traceback_kernel(const AffPair *__restrict__ pairs, const
         int state = 0;  // 0 = match, 1 = delete, 2 = insert
         emit(mdl.tME);
         for (;;) {
-            const uint32_t nib = tb_nibble<R>(P.tb, nsteps, i, j);
+            uint32_t nib = tb_nibble<R>(P.tb, nsteps, i, j);
+            // tag format of affine_fill16tb_kernel: bits 0-1 rank of the M winner (3 match ..
+            // 0 insert), bit 2 D extended, bit 3 I extended -> this kernel's own layout
+            if (J.reserved) nib = (((nib & 3u) ^ 3u) << 2) | ((nib & 4u) ? 0u : 2u) | ((nib & 8u) ? 0u : 1u);
             if (state == 0) {
                 const uint32_t dir = nib >> 2;
                 if (dir == 0) { emit(mdl.tMM); --i; --j; }

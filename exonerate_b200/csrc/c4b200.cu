@@ -236,6 +236,7 @@ struct c4b_batch {
     int fill_warps = 1;  // warps per lattice of the int32 fill (concurrent sweeps of long queries)
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
+    bool tb16_band = false, tb16_direct = false;  // traceback pass on affine_fill16tb_kernel
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
     DevBuf<uint8_t> d_seq;
@@ -370,6 +371,29 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
     }
     if (rc) return rc;
     C4B_CUDA(cudaGetLastError());
+    b->e->launches++;
+    return 0;
+}
+
+// traceback pass of `count` lattices, two per warp (affine_fill16tb_kernel), timed like launch_fill
+int launch_fill16tb(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
+    if (!count) return 0;
+    if ((size_t)b->fill_events_used >= b->fill_events.size()) {
+        EventPair nev;
+        C4B_CUDA(cudaEventCreate(&nev.a));
+        C4B_CUDA(cudaEventCreate(&nev.b));
+        b->fill_events.push_back(nev);
+    }
+    EventPair *ev = &b->fill_events[b->fill_events_used++];
+    C4B_CUDA(cudaEventRecord(ev->a, s));
+    const int blocks = (count + 1) / 2;
+    switch (b->R) {
+    case 8: affine_fill16tb_kernel<8><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    case 16: affine_fill16tb_kernel<16><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    default: affine_fill16tb_kernel<32><<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p); break;
+    }
+    C4B_CUDA(cudaGetLastError());
+    C4B_CUDA(cudaEventRecord(ev->b, s));
     b->e->launches++;
     return 0;
 }
@@ -576,6 +600,19 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
             for (int c = 0; c < 24 && used[a]; ++c) nonneg = nonneg && matrix[a * 24 + c] >= b->aff.openD;
         const char *v = getenv("C4B_P16_VARIANT");
         b->p16_unsigned = nonneg && b->aff.openI <= b->aff.extI && !(v && v[0] == 's');
+        // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
+        const char *tv = getenv("C4B_AFFINE_TB16");
+        const bool tb_ok = model_ok && nonneg && b->aff.openI <= b->aff.extI && b->aff.openD >= -24 &&
+                           b->aff.extD >= -24 && b->aff.extI >= -24 && b->aff.extD == b->aff.extI &&
+                           !(tv && atoi(tv) == 0);
+        auto fits_tb16 = [&](int p) {
+            const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
+            return Q + 1 <= 32 * b->R && 8 * (int64_t)max_sub * (std::min(Q, T) + 1) + 2048 < 65000;
+        };
+        b->tb16_band = tb_ok && b->want_path && !b->score_list.empty() && b->n16 == (int)b->score_list.size() &&
+                       std::all_of(b->score_list.begin(), b->score_list.end(), fits_tb16);
+        b->tb16_direct = tb_ok && b->want_path && !b->direct_list.empty() &&
+                         std::all_of(b->direct_list.begin(), b->direct_list.end(), fits_tb16);
     }
     const int ns = (int)b->score_list.size(), nd = (int)b->direct_list.size();
 
@@ -767,7 +804,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const int64_t span = band ? band_cols[p] : pairs[p].target_length;
         j.ops_cap = (int32_t)std::min<int64_t>(pairs[p].query_length + span + 4, INT32_MAX);
         j.ops_off = ops_cursor;
-        j.reserved = 0;
+        j.reserved = (band ? b->tb16_band : b->tb16_direct) ? 1 : 0;
         ops_cursor += j.ops_cap;
         return j;
     };
@@ -930,13 +967,15 @@ int affine_run(c4b_batch *b, c4b_score threshold) {
     // pass 2: refill only the band with the traceback record, then walk it
     for (const Chunk &c : b->band_chunks) {
         const int cnt = c.end - c.begin;
-        if (launch_fill(b, b->d_band.p + c.begin, b->d_out2.p, cnt, true, st, true)) return -1;
+        if (b->tb16_band ? launch_fill16tb(b, b->d_band.p + c.begin, b->d_out2.p, cnt, st)
+                         : launch_fill(b, b->d_band.p + c.begin, b->d_out2.p, cnt, true, st, true)) return -1;
         if (launch_traceback(b, b->d_band.p, b->d_out2.p, b->d_out1.p, b->d_band_j0.p,
                              b->d_jobs_band.p + c.begin, cnt)) return -1;
     }
     for (const Chunk &c : b->direct_chunks) {
         const int cnt = c.end - c.begin;
-        if (launch_fill(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, true, st, true)) return -1;
+        if (b->tb16_direct ? launch_fill16tb(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, st)
+                           : launch_fill(b, b->d_direct.p + c.begin, b->d_outd.p, cnt, true, st, true)) return -1;
         if (launch_traceback(b, b->d_direct.p, b->d_outd.p, nullptr, nullptr,
                              b->d_jobs_direct.p + c.begin, cnt)) return -1;
     }

@@ -176,6 +176,9 @@ def test_packed16_score_pass(eng, params, scoring, monkeypatch):
         monkeypatch.setenv("C4B_P16_VARIANT", "s")      # signed-halfword variant of the packed kernel
         assert opt.find_score(pairs) == scores and opt.find_path(pairs) == paths
         monkeypatch.delenv("C4B_P16_VARIANT")
+        monkeypatch.setenv("C4B_AFFINE_TB16", "0")      # int32 traceback pass under the packed score pass
+        assert opt.find_path(pairs) == paths
+        monkeypatch.delenv("C4B_AFFINE_TB16")
         for k in range(pairs.n):
             want = oracle_path(model, scoring, qs[k], ts[k])
             assert scores[k] == want["score"], (maxq, k)
