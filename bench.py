@@ -31,9 +31,9 @@ WORKLOADS = {
     "affine:local": {
         "metric": METRIC, "b_alg": B_ALG, "pairs": 10000, "cpu_pairs": 2,
         "workload": "affine:local --exhaustive, %d bp x %d bp DNA pairs",
-        "kernel": "affine_fill16 (score pass, two lattices per warp in 16-bit halves) + affine_systolic "
-                  "(banded traceback pass, int32)",
-        "traffic_key": "affine_fill16_kernel<32>",
+        "kernel": "affine_fill16u (score pass, two lattices per warp in 16-bit halves) + affine_fill16tb "
+                  "(banded traceback pass, tagged 16-bit halves) + walk",
+        "traffic_key": "affine_fill16u_kernel<32>",
         "note": "B_alg=20 B/cell (SURVEY 8d, reference row layout); the kernel keeps rows in registers and "
                 "writes 0.5 B/cell only inside the traceback band, so frac>1 is expected; see DESIGN.md. peak ",
     },
