@@ -453,6 +453,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     // ---- validation, alphabet use, lattice geometry
     int maxQ = 0;
     bool used[24] = {false};
+    std::vector<uint8_t> query_wide(n, 0);  // the query holds a symbol outside the primary four
     {
         std::set<SeqKey> seen;
         std::vector<SeqKey> distinct_q;
@@ -480,12 +481,24 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(
             std::min(8u, std::max(1u, std::thread::hardware_concurrency())), qtotal >> 20));
         std::vector<std::array<bool, 256>> seen_byte(nt);
+        // "narrow" queries hold only the four primary symbols (A, C, G, T of a DNA matrix):
+        // those get PRMT classes 0..3, which is what the packed kernels' 4-byte pools hold
+        bool prim[256];
+        for (int c = 0; c < 256; ++c)
+            prim[c] = match_kind == C4B_CALC_MATCH_DNA &&
+                      (index[c] == index['A'] || index[c] == index['C'] || index[c] == index['G'] || index[c] == index['T']);
+        std::vector<uint8_t> wide(distinct_q.size(), 0);
         auto scan = [&](unsigned t) {
             std::array<bool, 256> &sb = seen_byte[t];
             sb.fill(false);
             for (size_t k = t; k < distinct_q.size(); k += nt) {
                 const uint8_t *q = distinct_q[k].first;
-                for (int i = 0; i < distinct_q[k].second; ++i) sb[q[i]] = true;
+                bool w = false;
+                for (int i = 0; i < distinct_q[k].second; ++i) {
+                    sb[q[i]] = true;
+                    w |= !prim[q[i]];
+                }
+                wide[k] = w;
             }
         };
         {
@@ -503,6 +516,12 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                     }
                     used[index[c]] = true;
                 }
+        {
+            std::map<SeqKey, int> slot;
+            for (size_t k = 0; k < distinct_q.size(); ++k) slot[distinct_q[k]] = (int)k;
+            for (int p = 0; p < n; ++p)
+                query_wide[p] = wide[slot[SeqKey(pairs[p].query + pairs[p].query_start, pairs[p].query_length)]];
+        }
     }
     b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
     if (const char *env = getenv("C4B_AFFINE_R")) {  // tuning override: rows per lane
@@ -523,11 +542,21 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
             max_sub = std::max(max_sub, v);
             if (used[a] && (v - b->aff.openD < -127 || v - b->aff.openD > 127)) fits8 = false;
         }
-        if (used[a]) {
-            if (n_used < 7) code_of[n_used] = a;
-            cls_of[a] = n_used++;
-        }
     }
+    // PRMT classes: the primary four first (when used), then the other used rows
+    {
+        bool primary_row[24] = {false};
+        if (match_kind == C4B_CALC_MATCH_DNA)
+            for (char ch : {'A', 'C', 'G', 'T'})
+                if (index[(uint8_t)ch] < 24) primary_row[index[(uint8_t)ch]] = true;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int a = 0; a < 24; ++a)
+                if (used[a] && primary_row[a] == (pass == 0)) {
+                    if (n_used < 7) code_of[n_used] = a;
+                    cls_of[a] = n_used++;
+                }
+    }
+
     b->max_sub = max_sub;
     b->gap_min = std::min(-b->aff.openD, -b->aff.extD);
     b->score_mode = (n_used <= 7 && fits8) ? SCORE_PRMT : SCORE_SMEM;
@@ -584,12 +613,14 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     {
         const char *env = getenv("C4B_AFFINE_PACK16");
         const bool allow = !(env && atoi(env) == 0);
-        const bool model_ok = allow && local && b->score_mode == SCORE_PRMT && n_used <= 4 && max_sub > 0 &&
+        const bool model_ok = allow && local && b->score_mode == SCORE_PRMT && max_sub > 0 &&
                               b->aff.openD < 0 && b->aff.openD > -1000 && b->aff.extD < 0 && b->aff.extD > -1000 &&
                               b->aff.extI < 0 && b->aff.extI > -1000;
         auto fits16 = [&](int p) {
             const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
-            return model_ok && Q + 1 <= 32 * b->R && (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
+            // per lattice: a query of primary symbols only (classes 0..3), one sweep, values in 15 bits
+            return model_ok && !query_wide[p] && Q + 1 <= 32 * b->R &&
+                   (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
         };
         auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
         b->n16 = (int)(mid - b->score_list.begin());
@@ -607,7 +638,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                            !(tv && atoi(tv) == 0);
         auto fits_tb16 = [&](int p) {
             const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
-            return Q + 1 <= 32 * b->R && 8 * (int64_t)max_sub * (std::min(Q, T) + 1) + 2048 < 65000;
+            return !query_wide[p] && Q + 1 <= 32 * b->R && 8 * (int64_t)max_sub * (std::min(Q, T) + 1) + 2048 < 65000;
         };
         b->tb16_band = tb_ok && b->want_path && !b->score_list.empty() && b->n16 == (int)b->score_list.size() &&
                        std::all_of(b->score_list.begin(), b->score_list.end(), fits_tb16);

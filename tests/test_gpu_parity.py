@@ -255,6 +255,32 @@ def test_long_queries_pipelined_sweeps(eng, params, scoring, monkeypatch):
             assert got["8"][1][k]["region"] == want["region"] and got["8"][1][k]["ops"] == want["ops"], (name, k)
 
 
+def test_mixed_alphabets_share_a_batch(eng, params, scoring):
+    """Queries of A/C/G/T only take the packed kernels (PRMT classes 0..3), queries with N
+    or IUPAC codes the int32 kernels, in the same batch and launch sequence; long-target
+    (two-pass) and short-target (single pass) routes."""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    rng = random.Random(123)
+    qs, ts = [], []
+    for k in range(14):
+        ql = rng.choice([60, 300, 900])
+        tl = rng.choice([400, 1200, 9000])
+        q, t = helpers.dna_pair(33000 + k, ql, tl, rate=0.1)
+        if k % 2:   # sprinkle ambiguity codes into every other query
+            q = "".join(c if rng.random() > 0.03 else rng.choice("NRYK") for c in q)
+        qs.append(q)
+        ts.append(t)
+    pairs = PairSet(qs, ts)
+    scores, paths = opt.find_score(pairs), opt.find_path(pairs)
+    for k in range(pairs.n):
+        want = oracle_path(model, scoring, qs[k], ts[k])
+        assert scores[k] == want["score"], k
+        assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"], k
+        assert paths[k]["ops"] == want["ops"], k
+
+
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
     from exonerate_b200 import Optimal, PairSet
     model, _ = helpers.load_model("affine_local_protein", params)
