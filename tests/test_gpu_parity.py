@@ -281,6 +281,48 @@ def test_mixed_alphabets_share_a_batch(eng, params, scoring):
         assert paths[k]["ops"] == want["ops"], k
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_packed_kernels_fuzz_penalties_and_matrices(eng, params, scoring, monkeypatch, seed):
+    """Differential fuzz of the exactness guards of the packed kernels: random gap
+    penalties (incl. open == extend, the -24 limit of the tagged traceback pass and beyond
+    it), random match / mismatch / N scores (incl. mismatch below gap open, which the
+    offset-binary variant must refuse), ragged shapes.  Packed path == int32 path, and a
+    sample == oracle."""
+    import copy
+    from exonerate_b200 import Optimal, PairSet
+    from exonerate_b200.models import default_params, host_model
+    rng = random.Random(900 + seed)
+    for trial in range(4):
+        hp = default_params()
+        hp.gap_extend = -rng.choice([1, 2, 4, 9, 24, 30])
+        hp.gap_open = hp.gap_extend - rng.choice([0, 1, 8, 20, 60])
+        model, _ = host_model("affine:local", params=hp)
+        sc = copy.deepcopy(scoring)
+        match, mism, nsc = rng.choice([1, 2, 5, 9]), -rng.choice([1, 3, 4, 15, 40]), rng.choice([0, -1, -2])
+        for a in "ACGTN":
+            for b_ in "ACGTN":
+                v = nsc if "N" in (a, b_) else (match if a == b_ else mism)
+                sc.dna_matrix[sc.dna_index[ord(a)] * 24 + sc.dna_index[ord(b_)]] = v
+        qs, ts = [], []
+        for k in range(11):
+            ql, tl = rng.choice([(30, 200), (250, 300), (700, 900), (1000, 6000), (1023, 1024), (90, 9000)])
+            q, t = helpers.dna_pair(seed * 1000 + trial * 50 + k, ql, tl, rate=rng.choice([0.0, 0.08, 0.25]))
+            if k == 3:
+                t = t[:len(t) // 2] + "N" * 7 + t[len(t) // 2:]
+            qs.append(q)
+            ts.append(t)
+        pairs = PairSet(qs, ts)
+        opt = Optimal(eng, model, sc)
+        got = (opt.find_score(pairs), opt.find_path(pairs))
+        monkeypatch.setenv("C4B_AFFINE_PACK16", "0")
+        want = (opt.find_score(pairs), opt.find_path(pairs))
+        monkeypatch.delenv("C4B_AFFINE_PACK16")
+        assert got == want, (seed, trial, hp.gap_open, hp.gap_extend, match, mism, nsc)
+        for k in (0, 1, 2):
+            ref = oracle_path(model, sc, qs[k], ts[k])
+            assert got[0][k] == ref["score"] and got[1][k]["ops"] == ref["ops"], (seed, trial, k)
+
+
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
     from exonerate_b200 import Optimal, PairSet
     model, _ = helpers.load_model("affine_local_protein", params)
