@@ -1273,6 +1273,34 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model, const c4b_scori
     return -1;
 }
 
+int c4b_viterbi_end_matrix(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
+                           const c4b_pair *pair, c4b_score *matrix, c4b_result *result) {
+    if (!e || !model || !scoring || !pair || !matrix || !result) {
+        set_error("c4b_viterbi_end_matrix: bad arguments");
+        return -1;
+    }
+    C4B_CUDA(cudaSetDevice(e->device));
+    tl_pool_stream = e->stream;
+    GenericBatch *g = nullptr;
+    int rc = generic_batch_create(e->stream, &e->launches, model, scoring, 1, pair, false, &g, true);
+    if (rc) return rc;
+    rc = generic_batch_run(g, C4B_IMPOSSIBLY_LOW_SCORE);
+    if (!rc) rc = generic_batch_fetch(g, result, nullptr, 0);
+    if (!rc) {
+        const size_t cells = ((size_t)pair->query_length + 1) * ((size_t)pair->target_length + 1);
+        std::vector<int32_t> tmp(cells);
+        if (cudaMemcpy(tmp.data(), g->d_endm.p, cells * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("copying the END matrix back failed");
+            rc = -1;
+        } else {
+            for (size_t k = 0; k < cells; ++k)
+                if (tmp[k] != kEndMatrixUnset) matrix[k] = tmp[k];
+        }
+    }
+    generic_batch_destroy(g);
+    return rc;
+}
+
 int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hsp_param *param,
                          const uint8_t *query, int32_t query_len, const uint8_t *query_mask,
                          const uint8_t *target, int32_t target_len, const uint8_t *target_mask,

@@ -35,6 +35,7 @@ struct GenPair {
     int32_t q_start, t_start, Q, T;  // region origin + extents
     int32_t blk_dq, blk_dt;          // blocked coordinates are relative to (q_start-blk_dq, ...)
     uint8_t *tb;                     // PATH: (Q+1)*(T+1)*S winning transition ids (0xFF = none)
+    int32_t *end_matrix;             // optional (Q+1)*(T+1): END's score of every cell that reached END
     int64_t out_index;
 };
 
@@ -212,6 +213,9 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                 if ((set >> m.end_state) & 1u) {  // viterbi.c:778-791
                     const int32_t *ec = cell + m.end_state * C;
                     const int v = ec[0];
+                    // Heuristic_Bound_report_end_func (src/bsdp/heuristic.c:139-145): the model's
+                    // cell_end callback of BSDP bound fills, "matrix[%QP][%TP] = %C[0]"
+                    if (P.end_matrix) P.end_matrix[(size_t)i * (T + 1) + j] = v;
                     if (v > best || (v == best && (j < best_j || (j == best_j && i < best_i)))) {
                         best = v; best_i = i; best_j = j;
                         best_si = (qid >= 0) ? ec[qid] : 0;
@@ -347,7 +351,7 @@ __global__ void generic_score_results_kernel(const GenPair *__restrict__ pairs, 
 struct GenericBatch;
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                         GenericBatch **out);
+                         GenericBatch **out, bool end_matrix = false);
 int generic_batch_run(GenericBatch *g, c4b_score threshold);
 int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity);
 int64_t generic_batch_cells(const GenericBatch *g);

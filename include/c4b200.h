@@ -244,6 +244,16 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model,
                           int mode, c4b_result *result, int32_t *ops,
                           int64_t ops_capacity);
 
+/* ---- BSDP bound fills (first part) ------------------
+ * Heuristic_Bound_create (src/bsdp/heuristic.c:150-207) scores a copy of a derived model
+ * whose END state is in scope everywhere and whose cell_end callback is
+ * Heuristic_Bound_report_end_func (:139-145, "matrix[%QP][%TP] = %C[0]"): it wants END's
+ * score of EVERY cell.  One synchronous FIND_SCORE lattice; matrix is
+ * (query_length+1) x (target_length+1) row-major (query-major); cells where END was not
+ * reached are left untouched.  result as for c4b_viterbi_calculate mode 0. */
+int c4b_viterbi_end_matrix(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
+                           const c4b_pair *pair, c4b_score *matrix, c4b_result *result);
+
 /* ---- HSP seeding / extension ----------------------
  * Replaces the per-seed work of HSPset_seed_hsp (src/comparison/hspset.c:933-997):
  * HSP_trim_ends (:850-878), HSP_init (:725-745), HSP_extend with masking forbidden

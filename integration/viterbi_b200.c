@@ -71,6 +71,12 @@ static void classify_calc(C4_Model *model, C4_Calc *calc, c4b_calc *out){
     register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
     memset(out, 0, sizeof(c4b_calc));
     out->protect = calc->protect;
+    if(!calc->calc_func){ /* C4_Calc_score (c4.c:1700-1711): no callback => max_score;
+                           * that is every calc of a BSDP bound model (heuristic.c:172-180) */
+        out->kind = C4B_CALC_CONST;
+        out->param[0] = calc->max_score;
+        return;
+        }
     if(!m)
         g_error("libc4b200: calc [%s] of model [%s] has no macro to classify",
                 calc->name, model->name);
@@ -117,6 +123,13 @@ static void classify_calc(C4_Model *model, C4_Calc *calc, c4b_calc *out){
     }
 
 /* closed C4_Model -> c4b_model */
+/* Heuristic_Bound_create (src/bsdp/heuristic.c:150-207) scores a model whose only cell
+ * callback is Heuristic_Bound_report_end_func, recognised by its macro (:147-148). */
+static gboolean model_is_bound(C4_Model *model){
+    return model->end_state->cell_end_func && model->end_state->cell_end_macro
+        && !strcmp(model->end_state->cell_end_macro, "matrix[%QP][%TP] = %C[0]");
+    }
+
 static void flatten_model(C4_Model *model, c4b_model *out){
     register gint i, j;
     register C4_Transition *t;
@@ -130,9 +143,10 @@ static void flatten_model(C4_Model *model, c4b_model *out){
     || (model->total_shadow_designations > C4B_MAX_SHADOW_SLOTS))
         g_error("libc4b200: model [%s] exceeds the engine's table sizes",
                 model->name);
-    if(model->start_state->cell_start_func || model->end_state->cell_end_func)
-        g_error("libc4b200: model [%s] uses cell callbacks (BSDP derived model);"
-                " only --exhaustive models have a device form", model->name);
+    if(model->start_state->cell_start_func
+    || (model->end_state->cell_end_func && !model_is_bound(model)))
+        g_error("libc4b200: model [%s] uses cell callbacks (BSDP span model);"
+                " they have no device form yet", model->name);
     out->n_states = model->state_list->len;
     out->n_transitions = model->transition_list->len;
     out->n_calcs = model->calc_list->len;
@@ -330,6 +344,39 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     g_assert(Region_is_valid(region));
     if(vd->continuation || (viterbi->mode == Viterbi_Mode_FIND_CHECKPOINTS))
         g_error("libc4b200: continuation / checkpoint modes are not used");
+    if(model_is_bound(viterbi->model)){
+        /* user_data is the bound matrix [query_range+1][target_range+1]; the model reads
+         * no symbol (all calcs are constants), so the sequences are placeholders */
+        register C4_Score **matrix = user_data;
+        register gint Q = region->query_length, T = region->target_length;
+        register c4b_score *flat = g_new(c4b_score, (gsize)(Q+1)*(T+1));
+        qseq = g_strnfill(region->query_start+Q+4, 'A');
+        tseq = g_strnfill(region->target_start+T+4, 'A');
+        memset(&pair, 0, sizeof(pair));
+        memset(&scoring, 0, sizeof(scoring));
+        pair.query = (const uint8_t*)qseq;
+        pair.target = (const uint8_t*)tseq;
+        pair.query_len = region->query_start+Q;
+        pair.target_len = region->target_start+T;
+        pair.query_start = region->query_start;
+        pair.target_start = region->target_start;
+        pair.query_length = Q;
+        pair.target_length = T;
+        for(i = 0; i <= Q; i++)
+            for(j = 0; j <= T; j++)
+                flat[(gsize)i*(T+1)+j] = matrix[region->query_start+i][region->target_start+j];
+        if(c4b_viterbi_end_matrix(get_engine(), tables, &scoring, &pair, flat, &result))
+            g_error("libc4b200: %s", c4b_last_error());
+        for(i = 0; i <= Q; i++)
+            for(j = 0; j <= T; j++)
+                matrix[region->query_start+i][region->target_start+j] = flat[(gsize)i*(T+1)+j];
+        g_free(flat);
+        g_free(qseq);
+        g_free(tseq);
+        vd->curr_query_end = result.query_end - region->query_start;
+        vd->curr_target_end = result.target_end - region->target_start;
+        return result.score;
+        }
     switch(viterbi->mode){
         case Viterbi_Mode_FIND_SCORE:  mode = 0; break;
         case Viterbi_Mode_FIND_PATH:   mode = 1; break;

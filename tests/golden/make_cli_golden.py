@@ -37,6 +37,12 @@ COMMANDS = {
     "protein2genome": ("q_prot.fa", "t_gene_p.fa", ["--model", "protein2genome", "--exhaustive", "yes",
                                                     "--subopt", "no"]),
     "coding2coding": ("q_cds.fa", "t_cds.fa", ["--model", "coding2coding", "--exhaustive", "yes", "--subopt", "no"]),
+    # heuristic (BSDP) mode: HSP seeding + SAR terminal / join fills on derived models and the
+    # bound fills of Heuristic_create -- every Viterbi call still goes through our viterbi.o
+    "bsdp_affine_local_dna": ("q_dna.fa", "t_dna.fa", ["--model", "affine:local", "--exhaustive", "no",
+                                                       "--gappedextension", "no"]),
+    "bsdp_affine_local_protein": ("q_prot.fa", "t_prot.fa", ["--model", "affine:local", "--exhaustive", "no",
+                                                             "--gappedextension", "no"]),
     "ryo": ("q_dna.fa", "t_dna.fa", ["--model", "affine:local", "--exhaustive", "yes",
                                                    "--subopt", "no", "--ryo", "%qi %ti %s %pi %em\\n"]),
 }
