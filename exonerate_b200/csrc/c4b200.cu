@@ -1273,28 +1273,32 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model, const c4b_scori
     return -1;
 }
 
-int c4b_viterbi_end_matrix(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
-                           const c4b_pair *pair, c4b_score *matrix, c4b_result *result) {
-    if (!e || !model || !scoring || !pair || !matrix || !result) {
-        set_error("c4b_viterbi_end_matrix: bad arguments");
+int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
+                                const c4b_pair *pair, int mode, const c4b_score *start_cells,
+                                c4b_score *end_cells, c4b_result *result, int32_t *ops, int64_t ops_capacity) {
+    if (!e || !model || !scoring || !pair || !result || (mode != 0 && mode != 1)) {
+        set_error("c4b_viterbi_calculate_cells: bad arguments");
         return -1;
     }
     C4B_CUDA(cudaSetDevice(e->device));
     tl_pool_stream = e->stream;
     GenericBatch *g = nullptr;
-    int rc = generic_batch_create(e->stream, &e->launches, model, scoring, 1, pair, false, &g, true);
+    int rc = generic_batch_create(e->stream, &e->launches, model, scoring, 1, pair, mode == 1, &g, start_cells,
+                                  end_cells != nullptr);
     if (rc) return rc;
     rc = generic_batch_run(g, C4B_IMPOSSIBLY_LOW_SCORE);
-    if (!rc) rc = generic_batch_fetch(g, result, nullptr, 0);
-    if (!rc) {
+    if (!rc) rc = generic_batch_fetch(g, result, ops, ops_capacity);
+    if (!rc && end_cells) {
+        const size_t C = 1 + (size_t)model->n_shadow_slots;
         const size_t cells = ((size_t)pair->query_length + 1) * ((size_t)pair->target_length + 1);
-        std::vector<int32_t> tmp(cells);
-        if (cudaMemcpy(tmp.data(), g->d_endm.p, cells * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
-            set_error("copying the END matrix back failed");
+        std::vector<int32_t> tmp(cells * C);
+        if (cudaMemcpy(tmp.data(), g->d_endm.p, cells * C * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("copying the END cells back failed");
             rc = -1;
         } else {
             for (size_t k = 0; k < cells; ++k)
-                if (tmp[k] != kEndMatrixUnset) matrix[k] = tmp[k];
+                if (tmp[k * C] != kEndMatrixUnset)
+                    for (size_t l = 0; l < C; ++l) end_cells[k * C + l] = tmp[k * C + l];
         }
     }
     generic_batch_destroy(g);

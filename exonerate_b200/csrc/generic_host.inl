@@ -26,11 +26,11 @@ struct GenericBatch {
     DevBuf<c4b_result> d_results;
     DevBuf<int32_t> d_ops_slots, d_ops_packed;
     DevBuf<int64_t> d_new_off;
-    DevBuf<int32_t> d_endm;      // END-score matrix of lattice 0 (BSDP bound fills), else empty
+    DevBuf<int32_t> d_endm, d_startc;  // END-cell / START-cell tables of lattice 0 (BSDP cell callbacks), else empty
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     double fill_ms = -1;
     ~GenericBatch() {
-        d_endm.release();
+        d_endm.release(); d_startc.release();
         d_tables.release(); d_seq.release(); d_ints.release(); d_full.release(); d_box.release();
         d_out_a.release(); d_out_b.release(); d_jobs.release(); d_ring.release(); d_cursor.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
@@ -83,7 +83,7 @@ constexpr int32_t kEndMatrixUnset = (int32_t)0x80808080;  // what cudaMemset(0x8
 
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                         GenericBatch **out, bool end_matrix) {
+                         GenericBatch **out, const int32_t *start_cells, bool end_cells) {
     if (check_model(*model)) return -1;
     GenericBatch *g = new GenericBatch();
     g->stream = stream;
@@ -191,18 +191,30 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         G.Q = pp.query_length; G.T = pp.target_length;
         G.blk_dq = 0; G.blk_dt = 0;
         G.tb = nullptr;
-        G.end_matrix = nullptr;
+        G.start_cells = nullptr;
+        G.end_cells = nullptr;
         G.out_index = p;
     }
-    if (end_matrix && n == 1 && !want_path) {
-        const size_t cells = ((size_t)pairs[0].query_length + 1) * ((size_t)pairs[0].target_length + 1);
-        if (g->d_endm.alloc(cells)) { delete g; return -1; }
-        if (cudaMemsetAsync(g->d_endm.p, 0x80, cells * sizeof(int32_t), stream) != cudaSuccess) {
-            set_error("cudaMemset failed");
+    if ((start_cells || end_cells) && n == 1) {
+        const size_t cells = ((size_t)pairs[0].query_length + 1) * ((size_t)pairs[0].target_length + 1) *
+                             (1 + (size_t)m.n_shadow_slots);
+        bool ok = true;
+        if (end_cells) {
+            ok = ok && !g->d_endm.alloc(cells);
+            ok = ok && cudaMemsetAsync(g->d_endm.p, 0x80, cells * sizeof(int32_t), stream) == cudaSuccess;
+            g->h_full[0].end_cells = g->d_endm.p;
+        }
+        if (start_cells) {
+            ok = ok && !g->d_startc.alloc(cells);
+            ok = ok && cudaMemcpyAsync(g->d_startc.p, start_cells, cells * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                       stream) == cudaSuccess;
+            g->h_full[0].start_cells = g->d_startc.p;
+        }
+        if (!ok) {
+            set_error("staging the cell-callback tables failed");
             delete g;
             return -1;
         }
-        g->h_full[0].end_matrix = g->d_endm.p;
     }
     if (cudaMemcpyAsync(g->d_tables.p, &g->tables, sizeof(GenTables), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
         cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) != cudaSuccess ||

@@ -35,7 +35,9 @@ struct GenPair {
     int32_t q_start, t_start, Q, T;  // region origin + extents
     int32_t blk_dq, blk_dt;          // blocked coordinates are relative to (q_start-blk_dq, ...)
     uint8_t *tb;                     // PATH: (Q+1)*(T+1)*S winning transition ids (0xFF = none)
-    int32_t *end_matrix;             // optional (Q+1)*(T+1): END's score of every cell that reached END
+    // cell callbacks of BSDP derived models, as tables ((Q+1)*(T+1) cells of 1 + n_shadow_slots ints):
+    const int32_t *start_cells;      // what cell_start_func returns per cell (viterbi.c:727-741), or null
+    int32_t *end_cells;              // END's cell wherever END is reached (cell_end_func's input), or null
     int64_t out_index;
 };
 
@@ -183,7 +185,9 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                     const int32_t *src = ring + (size_t)(sj % depth) * col_stride + ((size_t)si * S + tr.input) * C;
                     int32_t *dst = cell + tr.output * C;
                     const bool from_start = (tr.input == m.start_state);
-                    int t = from_start ? 0 : src[0];
+                    const bool start_cb = from_start && P.start_cells;
+                    if (start_cb) src = P.start_cells + ((size_t)si * (T + 1) + sj) * (1 + m.n_shadow_slots);
+                    int t = from_start ? (start_cb ? src[0] : 0) : src[0];
                     t += gen_calc(G, P, tr.calc, P.q_start + si, P.t_start + sj, src);
                     if (tr.calc >= 0) {
                         const int prot = m.calcs[tr.calc].protect;
@@ -198,7 +202,11 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                     // Viterbi_Data_assign (viterbi.c:445-462); shadow stamps are
                     // applied to the transported copy (DESIGN.md "shadows")
                     dst[0] = t;
-                    for (int l = 1; l < C; ++l) dst[l] = src[l];
+                    if (start_cb) {
+                        for (int l = 1; l < C; ++l) dst[l] = (l <= m.n_shadow_slots) ? src[l] : 0;
+                    } else {
+                        for (int l = 1; l < C; ++l) dst[l] = src[l];
+                    }
                     for (int l = 0; l < m.n_shadow_slots; ++l) {
                         const int kind = m.shadow_start[tr.input][l];
                         if (kind == 1) dst[1 + l] = P.t_start + sj;
@@ -213,9 +221,12 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                 if ((set >> m.end_state) & 1u) {  // viterbi.c:778-791
                     const int32_t *ec = cell + m.end_state * C;
                     const int v = ec[0];
-                    // Heuristic_Bound_report_end_func (src/bsdp/heuristic.c:139-145): the model's
-                    // cell_end callback of BSDP bound fills, "matrix[%QP][%TP] = %C[0]"
-                    if (P.end_matrix) P.end_matrix[(size_t)i * (T + 1) + j] = v;
+                    // cell_end_func (viterbi.c:792-797) is called by the host binding on these:
+                    // Heuristic_Bound_report_end_func / Heuristic_Span_src_report_end_func
+                    // (src/bsdp/heuristic.c:139-145,385-410)
+                    if (P.end_cells)
+                        for (int l = 0; l <= m.n_shadow_slots; ++l)
+                            P.end_cells[((size_t)i * (T + 1) + j) * (1 + m.n_shadow_slots) + l] = ec[l];
                     if (v > best || (v == best && (j < best_j || (j == best_j && i < best_i)))) {
                         best = v; best_i = i; best_j = j;
                         best_si = (qid >= 0) ? ec[qid] : 0;
@@ -351,7 +362,7 @@ __global__ void generic_score_results_kernel(const GenPair *__restrict__ pairs, 
 struct GenericBatch;
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                         GenericBatch **out, bool end_matrix = false);
+                         GenericBatch **out, const int32_t *start_cells = nullptr, bool end_cells = false);
 int generic_batch_run(GenericBatch *g, c4b_score threshold);
 int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity);
 int64_t generic_batch_cells(const GenericBatch *g);

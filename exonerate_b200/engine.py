@@ -20,7 +20,7 @@ EXPORTS = [
     "c4b_engine_set_stream", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
-    "c4b_viterbi_calculate", "c4b_viterbi_end_matrix", "c4b_hsp_extend_batch",
+    "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch",
 ]
 
 _lib = None

@@ -244,15 +244,26 @@ int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model,
                           int mode, c4b_result *result, int32_t *ops,
                           int64_t ops_capacity);
 
-/* ---- BSDP bound fills (first part) ------------------
- * Heuristic_Bound_create (src/bsdp/heuristic.c:150-207) scores a copy of a derived model
- * whose END state is in scope everywhere and whose cell_end callback is
- * Heuristic_Bound_report_end_func (:139-145, "matrix[%QP][%TP] = %C[0]"): it wants END's
- * score of EVERY cell.  One synchronous FIND_SCORE lattice; matrix is
- * (query_length+1) x (target_length+1) row-major (query-major); cells where END was not
- * reached are left untouched.  result as for c4b_viterbi_calculate mode 0. */
-int c4b_viterbi_end_matrix(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
-                           const c4b_pair *pair, c4b_score *matrix, c4b_result *result);
+/* ---- BSDP derived models with cell callbacks -------
+ * The heuristic path scores derived models whose START / END states carry callbacks
+ * (C4_Model_configure_start_state / _end_state, src/c4/c4.h; used by
+ * src/bsdp/heuristic.c only):
+ *   cell_end_func(cell, cell_size, query_pos, target_pos, user_data)   viterbi.c:792-797
+ *     Heuristic_Bound_report_end_func (heuristic.c:139-145, bound fills :150-207) and
+ *     Heuristic_Span_src_report_end_func (:385-410) -- both only READ END's cell of every
+ *     lattice cell that reaches END;
+ *   cell_start_func(query_pos, target_pos, user_data) -> cell              viterbi.c:727-741
+ *     Heuristic_Span_dst_init_start_func (:412-443) -- START's score and shadow slots per cell.
+ * Callbacks cannot run on the device, and they do not need to: the binding evaluates
+ * cell_start_func for every cell of the region beforehand (start_cells) and calls
+ * cell_end_func afterwards on what the device returns (end_cells).  Both tables are
+ * (query_length+1) x (target_length+1) cells (query-major) of 1 + n_shadow_slots ints;
+ * end_cells entries of cells that never reach END are left untouched; either may be NULL.
+ * mode 0 FIND_SCORE, 1 FIND_PATH; one synchronous lattice, table-driven kernel. */
+int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
+                                const c4b_pair *pair, int mode, const c4b_score *start_cells,
+                                c4b_score *end_cells, c4b_result *result, int32_t *ops,
+                                int64_t ops_capacity);
 
 /* ---- HSP seeding / extension ----------------------
  * Replaces the per-seed work of HSPset_seed_hsp (src/comparison/hspset.c:933-997):

@@ -143,10 +143,8 @@ static void flatten_model(C4_Model *model, c4b_model *out){
     || (model->total_shadow_designations > C4B_MAX_SHADOW_SLOTS))
         g_error("libc4b200: model [%s] exceeds the engine's table sizes",
                 model->name);
-    if(model->start_state->cell_start_func
-    || (model->end_state->cell_end_func && !model_is_bound(model)))
-        g_error("libc4b200: model [%s] uses cell callbacks (BSDP span model);"
-                " they have no device form yet", model->name);
+    /* cell_start_func / cell_end_func (BSDP derived models) are evaluated by
+     * Viterbi_calculate around the device fill: see c4b_viterbi_calculate_cells */
     out->n_states = model->state_list->len;
     out->n_transitions = model->transition_list->len;
     out->n_calcs = model->calc_list->len;
@@ -365,7 +363,8 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         for(i = 0; i <= Q; i++)
             for(j = 0; j <= T; j++)
                 flat[(gsize)i*(T+1)+j] = matrix[region->query_start+i][region->target_start+j];
-        if(c4b_viterbi_end_matrix(get_engine(), tables, &scoring, &pair, flat, &result))
+        if(c4b_viterbi_calculate_cells(get_engine(), tables, &scoring, &pair, 0,
+                                       NULL, flat, &result, NULL, 0))
             g_error("libc4b200: %s", c4b_last_error());
         for(i = 0; i <= Q; i++)
             for(j = 0; j <= T; j++)
@@ -441,7 +440,49 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         path = g_new0(B200_Path, 1);
         path->ops = g_new(gint32, 2*ops_capacity);
         }
-    if(c4b_viterbi_calculate(get_engine(), tables, &scoring, &pair, mode,
+    if(viterbi->model->start_state->cell_start_func
+    || viterbi->model->end_state->cell_end_func){
+        /* BSDP span models (src/bsdp/heuristic.c:445-528): the callbacks read / write the
+         * integration matrices on the host; the device gets START's cell of every lattice
+         * cell as a table and returns END's cell wherever END was reached */
+        register gint C = 1 + viterbi->model->total_shadow_designations,
+                      Q = region->query_length, T = region->target_length;
+        register gsize ncell = (gsize)(Q+1)*(T+1);
+        register c4b_score *start_cells = NULL, *end_cells = NULL, *cell;
+        register gint l;
+        if(mode == 2)
+            g_error("libc4b200: FIND_REGION on a model with cell callbacks");
+        if(viterbi->model->start_state->cell_start_func){
+            start_cells = g_new(c4b_score, ncell*C);
+            for(i = 0; i <= Q; i++)
+                for(j = 0; j <= T; j++){
+                    cell = viterbi->model->start_state->cell_start_func(
+                               region->query_start+i, region->target_start+j, user_data);
+                    for(l = 0; l < C; l++)
+                        start_cells[((gsize)i*(T+1)+j)*C+l] = cell[l];
+                    }
+            }
+        if(viterbi->model->end_state->cell_end_func){
+            end_cells = g_new(c4b_score, ncell*C);
+            for(i = 0; i < ncell*C; i++)
+                end_cells[i] = C4_IMPOSSIBLY_LOW_SCORE - 1; /* "END not reached" */
+            }
+        if(c4b_viterbi_calculate_cells(get_engine(), tables, &scoring, &pair, mode,
+                start_cells, end_cells, &result, path?path->ops:NULL, ops_capacity))
+            g_error("libc4b200: %s", c4b_last_error());
+        if(end_cells){ /* same visiting order as the fill: target outer, query inner */
+            for(j = 0; j <= T; j++)
+                for(i = 0; i <= Q; i++){
+                    cell = &end_cells[((gsize)i*(T+1)+j)*C];
+                    if(cell[0] != (C4_IMPOSSIBLY_LOW_SCORE - 1))
+                        viterbi->model->end_state->cell_end_func(cell, C,
+                            region->query_start+i, region->target_start+j, user_data);
+                    }
+            g_free(end_cells);
+            }
+        if(start_cells)
+            g_free(start_cells);
+    } else if(c4b_viterbi_calculate(get_engine(), tables, &scoring, &pair, mode,
                              &result, path?path->ops:NULL, ops_capacity))
         g_error("libc4b200: %s", c4b_last_error());
     /* what a Viterbi_DP_Func leaves in vd (viterbi.c:464-478,633-653) */

@@ -43,6 +43,14 @@ COMMANDS = {
                                                        "--gappedextension", "no"]),
     "bsdp_affine_local_protein": ("q_prot.fa", "t_prot.fa", ["--model", "affine:local", "--exhaustive", "no",
                                                              "--gappedextension", "no"]),
+    # ... and the span models of the spliced / codon models (cell_start / cell_end callbacks
+    # evaluated by the binding around the device fill, c4b_viterbi_calculate_cells)
+    "bsdp_est2genome": ("q_cdna.fa", "t_gene.fa", ["--model", "est2genome", "--exhaustive", "no",
+                                                   "--gappedextension", "no"]),
+    "bsdp_protein2genome": ("q_prot.fa", "t_gene_p.fa", ["--model", "protein2genome", "--exhaustive", "no",
+                                                         "--gappedextension", "no"]),
+    "bsdp_coding2coding": ("q_cds.fa", "t_cds.fa", ["--model", "coding2coding", "--exhaustive", "no",
+                                                    "--gappedextension", "no"]),
     "ryo": ("q_dna.fa", "t_dna.fa", ["--model", "affine:local", "--exhaustive", "yes",
                                                    "--subopt", "no", "--ryo", "%qi %ti %s %pi %em\\n"]),
 }

@@ -10,8 +10,9 @@ percent identity, sub-optimal series (--subopt yes), reverse-complement passes.
 
 The bsdp_* command lines run the heuristic path instead (--exhaustive no
 --gappedextension no): HSP seeding and SAR stay the reference's host code, and
-every DP they ask for -- the bound fills of Heuristic_create (END-score matrix),
-terminal and join fills on derived models with SubOpt blocking -- is ours.
+every DP they ask for -- the bound fills of Heuristic_create (END-cell table),
+terminal and join fills on derived models with SubOpt blocking, the span models of
+est2genome / protein2genome / coding2coding with their cell callbacks -- is ours.
 
 The binary exists only where the reference was present at build time; it
 travels to the GPU box with the snapshot.  Skipped (not failed) if absent."""
