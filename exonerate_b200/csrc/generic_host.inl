@@ -96,7 +96,9 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     const c4b_model &m = *model;
     const bool splice = model_needs_splice(m);
     // REGION-then-box is only self-consistent for ANYWHERE starts (see tests/test_oracle_golden.py)
-    g->use_region = want_path && m.start_scope == C4B_SCOPE_ANYWHERE && m.end_scope == C4B_SCOPE_ANYWHERE;
+    // (cell-callback tables are indexed by region cell: those lattices take the direct PATH pass)
+    g->use_region = want_path && m.start_scope == C4B_SCOPE_ANYWHERE && m.end_scope == C4B_SCOPE_ANYWHERE &&
+                    !start_cells && !end_cells;
     g->cmax = 1 + m.n_shadow_slots + (g->use_region ? 2 : 0);
     int dev = 0;
     cudaGetDevice(&dev);

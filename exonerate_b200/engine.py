@@ -59,6 +59,9 @@ def load_library():
     lib.c4b_batch_device_results.restype = C.c_void_p
     lib.c4b_batch_cells.argtypes = [C.c_void_p]
     lib.c4b_batch_cells.restype = C.c_int64
+    lib.c4b_viterbi_calculate_cells.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), P(abi.Pair), C.c_int,
+                                                C.c_void_p, C.c_void_p, P(abi.Result), C.c_void_p, C.c_int64]
+    lib.c4b_viterbi_calculate_cells.restype = C.c_int
     lib.c4b_hsp_extend_batch.argtypes = [C.c_void_p, P(abi.Scoring), P(abi.HspParam), C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p]
@@ -257,6 +260,19 @@ class Optimal:
     def find_path(self, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE, ops_capacity=None):
         results, ops = self.find_path_raw(pairs, threshold, ops_capacity)
         return results_to_list(results, ops, pairs.n)
+
+
+def viterbi_calculate_cells(engine, model, scoring, pairs, mode, start_cells=None, end_cells=None, max_ops=1 << 14):
+    """c4b_viterbi_calculate_cells on lattice 0 of `pairs` (BSDP derived models: START-cell
+    table in, END-cell table out; int32 numpy arrays).  Returns results_to_list()[0]."""
+    lib = engine.lib
+    res = (abi.Result * 1)()
+    ops = np.zeros(2 * max_ops, dtype=np.int32)
+    _check(lib, lib.c4b_viterbi_calculate_cells(engine.h, C.byref(model), C.byref(scoring), pairs.array, mode,
+                                                start_cells.ctypes.data if start_cells is not None else None,
+                                                end_cells.ctypes.data if end_cells is not None else None,
+                                                res, ops.ctypes.data, max_ops), "c4b_viterbi_calculate_cells")
+    return results_to_list(res, ops, 1)[0]
 
 
 class HSPset:

@@ -131,7 +131,16 @@ static int ops_add(int32_t *ops, int64_t cap, int32_t *n_ops, int transition) {
 /* ---- the fill: Viterbi_interpreted, src/c4/viterbi.c:655-837 ----------- */
 int c4o_viterbi(const c4b_model *m, const c4b_scoring *s, const c4b_pair *p, int mode,
                 c4b_result *res, int32_t *ops, int64_t ops_capacity) {
+    return c4o_viterbi_cells(m, s, p, mode, NULL, NULL, res, ops, ops_capacity);
+}
+
+/* ... with the START / END cell callbacks of BSDP derived models as tables
+ * (cell_start_func viterbi.c:727-741, cell_end_func :792-797; see c4b_viterbi_calculate_cells) */
+int c4o_viterbi_cells(const c4b_model *m, const c4b_scoring *s, const c4b_pair *p, int mode,
+                      const c4b_score *start_cells, c4b_score *end_cells,
+                      c4b_result *res, int32_t *ops, int64_t ops_capacity) {
     const int S = m->n_states, Tn = m->n_transitions;
+    c4b_score dummy_start[1 + C4B_MAX_SHADOW_SLOTS + 2];
     const int ql = p->query_length, tl = p->target_length;
     const int mta = m->max_target_advance;
     int C = 1 + m->n_shadow_slots; /* Viterbi_get_cell_size, viterbi.c:42-56 */
@@ -177,7 +186,14 @@ int c4o_viterbi(const c4b_model *m, const c4b_scoring *s, const c4b_pair *p, int
                 if (tr->label == C4B_LABEL_MATCH && p->n_blocked && is_blocked(p, i, j))
                     continue; /* :701-704 */
                 dst = CELL(j, i, tr->output);
-                if (tr->input == m->start_state) {
+                if (tr->input == m->start_state && start_cells) {
+                    /* cell_start_func's cell is copied and stands in for the source (:727-741) */
+                    for (l = 0; l < C; l++)
+                        dummy_start[l] = (l <= m->n_shadow_slots)
+                            ? start_cells[((size_t)sq * (tl + 1) + st) * (1 + m->n_shadow_slots) + l] : 0;
+                    src = dummy_start;
+                    t = src[0];
+                } else if (tr->input == m->start_state) {
                     /* t = 0 without a cell_start_func (:720-745); the START
                      * state's own row cell supplies the shadow slots. */
                     src = CELL(st, sq, tr->input);
@@ -212,6 +228,9 @@ int c4o_viterbi(const c4b_model *m, const c4b_scoring *s, const c4b_pair *p, int
             }
             if (is_set[m->end_state]) { /* :778-791, Viterbi_Data_register_end :464-478 */
                 c4b_score *cell = CELL(j, i, m->end_state);
+                if (end_cells) /* what cell_end_func is handed (:792-797) */
+                    for (l = 0; l <= m->n_shadow_slots; l++)
+                        end_cells[((size_t)i * (tl + 1) + j) * (1 + m->n_shadow_slots) + l] = cell[l];
                 if (!end_is_set || score < cell[0]) {
                     score = cell[0];
                     end_is_set = 1;

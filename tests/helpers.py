@@ -250,6 +250,10 @@ def oracle():
                                          C.POINTER(abi.Result), C.c_void_p]
         lib.c4o_rescore_path.restype = C.c_int32
         lib.c4o_transition_is_valid.argtypes = [C.POINTER(abi.Model)] + [C.c_int] * 5
+        lib.c4o_viterbi_cells.argtypes = [C.POINTER(abi.Model), C.POINTER(abi.Scoring), C.POINTER(abi.Pair),
+                                          C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.Result), C.c_void_p,
+                                          C.c_int64]
+        lib.c4o_viterbi_cells.restype = C.c_int
         lib.c4o_hsp_extend_one.argtypes = [C.POINTER(abi.Scoring), C.POINTER(abi.HspParam), C.c_void_p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, abi.HspSeed,
                                            C.POINTER(abi.Hsp)]
@@ -425,3 +429,16 @@ def hspset_replay(param, qlen, seeds, ext):
     out = (abi.Hsp * max(1, n))()
     cnt = lib.c4o_hspset_replay(C.byref(param), qlen, n, sd, ext, out)
     return [hsp_tuple(out[k]) for k in range(cnt)]
+
+
+def oracle_viterbi_cells(model, scoring, pb, mode, start_cells=None, end_cells=None, max_ops=1 << 14):
+    """c4o_viterbi_cells: the fill with cell_start_func / cell_end_func as tables"""
+    lib = oracle()
+    res = abi.Result()
+    ops = np.zeros(2 * max_ops, dtype=np.int32)
+    rc = lib.c4o_viterbi_cells(C.byref(model), C.byref(scoring), C.byref(pb.pair), mode,
+                               start_cells.ctypes.data if start_cells is not None else None,
+                               end_cells.ctypes.data if end_cells is not None else None,
+                               C.byref(res), ops.ctypes.data, max_ops)
+    assert rc == 0, rc
+    return result_to_dict(res, ops)

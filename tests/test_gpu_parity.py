@@ -634,3 +634,51 @@ def test_hsp_extend_large_random_vs_oracle(eng, scoring):
         h4 = HSPset(eng, scoring, param, "ACGT-ACGTACGTACG", "ACGTACGTACGTACGT")
         h4.seed_hsp(0, 0)
         h4.finalise()
+
+
+# ---------------------------------------------------------------------------
+# BSDP derived models: cell callbacks as tables
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["est2genome", "affine_local_dna", "protein2genome"])
+def test_cell_callback_tables_vs_oracle(eng, params, scoring, name):
+    """c4b_viterbi_calculate_cells: START's score and shadow slots per cell come from a
+    table (what cell_start_func returns), END's cell is returned wherever END is reached
+    (what cell_end_func is handed) -- random tables incl. impossible starts, FIND_SCORE
+    and FIND_PATH, against the oracle."""
+    from exonerate_b200 import PairSet
+    from exonerate_b200.engine import viterbi_calculate_cells
+    from exonerate_b200.models import splice_arrays
+    model, _ = helpers.load_model(name, params)
+    rng = np.random.default_rng(17)
+    C_ = 1 + model.n_shadow_slots
+    for trial, (ql, tl) in enumerate([(40, 90), (25, 300), (70, 70)]):
+        if name == "protein2genome":
+            q, _t = helpers.protein_pair(5100 + trial, ql, 30)
+            t = helpers.rand_dna(random.Random(trial), tl)
+        else:
+            q, t = helpers.gene_pair(5000 + trial, ql, tl, n_exons=2) if name == "est2genome" else \
+                helpers.dna_pair(5000 + trial, ql, tl)
+        sp = splice_arrays(t) if name in ("est2genome", "protein2genome") else None
+        cells = (len(q) + 1) * (len(t) + 1)
+        start = np.zeros((cells, C_), dtype=np.int32)
+        start[:, 0] = rng.integers(-40, 60, cells)
+        start[rng.random(cells) < 0.5, 0] = abi.IMPOSSIBLY_LOW_SCORE
+        if C_ > 1:   # shadow slots are sequence positions (<= the cell's own column)
+            cols = np.tile(np.arange(len(t) + 1), len(q) + 1)
+            for l in range(1, C_):
+                start[:, l] = (cols * rng.random(cells)).astype(np.int32)
+        pairs = PairSet([q], [t], splice=[sp])
+        pb = helpers.PairBuf(q, t, splice=sp)
+        for mode in (abi.MODE_FIND_SCORE, abi.MODE_FIND_PATH):
+            end_got = np.full((cells, C_), -7, dtype=np.int32)
+            end_want = np.full((cells, C_), -7, dtype=np.int32)
+            got = viterbi_calculate_cells(eng, model, scoring, pairs, mode, start, end_got)
+            want = helpers.oracle_viterbi_cells(model, scoring, pb, mode, start, end_want)
+            assert got["score"] == want["score"], (name, trial, mode)
+            assert (end_got == end_want).all(), (name, trial, mode)
+            if mode == abi.MODE_FIND_PATH:
+                assert got["region"] == want["region"] and got["ops"] == want["ops"], (name, trial)
+        # without tables the call is the plain fill
+        plain = viterbi_calculate_cells(eng, model, scoring, pairs, abi.MODE_FIND_PATH)
+        ref = helpers.oracle_viterbi(model, scoring, pb, abi.MODE_FIND_PATH)
+        assert plain["score"] == ref["score"] and plain["ops"] == ref["ops"]
