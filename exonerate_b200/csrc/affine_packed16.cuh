@@ -236,6 +236,7 @@ __device__ __forceinline__ uint32_t imad_add(uint32_t a, int one, uint32_t k) {
     return d;
 }
 
+// one sweep, one warp per pair of lattices (the metric configuration): 168 registers, 12 CTAs per SM
 template <int R>
 __global__ void __launch_bounds__(32, 12)
 affine_fill16u_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
@@ -395,6 +396,246 @@ affine_fill16u_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ ou
     }
 }
 
+
+// The same kernel for queries of several sweeps (kept separate: folding the sweep loop away at
+// compile time still cost the one-sweep kernel 10 % on the B200).  MULTI is always true here.
+template <int R, bool MULTI>
+__device__ __forceinline__ void affine_fill16u_body(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
+                                                    const int n, const AffModel &mdl,
+                                                    const void *__restrict__ score_table) {
+    // blockDim.x = 32 W.  Queries longer than one sweep (32 R rows) are swept in strips,
+    // and the W warps of the CTA run the strips of this PAIR of lattices concurrently as a
+    // pipeline, exactly as affine_fill_kernel does (hand-off row {G, I} of both lattices in
+    // lattice A's top0/top1 buffers, published through a monotone counter in shared memory).
+    __shared__ uint32_t xt4[25];
+    __shared__ volatile long long vprog[kAffMaxWarps];
+    __shared__ int red[kAffMaxWarps][6];
+    const int lane = threadIdx.x & 31, warp = MULTI ? (int)(threadIdx.x >> 5) : 0, W = MULTI ? (int)(blockDim.x >> 5) : 1;
+    const int ia = 2 * blockIdx.x, ib = min(ia + 1, n - 1);
+    const AffPair PA = pairs[ia], PB = pairs[ib];
+    const int QA = PA.Q, TA = PA.T, QB = PB.Q, TB_ = PB.T;
+    const int T = max(TA, TB_);
+    if (threadIdx.x < 25) xt4[threadIdx.x] = reinterpret_cast<const uint2 *>(score_table)[threadIdx.x].x;  // classes 0..3, all >= 0
+    if (MULTI && threadIdx.x < kAffMaxWarps) vprog[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int open = mdl.openD, one = mdl.one;
+    // x + {p, p} for a penalty p < 0 and halves >= |p|: one 32-bit add of p * 0x10001
+    const uint32_t openK = (uint32_t)(open * 0x10001), extDK = (uint32_t)(mdl.extD * 0x10001);
+    const uint32_t extI2 = pack16(mdl.extI);  // per-half operand of VIADDMNMX.U16x2 (wraps per half)
+    const int nsteps = T + 1 + 31;
+    const int rows_per_sweep = 32 * R;
+    const int nsweeps = MULTI ? (max(QA, QB) + 1 + rows_per_sweep - 1) / rows_per_sweep : 1;
+
+    uint32_t best2 = 0u;  // below every stored value
+    int bjA = 0, biA = 0, bjB = 0, biB = 0;
+
+    for (int sweep = warp; sweep < nsweeps; sweep += W) {
+        const int row0 = sweep * rows_per_sweep + lane * R;
+        const bool later_sweep = MULTI && (sweep > 0);
+        const bool first_row_lane = (sweep == 0 && lane == 0);
+        // within one sweep columns arrive in increasing j, so only a strictly greater score can
+        // be an earlier END; a LATER sweep of this warp can tie an earlier one at a smaller j
+        const bool tie_possible = MULTI && (sweep != warp);
+        uint32_t sel[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + r;
+            uint32_t sa = 0x88u, sb = 0xCCu;  // padding: sign of a (non-negative) pool byte = 0
+            if (i >= 1 && i <= QA) { const uint32_t c = PA.q[i - 1]; sa = c | ((c | 8u) << 4); }
+            if (i >= 1 && i <= QB) { const uint32_t c = 4u + PB.q[i - 1]; sb = c | ((c | 8u) << 4); }
+            sel[r] = sa | (sb << 8);
+        }
+        uint32_t Mp[R], Dp[R];  // G = M + open and D of the previous column (offset binary)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Mp[r] = kNegU16x2;
+            Dp[r] = kNegU16x2;
+        }
+        const uint2 *top_in = reinterpret_cast<const uint2 *>((sweep & 1) ? PA.top0 : PA.top1);  // written by sweep-1
+        uint2 *top_out = reinterpret_cast<uint2 *>((sweep & 1) ? PA.top1 : PA.top0);
+        const bool write_top = MULTI && (sweep + 1 < nsweeps) && (lane == 31);
+        const bool piped = MULTI && later_sweep && W > 1;
+        const int wp = (sweep - 1) % W;
+        const long long in_base = (long long)(sweep - 1) * (T + 1);
+        long long avail = 0;
+        auto wait_column = [&](int col) {
+            const long long need = in_base + col + 1;
+            if (avail < need) {
+                while ((avail = vprog[wp]) < need) __nanosleep(40);
+                __threadfence_block();
+            }
+        };
+        uint32_t topM = kNegU16x2, topI = kNegU16x2, topMprev = kNegU16x2;
+        uint32_t in_code = kTargetNone | (kTargetNone << 8), code0 = in_code;
+        uint2 top0v = make_uint2(kNegU16x2, kNegU16x2);
+        if (later_sweep) {
+            if (piped) wait_column(0);
+            top0v = __ldcg(top_in);
+        }
+
+        uint32_t pend = 0u;
+        int pend_j = 0;
+        auto settle_pending = [&]() {
+            const uint32_t nb = __vmaxu2(best2, pend);
+            // strictly greater in some half, or (later sweeps of this warp) a tie at a smaller j
+            bool trig = (nb != best2);
+            if (tie_possible)
+                trig = trig || (pend != 0u && ((((pend ^ best2) & 0xFFFFu) == 0 && pend_j < bjA) ||
+                                               (((pend ^ best2) >> 16) == 0 && pend_j < bjB)));
+            if (trig) {
+                const uint32_t pl = pend & 0xFFFFu, bl = best2 & 0xFFFFu, ph = pend >> 16, bh = best2 >> 16;
+                if (pl > bl || (pl == bl && pl != 0u && pend_j < bjA)) {
+                    int bi = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (!found && ((Mp[r] ^ pend) & 0xFFFFu) == 0) { bi = row0 + r; found = true; }
+                    biA = bi;
+                    bjA = pend_j;
+                }
+                if (ph > bh || (ph == bh && ph != 0u && pend_j < bjB)) {
+                    int bi = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (!found && ((Mp[r] ^ pend) >> 16) == 0) { bi = row0 + r; found = true; }
+                    biB = bi;
+                    bjB = pend_j;
+                }
+                best2 = nb;
+            }
+            pend = 0u;
+        };
+
+        auto step = [&](const int s, auto ALL) {
+            constexpr bool all_active = decltype(ALL)::value;
+            const int j = s - lane;
+            settle_pending();
+            const uint32_t code = (lane == 0) ? code0 : in_code;
+            if (later_sweep && lane == 0) {
+                topM = top0v.x;
+                topI = top0v.y;
+            }
+            {
+                const uint32_t ca = (s + 1 <= TA) ? (uint32_t)PA.t[s] : (uint32_t)kTargetNone;
+                const uint32_t cb = (s + 1 <= TB_) ? (uint32_t)PB.t[s] : (uint32_t)kTargetNone;
+                code0 = ca | (cb << 8);
+                if (later_sweep && s + 1 <= T) {
+                    if (piped) wait_column(s + 1);
+                    top0v = __ldcg(top_in + s + 1);
+                }
+            }
+            uint32_t botM = kNegU16x2, botI = kNegU16x2;
+            if (all_active || (j >= 0 && j <= T)) {
+                const uint32_t Xa = xt4[code & 0xFFu], Xb = xt4[code >> 8];
+                uint32_t cm = 0u;
+                // phase A, bottom-up, rows independent: D, then G~ = max(match, D, START) + open
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) {
+                    uint32_t sc;
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(Xa), "r"(Xb), "r"(sel[r]));
+                    const uint32_t diag = (r == 0) ? topMprev : Mp[r - 1];
+                    Dp[r] = __vmaxu2(imad_add(Dp[r], one, extDK), Mp[r]);
+                    const uint32_t x = __vimax3_u16x2(imad_add(diag, one, sc), Dp[r], kBias16x2);
+                    Mp[r] = imad_add(x, one, openK);
+                }
+                // phase B, top-down: I chain (one op per row), G = max(G~, I + open) off the chain
+                uint32_t Iv = __viaddmax_u16x2(topI, extI2, topM);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t gt = Mp[r];
+                    const uint32_t Gv = __vmaxu2(gt, imad_add(Iv, one, openK));
+                    Mp[r] = Gv;
+                    if (r & 1) cm = __vimax3_u16x2(cm, Gv, Mp[r - 1]);
+                    if (r + 1 < R) Iv = __viaddmax_u16x2(Iv, extI2, gt);
+                }
+                botM = Mp[R - 1];
+                botI = Iv;
+                topMprev = topM;
+                pend = cm;
+                pend_j = j;
+                if (write_top) {
+                    top_out[j] = make_uint2(botM, botI);
+                    if (MULTI && W > 1) {
+                        __threadfence_block();
+                        vprog[warp] = (long long)sweep * (T + 1) + j + 1;
+                    }
+                }
+            }
+            if (first_row_lane) { topM = kNegU16x2; topI = kNegU16x2; }
+            const uint32_t nM = __shfl_up_sync(0xffffffffu, botM, 1);
+            const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
+            const uint32_t nC = __shfl_up_sync(0xffffffffu, code, 1);
+            if (lane > 0) {
+                topM = nM;
+                topI = nI;
+                in_code = nC;
+            }
+        };
+
+        const int fill_end = min(31, nsteps);
+        const int steady_end = max(fill_end, min(T + 1, nsteps));
+        int s = 0;
+        for (; s < fill_end; ++s) step(s, std::false_type{});
+        for (; s < steady_end; ++s) step(s, std::true_type{});
+        for (; s < nsteps; ++s) step(s, std::false_type{});
+        settle_pending();
+        __syncwarp();
+    }
+
+    int bA = (int)(best2 & 0xFFFFu), bB = (int)(best2 >> 16);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bA, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjA, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biA, off);
+            if ((ob > bA) || (ob == bA && (oj < bjA || (oj == bjA && oi < biA)))) { bA = ob; bjA = oj; biA = oi; }
+        }
+        {
+            const int ob = __shfl_xor_sync(0xffffffffu, bB, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bjB, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, biB, off);
+            if ((ob > bB) || (ob == bB && (oj < bjB || (oj == bjB && oi < biB)))) { bB = ob; bjB = oj; biB = oi; }
+        }
+    }
+    if (MULTI && W > 1) {   // combine the warps' sweeps (idle warps carry 0 = below every stored value)
+        if (lane == 0) {
+            red[warp][0] = bA; red[warp][1] = bjA; red[warp][2] = biA;
+            red[warp][3] = bB; red[warp][4] = bjB; red[warp][5] = biB;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w < W; ++w) {
+                int ob = red[w][0], oj = red[w][1], oi = red[w][2];
+                if ((ob > bA) || (ob == bA && (oj < bjA || (oj == bjA && oi < biA)))) { bA = ob; bjA = oj; biA = oi; }
+                ob = red[w][3]; oj = red[w][4]; oi = red[w][5];
+                if ((ob > bB) || (ob == bB && (oj < bjB || (oj == bjB && oi < biB)))) { bB = ob; bjB = oj; biB = oi; }
+            }
+    }
+    if (threadIdx.x == 0) {
+        AffOut o;
+        o.best = bA - (int)kBias16 - open;  // tracked as G = M + open, offset binary
+        o.end_i = biA;
+        o.end_j = bjA;
+        o.flags = 0;
+        outs[PA.out_index] = o;
+        if (ia + 1 < n) {
+            o.best = bB - (int)kBias16 - open;
+            o.end_i = biB;
+            o.end_j = bjB;
+            outs[PB.out_index] = o;
+        }
+    }
+}
+
+// long queries: up to 8 warps per pair of lattices, sweeps pipelined
+__global__ void __maxnreg__(168)   // 3 CTAs of 4 warps, or 1 of 8, per SM
+affine_fill16u_multi_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
+                            const AffModel mdl, const void *__restrict__ score_table) {
+    affine_fill16u_body<32, true>(pairs, outs, n, mdl, score_table);
+}
 
 // -----------------------------------------------------------------------------
 // affine_fill16tb_kernel: the TRACEBACK pass with two lattices per warp.  Used for

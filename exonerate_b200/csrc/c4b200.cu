@@ -236,6 +236,7 @@ struct c4b_batch {
     int fill_warps = 1;  // warps per lattice of the int32 fill (concurrent sweeps of long queries)
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
+    bool p16_multi = false;     // some packed lattice needs more than one sweep
     bool tb16_band = false, tb16_direct = false;  // traceback pass on affine_fill16tb_kernel
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
@@ -351,12 +352,16 @@ int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, boo
 int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
     if (!count) return 0;
     const int blocks = (count + 1) / 2;
+    // the offset-binary variant sweeps long queries with up to 8 pipelined warps per CTA
+    const int threads = (b->p16_unsigned && b->p16_multi) ? 32 * b->fill_warps : 32;
     auto go = [&](auto kernel) -> int {
-        kernel<<<blocks, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
+        kernel<<<blocks, threads, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
         return 0;
     };
     int rc;
-    if (b->p16_unsigned) {
+    if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep (R is 32 then)
+        rc = go(affine_fill16u_multi_kernel);
+    } else if (b->p16_unsigned) {
         switch (b->R) {
         case 8: rc = go(affine_fill16u_kernel<8>); break;
         case 16: rc = go(affine_fill16u_kernel<16>); break;
@@ -616,21 +621,24 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const bool model_ok = allow && local && b->score_mode == SCORE_PRMT && max_sub > 0 &&
                               b->aff.openD < 0 && b->aff.openD > -1000 && b->aff.extD < 0 && b->aff.extD > -1000 &&
                               b->aff.extI < 0 && b->aff.extI > -1000;
-        auto fits16 = [&](int p) {
-            const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
-            // per lattice: a query of primary symbols only (classes 0..3), one sweep, values in 15 bits
-            return model_ok && !query_wide[p] && Q + 1 <= 32 * b->R &&
-                   (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
-        };
-        auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
-        b->n16 = (int)(mid - b->score_list.begin());
         // the offset-binary variant adds score' = s - open as an unsigned halfword and
-        // shortens the I chain with open <= extend
+        // shortens the I chain with open <= extend; it also sweeps queries longer than 32 R rows
         bool nonneg = true;
         for (int a = 0; a < 24; ++a)
             for (int c = 0; c < 24 && used[a]; ++c) nonneg = nonneg && matrix[a * 24 + c] >= b->aff.openD;
         const char *v = getenv("C4B_P16_VARIANT");
         b->p16_unsigned = nonneg && b->aff.openI <= b->aff.extI && !(v && v[0] == 's');
+        auto fits16 = [&](int p) {
+            const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
+            // per lattice: a query of primary symbols only (classes 0..3), values in 15 bits
+            // (the signed variant: one sweep only)
+            return model_ok && !query_wide[p] && (b->p16_unsigned || Q + 1 <= 32 * b->R) &&
+                   (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
+        };
+        auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
+        b->n16 = (int)(mid - b->score_list.begin());
+        for (int k = 0; k < b->n16; ++k)
+            b->p16_multi = b->p16_multi || pairs[b->score_list[k]].query_length + 1 > 32 * b->R;
         // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
         const char *tv = getenv("C4B_AFFINE_TB16");
         const bool tb_ok = model_ok && nonneg && b->aff.openI <= b->aff.extI && b->aff.openD >= -24 &&
@@ -791,12 +799,21 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (b->d_new_off.alloc((size_t)n + 1)) return -1;
     }
     // sweep hand-off rows for queries longer than one sweep
-    std::vector<size_t> top_off(n, (size_t)-1);
+    // (the packed score pass keeps the hand-off row of a PAIR of lattices in the first one's
+    // buffers: they are sized for the longer target / needed if either query is long)
+    std::vector<size_t> top_off(n, (size_t)-1), top_len(n, 0);
+    for (int p = 0; p < n; ++p)
+        if (pairs[p].query_length + 1 > 32 * b->R) top_len[p] = (size_t)pairs[p].target_length + 1;
+    for (int k = 0; k + 1 < b->n16; k += 2) {
+        const int pa = b->score_list[k], pb = b->score_list[k + 1];
+        if (std::max(pairs[pa].query_length, pairs[pb].query_length) + 1 > 32 * b->R)
+            top_len[pa] = std::max(top_len[pa], (size_t)std::max(pairs[pa].target_length, pairs[pb].target_length) + 1);
+    }
     size_t top_elems = 0;
     for (int p = 0; p < n; ++p)
-        if (pairs[p].query_length + 1 > 32 * b->R) {
+        if (top_len[p]) {
             top_off[p] = top_elems;
-            top_elems += 2 * (size_t)(pairs[p].target_length + 1);
+            top_elems += 2 * top_len[p];
         }
     if (b->d_top.alloc(top_elems)) return -1;
 
@@ -819,7 +836,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         a.top0 = a.top1 = nullptr;
         if (top_off[p] != (size_t)-1) {
             a.top0 = b->d_top.p + top_off[p];
-            a.top1 = a.top0 + (pairs[p].target_length + 1);
+            a.top1 = a.top0 + top_len[p];
         }
         a.out_index = slot;
         return a;

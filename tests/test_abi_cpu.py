@@ -45,6 +45,22 @@ def test_struct_sizes_match_header():
     assert C.sizeof(abi.Scoring) == 2 * 576 * 4 + 3 * 256 + 4096 + 8
     assert C.sizeof(abi.Pair) == 16 + 24 + 32 + 16 + 8
     assert C.sizeof(abi.Result) == 40
+    assert C.sizeof(abi.HspParam) == 16 and C.sizeof(abi.HspSeed) == 8 and C.sizeof(abi.Hsp) == 32
+
+
+def test_struct_sizes_match_the_c_compiler(tmp_path):
+    """compile include/c4b200.h with gcc and compare every sizeof with the ctypes mirror"""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "c4b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(c4b_calc),sizeof(c4b_transition),sizeof(c4b_model),sizeof(c4b_scoring),sizeof(c4b_pair),'
+                   'sizeof(c4b_result),sizeof(c4b_hsp_param),sizeof(c4b_hsp_seed),sizeof(c4b_hsp));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(helpers.ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(t) for t in (abi.Calc, abi.Transition, abi.Model, abi.Scoring, abi.Pair, abi.Result,
+                                  abi.HspParam, abi.HspSeed, abi.Hsp)]
+    assert got == want
 
 
 def test_no_cpu_fallback(lib):

@@ -231,8 +231,10 @@ def test_staging_pipeline_many_slices(eng, params, scoring, monkeypatch):
 
 def test_long_queries_pipelined_sweeps(eng, params, scoring, monkeypatch):
     """Queries of many 1024-row sweeps: the warps of a CTA run the sweeps of one lattice
-    concurrently (hand-off row published through a shared-memory counter).  Same answers
-    with 1, 3 and 8 warps, and as the oracle; local and global scopes; ragged batch."""
+    (int32 kernel) or of one pair of lattices (packed score pass, queries up to 6399 bp)
+    concurrently, hand-off row published through a shared-memory counter.  Same answers
+    with 1, 3 and 8 warps, with the packed kernels off, and as the oracle; local and
+    global scopes; ragged batch (partners with different sweep counts)."""
     from exonerate_b200 import Optimal, PairSet
     for name in ("affine_local_dna", "affine_global_dna"):
         model, _ = helpers.load_model(name, params)
@@ -248,7 +250,10 @@ def test_long_queries_pipelined_sweeps(eng, params, scoring, monkeypatch):
             monkeypatch.setenv("C4B_AFFINE_WARPS", w)
             got[w] = (opt.find_score(pairs), opt.find_path(pairs))
         monkeypatch.delenv("C4B_AFFINE_WARPS")
-        assert got["1"] == got["3"] == got["8"]
+        monkeypatch.setenv("C4B_AFFINE_PACK16", "0")   # int32 kernels only
+        got["int32"] = (opt.find_score(pairs), opt.find_path(pairs))
+        monkeypatch.delenv("C4B_AFFINE_PACK16")
+        assert got["1"] == got["3"] == got["8"] == got["int32"]
         for k in range(pairs.n):
             want = oracle_path(model, scoring, qs[k], ts[k])
             assert got["8"][0][k] == want["score"], (name, k)
