@@ -299,6 +299,8 @@ def ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the C4 fill has no CPU fallback)")
     torch.cuda.set_device(local)
+    # host-side staging threads of the engine: the ranks of one box share its cores
+    os.environ.setdefault("C4B_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 16) // world))))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

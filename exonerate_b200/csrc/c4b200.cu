@@ -62,6 +62,14 @@ struct Chunk {
 // batch, allocation and free are bookkeeping, not driver calls that serialise.
 static thread_local cudaStream_t tl_pool_stream = nullptr;
 
+// worker threads for host-side staging: min(16, cores), or C4B_HOST_THREADS (one process
+// per GPU on a shared host should divide the cores: bench.py sets cores / world size)
+static unsigned host_threads() {
+    unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char *env = getenv("C4B_HOST_THREADS")) hw = (unsigned)std::max(1, std::min(64, atoi(env)));
+    return hw;
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -484,7 +492,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         size_t qtotal = 0;
         for (const SeqKey &k : distinct_q) qtotal += (size_t)k.second;
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(
-            std::min(8u, std::max(1u, std::thread::hardware_concurrency())), qtotal >> 20));
+            host_threads(), qtotal >> 20));
         std::vector<std::array<bool, 256>> seen_byte(nt);
         // "narrow" queries hold only the four primary symbols (A, C, G, T of a DNA matrix):
         // those get PRMT classes 0..3, which is what the packed kernels' 4-byte pools hold
@@ -909,7 +917,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     }
     uint8_t *h_seq = e->h_stage;
     memset(h_seq + qbytes + tbytes, tfill, 64);
-    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned hw = host_threads();
     size_t next_group = 0;
     for (size_t si = 0; si < slices.size(); ++si) {
         const Slice &S = slices[si];

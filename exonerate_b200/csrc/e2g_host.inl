@@ -105,7 +105,7 @@ static thread_local PinnedScratch tl_e2g_scratch;
 
 template <typename F>
 static void parallel_for(int n, F f) {
-    const unsigned nt = std::max(1u, std::min<unsigned>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n));
+    const unsigned nt = std::max(1u, std::min<unsigned>(host_threads(), (unsigned)n));
     if (nt <= 1) {
         for (int k = 0; k < n; ++k) f(k);
         return;
