@@ -11,6 +11,7 @@ struct GenericBatch {
     GenTables tables;
     int64_t cells = 0;
     int sm_count = 0, grid = 0, cmax = 1;
+    int threads = 256;  // per CTA: one anti-diagonal of the longest query in one pass if it fits 1024
     std::vector<c4b_pair> host_pairs;
     std::vector<GenPair> h_full;
     DevBuf<GenTables> d_tables;
@@ -170,7 +171,8 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     rc |= g->d_out_b.alloc(n);
     rc |= g->d_results.alloc(n);
     rc |= g->d_cursor.alloc(1);
-    g->grid = std::max(1, std::min(n, g->sm_count * 4));
+    g->threads = (maxQ + 1 > 512) ? 1024 : (maxQ + 1 > 256 ? 512 : 256);
+    g->grid = std::max(1, std::min(n, g->sm_count * (1024 / g->threads)));
     const int depth = m.max_target_advance + m.max_query_advance + 1;
     g->ring_stride = align_up((size_t)depth * (maxQ + 1) * m.n_states * g->cmax, 4);
     rc |= g->d_ring.alloc(g->ring_stride * g->grid);
@@ -237,7 +239,7 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
     if (!count) return 0;
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
     const int grid = std::min(g->grid, count);
-    generic_fill_kernel<<<grid, kGenThreads, 0, g->stream>>>(pairs, count, outs, g->d_tables.p, mode,
+    generic_fill_kernel<<<grid, g->threads, 0, g->stream>>>(pairs, count, outs, g->d_tables.p, mode,
                                                             g->d_ring.p, g->ring_stride, g->d_cursor.p);
     C4B_CUDA(cudaGetLastError());
     (*g->launches)++;

@@ -24,7 +24,7 @@
 
 namespace c4b {
 
-constexpr int kGenThreads = 256;
+constexpr int kGenThreads = 1024;  // upper bound; the host launches 256 / 512 / 1024 by the longest query
 constexpr int kMaxCell = 1 + C4B_MAX_SHADOW_SLOTS + 2;
 
 struct GenPair {
@@ -172,7 +172,8 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
             const int lo = max(0, d - T), hi = min(Q, d);
             for (int i = lo + (int)threadIdx.x; i <= hi; i += blockDim.x) {
                 const int j = d - i;
-                int32_t *cell = ring + (size_t)(j % depth) * col_stride + (size_t)i * S * C;
+                const int jslot = j % depth;   // ring column of this cell; sources are jslot - advance (mod depth)
+                int32_t *cell = ring + (size_t)jslot * col_stride + (size_t)i * S * C;
                 for (int k = 0; k < S; ++k) cell[k * C] = LOW;  // viterbi.c:691-694
                 uint32_t set = 0;
                 for (int k = 0; k < Tn; ++k) {
@@ -182,7 +183,9 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                         !gen_state_active(m, tr.output, i, j, Q, T))
                         continue;  // Layout_is_transition_valid
                     if (tr.label == C4B_LABEL_MATCH && P.n_blocked && gen_blocked(P, i, j)) continue;
-                    const int32_t *src = ring + (size_t)(sj % depth) * col_stride + ((size_t)si * S + tr.input) * C;
+                    int sslot = jslot - tr.advance_target;
+                    if (sslot < 0) sslot += depth;
+                    const int32_t *src = ring + (size_t)sslot * col_stride + ((size_t)si * S + tr.input) * C;
                     int32_t *dst = cell + tr.output * C;
                     const bool from_start = (tr.input == m.start_state);
                     const bool start_cb = from_start && P.start_cells;
@@ -239,7 +242,7 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
         red_score[threadIdx.x] = best; red_i[threadIdx.x] = best_i; red_j[threadIdx.x] = best_j;
         red_si[threadIdx.x] = best_si; red_sj[threadIdx.x] = best_sj;
         __syncthreads();
-        for (int off = kGenThreads / 2; off > 0; off >>= 1) {
+        for (int off = (int)blockDim.x / 2; off > 0; off >>= 1) {
             if ((int)threadIdx.x < off) {
                 const int a = threadIdx.x, b = threadIdx.x + off;
                 const bool take = red_score[b] > red_score[a] ||
