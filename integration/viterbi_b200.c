@@ -40,7 +40,10 @@ Viterbi_ArgumentSet *Viterbi_ArgumentSet_create(Argument *arg){
 /* ---- engine + per-Viterbi tables --------------------------------------------- */
 static c4b_engine *engine = NULL;
 
-static c4b_engine *get_engine(void){
+c4b_engine *exonerate_b200_engine(void); /* shared with hspset_b200.c */
+#define get_engine exonerate_b200_engine
+
+c4b_engine *exonerate_b200_engine(void){
     if(!engine){
         register const gchar *dev = g_getenv("EXONERATE_B200_DEVICE");
         if(c4b_engine_create(dev?atoi(dev):0, &engine))

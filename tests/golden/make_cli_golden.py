@@ -51,6 +51,11 @@ COMMANDS = {
                                                          "--gappedextension", "no"]),
     "bsdp_coding2coding": ("q_cds.fa", "t_cds.fa", ["--model", "coding2coding", "--exhaustive", "no",
                                                     "--gappedextension", "no"]),
+    # default heuristic mode (--gappedextension yes): HSPs seeded on the device through the
+    # hspset binding, gapped extension by the reference's own SDP code (out of scope, CPU)
+    "sdp_affine_local_dna": ("q_dna.fa", "t_dna.fa", ["--model", "affine:local"]),
+    "sdp_est2genome": ("q_cdna.fa", "t_gene.fa", ["--model", "est2genome"]),
+    "ungapped_dna": ("q_dna.fa", "t_dna.fa", ["--model", "ungapped"]),
     "ryo": ("q_dna.fa", "t_dna.fa", ["--model", "affine:local", "--exhaustive", "yes",
                                                    "--subopt", "no", "--ryo", "%qi %ti %s %pi %em\\n"]),
 }

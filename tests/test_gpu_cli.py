@@ -39,3 +39,18 @@ def test_cli_output_identical_to_reference(name):
     assert got.returncode == 0, got.stderr[-2000:]
     assert got.stdout == want
     assert len(want.splitlines()) >= 2
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")
+@pytest.mark.parametrize("name", ["bsdp_affine_local_dna", "bsdp_protein2genome", "ungapped_dna"])
+def test_cli_heuristic_runs_extend_hsps_on_the_device(name):
+    """the hspset binding (integration/hspset_b200.c) really is on the path: the seeds of
+    DNA2DNA / PROTEIN2DNA comparisons are extended by c4b_hsp_extend_batch"""
+    import re
+    env = dict(os.environ, EXONERATE_B200_STATS="1")
+    got = subprocess.run([BIN] + COMMANDS[name], cwd=CLI, capture_output=True, text=True, timeout=600, env=env)
+    assert got.returncode == 0, got.stderr[-2000:]
+    m = re.search(r"hsp batches (\d+), seeds extended on the device (\d+), seeds passed to the reference (\d+)",
+                  got.stderr)
+    assert m, got.stderr[-500:]
+    assert int(m.group(1)) >= 1 and int(m.group(2)) >= 1 and int(m.group(3)) == 0
