@@ -1340,7 +1340,8 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
         return -1;
     }
     const int kind = param->match_kind;
-    if (kind != C4B_CALC_MATCH_DNA && kind != C4B_CALC_MATCH_PROTEIN && kind != C4B_CALC_MATCH_1_3) {
+    if (kind != C4B_CALC_MATCH_DNA && kind != C4B_CALC_MATCH_PROTEIN && kind != C4B_CALC_MATCH_1_3 &&
+        kind != C4B_CALC_MATCH_3_1 && kind != C4B_CALC_MATCH_3_3) {
         set_error("c4b_hsp_extend_batch: match kind has no device form");
         return -1;
     }
@@ -1349,10 +1350,11 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
         return -1;
     }
     if (n_seeds == 0) return 0;
-    const int tadv = (kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    const int tadv = (kind == C4B_CALC_MATCH_1_3 || kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
+    const int qadv = (kind == C4B_CALC_MATCH_3_1 || kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
     for (int k = 0; k < n_seeds; ++k)   // HSP_check (hspset.c): the seed lies inside both sequences
         if (seeds[k].query_start < 0 || seeds[k].target_start < 0 ||
-            (int64_t)seeds[k].query_start + param->seedlen > query_len ||
+            (int64_t)seeds[k].query_start + (int64_t)param->seedlen * qadv > query_len ||
             (int64_t)seeds[k].target_start + (int64_t)param->seedlen * tadv > target_len) {
             set_error("seed " + std::to_string(k) + " outside the sequences");
             return -1;
@@ -1397,14 +1399,15 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
     C4B_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
     if (query_len)
         hsp_encode_kernel<<<(query_len + 255) / 256, 256, 0, st>>>(d_q.p, query_len, d_tab.p, d_tab.p + 512,
-                                                                   d_tab.p + 768, 0, d_qc.p, d_qm.p, d_qmo.p, d_bad.p);
+                                                                   d_tab.p + 768, qadv == 3, d_qc.p, d_qm.p, d_qmo.p,
+                                                                   d_bad.p);
     if (target_len)
         hsp_encode_kernel<<<(target_len + 255) / 256, 256, 0, st>>>(d_t.p, target_len, d_tab.p + 256, d_tab.p + 512,
                                                                     d_tab.p + 768, tadv == 3, d_tc.p, d_tm.p,
                                                                     d_tmo.p, d_bad.p);
     HspArgs A;
     A.qc = d_qc.p; A.tc = d_tc.p; A.qm = query_mask ? d_qmo.p : nullptr; A.tm = target_mask ? d_tmo.p : nullptr;
-    A.ql = query_len; A.tl = target_len; A.tadv = tadv;
+    A.ql = query_len; A.tl = target_len; A.qadv = qadv; A.tadv = tadv;
     A.seedlen = param->seedlen; A.dropoff = param->dropoff; A.threshold = param->threshold;
     hsp_extend_kernel<<<(n_seeds + 127) / 128, 128, 0, st>>>(A, d_matrix.p, n_seeds, d_seeds.p, d_out.p);
     e->launches += 3;

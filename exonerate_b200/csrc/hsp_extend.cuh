@@ -44,7 +44,7 @@ __global__ void hsp_encode_kernel(const uint8_t *__restrict__ seq, int n, const 
 
 struct HspArgs {
     const uint8_t *qc, *tc, *qm, *tm;  // codes and (already combined) masks; masks may be null
-    int ql, tl, tadv;
+    int ql, tl, qadv, tadv;
     int seedlen, dropoff, threshold;
 };
 
@@ -55,7 +55,7 @@ __global__ void hsp_extend_kernel(const HspArgs A, const int32_t *__restrict__ m
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
-    const int tadv = A.tadv;
+    const int tadv = A.tadv, qadv = A.qadv;
     auto score_at = [&](int qp, int tp) -> int { return sm[A.qc[qp] * 24 + A.tc[tp]]; };
     auto masked = [&](int qp, int tp) -> bool { return (A.qm && A.qm[qp]) || (A.tm && A.tm[tp]); };
 
@@ -69,20 +69,20 @@ __global__ void hsp_extend_kernel(const HspArgs A, const int32_t *__restrict__ m
         int i = 0;
         for (; i < h.length; ++i) {
             if (score_at(h.query_start, h.target_start) > 0) break;
-            h.query_start += 1;
+            h.query_start += qadv;
             h.target_start += tadv;
         }
         h.length -= i;
-        int qp = h.query_start + h.length - 1, tp = h.target_start + (h.length - 1) * tadv;
+        int qp = h.query_start + (h.length - 1) * qadv, tp = h.target_start + (h.length - 1) * tadv;
         while (h.length > 0) {
             if (score_at(qp, tp) > 0) break;
             --h.length;
-            --qp;
+            qp -= qadv;
             tp -= tadv;
         }
     }
     // HSP_init: seed score
-    for (int i = 0, qp = h.query_start, tp = h.target_start; i < h.length; ++i, ++qp, tp += tadv)
+    for (int i = 0, qp = h.query_start, tp = h.target_start; i < h.length; ++i, qp += qadv, tp += tadv)
         h.score += score_at(qp, tp);
     if (h.score < 0) {
         h.status = 1;  // "Initial HSP score less than zero" is fatal in the reference
@@ -94,28 +94,28 @@ __global__ void hsp_extend_kernel(const HspArgs A, const int32_t *__restrict__ m
     // `dropoff` from its maximum; ties move the maximum outwards (maxscore <= score)
     auto extend = [&](bool forbid_masked) {
         int score = h.score, maxscore = h.score;
-        int qp = h.query_start - 1, tp = h.target_start - tadv, maxext = 0;
+        int qp = h.query_start - qadv, tp = h.target_start - tadv, maxext = 0;
         for (int ext = 1; qp >= 0 && tp >= 0; ++ext) {
             if (forbid_masked && masked(qp, tp)) break;
             score += score_at(qp, tp);
             if (maxscore <= score) { maxscore = score; maxext = ext; }
             else if (score < 0 || maxscore - score >= A.dropoff) break;
-            --qp;
+            qp -= qadv;
             tp -= tadv;
         }
-        qp = h.query_start + h.length;
+        qp = h.query_start + h.length * qadv;
         tp = h.target_start + h.length * tadv;
-        h.query_start -= maxext;
+        h.query_start -= maxext * qadv;
         h.target_start -= maxext * tadv;
         h.length += maxext;
         score = maxscore;
         maxext = 0;
-        for (int ext = 1; qp + 1 <= A.ql && tp + tadv <= A.tl; ++ext) {
+        for (int ext = 1; qp + qadv <= A.ql && tp + tadv <= A.tl; ++ext) {
             if (forbid_masked && masked(qp, tp)) break;
             score += score_at(qp, tp);
             if (maxscore <= score) { maxscore = score; maxext = ext; }
             else if (score < 0 || maxscore - score >= A.dropoff) break;
-            ++qp;
+            qp += qadv;
             tp += tadv;
         }
         h.score = maxscore;
@@ -127,7 +127,7 @@ __global__ void hsp_extend_kernel(const HspArgs A, const int32_t *__restrict__ m
     h.stored = h.score >= A.threshold ? 1 : 0;
     if (h.stored) {  // HSP_find_cobs: first position where the prefix score reaches half
         int score = 0, i = 0;
-        for (int qp = h.query_start, tp = h.target_start; i < h.length; ++i, ++qp, tp += tadv) {
+        for (int qp = h.query_start, tp = h.target_start; i < h.length; ++i, qp += qadv, tp += tadv) {
             score += score_at(qp, tp);
             if (score >= (h.score >> 1)) break;
         }

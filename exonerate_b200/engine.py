@@ -311,14 +311,15 @@ class HSPset:
 
     def finalise(self):
         ext = self.extend_all()
-        tadv = 3 if self.param.match_kind == abi.CALC_MATCH_1_3 else 1
+        tadv = 3 if self.param.match_kind in (abi.CALC_MATCH_1_3, abi.CALC_MATCH_3_3) else 1
+        qadv = 3 if self.param.match_kind in (abi.CALC_MATCH_3_1, abi.CALC_MATCH_3_3) else 1
         ql = len(self.q)
         horizon = {}
         self.hsp_list = []
         for k, (qs, ts) in enumerate(self.seeds):
             if ext[k].status != 0:   # the reference aborts here (hspset.c:740-743)
                 raise C4BError("Initial HSP score less than zero for seed (%d, %d)" % (qs, ts))
-            key = ((ts - qs * tadv + ql) % ql, ts % tadv)
+            key = ((ts * qadv - qs * tadv + ql) % ql, qs % qadv, ts % tadv)
             if ts < horizon.get(key, 0):
                 continue
             horizon[key] = ext[k].target_end

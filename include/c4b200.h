@@ -273,8 +273,10 @@ int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b
  * launch.  The diagonal horizon (:951-972,991-996) is sequential state over the seed
  * list; it only decides which seeds are looked at, so the caller (our hspset.c
  * binding, exonerate_b200.engine.HSPset) replays it over these results in seed order.
- * match_kind: C4B_CALC_MATCH_DNA (advance 1,1), C4B_CALC_MATCH_PROTEIN (1,1) or
- * C4B_CALC_MATCH_1_3 (protein query vs translated DNA target, advance 1,3).
+ * match_kind: C4B_CALC_MATCH_DNA (advance 1,1), C4B_CALC_MATCH_PROTEIN (1,1),
+ * C4B_CALC_MATCH_1_3 (protein query vs translated DNA target, advance 1,3),
+ * C4B_CALC_MATCH_3_1 (translated DNA query vs protein target, 3,1) or
+ * C4B_CALC_MATCH_3_3 (both translated: codon2codon, 3,3) -- Match_Type_* of match.h:45-51.
  * query_mask / target_mask: one byte per position, non-zero = masked
  * (Alphabet_is_masked, src/sequence/alphabet.h:87-88); NULL = nothing masked. */
 typedef struct {

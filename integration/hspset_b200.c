@@ -11,8 +11,8 @@
  * diagonal horizon over the results in arrival order, and hand every surviving HSP to the
  * reference's own HSPset_add_known_hsp (HSP_init + HSP_store: threshold, --hspfilter
  * queues, hsp_list) -- so everything downstream of the extension is still the reference.
- * DNA2DNA, PROTEIN2PROTEIN and PROTEIN2DNA matches have a device form; DNA2PROTEIN and
- * CODON2CODON seeds are passed straight to the reference's function (not replaced). */
+ * Every Match_Type (DNA2DNA, PROTEIN2PROTEIN, DNA2PROTEIN, PROTEIN2DNA, CODON2CODON) has a
+ * device form; an unknown one would be passed straight to the reference's function. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -59,6 +59,8 @@ static gint device_match_kind(Match *match){
         case Match_Type_DNA2DNA:         return C4B_CALC_MATCH_DNA;
         case Match_Type_PROTEIN2PROTEIN: return C4B_CALC_MATCH_PROTEIN;
         case Match_Type_PROTEIN2DNA:     return C4B_CALC_MATCH_1_3;
+        case Match_Type_DNA2PROTEIN:     return C4B_CALC_MATCH_3_1;
+        case Match_Type_CODON2CODON:     return C4B_CALC_MATCH_3_3;
         default:                         return -1;
         }
     }

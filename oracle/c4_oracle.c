@@ -431,13 +431,26 @@ static int hsp_score(const hsp_ctx *c, int qp, int tp) {
     switch (c->p->match_kind) {
     case C4B_CALC_MATCH_DNA: return submat(c->s->dna_matrix, c->s->dna_index, c->q[qp], c->t[tp]);
     case C4B_CALC_MATCH_PROTEIN: return submat(c->s->protein_matrix, c->s->protein_index, c->q[qp], c->t[tp]);
-    default:
+    case C4B_CALC_MATCH_1_3:
         return submat(c->s->protein_matrix, c->s->protein_index, c->q[qp],
+                      translate(c->s, c->t[tp], c->t[tp + 1], c->t[tp + 2]));
+    case C4B_CALC_MATCH_3_1:
+        return submat(c->s->protein_matrix, c->s->protein_index,
+                      translate(c->s, c->q[qp], c->q[qp + 1], c->q[qp + 2]), c->t[tp]);
+    default: /* 3:3, match.c:508-530 */
+        return submat(c->s->protein_matrix, c->s->protein_index,
+                      translate(c->s, c->q[qp], c->q[qp + 1], c->q[qp + 2]),
                       translate(c->s, c->t[tp], c->t[tp + 1], c->t[tp + 2]));
     }
 }
 /* Match_1_mask_func / Match_3_mask_func (match.c:178-183,212-220) */
-static int hsp_qmasked(const hsp_ctx *c, int qp) { return c->qm && c->qm[qp]; }
+static int hsp_qmasked(const hsp_ctx *c, int qp) {
+    int k;
+    if (!c->qm) return 0;
+    for (k = 0; k < c->qadv; ++k)
+        if (c->qm[qp + k]) return 1;
+    return 0;
+}
 static int hsp_tmasked(const hsp_ctx *c, int tp) {
     int k;
     if (!c->tm) return 0;
@@ -496,8 +509,8 @@ void c4o_hsp_extend_one(const c4b_scoring *s, const c4b_hsp_param *p, const uint
     hsp_ctx c;
     int i, qp, tp, score;
     c.s = s; c.p = p; c.q = q; c.t = t; c.qm = qm; c.tm = tm; c.ql = ql; c.tl = tl;
-    c.qadv = 1;
-    c.tadv = (p->match_kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    c.qadv = (p->match_kind == C4B_CALC_MATCH_3_1 || p->match_kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
+    c.tadv = (p->match_kind == C4B_CALC_MATCH_1_3 || p->match_kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
     memset(h, 0, sizeof(*h));
     h->query_start = seed.query_start;
     h->target_start = seed.target_start;
@@ -556,7 +569,8 @@ void c4o_hsp_extend_one(const c4b_scoring *s, const c4b_hsp_param *p, const uint
  * device); returns the number of HSPs written to out. */
 int c4o_hspset_replay(const c4b_hsp_param *p, int ql, int n_seeds, const c4b_hsp_seed *seeds,
                       const c4b_hsp *ext, c4b_hsp *out) {
-    const int qadv = 1, tadv = (p->match_kind == C4B_CALC_MATCH_1_3) ? 3 : 1;
+    const int qadv = (p->match_kind == C4B_CALC_MATCH_3_1 || p->match_kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
+    const int tadv = (p->match_kind == C4B_CALC_MATCH_1_3 || p->match_kind == C4B_CALC_MATCH_3_3) ? 3 : 1;
     int *horizon = (int *)calloc((size_t)ql * qadv * tadv, sizeof(int));
     int k, n = 0;
     for (k = 0; k < n_seeds; ++k) {

@@ -388,7 +388,8 @@ def gene_pair(seed, qlen, tlen, n_exons=5, rate=0.02, reverse=False):
 # HSP seeding / extension
 # ---------------------------------------------------------------------------
 HSP_MATCH_KIND = {"dna2dna": abi.CALC_MATCH_DNA, "protein2protein": abi.CALC_MATCH_PROTEIN,
-                  "protein2dna": abi.CALC_MATCH_1_3}
+                  "protein2dna": abi.CALC_MATCH_1_3, "dna2protein": abi.CALC_MATCH_3_1,
+                  "codon2codon": abi.CALC_MATCH_3_3}
 
 
 def hsp_param(case):
