@@ -328,6 +328,28 @@ def test_packed_kernels_fuzz_penalties_and_matrices(eng, params, scoring, monkey
             assert got[0][k] == ref["score"] and got[1][k]["ops"] == ref["ops"], (seed, trial, k)
 
 
+def test_degenerate_lattices(eng, params, scoring):
+    """Empty and one-symbol regions (query_length or target_length 0 / 1) mixed with normal
+    lattices, on the packed affine kernels and the packed est2genome kernel."""
+    from exonerate_b200 import Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    q, t = helpers.dna_pair(4711, 120, 400)
+    regions = [(0, 0, 0, 400), (0, 0, 120, 0), (5, 7, 0, 0), (0, 0, 1, 1), (3, 10, 1, 300), (0, 0, 120, 1),
+               (0, 0, 120, 400), (119, 399, 1, 1)]
+    for name in ("affine_local_dna", "affine_global_dna", "est2genome"):
+        model, _ = helpers.load_model(name, params)
+        sp = splice_arrays(t) if name == "est2genome" else None
+        pairs = PairSet([q] * len(regions), [t] * len(regions), splice=[sp] * len(regions), regions=regions)
+        opt = Optimal(eng, model, scoring)
+        scores, paths = opt.find_score(pairs), opt.find_path(pairs)
+        for k, reg in enumerate(regions):
+            want = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, splice=sp, region=reg),
+                                          abi.MODE_FIND_PATH)
+            assert scores[k] == want["score"], (name, reg)
+            assert paths[k]["score"] == want["score"] and paths[k]["region"] == want["region"], (name, reg)
+            assert paths[k]["ops"] == want["ops"], (name, reg)
+
+
 def test_protein_smem_scoring_vs_oracle(eng, params, scoring):
     from exonerate_b200 import Optimal, PairSet
     model, _ = helpers.load_model("affine_local_protein", params)
