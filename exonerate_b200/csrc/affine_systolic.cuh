@@ -23,7 +23,10 @@
 //
 // TB=true additionally records, per cell, which transition won for M (2 bits),
 // D (1 bit) and I (1 bit): 4 bits/cell, R/2 bytes per lane per step, written as
-// one coalesced vector store in the skewed order the warp produces them.
+// one coalesced vector store in the skewed order the warp produces them.  The
+// winners are not found with compares: TB works on 8 * value + rank tag (see the
+// kernel), nibble = {bits 0-1 rank of M's winner (3 match .. 0 insert), bit 2 D
+// extended, bit 3 I extended} -- the same format as affine_fill16tb_kernel.
 #pragma once
 #include <type_traits>
 
@@ -91,6 +94,12 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
 
     const int open = mdl.openD, extD = mdl.extD, extI = mdl.extI;  // openD == openI (checked)
     const int one = mdl.one;
+    // TB = true works on 8 * value + TAG: the candidates of a max carry their rank in the
+    // closed-model order in the low bits, so "first assigns, later replace only if strictly
+    // greater" IS the max and the winner is read off the tag (cleaned with & ~7 before reuse):
+    //   M = max(match|3, START|2, D|1, I|0)   D = max(D<- + ext |4, G<- |0)   I likewise
+    constexpr int NEGK = TB ? -(1 << 28) : NEG2;   // "not reachable" in the kernel's units
+    const int open8 = 8 * open, extD8t = 8 * extD + 4 - 1 /* from D|1 */, extI8t = 8 * extI + 4;
     // where may START be entered / END be left (src/c4/layout.c:21-88)
     const int ss = mdl.start_scope, es = mdl.end_scope;
     const bool start_any = (ss == C4B_SCOPE_ANYWHERE);
@@ -130,8 +139,8 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         int Mp[R], Dp[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            Mp[r] = NEG2;
-            Dp[r] = NEG2;
+            Mp[r] = NEGK;
+            Dp[r] = TB ? (NEGK | 1) : NEG2;   // TB: D is kept with its M-level tag
         }
         // END at the last lattice row: which of my registers holds row Q
         const int rQ = (Q >= row0 && Q < row0 + R) ? (Q - row0) : -1;
@@ -140,7 +149,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         int2 *top_out = (sweep & 1) ? P.top1 : P.top0;
         const bool write_top = (sweep + 1 < nsweeps) && (lane == 31);
 
-        int topM = NEG2, topI = NEG2, topMprev = NEG2;  // row above my strip
+        int topM = NEGK, topI = NEGK, topMprev = NEGK;  // row above my strip
         int in_code = kTargetNone;                      // column code handed down
         int code0 = kTargetNone;                        // lane 0: column 0 has no symbol
         // hand-off from the sweep above, which another warp may still be producing
@@ -155,7 +164,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 __threadfence_block();
             }
         };
-        int2 top0v = make_int2(NEG2, NEG2);
+        int2 top0v = make_int2(NEGK, NEGK);
         if (later_sweep) {
             if (piped) wait_column(0);
             top0v = __ldcg(top_in);                     // uniform load, lane 0 uses it
@@ -205,14 +214,14 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
             } else {
                 code0 = kTargetNone;
             }
-            int botM = NEG2, botI = NEG2;
+            int botM = NEGK, botI = NEGK;
             if (all_active || (j >= 0 && j <= T)) {
                 uint2 X = make_uint2(0, 0);
                 const int32_t *subcol = nullptr;
                 if (SM == SCORE_PRMT) X = xtab[code];
                 else subcol = subm + code;
                 // START candidate value per cell (T5); NEG2 where START is out of scope
-                const int sv_col = (start_any || (j == 0 && start_col0)) ? 0 : NEG2;
+                const int sv_col = (start_any || (j == 0 && start_col0)) ? 0 : NEGK;
                 // "G" = M + gap_open everywhere: the open penalty is paid once per cell
                 // (it feeds both D of the next column and I of the next row) and the
                 // substitution table holds s - gap_open, so diagG + s' == M_diag + s.
@@ -236,12 +245,17 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                         Dp[r] = __viaddmax_s32(Dp[r], extD, Mp[r]);
                         Mp[r] = __viaddmax_s32(diag, sc, Dp[r]);   // max(match, D); START and I follow
                     } else {
-                        // D: T0 extend first, T2 open replaces only if strictly greater
-                        const int da = Dp[r] + extD;
-                        const bool pD = Mp[r] > da;
-                        Dp[r] = max(da, Mp[r]);
-                        Mp[r] = diag + sc;                         // T4 candidate only
-                        w[r / 8] |= ((uint32_t)pD << 1) << (4 * (r % 8));
+                        // D: T0 extend (tag 4) first, T2 open (tag 0) replaces only if strictly greater
+                        const int Dt = __viaddmax_s32(Dp[r], extD8t, Mp[r]);
+                        const int dm = (Dt & ~7) | 1;
+                        // START candidate (T5): 0 where START is in scope
+                        int sv = LOCAL ? 0 : sv_col;
+                        if (!LOCAL && r == 0 && first_row_lane && (start_row0 || j == 0)) sv = 0;
+                        // M without I: T4 match|3, T5 start|2, T6 from D|1
+                        const int mt = __vimax3_s32(diag + (sc * 8 + 3), sv + 2, dm);
+                        Dp[r] = dm;
+                        Mp[r] = mt;
+                        w[r / 8] |= (uint32_t)((mt & 3) | (Dt & 4)) << (4 * (r % 8));
                     }
                 }
                 // Phase B, rows TOP-DOWN: the vertical chain I -> M -> G.
@@ -260,20 +274,16 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                         if (LOCAL) Mv = __vimax_s32_relu(Mp[r], Iv);  // full-rate VIMNMX.RELU
                         else Mv = __vimax3_s32(Mp[r], sv, Iv);
                     } else {
-                        // I: T1 extend first, T3 open replaces only if strictly greater
-                        const int ia = upI + extI;
-                        const bool pI = upM > ia;
-                        Iv = max(ia, upM);
-                        // M: T4 match, T5 start, T6 from D, T7 from I
-                        int cur = Mp[r];
-                        int dir = 0;
-                        if (cur < sv) { cur = sv; dir = 1; }
-                        if (cur < Dp[r]) { cur = Dp[r]; dir = 2; }
-                        if (cur < Iv) { cur = Iv; dir = 3; }
-                        Mv = cur;
-                        w[r / 8] |= ((uint32_t)pI | ((uint32_t)dir << 2)) << (4 * (r % 8));
+                        // I: T1 extend (tag 4) first, T3 open (tag 0)
+                        const int It = __viaddmax_s32(upI, extI8t, upM);
+                        Iv = It & ~7;
+                        // M: the tagged max of phase A against T7 from I|0 (last in order)
+                        const int mt = Mp[r];
+                        const int m2 = max(mt, Iv);
+                        Mv = m2 & ~7;
+                        w[r / 8] ^= (uint32_t)(((mt ^ m2) & 3) | ((It & 4) << 1)) << (4 * (r % 8));
                     }
-                    const int Gv = add_open(Mv, one, open);
+                    const int Gv = TB ? Mv + open8 : add_open(Mv, one, open);
                     Mp[r] = Gv;
                     upM = Gv;
                     upI = Iv;
@@ -358,7 +368,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     }
     if (threadIdx.x == 0) {
         AffOut o;
-        o.best = (best == INT32_MIN) ? best : best - open;  // tracked as G = M + open
+        o.best = (best == INT32_MIN) ? best : (TB ? best / 8 : best) - open;  // tracked as G = M + open (TB: x 8)
         o.end_i = best_i;
         o.end_j = best_j;
         o.flags = (best == INT32_MIN) ? 1 : 0;

@@ -20,7 +20,7 @@ struct TbJob {
     int32_t score_slot; // slot of the score-only pass result, or -1
     int64_t ops_off;    // first (transition,length) pair of this job's ops slot
     int32_t ops_cap;    // capacity of the slot in pairs
-    int32_t reserved;   // record format: 0 = affine_fill_kernel nibbles, 1 = tag format (affine_fill16tb_kernel)
+    int32_t reserved;   // record format: 1 = tag format (both traceback fills write it); 0 = decoded layout
 };
 
 // Longest target span an optimal local path ending at lattice row end_i can

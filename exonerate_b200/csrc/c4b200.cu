@@ -860,7 +860,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const int64_t span = band ? band_cols[p] : pairs[p].target_length;
         j.ops_cap = (int32_t)std::min<int64_t>(pairs[p].query_length + span + 4, INT32_MAX);
         j.ops_off = ops_cursor;
-        j.reserved = (band ? b->tb16_band : b->tb16_direct) ? 1 : 0;
+        j.reserved = 1;   // every affine traceback pass records nibbles in tag format
         ops_cursor += j.ops_cap;
         return j;
     };
