@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -61,6 +62,20 @@ struct Chunk {
 // with an unbounded release threshold, set in c4b_engine_create): after the first
 // batch, allocation and free are bookkeeping, not driver calls that serialise.
 static thread_local cudaStream_t tl_pool_stream = nullptr;
+
+// C4B_TIMING=1: host-side timeline of one batch on stderr (tuning aid)
+struct HostTimeline {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    HostTimeline() : on(getenv("C4B_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[c4b timing] %8.2f ms  %s\n", ms, what);
+    }
+};
+static thread_local HostTimeline *tl_timeline = nullptr;
+static void tmark(const char *what) { if (tl_timeline) tl_timeline->mark(what); }
 
 // worker threads for host-side staging: min(16, cores), or C4B_HOST_THREADS (one process
 // per GPU on a shared host should divide the cores: bench.py sets cores / world size)
@@ -536,6 +551,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                 query_wide[p] = wide[slot[SeqKey(pairs[p].query + pairs[p].query_start, pairs[p].query_length)]];
         }
     }
+    tmark("create: validated, alphabet scanned");
     b->R = (maxQ + 1 > 512) ? 32 : (maxQ + 1 > 256 ? 16 : 8);
     if (const char *env = getenv("C4B_AFFINE_R")) {  // tuning override: rows per lane
         const int r = atoi(env);
@@ -791,6 +807,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         if (chunkify(b->direct_list, tb_off_d, b->direct_chunks, false)) return -1;
     }
 
+    tmark("create: lists, placement, chunks planned");
     // ---- device allocations (stream-ordered on the engine stream)
     if (b->d_seq.alloc(stage_bytes)) return -1;
     if (b->d_lut.alloc(512)) return -1;
@@ -900,6 +917,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     C4B_CUDA(cudaEventRecord(b->ev_p1a, st));
     C4B_CUDA(cudaEventRecord(b->ev_base, st));  // allocations + tables + descriptors are in place
 
+    tmark("create: allocations + descriptors uploaded");
     // ---- stage sequences: pinned bounce buffer -> HBM -> encode in place, slice by
     // slice on the copy stream.  Worker threads fill the bounce buffer (grow-only,
     // owned by the engine); as soon as a slice is issued, the score pass of every
@@ -965,6 +983,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         ++next_group;
     }
     b->pass1_inflight = true;
+    tmark("create: all slices staged, pass 1 queued");
     if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
     C4B_CUDA(cudaEventRecord(e->stage_free, cs));
     b->kernel_name = "affine_systolic";
@@ -1259,12 +1278,18 @@ int c4b_find_score_batch(c4b_engine *e, const c4b_model *model, const c4b_scorin
 int c4b_find_path_batch(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
                         const c4b_pair *pairs, c4b_score threshold, c4b_result *results, int32_t *ops,
                         int64_t ops_capacity) {
+    HostTimeline tl;
+    tl_timeline = &tl;
     c4b_batch *b = nullptr;
     int rc = c4b_batch_create(e, model, scoring, n, pairs, 1, &b);
-    if (rc) return rc;
+    if (rc) { tl_timeline = nullptr; return rc; }
     rc = c4b_batch_run(b, threshold);
+    tmark("run: everything queued");
     if (!rc) rc = c4b_batch_fetch(b, results, ops, ops_capacity);
+    tmark("fetch: results and ops on the host");
     c4b_batch_destroy(b);
+    tmark("batch destroyed");
+    tl_timeline = nullptr;
     return rc;
 }
 
