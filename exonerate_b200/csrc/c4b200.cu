@@ -15,6 +15,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 #include "affine_systolic.cuh"
 #include "affine_packed16.cuh"
@@ -238,6 +239,7 @@ __global__ void ops_compact_kernel(c4b_result *results, int n, const int64_t *ne
 
 }  // namespace
 
+#include "generic_jit.inl"
 #include "generic_host.inl"
 #include "e2g_host.inl"
 
@@ -1182,7 +1184,10 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
         *out = b;  // an empty batch runs and fetches nothing
         return 0;
     }
-    if (!any_blocked && analyze_affine(*model, &b->aff, &match_kind)) {
+    const bool force_generic = getenv("C4B_FORCE_GENERIC") != nullptr;  // testing: every model through the table-driven path
+    if (force_generic) {
+        rc = 1;
+    } else if (!any_blocked && analyze_affine(*model, &b->aff, &match_kind)) {
         b->affine = true;
         rc = affine_create(b, pairs, match_kind);
     } else {
@@ -1257,7 +1262,25 @@ double c4b_batch_last_fill_ms(c4b_batch *b) {
     return ms;
 }
 
-const char *c4b_batch_kernel_name(const c4b_batch *b) { return b->kernel_name; }
+int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threads, int64_t *cubin_bytes) {
+    if (!model || mode < 0 || mode > 2 || (cta_threads != 128 && cta_threads != 256 && cta_threads != 512)) {
+        set_error("c4b_model_specialise: bad arguments");
+        return -1;
+    }
+    if (check_model(*model)) return -1;
+    std::vector<char> cubin;
+    std::string log;
+    if (!jit_compile(jit_program_source(*model, mode, cta_threads), &cubin, &log)) {
+        set_error("model specialisation failed: " + log);
+        return -1;
+    }
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return 0;
+}
+
+const char *c4b_batch_kernel_name(const c4b_batch *b) {
+    return b->generic ? b->generic->kernel_used : b->kernel_name;
+}
 
 void c4b_batch_destroy(c4b_batch *b) { delete b; }
 

@@ -12,6 +12,10 @@ struct GenericBatch {
     int64_t cells = 0;
     int sm_count = 0, grid = 0, cmax = 1;
     int threads = 256;  // per CTA: one anti-diagonal of the longest query in one pass if it fits 1024
+    bool use_jit = false;  // model-specialised kernel (generic_jit.inl) instead of the interpreter
+    int jit_threads = 128;
+    int ring_ctas = 0;     // CTAs the lattice ring was sized for
+    const char *kernel_used = "generic_wavefront";
     std::vector<c4b_pair> host_pairs;
     std::vector<GenPair> h_full;
     DevBuf<GenTables> d_tables;
@@ -173,9 +177,14 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     rc |= g->d_cursor.alloc(1);
     g->threads = (maxQ + 1 > 512) ? 1024 : (maxQ + 1 > 256 ? 512 : 256);
     g->grid = std::max(1, std::min(n, g->sm_count * (1024 / g->threads)));
+    const int policy = jit_policy();
+    g->use_jit = policy == 1 || (policy == 2 && g->cells >= ((int64_t)1 << 30));
+    g->jit_threads = jit_threads_for(maxQ);
+    g->ring_ctas = g->grid;
+    if (g->use_jit) g->ring_ctas = std::max(g->ring_ctas, std::min(n, g->sm_count * (2048 / g->jit_threads)));
     const int depth = m.max_target_advance + m.max_query_advance + 1;
     g->ring_stride = align_up((size_t)depth * (maxQ + 1) * m.n_states * g->cmax, 4);
-    rc |= g->d_ring.alloc(g->ring_stride * g->grid);
+    rc |= g->d_ring.alloc(g->ring_stride * g->ring_ctas);
     if (rc) { delete g; return -1; }
     std::vector<uint8_t> hs(sbytes + 64, 0);
     for (auto &kv : smap) memcpy(hs.data() + kv.second, kv.first.first, (size_t)kv.first.second);
@@ -238,6 +247,22 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
 static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode) {
     if (!count) return 0;
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
+    if (g->use_jit) {
+        if (JitKernel *jk = jit_get(g->tables.model, mode, g->jit_threads)) {
+            const int grid = std::max(1, std::min(std::min(count, g->ring_ctas), g->sm_count * jk->blocks_per_sm));
+            const GenTables *tables = g->d_tables.p;
+            int32_t *ring = g->d_ring.p;
+            size_t stride = g->ring_stride;
+            int *cursor = g->d_cursor.p;
+            void *args[] = {(void *)&pairs, (void *)&count, (void *)&outs, (void *)&tables,
+                            (void *)&ring, (void *)&stride, (void *)&cursor};
+            C4B_CUDA(cudaLaunchKernel((const void *)jk->kern, dim3(grid), dim3(jk->threads), args, 0, g->stream));
+            (*g->launches)++;
+            g->kernel_used = "generic_jit";
+            return 0;
+        }
+        g->use_jit = false;
+    }
     const int grid = std::min(g->grid, count);
     generic_fill_kernel<<<grid, g->threads, 0, g->stream>>>(pairs, count, outs, g->d_tables.p, mode,
                                                             g->d_ring.p, g->ring_stride, g->d_cursor.p);

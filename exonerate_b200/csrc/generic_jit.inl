@@ -1,0 +1,232 @@
+// generic_jit.inl -- run-time specialisation of the table-driven fill (host side).
+//
+// The reference compiles each model to C at build time (codegen + bootstrapper,
+// src/c4/codegen.c, src/c4/viterbi.c:1638-1727).  Here the closed model is
+// written out as constexpr tables in front of generic_jit_kernel.cuh and
+// compiled for sm_100a with NVRTC the first time a (model, mode, CTA size) is
+// needed; the cubin is kept for the life of the process (and on disk when
+// C4B_JIT_CACHE_DIR is set).  libnvrtc is dlopen'ed: without it, or when the
+// compile fails, the caller keeps the interpreter kernel (generic_wavefront.cuh)
+// -- both are device kernels, there is no CPU path.
+//
+// C4B_GENERIC_JIT=0 never, =1 always, unset: batches of >= 2^30 lattice cells
+// (below that the compile costs more than it saves in a one-shot process).
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <mutex>
+#include <sstream>
+
+#include "jit_embedded.inc"
+
+namespace c4b {
+
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    int threads = 0;
+    int blocks_per_sm = 1;
+};
+
+struct NvrtcApi {
+    void *handle = nullptr;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    bool ok = false;
+};
+
+static NvrtcApi *nvrtc_api() {
+    static NvrtcApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char *nm : names)
+            if ((api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!api.handle) return;
+        api.create = (decltype(api.create))dlsym(api.handle, "nvrtcCreateProgram");
+        api.compile = (decltype(api.compile))dlsym(api.handle, "nvrtcCompileProgram");
+        api.log_size = (decltype(api.log_size))dlsym(api.handle, "nvrtcGetProgramLogSize");
+        api.log = (decltype(api.log))dlsym(api.handle, "nvrtcGetProgramLog");
+        api.cubin_size = (decltype(api.cubin_size))dlsym(api.handle, "nvrtcGetCUBINSize");
+        api.cubin = (decltype(api.cubin))dlsym(api.handle, "nvrtcGetCUBIN");
+        api.destroy = (decltype(api.destroy))dlsym(api.handle, "nvrtcDestroyProgram");
+        api.ok = api.create && api.compile && api.log_size && api.log && api.cubin_size && api.cubin && api.destroy;
+    });
+    return api.ok ? &api : nullptr;
+}
+
+// The closed model as compile-time tables (what generic_jit_kernel.cuh expects).
+static std::string jit_program_source(const c4b_model &m, int mode, int threads) {
+    std::ostringstream o;
+    o << "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t;\n"
+         "typedef unsigned short uint16_t; typedef int int32_t; typedef unsigned int uint32_t;\n"
+         "typedef long long int64_t; typedef unsigned long long uint64_t;\n"
+         "#define INT_MIN (-2147483647 - 1)\n"
+         "#define C4B200_TYPES_ONLY 1\n#include \"c4b200.h\"\n#include \"generic_types.h\"\n";
+    o << "#define JIT_MODE " << mode << "\n#define JIT_THREADS " << threads << "\n";
+    o << "namespace c4bjit {\n";
+    const int S = m.n_states, TN = m.n_transitions, NC = std::max(1, m.n_calcs);
+    std::vector<int> saved(S, -1);
+    int nsaved = 0;
+    for (int k = 0; k < TN; ++k) {
+        const c4b_transition &t = m.transitions[k];
+        if (t.input != m.start_state && t.advance_query + t.advance_target > 0 && saved[t.input] < 0)
+            saved[t.input] = 0;
+    }
+    for (int s = 0; s < S; ++s)
+        if (saved[s] == 0) saved[s] = nsaved++;
+    o << "constexpr int S = " << S << ", TN = " << TN << ", NSH = " << m.n_shadow_slots << ", START = "
+      << m.start_state << ", END = " << m.end_state << ", START_SCOPE = " << m.start_scope
+      << ", END_SCOPE = " << m.end_scope << ", DEPTH = " << (m.max_target_advance + m.max_query_advance + 1)
+      << ", NSAVED = " << std::max(1, nsaved) << ";\n";
+    auto tr_array = [&](const char *name, auto field) {
+        o << "constexpr int " << name << "[TN] = {";
+        for (int k = 0; k < TN; ++k) o << (k ? "," : "") << field(m.transitions[k]);
+        o << "};\n";
+    };
+    tr_array("kTrIn", [](const c4b_transition &t) { return t.input; });
+    tr_array("kTrOut", [](const c4b_transition &t) { return t.output; });
+    tr_array("kTrAq", [](const c4b_transition &t) { return t.advance_query; });
+    tr_array("kTrAt", [](const c4b_transition &t) { return t.advance_target; });
+    tr_array("kTrCalc", [](const c4b_transition &t) { return t.calc; });
+    tr_array("kTrLabel", [](const c4b_transition &t) { return t.label; });
+    auto calc_array = [&](const char *name, auto field) {
+        o << "constexpr int " << name << "[" << NC << "] = {";
+        for (int k = 0; k < NC; ++k) o << (k ? "," : "") << (k < m.n_calcs ? field(m.calcs[k]) : 0);
+        o << "};\n";
+    };
+    calc_array("kCalcKind", [](const c4b_calc &c) { return c.kind; });
+    calc_array("kCalcProt", [](const c4b_calc &c) { return c.protect; });
+    calc_array("kCalcP0", [](const c4b_calc &c) { return c.param[0]; });
+    calc_array("kCalcP1", [](const c4b_calc &c) { return c.param[1]; });
+    calc_array("kCalcP2", [](const c4b_calc &c) { return c.param[2]; });
+    o << "constexpr int kShadow[S * C4B_MAX_SHADOW_SLOTS] = {";
+    for (int s = 0; s < S; ++s)
+        for (int l = 0; l < C4B_MAX_SHADOW_SLOTS; ++l)
+            o << ((s || l) ? "," : "") << (l < m.n_shadow_slots ? (int)m.shadow_start[s][l] : 0);
+    o << "};\nconstexpr int kSaved[S] = {";
+    for (int s = 0; s < S; ++s) o << (s ? "," : "") << saved[s];
+    o << "};\n}  // namespace c4bjit\n";
+    o << kJitSrc_generic_jit_kernel_cuh;
+    return o.str();
+}
+
+static uint64_t fnv1a(const std::string &s) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+
+static bool jit_compile(const std::string &src, std::vector<char> *cubin, std::string *log) {
+    NvrtcApi *rt = nvrtc_api();
+    if (!rt) { *log = "libnvrtc not found"; return false; }
+    const char *headers[] = {kJitSrc_c4b200_h, kJitSrc_generic_types_h, "", ""};
+    const char *names[] = {"c4b200.h", "generic_types.h", "stdint.h", "stddef.h"};
+    nvrtcProgram prog = nullptr;
+    if (rt->create(&prog, src.c_str(), "c4b_jit_fill.cu", 4, headers, names) != NVRTC_SUCCESS) {
+        *log = "nvrtcCreateProgram failed";
+        return false;
+    }
+    const bool verbose = getenv("C4B_JIT_VERBOSE") != nullptr;  // ptxas resource usage on stderr
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v"};
+    const nvrtcResult res = rt->compile(prog, verbose ? 4 : 3, opts);
+    size_t ls = 0;
+    rt->log_size(prog, &ls);
+    if (ls > 1) { log->resize(ls); rt->log(prog, &(*log)[0]); }
+    if (verbose && ls > 1) fprintf(stderr, "%s\n", log->c_str());
+    bool ok = res == NVRTC_SUCCESS;
+    if (ok) {
+        size_t cs = 0;
+        ok = rt->cubin_size(prog, &cs) == NVRTC_SUCCESS && cs > 0;
+        if (ok) { cubin->resize(cs); ok = rt->cubin(prog, cubin->data()) == NVRTC_SUCCESS; }
+    }
+    rt->destroy(&prog);
+    return ok;
+}
+
+static std::string jit_cache_path(const std::string &src) {
+    const char *dir = getenv("C4B_JIT_CACHE_DIR");
+    if (!dir || !*dir) return std::string();
+    char name[64];
+    snprintf(name, sizeof name, "/c4bjit_%016llx_%zu.cubin", (unsigned long long)fnv1a(src), src.size());
+    return std::string(dir) + name;
+}
+
+// nullptr = no specialised kernel (reason on stderr once per program)
+static JitKernel *jit_get(const c4b_model &m, int mode, int threads) {
+    static std::mutex mu;
+    static std::map<std::string, JitKernel *> cache;
+    const std::string src = jit_program_source(m, mode, threads);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(src);
+    if (it != cache.end()) return it->second;
+    JitKernel *jk = nullptr;
+    std::vector<char> cubin;
+    std::string log;
+    const std::string path = jit_cache_path(src);
+    if (!path.empty())
+        if (FILE *f = fopen(path.c_str(), "rb")) {
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            if (sz > 0) {
+                cubin.resize((size_t)sz);
+                if (fread(cubin.data(), 1, (size_t)sz, f) != (size_t)sz) cubin.clear();
+            }
+            fclose(f);
+        }
+    const bool from_disk = !cubin.empty();
+    if (from_disk || jit_compile(src, &cubin, &log)) {
+        if (!from_disk && !path.empty()) {
+            const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+            if (FILE *f = fopen(tmp.c_str(), "wb")) {
+                const bool w = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+                fclose(f);
+                if (!w || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+            }
+        }
+        jk = new JitKernel();
+        jk->threads = threads;
+        if (cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+            cudaLibraryGetKernel(&jk->kern, jk->lib, "c4b_jit_fill") != cudaSuccess) {
+            log = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+            if (jk->lib) cudaLibraryUnload(jk->lib);
+            delete jk;
+            jk = nullptr;
+        } else {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)jk->kern, threads, 0) != cudaSuccess ||
+                nb < 1) {
+                cudaGetLastError();
+                nb = 1;
+            }
+            jk->blocks_per_sm = nb;
+        }
+    }
+    if (!jk)
+        fprintf(stderr, "libc4b200: model specialisation unavailable, using the interpreter kernel: %s\n",
+                log.c_str());
+    cache[src] = jk;
+    return jk;
+}
+
+// 0 = never, 1 = always, 2 = by batch size
+static int jit_policy() {
+    const char *env = getenv("C4B_GENERIC_JIT");
+    if (!env || !*env) return 2;
+    return atoi(env) ? 1 : 0;
+}
+
+constexpr int kJitMaxThreads = 512;
+static int jit_threads_for(int maxQ) {
+    const int rows = maxQ + 1;
+    return rows > 256 ? 512 : (rows > 128 ? 256 : 128);
+}
+
+}  // namespace c4b

@@ -1,0 +1,39 @@
+// generic_types.h -- lattice descriptors of the table-driven path, shared by the
+// nvcc-built interpreter kernel (generic_wavefront.cuh) and the NVRTC-built
+// model-specialised kernel (generic_jit_kernel.cuh).  Plain structs only: this
+// file is also handed to NVRTC as an in-memory header.
+#pragma once
+#include <stdint.h>
+
+#include "c4b200.h"
+
+namespace c4b {
+
+constexpr int kMaxCell = 1 + C4B_MAX_SHADOW_SLOTS + 2;
+
+struct GenPair {
+    const uint8_t *q, *t;  // raw symbol bytes, whole sequences
+    const int32_t *splice[4];
+    const int32_t *blk_q, *blk_t;
+    int32_t n_blocked;
+    int32_t q_start, t_start, Q, T;  // region origin + extents
+    int32_t blk_dq, blk_dt;          // blocked coordinates are relative to (q_start-blk_dq, ...)
+    uint8_t *tb;                     // PATH: (Q+1)*(T+1)*S winning transition ids (0xFF = none)
+    // cell callbacks of BSDP derived models, as tables ((Q+1)*(T+1) cells of 1 + n_shadow_slots ints):
+    const int32_t *start_cells;      // what cell_start_func returns per cell (viterbi.c:727-741), or null
+    int32_t *end_cells;              // END's cell wherever END is reached (cell_end_func's input), or null
+    int64_t out_index;
+};
+
+struct GenOut {
+    int32_t score, end_i, end_j, start_i, start_j, flags;
+};
+
+struct GenTables {
+    c4b_model model;
+    c4b_scoring scoring;
+};
+
+enum { GEN_SCORE = 0, GEN_PATH = 1, GEN_REGION = 2 };
+
+}  // namespace c4b

@@ -21,36 +21,11 @@
 #include <vector>
 
 #include "c4b_common.cuh"
+#include "generic_types.h"
 
 namespace c4b {
 
 constexpr int kGenThreads = 1024;  // upper bound; the host launches 256 / 512 / 1024 by the longest query
-constexpr int kMaxCell = 1 + C4B_MAX_SHADOW_SLOTS + 2;
-
-struct GenPair {
-    const uint8_t *q, *t;  // raw symbol bytes, whole sequences
-    const int32_t *splice[4];
-    const int32_t *blk_q, *blk_t;
-    int32_t n_blocked;
-    int32_t q_start, t_start, Q, T;  // region origin + extents
-    int32_t blk_dq, blk_dt;          // blocked coordinates are relative to (q_start-blk_dq, ...)
-    uint8_t *tb;                     // PATH: (Q+1)*(T+1)*S winning transition ids (0xFF = none)
-    // cell callbacks of BSDP derived models, as tables ((Q+1)*(T+1) cells of 1 + n_shadow_slots ints):
-    const int32_t *start_cells;      // what cell_start_func returns per cell (viterbi.c:727-741), or null
-    int32_t *end_cells;              // END's cell wherever END is reached (cell_end_func's input), or null
-    int64_t out_index;
-};
-
-struct GenOut {
-    int32_t score, end_i, end_j, start_i, start_j, flags;
-};
-
-struct GenTables {
-    c4b_model model;
-    c4b_scoring scoring;
-};
-
-enum { GEN_SCORE = 0, GEN_PATH = 1, GEN_REGION = 2 };
 
 __device__ __forceinline__ bool gen_state_active(const c4b_model &m, int state, int qp, int tp, int ql, int tl) {
     if (qp < 0 || tp < 0 || qp > ql || tp > tl) return false;

@@ -186,6 +186,10 @@ typedef struct {
 typedef struct c4b_engine c4b_engine;
 typedef struct c4b_batch c4b_batch;
 
+/* The device compiler of c4b_model_specialise includes this header for the types
+ * above only. */
+#ifndef C4B200_TYPES_ONLY
+
 /* ---- engine ------------------------------------------------------------ */
 int c4b_abi_version(void);
 const char *c4b_last_error(void);
@@ -304,6 +308,19 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
                          const uint8_t *query, int32_t query_len, const uint8_t *query_mask,
                          const uint8_t *target, int32_t target_len, const uint8_t *target_mask,
                          int32_t n_seeds, const c4b_hsp_seed *seeds, c4b_hsp *out);
+
+/* ---- model specialisation ---------------------------------------------------
+ * Device counterpart of the reference's per-model code generation (Viterbi_compile /
+ * Codegen, src/c4/viterbi.c:1638-1727, src/c4/codegen.c; archived by the bootstrapper,
+ * src/c4/bootstrapper.c): the table-driven fill is compiled for ONE closed model at run
+ * time (NVRTC, sm_100a) and cached.  The batch entry points do this themselves for large
+ * batches (env C4B_GENERIC_JIT: 0 never, 1 always); this call only compiles, so a host
+ * can warm the cache -- or check that a model specialises -- without a GPU.
+ * mode: 0 FIND_SCORE, 1 FIND_PATH, 2 FIND_REGION; cta_threads: 128, 256 or 512.
+ * Returns 0 and the cubin size, or -1 with c4b_last_error(). */
+int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threads, int64_t *cubin_bytes);
+
+#endif /* C4B200_TYPES_ONLY */
 
 #ifdef __cplusplus
 }

@@ -75,3 +75,23 @@ def test_no_cpu_fallback(lib):
     assert b"no CPU fallback" in lib.c4b_last_error()
     with pytest.raises(engine.C4BError):
         engine.Engine(0)
+
+
+@pytest.mark.parametrize("name,q_protein", [("affine:local", False), ("est2genome", False),
+                                            ("protein2genome", True), ("coding2coding", False),
+                                            ("ungapped", False)])
+def test_every_shipped_model_specialises_for_sm100a(name, q_protein):
+    """c4b_model_specialise: the run-time generated kernel of each shipped model compiles
+    (NVRTC, sm_100a) in all three fill modes -- the device analogue of the reference's
+    bootstrapper building its model archive.  Compile only: no GPU needed."""
+    from exonerate_b200 import load_library
+    from exonerate_b200.models import host_model
+    lib = load_library()
+    model, _ = host_model(name, query_is_protein=q_protein)
+    for mode in (0, 1, 2):
+        size = C.c_int64(0)
+        rc = lib.c4b_model_specialise(C.byref(model), mode, 256, C.byref(size))
+        assert rc == 0, lib.c4b_last_error().decode()[:2000]
+        assert size.value > 10000
+    assert lib.c4b_model_specialise(C.byref(model), 7, 256, None) == -1
+    assert lib.c4b_model_specialise(C.byref(model), 0, 100, None) == -1

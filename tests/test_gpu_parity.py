@@ -64,6 +64,64 @@ def test_golden_vectors(eng, name, params, scoring):
         assert helpers.report_line("cigar", model, "qy", "tg", *strands(name), r) == ref["cigar"]
 
 
+@pytest.mark.parametrize("name", AFFINE + GENERIC)
+def test_golden_vectors_specialised_kernel(eng, name, params, scoring, monkeypatch):
+    """The same golden cases through the run-time SPECIALISED table-driven kernel
+    (generic_jit_kernel.cuh compiled for this model by NVRTC): every model, the affine
+    and est2genome families included, forced off their own kernels."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
+    monkeypatch.setenv("C4B_GENERIC_JIT", "1")
+    model, _ = helpers.load_model(name, params)
+    cases = helpers.load_cases(name)
+    pairs = PairSet([c["q"] for c in cases], [c["t"] for c in cases],
+                    splice=[splice_for(name, c) for c in cases])
+    b = Batch(eng, model, scoring, pairs, want_path=True)
+    b.run()
+    assert b.kernel_name == "generic_jit"
+    b.close()
+    opt = Optimal(eng, model, scoring)
+    scores = opt.find_score(pairs)
+    paths = opt.find_path(pairs)
+    for c, s, r in zip(cases, scores, paths):
+        ref = c["path"]
+        assert s == c["score"], c["name"]
+        assert r["score"] == ref["score"], c["name"]
+        assert r["region"] == ref["region"], c["name"]
+        assert r["ops"] == [tuple(o) for o in ref["ops"]], c["name"]
+        assert helpers.report_line("vulgar", model, "qy", "tg", *strands(name), r) == ref["vulgar"]
+
+
+def test_specialised_kernel_matches_interpreter_at_size(eng, params, scoring, monkeypatch):
+    """protein2genome and coding2coding on lattices with several rows per thread
+    (query longer than the 512-thread CTA) and suboptimal-blocked cells: the
+    specialised kernel and the interpreter kernel must agree op for op."""
+    from exonerate_b200 import Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    rng = random.Random(77)
+    for name in ("protein2genome", "coding2coding", "est2genome"):
+        model, _ = helpers.load_model(name, params)
+        qs, ts, sp = [], [], []
+        for k in range(6):
+            if name == "protein2genome":
+                q = "".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(rng.choice([90, 300, 620])))
+                t = helpers.rand_dna(rng, rng.choice([700, 2500, 4000]))
+            else:
+                q, t = helpers.dna_pair(4400 + k, rng.choice([150, 400, 700]), rng.choice([900, 2000]))
+            qs.append(q); ts.append(t)
+            sp.append(splice_arrays(t) if name != "coding2coding" else None)
+        pairs = PairSet(qs, ts, splice=sp)
+        got = {}
+        for jit in ("0", "1"):
+            monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
+            monkeypatch.setenv("C4B_GENERIC_JIT", jit)
+            opt = Optimal(eng, model, scoring)
+            got[jit] = (opt.find_score(pairs), opt.find_path(pairs))
+        assert got["0"][0] == got["1"][0], name
+        for a, b in zip(got["0"][1], got["1"][1]):
+            assert a["score"] == b["score"] and a["region"] == b["region"] and a["ops"] == b["ops"], name
+
+
 def oracle_path(model, scoring, q, t):
     return helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t), abi.MODE_FIND_PATH,
                                   max_ops=len(q) + len(t) + 8)
