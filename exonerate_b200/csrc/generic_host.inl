@@ -15,6 +15,7 @@ struct GenericBatch {
     bool use_jit = false;  // model-specialised kernel (generic_jit.inl) instead of the interpreter
     int jit_threads = 128;
     int ring_ctas = 0;     // CTAs the lattice ring was sized for
+    int max_q = 0;
     const char *kernel_used = "generic_wavefront";
     std::vector<c4b_pair> host_pairs;
     std::vector<GenPair> h_full;
@@ -180,6 +181,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     const int policy = jit_policy();
     g->use_jit = policy == 1 || (policy == 2 && g->cells >= ((int64_t)1 << 30));
     g->jit_threads = jit_threads_for(maxQ);
+    g->max_q = maxQ;
     g->ring_ctas = g->grid;
     if (g->use_jit) g->ring_ctas = std::max(g->ring_ctas, std::min(n, g->sm_count * (2048 / g->jit_threads)));
     const int depth = m.max_target_advance + m.max_query_advance + 1;
@@ -248,7 +250,10 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
     if (!count) return 0;
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
     if (g->use_jit) {
-        if (JitKernel *jk = jit_get(g->tables.model, mode, g->jit_threads)) {
+        // the lattice ring goes to shared memory when DEPTH columns of the longest query fit
+        const size_t ring_bytes = (size_t)jit_ring_words_per_row(g->tables.model, mode) * (g->max_q + 1) * 4;
+        const bool smem_ring = ring_bytes <= (size_t)kJitSmemRingBytes && !getenv("C4B_JIT_GLOBAL_RING");
+        if (JitKernel *jk = jit_get(g->tables.model, mode, g->jit_threads, smem_ring)) {
             const int grid = std::max(1, std::min(std::min(count, g->ring_ctas), g->sm_count * jk->blocks_per_sm));
             const GenTables *tables = g->d_tables.p;
             int32_t *ring = g->d_ring.p;
@@ -256,7 +261,8 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
             int *cursor = g->d_cursor.p;
             void *args[] = {(void *)&pairs, (void *)&count, (void *)&outs, (void *)&tables,
                             (void *)&ring, (void *)&stride, (void *)&cursor};
-            C4B_CUDA(cudaLaunchKernel((const void *)jk->kern, dim3(grid), dim3(jk->threads), args, 0, g->stream));
+            C4B_CUDA(cudaLaunchKernel((const void *)jk->kern, dim3(grid), dim3(jk->threads), args,
+                                      smem_ring ? ring_bytes : 0, g->stream));
             (*g->launches)++;
             g->kernel_used = "generic_jit";
             return 0;

@@ -21,6 +21,10 @@
 
 namespace c4b {
 
+// dynamic shared memory a specialised kernel may use for its lattice ring: 227 KB per
+// CTA less its static tables (scoring 9.5 KB, 20 B per thread of reduction scratch)
+constexpr int kJitSmemRingBytes = 232448 - 1024 - 9600 - 20 * 512;
+
 struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
@@ -62,29 +66,46 @@ static NvrtcApi *nvrtc_api() {
 }
 
 // The closed model as compile-time tables (what generic_jit_kernel.cuh expects).
-static std::string jit_program_source(const c4b_model &m, int mode, int threads) {
+// Columns of state s a reader can still ask for: the largest advance_query +
+// advance_target of the advancing transitions that leave s, plus one (0: never read
+// from the ring).  generic_jit_kernel.cuh lays the lattice ring out by these.
+static std::vector<int> jit_state_depths(const c4b_model &m) {
+    std::vector<int> depth(m.n_states, 0);
+    for (int k = 0; k < m.n_transitions; ++k) {
+        const c4b_transition &t = m.transitions[k];
+        const int adv = t.advance_query + t.advance_target;
+        if (t.input != m.start_state && adv > 0) depth[t.input] = std::max(depth[t.input], adv + 1);
+    }
+    return depth;
+}
+
+// ring words one lattice row needs (as the kernel lays it out)
+static int jit_ring_words_per_row(const c4b_model &m, int mode) {
+    int rows = 0;
+    for (int d : jit_state_depths(m)) rows += d;
+    int C = 1 + m.n_shadow_slots;
+    if (mode == GEN_REGION && m.start_scope != C4B_SCOPE_CORNER)
+        C += (m.start_scope != C4B_SCOPE_QUERY) + (m.start_scope != C4B_SCOPE_TARGET);
+    return std::max(1, rows) * C;
+}
+
+static std::string jit_program_source(const c4b_model &m, int mode, int threads, bool smem_ring) {
     std::ostringstream o;
     o << "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t;\n"
          "typedef unsigned short uint16_t; typedef int int32_t; typedef unsigned int uint32_t;\n"
          "typedef long long int64_t; typedef unsigned long long uint64_t;\n"
          "#define INT_MIN (-2147483647 - 1)\n"
          "#define C4B200_TYPES_ONLY 1\n#include \"c4b200.h\"\n#include \"generic_types.h\"\n";
-    o << "#define JIT_MODE " << mode << "\n#define JIT_THREADS " << threads << "\n";
+    int min_ctas = 1;  // resident CTAs per SM the register allocation must allow
+    if (const char *env = getenv("C4B_JIT_MIN_CTAS")) min_ctas = std::max(1, std::min(16, atoi(env)));
+    o << "#define JIT_MODE " << mode << "\n#define JIT_THREADS " << threads << "\n#define JIT_MIN_CTAS " << min_ctas
+      << "\n#define JIT_SMEM_RING " << (smem_ring ? 1 : 0) << "\n";
     o << "namespace c4bjit {\n";
     const int S = m.n_states, TN = m.n_transitions, NC = std::max(1, m.n_calcs);
-    std::vector<int> saved(S, -1);
-    int nsaved = 0;
-    for (int k = 0; k < TN; ++k) {
-        const c4b_transition &t = m.transitions[k];
-        if (t.input != m.start_state && t.advance_query + t.advance_target > 0 && saved[t.input] < 0)
-            saved[t.input] = 0;
-    }
-    for (int s = 0; s < S; ++s)
-        if (saved[s] == 0) saved[s] = nsaved++;
+    const std::vector<int> depth = jit_state_depths(m);
     o << "constexpr int S = " << S << ", TN = " << TN << ", NSH = " << m.n_shadow_slots << ", START = "
       << m.start_state << ", END = " << m.end_state << ", START_SCOPE = " << m.start_scope
-      << ", END_SCOPE = " << m.end_scope << ", DEPTH = " << (m.max_target_advance + m.max_query_advance + 1)
-      << ", NSAVED = " << std::max(1, nsaved) << ";\n";
+      << ", END_SCOPE = " << m.end_scope << ";\n";
     auto tr_array = [&](const char *name, auto field) {
         o << "constexpr int " << name << "[TN] = {";
         for (int k = 0; k < TN; ++k) o << (k ? "," : "") << field(m.transitions[k]);
@@ -110,8 +131,10 @@ static std::string jit_program_source(const c4b_model &m, int mode, int threads)
     for (int s = 0; s < S; ++s)
         for (int l = 0; l < C4B_MAX_SHADOW_SLOTS; ++l)
             o << ((s || l) ? "," : "") << (l < m.n_shadow_slots ? (int)m.shadow_start[s][l] : 0);
-    o << "};\nconstexpr int kSaved[S] = {";
-    for (int s = 0; s < S; ++s) o << (s ? "," : "") << saved[s];
+    o << "};\nconstexpr int kDepth[S] = {";
+    for (int s = 0; s < S; ++s) o << (s ? "," : "") << depth[s];
+    o << "};\nconstexpr int kRingOff[S] = {";
+    for (int s = 0, off = 0; s < S; ++s) { o << (s ? "," : "") << off; off += depth[s]; }
     o << "};\n}  // namespace c4bjit\n";
     o << kJitSrc_generic_jit_kernel_cuh;
     return o.str();
@@ -147,6 +170,9 @@ static bool jit_compile(const std::string &src, std::vector<char> *cubin, std::s
         if (ok) { cubin->resize(cs); ok = rt->cubin(prog, cubin->data()) == NVRTC_SUCCESS; }
     }
     rt->destroy(&prog);
+    if (ok)
+        if (const char *dump = getenv("C4B_JIT_DUMP"))  // tuning aid: cuobjdump -sass on the result
+            if (FILE *f = fopen(dump, "wb")) { fwrite(cubin->data(), 1, cubin->size(), f); fclose(f); }
     return ok;
 }
 
@@ -159,10 +185,10 @@ static std::string jit_cache_path(const std::string &src) {
 }
 
 // nullptr = no specialised kernel (reason on stderr once per program)
-static JitKernel *jit_get(const c4b_model &m, int mode, int threads) {
+static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_ring) {
     static std::mutex mu;
     static std::map<std::string, JitKernel *> cache;
-    const std::string src = jit_program_source(m, mode, threads);
+    const std::string src = jit_program_source(m, mode, threads, smem_ring);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(src);
     if (it != cache.end()) return it->second;
@@ -199,6 +225,16 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads) {
             if (jk->lib) cudaLibraryUnload(jk->lib);
             delete jk;
             jk = nullptr;
+        } else if (smem_ring) {
+            jk->blocks_per_sm = 1;  // the ring takes the SM's shared memory
+            if (cudaFuncSetAttribute((const void *)jk->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kJitSmemRingBytes) != cudaSuccess) {
+                log = std::string("opting in to the shared-memory ring failed: ") +
+                      cudaGetErrorString(cudaGetLastError());
+                cudaLibraryUnload(jk->lib);
+                delete jk;
+                jk = nullptr;
+            }
         } else {
             int nb = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)jk->kern, threads, 0) != cudaSuccess ||
