@@ -1270,8 +1270,8 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
     if (check_model(*model)) return -1;
     std::vector<char> cubin;
     std::string log;
-    for (int smem_ring = 0; smem_ring < 2; ++smem_ring)  // both lattice-ring placements
-        if (!jit_compile(jit_program_source(*model, mode, cta_threads, smem_ring != 0), &cubin, &log)) {
+    for (int variant = 0; variant < 2; ++variant)  // both lattice-ring placements / start-slot layouts
+        if (!jit_compile(jit_program_source(*model, mode, cta_threads, variant != 0, variant != 0), &cubin, &log)) {
             set_error("model specialisation failed: " + log);
             return -1;
         }

@@ -15,7 +15,7 @@ struct GenericBatch {
     bool use_jit = false;  // model-specialised kernel (generic_jit.inl) instead of the interpreter
     int jit_threads = 128;
     int ring_ctas = 0;     // CTAs the lattice ring was sized for
-    int max_q = 0;
+    int max_q = 0, max_t = 0;
     const char *kernel_used = "generic_wavefront";
     std::vector<c4b_pair> host_pairs;
     std::vector<GenPair> h_full;
@@ -164,6 +164,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
             ilen[pp.blocked_query_pos] = ilen[pp.blocked_target_pos] = (size_t)pp.n_blocked;
         }
         maxQ = std::max(maxQ, pp.query_length);
+        g->max_t = std::max(g->max_t, pp.target_length);
         g->cells += (int64_t)pp.query_length * pp.target_length;
     }
     int rc = 0;
@@ -179,7 +180,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     g->threads = (maxQ + 1 > 512) ? 1024 : (maxQ + 1 > 256 ? 512 : 256);
     g->grid = std::max(1, std::min(n, g->sm_count * (1024 / g->threads)));
     const int policy = jit_policy();
-    g->use_jit = policy == 1 || (policy == 2 && g->cells >= ((int64_t)1 << 30));
+    g->use_jit = policy == 1 || (policy == 2 && g->cells >= ((int64_t)1 << 31));
     g->jit_threads = jit_threads_for(maxQ);
     g->max_q = maxQ;
     g->ring_ctas = g->grid;
@@ -251,9 +252,11 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
     if (g->use_jit) {
         // the lattice ring goes to shared memory when DEPTH columns of the longest query fit
-        const size_t ring_bytes = (size_t)jit_ring_words_per_row(g->tables.model, mode) * (g->max_q + 1) * 4;
+        const bool pack_start = mode == GEN_REGION && ((int64_t)g->max_q + 1) * ((int64_t)g->max_t + 1) < ((int64_t)1 << 31);
+        const size_t ring_bytes =
+            (size_t)jit_ring_words_per_row(g->tables.model, mode, pack_start) * (g->max_q + 1) * 4;
         const bool smem_ring = ring_bytes <= (size_t)kJitSmemRingBytes && !getenv("C4B_JIT_GLOBAL_RING");
-        if (JitKernel *jk = jit_get(g->tables.model, mode, g->jit_threads, smem_ring)) {
+        if (JitKernel *jk = jit_get(g->tables.model, mode, g->jit_threads, smem_ring, pack_start)) {
             const int grid = std::max(1, std::min(std::min(count, g->ring_ctas), g->sm_count * jk->blocks_per_sm));
             const GenTables *tables = g->d_tables.p;
             int32_t *ring = g->d_ring.p;

@@ -9,8 +9,9 @@
 // compile fails, the caller keeps the interpreter kernel (generic_wavefront.cuh)
 // -- both are device kernels, there is no CPU path.
 //
-// C4B_GENERIC_JIT=0 never, =1 always, unset: batches of >= 2^30 lattice cells
-// (below that the compile costs more than it saves in a one-shot process).
+// C4B_GENERIC_JIT=0 never, =1 always, unset: batches of >= 2^31 lattice cells
+// (below that the ~1 s compile per fill mode costs more than it saves in a
+// one-shot process; BSDP's many small region fills stay on the interpreter).
 #include <dlfcn.h>
 #include <nvrtc.h>
 
@@ -80,16 +81,19 @@ static std::vector<int> jit_state_depths(const c4b_model &m) {
 }
 
 // ring words one lattice row needs (as the kernel lays it out)
-static int jit_ring_words_per_row(const c4b_model &m, int mode) {
+static int jit_ring_words_per_row(const c4b_model &m, int mode, bool pack_start) {
     int rows = 0;
     for (int d : jit_state_depths(m)) rows += d;
     int C = 1 + m.n_shadow_slots;
-    if (mode == GEN_REGION && m.start_scope != C4B_SCOPE_CORNER)
-        C += (m.start_scope != C4B_SCOPE_QUERY) + (m.start_scope != C4B_SCOPE_TARGET);
+    if (mode == GEN_REGION && m.start_scope != C4B_SCOPE_CORNER) {
+        const int extra = (m.start_scope != C4B_SCOPE_QUERY) + (m.start_scope != C4B_SCOPE_TARGET);
+        C += (extra == 2 && pack_start) ? 1 : extra;
+    }
     return std::max(1, rows) * C;
 }
 
-static std::string jit_program_source(const c4b_model &m, int mode, int threads, bool smem_ring) {
+static std::string jit_program_source(const c4b_model &m, int mode, int threads, bool smem_ring,
+                                      bool pack_start) {
     std::ostringstream o;
     o << "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t;\n"
          "typedef unsigned short uint16_t; typedef int int32_t; typedef unsigned int uint32_t;\n"
@@ -99,7 +103,8 @@ static std::string jit_program_source(const c4b_model &m, int mode, int threads,
     int min_ctas = 1;  // resident CTAs per SM the register allocation must allow
     if (const char *env = getenv("C4B_JIT_MIN_CTAS")) min_ctas = std::max(1, std::min(16, atoi(env)));
     o << "#define JIT_MODE " << mode << "\n#define JIT_THREADS " << threads << "\n#define JIT_MIN_CTAS " << min_ctas
-      << "\n#define JIT_SMEM_RING " << (smem_ring ? 1 : 0) << "\n";
+      << "\n#define JIT_SMEM_RING " << (smem_ring ? 1 : 0) << "\n#define JIT_PACK_START " << (pack_start ? 1 : 0)
+      << "\n";
     o << "namespace c4bjit {\n";
     const int S = m.n_states, TN = m.n_transitions, NC = std::max(1, m.n_calcs);
     const std::vector<int> depth = jit_state_depths(m);
@@ -185,10 +190,10 @@ static std::string jit_cache_path(const std::string &src) {
 }
 
 // nullptr = no specialised kernel (reason on stderr once per program)
-static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_ring) {
+static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_ring, bool pack_start) {
     static std::mutex mu;
     static std::map<std::string, JitKernel *> cache;
-    const std::string src = jit_program_source(m, mode, threads, smem_ring);
+    const std::string src = jit_program_source(m, mode, threads, smem_ring, pack_start);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(src);
     if (it != cache.end()) return it->second;

@@ -22,7 +22,8 @@
 // for cell the same as generic_wavefront.cuh (the interpreter kernel, which is
 // the reading reference for this file).
 //
-// Expected in front of this file: JIT_MODE (GEN_*), JIT_THREADS, JIT_MIN_CTAS, JIT_SMEM_RING, and namespace
+// Expected in front of this file: JIT_MODE (GEN_*), JIT_THREADS, JIT_MIN_CTAS, JIT_SMEM_RING,
+// JIT_PACK_START, and namespace
 // c4bjit { S, TN, NSH, START, END, START_SCOPE, END_SCOPE,
 // kTrIn/kTrOut/kTrAq/kTrAt/kTrCalc/kTrLabel[TN], kCalcKind/kCalcProt/kCalcP0/
 // kCalcP1/kCalcP2[], kShadow[S*C4B_MAX_SHADOW_SLOTS], kDepth[S], kRingOff[S] }.
@@ -32,8 +33,13 @@ using namespace c4b;
 
 constexpr int LOWV = C4B_IMPOSSIBLY_LOW_SCORE;
 constexpr bool kRegion = (JIT_MODE == GEN_REGION) && START_SCOPE != C4B_SCOPE_CORNER;
+// REGION mode carries where the path left START in extra cell slots (viterbi.c:403-411):
+// QID / TID, or -- when the host saw that every lattice of the batch has fewer than 2^31
+// cells (JIT_PACK_START) -- both in the one slot QID as start_i * (T+1) + start_j.
+constexpr bool kPackStart = JIT_PACK_START && kRegion && START_SCOPE != C4B_SCOPE_QUERY &&
+                            START_SCOPE != C4B_SCOPE_TARGET;
 constexpr int QID = (kRegion && START_SCOPE != C4B_SCOPE_QUERY) ? 1 + NSH : -1;
-constexpr int TID = (kRegion && START_SCOPE != C4B_SCOPE_TARGET) ? 1 + NSH + (QID >= 0 ? 1 : 0) : -1;
+constexpr int TID = (kRegion && START_SCOPE != C4B_SCOPE_TARGET && !kPackStart) ? 1 + NSH + (QID >= 0 ? 1 : 0) : -1;
 constexpr int C = 1 + NSH + (QID >= 0 ? 1 : 0) + (TID >= 0 ? 1 : 0);
 // The lattice ring keeps, per saved state s, only the kDepth[s] most recent
 // columns a reader can still ask for (largest advance_query + advance_target
@@ -243,7 +249,7 @@ __device__ __forceinline__ void transitions(const Ctx &X, int i, int j, bool mat
                 else if (kShadow[base + l] == 2) cur[out * C + 1 + l] = X.q_start + si;
             }
             if constexpr (from_start) {
-                if constexpr (QID >= 0) cur[out * C + (QID >= 0 ? QID : 0)] = si;
+                if constexpr (QID >= 0) cur[out * C + (QID >= 0 ? QID : 0)] = kPackStart ? si * (X.T + 1) + sj : si;
                 if constexpr (TID >= 0) cur[out * C + (TID >= 0 ? TID : 0)] = sj;
             }
             win[out] = (unsigned char)K;
@@ -371,7 +377,8 @@ c4b_jit_fill(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *_
         if (threadIdx.x == 0) {
             GenOut o;
             o.score = red_score[0]; o.end_i = red_i[0]; o.end_j = red_j[0];
-            o.start_i = red_si[0]; o.start_j = red_sj[0];
+            o.start_i = kPackStart ? red_si[0] / (T + 1) : red_si[0];
+            o.start_j = kPackStart ? red_si[0] % (T + 1) : red_sj[0];
             o.flags = (red_score[0] == INT_MIN) ? 1 : 0;
             outs[P.out_index] = o;
         }
