@@ -47,6 +47,9 @@ struct c4b_engine {
     // runs on the aux streams (concurrent launches fill each other's tails)
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device copies of host buffers the caller declared stable (C4B_PAIR_BUFFERS_STABLE):
+    // (host address, bytes) -> device address; dropped by c4b_engine_forget_buffers
+    c4b::ResidentBuffers resident;
 };
 
 namespace {
@@ -1144,6 +1147,7 @@ int c4b_engine_create(int device, c4b_engine **out) {
 void c4b_engine_destroy(c4b_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto &kv : e->resident.map) cudaFree(kv.second);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->stage_free) cudaEventDestroy(e->stage_free);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -1201,7 +1205,7 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
     }
     if (rc == 1) {  // neither specialised template applies: table-driven wavefront
         rc = generic_batch_create(e->stream, &e->launches, model, scoring, n, pairs, want_path != 0,
-                                  &b->generic);
+                                  &b->generic, nullptr, false, e->sm_count, &e->resident);
         if (!rc) {
             b->kernel_name = "generic_wavefront";
             b->cells = generic_batch_cells(b->generic);
@@ -1307,6 +1311,7 @@ int c4b_find_path_batch(c4b_engine *e, const c4b_model *model, const c4b_scoring
     c4b_batch *b = nullptr;
     int rc = c4b_batch_create(e, model, scoring, n, pairs, 1, &b);
     if (rc) { tl_timeline = nullptr; return rc; }
+    tmark("batch created");
     rc = c4b_batch_run(b, threshold);
     tmark("run: everything queued");
     if (!rc) rc = c4b_batch_fetch(b, results, ops, ops_capacity);
@@ -1358,7 +1363,7 @@ int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b
     tl_pool_stream = e->stream;
     GenericBatch *g = nullptr;
     int rc = generic_batch_create(e->stream, &e->launches, model, scoring, 1, pair, mode == 1, &g, start_cells,
-                                  end_cells != nullptr);
+                                  end_cells != nullptr, e->sm_count, &e->resident);
     if (rc) return rc;
     rc = generic_batch_run(g, C4B_IMPOSSIBLY_LOW_SCORE);
     if (!rc) rc = generic_batch_fetch(g, result, ops, ops_capacity);
@@ -1377,6 +1382,15 @@ int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b
     }
     generic_batch_destroy(g);
     return rc;
+}
+
+void c4b_engine_forget_buffers(c4b_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto &kv : e->resident.map) cudaFree(kv.second);
+    e->resident.map.clear();
+    e->resident.bytes = 0;
 }
 
 int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hsp_param *param,

@@ -87,9 +87,33 @@ static int check_model(const c4b_model &m) {
 
 constexpr int32_t kEndMatrixUnset = (int32_t)0x80808080;  // what cudaMemset(0x80) leaves
 
+// Device copy of a host buffer the caller declared stable (C4B_PAIR_BUFFERS_STABLE): uploaded
+// once, found again by (address, bytes) until c4b_engine_forget_buffers.  `pad` zero bytes follow
+// the copy (codon reads may run 2 past the end).  nullptr = not cached (cap reached / failure):
+// the caller stages the buffer with the batch as usual.
+static void *resident_copy(ResidentBuffers *rb, const void *host, size_t bytes, size_t pad) {
+    constexpr size_t kCap = (size_t)16 << 30;
+    auto key = std::make_pair(host, bytes);
+    auto it = rb->map.find(key);
+    if (it != rb->map.end()) return it->second;
+    if (rb->bytes + bytes + pad > kCap) return nullptr;
+    void *dev = nullptr;
+    if (cudaMalloc(&dev, bytes + pad + 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(dev, 0, bytes + pad + 16) != cudaSuccess ||
+        cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(dev);
+        return nullptr;
+    }
+    rb->map[key] = dev;
+    rb->bytes += bytes + pad + 16;
+    return dev;
+}
+
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                         GenericBatch **out, const int32_t *start_cells, bool end_cells) {
+                         GenericBatch **out, const int32_t *start_cells, bool end_cells, int sm_count,
+                         ResidentBuffers *resident) {
     if (check_model(*model)) return -1;
     GenericBatch *g = new GenericBatch();
     g->stream = stream;
@@ -106,11 +130,16 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     g->use_region = want_path && m.start_scope == C4B_SCOPE_ANYWHERE && m.end_scope == C4B_SCOPE_ANYWHERE &&
                     !start_cells && !end_cells;
     g->cmax = 1 + m.n_shadow_slots + (g->use_region ? 2 : 0);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete g; set_error("no device"); return -1; }
-    g->sm_count = prop.multiProcessorCount;
+    if (sm_count <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            delete g;
+            set_error("no device");
+            return -1;
+        }
+    }
+    g->sm_count = sm_count;
 
     // ---- stage sequences (dedupe by host pointer), splice arrays, blocked lists
     std::map<std::pair<const uint8_t *, int>, size_t> smap;
@@ -119,6 +148,9 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     int maxQ = 0;
     std::vector<size_t> qo(n), to(n);
     std::vector<size_t> sp(4 * (size_t)n, 0), bq(n, 0), bt(n, 0);
+    // buffers found in (or added to) the engine's resident set: device addresses, not offsets
+    std::vector<const uint8_t *> qdev(n, nullptr), tdev(n, nullptr);
+    std::vector<const int32_t *> spdev(4 * (size_t)n, nullptr);
     auto place_seq = [&](const uint8_t *p, int len) {
         auto key = std::make_pair(p, len);
         auto it = smap.find(key);
@@ -146,8 +178,13 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
             delete g;
             return -1;
         }
-        qo[p] = place_seq(pp.query, pp.query_len);
-        to[p] = place_seq(pp.target, pp.target_len);
+        const bool stable = resident && (pp.reserved & C4B_PAIR_BUFFERS_STABLE);
+        if (stable) {
+            qdev[p] = (const uint8_t *)resident_copy(resident, pp.query, (size_t)pp.query_len, 4);
+            tdev[p] = (const uint8_t *)resident_copy(resident, pp.target, (size_t)pp.target_len, 4);
+        }
+        if (!qdev[p]) qo[p] = place_seq(pp.query, pp.query_len);
+        if (!tdev[p]) to[p] = place_seq(pp.target, pp.target_len);
         if (splice)
             for (int k = 0; k < 4; ++k) {
                 if (!pp.splice[k]) {
@@ -155,6 +192,10 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
                     delete g;
                     return -1;
                 }
+                if (stable)
+                    spdev[4 * p + k] = (const int32_t *)resident_copy(resident, pp.splice[k],
+                                                                      (size_t)pp.target_len * sizeof(int32_t), 16);
+                if (spdev[4 * p + k]) continue;
                 sp[4 * p + k] = place_ints(pp.splice[k], (size_t)pp.target_len);
                 ilen[pp.splice[k]] = (size_t)pp.target_len;
             }
@@ -197,9 +238,10 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     for (int p = 0; p < n; ++p) {
         const c4b_pair &pp = pairs[p];
         GenPair &G = g->h_full[p];
-        G.q = g->d_seq.p + qo[p];
-        G.t = g->d_seq.p + to[p];
-        for (int k = 0; k < 4; ++k) G.splice[k] = splice ? g->d_ints.p + sp[4 * p + k] : nullptr;
+        G.q = qdev[p] ? qdev[p] : g->d_seq.p + qo[p];
+        G.t = tdev[p] ? tdev[p] : g->d_seq.p + to[p];
+        for (int k = 0; k < 4; ++k)
+            G.splice[k] = !splice ? nullptr : (spdev[4 * p + k] ? spdev[4 * p + k] : g->d_ints.p + sp[4 * p + k]);
         G.n_blocked = pp.n_blocked;
         G.blk_q = pp.n_blocked ? g->d_ints.p + bq[p] : nullptr;
         G.blk_t = pp.n_blocked ? g->d_ints.p + bt[p] : nullptr;
@@ -243,6 +285,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     }
     cudaEventCreate(&g->ev_a);
     cudaEventCreate(&g->ev_b);
+    tmark("generic: staged");
     *out = g;
     return 0;
 }
@@ -273,8 +316,22 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
         g->use_jit = false;
     }
     const int grid = std::min(g->grid, count);
-    generic_fill_kernel<<<grid, g->threads, 0, g->stream>>>(pairs, count, outs, g->d_tables.p, mode,
-                                                            g->d_ring.p, g->ring_stride, g->d_cursor.p);
+    // small lattices (BSDP's region fills): the ring fits the CTA's shared memory, and the fill is
+    // a chain of dependent ring accesses per cell -- shared-memory latency instead of L2's
+    constexpr size_t kSmemRingMax = 160 * 1024;
+    const size_t ring_bytes = g->ring_stride * sizeof(int32_t);
+    // (taken when it does not cost residency: few lattices, or a ring small enough for 4 CTAs per SM)
+    const bool smem_ring = ring_bytes <= kSmemRingMax && (count <= g->sm_count || ring_bytes <= 20 * 1024);
+    if (smem_ring) {
+        static bool opted_in = false;
+        if (!opted_in) {
+            C4B_CUDA(cudaFuncSetAttribute(generic_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kSmemRingMax));
+            opted_in = true;
+        }
+    }
+    generic_fill_kernel<<<grid, g->threads, smem_ring ? ring_bytes : 0, g->stream>>>(
+        pairs, count, outs, g->d_tables.p, mode, g->d_ring.p, g->ring_stride, g->d_cursor.p, smem_ring ? 1 : 0);
     C4B_CUDA(cudaGetLastError());
     (*g->launches)++;
     return 0;
@@ -301,6 +358,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         if (generic_launch_fill(g, g->d_full.p, n, g->d_out_a.p, GEN_REGION)) return -1;
         C4B_CUDA(cudaMemcpyAsync(reg.data(), g->d_out_a.p, n * sizeof(GenOut), cudaMemcpyDeviceToHost, st));
         C4B_CUDA(cudaStreamSynchronize(st));
+        tmark("generic: region pass done");
         for (int p = 0; p < n; ++p) {
             GenPair &B = box[p];
             const GenOut &o = reg[p];
@@ -311,9 +369,16 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         }
     }
     // 2) PATH fill inside the boxes, chunked to the traceback arena
-    size_t free_b = 0, total_b = 0;
-    C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = free_b > (3ull << 30) ? (free_b - (2ull << 30)) / 2 : (256ull << 20);
+    size_t budget = 256ull << 20;  // small jobs (BSDP region fills) never need to ask the driver
+    {
+        size_t all = 0;
+        for (int p = 0; p < n; ++p) all += align_up((size_t)(box[p].Q + 1) * (box[p].T + 1) * S, 16);
+        if (all > budget) {
+            size_t free_b = 0, total_b = 0;
+            C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            if (free_b > (3ull << 30)) budget = (free_b - (2ull << 30)) / 2;
+        }
+    }
     std::vector<size_t> tb_off(n);
     std::vector<Chunk> chunks;
     std::vector<GenJob> jobs(n);
@@ -361,7 +426,9 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     (*g->launches) += 3;
     C4B_CUDA(cudaGetLastError());
     // host_pairs/box vectors die here; the copies above were from pageable memory
+    tmark("generic: path pass queued");
     C4B_CUDA(cudaStreamSynchronize(st));
+    tmark("generic: path pass done");
     return 0;
 }
 

@@ -11,7 +11,9 @@
 //
 // C4B_GENERIC_JIT=0 never, =1 always, unset: batches of >= 2^31 lattice cells
 // (below that the ~1 s compile per fill mode costs more than it saves in a
-// one-shot process; BSDP's many small region fills stay on the interpreter).
+// one-shot process; BSDP's many small region fills stay on the interpreter) --
+// unless C4B_JIT_CACHE_DIR is set: then the compile is paid once per model for
+// good and every batch specialises (BSDP region fills: 0.5 ms instead of 1.5 ms).
 #include <dlfcn.h>
 #include <nvrtc.h>
 
@@ -257,10 +259,14 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
     return jk;
 }
 
-// 0 = never, 1 = always, 2 = by batch size
+// 0 = never, 1 = always, 2 = by batch size.  With a disk cache the compile is paid once per
+// model for good (the reference's "bootstrapper" trade), so every batch specialises.
 static int jit_policy() {
     const char *env = getenv("C4B_GENERIC_JIT");
-    if (!env || !*env) return 2;
+    if (!env || !*env) {
+        const char *dir = getenv("C4B_JIT_CACHE_DIR");
+        return (dir && *dir) ? 1 : 2;
+    }
     return atoi(env) ? 1 : 0;
 }
 

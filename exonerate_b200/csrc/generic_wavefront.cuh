@@ -18,6 +18,7 @@
 // blocking ...).  The affine family takes affine_systolic.cuh instead.
 #pragma once
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "c4b_common.cuh"
@@ -109,8 +110,9 @@ __device__ __forceinline__ bool gen_blocked(const GenPair &P, int i, int j) {
 // grid = resident CTAs; each loops over lattices through an atomic cursor.
 __global__ void __launch_bounds__(kGenThreads)
 generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__restrict__ outs,
-                    const GenTables *__restrict__ tables, int mode, int32_t *__restrict__ ring_base,
-                    size_t ring_stride, int *__restrict__ cursor) {
+                    const GenTables *__restrict__ tables, int mode, int32_t *ring_base,
+                    size_t ring_stride, int *__restrict__ cursor, int smem_ring) {
+    extern __shared__ int32_t s_ring[];  // the lattice ring of small lattices (BSDP region fills) stays on the SM
     __shared__ GenTables G;
     __shared__ int s_pair;
     __shared__ int red_score[kGenThreads], red_i[kGenThreads], red_j[kGenThreads];
@@ -129,7 +131,7 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
         if (m.start_scope != C4B_SCOPE_TARGET) tid = C++;
     }
     const int depth = m.max_target_advance + m.max_query_advance + 1;
-    int32_t *ring = ring_base + (size_t)blockIdx.x * ring_stride;
+    int32_t *ring = smem_ring ? s_ring : ring_base + (size_t)blockIdx.x * ring_stride;
 
     for (;;) {
         if (threadIdx.x == 0) s_pair = atomicAdd(cursor, 1);
@@ -338,9 +340,15 @@ __global__ void generic_score_results_kernel(const GenPair *__restrict__ pairs, 
 
 // ---- host side ---------------------------------------------------------------
 struct GenericBatch;
+// device copies of caller-declared stable host buffers: (host address, bytes) -> device address
+struct ResidentBuffers {
+    std::map<std::pair<const void *, size_t>, void *> map;
+    size_t bytes = 0;
+};
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                         GenericBatch **out, const int32_t *start_cells = nullptr, bool end_cells = false);
+                         GenericBatch **out, const int32_t *start_cells = nullptr, bool end_cells = false,
+                         int sm_count = 0, ResidentBuffers *resident = nullptr);
 int generic_batch_run(GenericBatch *g, c4b_score threshold);
 int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity);
 int64_t generic_batch_cells(const GenericBatch *g);

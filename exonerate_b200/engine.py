@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("C4B_LIB", os.path.join(_HERE, "libc4b200.so"))  # ove
 
 EXPORTS = [
     "c4b_abi_version", "c4b_last_error", "c4b_engine_create", "c4b_engine_destroy",
-    "c4b_engine_set_stream", "c4b_engine_kernel_launches", "c4b_find_score_batch",
+    "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
     "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise",
@@ -64,6 +64,8 @@ def load_library():
     lib.c4b_viterbi_calculate_cells.restype = C.c_int
     lib.c4b_model_specialise.argtypes = [P(abi.Model), C.c_int32, C.c_int32, P(C.c_int64)]
     lib.c4b_model_specialise.restype = C.c_int
+    lib.c4b_engine_forget_buffers.argtypes = [C.c_void_p]
+    lib.c4b_engine_forget_buffers.restype = None
     lib.c4b_hsp_extend_batch.argtypes = [C.c_void_p, P(abi.Scoring), P(abi.HspParam), C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p]

@@ -166,8 +166,15 @@ typedef struct {
     const int32_t *blocked_query_pos;
     const int32_t *blocked_target_pos;
     int32_t n_blocked;
-    int32_t reserved;
+    int32_t reserved; /* flags: C4B_PAIR_* below; 0 = none */
 } c4b_pair;
+
+/* c4b_pair.reserved bit: the query / target / splice buffers of this pair stay valid and
+ * unchanged until c4b_engine_forget_buffers(): the engine may keep its device copies and find
+ * them again by (address, length).  For the reference's heuristic mode, which asks for
+ * thousands of small region fills on one (query, target) (src/bsdp/sar.c): each fill then
+ * uploads its own descriptors only.  Blocked-cell lists are per call and never kept. */
+#define C4B_PAIR_BUFFERS_STABLE 1
 
 /* Result of one lattice.  Coordinates are SEQUENCE coordinates like
  * Alignment.region (src/c4/alignment.h:39-45); ops index into ops[] buffers as
@@ -199,6 +206,9 @@ void c4b_engine_destroy(c4b_engine *e);
 /* Use an existing CUDA stream (cudaStream_t as void*) instead of the engine's
  * own; lets a host framework order our launches with its copies. */
 int c4b_engine_set_stream(c4b_engine *e, void *cuda_stream);
+/* Drop every device copy kept under C4B_PAIR_BUFFERS_STABLE (call before freeing or
+ * rewriting such a buffer).  Waits for the engine's stream. */
+void c4b_engine_forget_buffers(c4b_engine *e);
 /* Counters since engine creation: kernels launched by this library. */
 int64_t c4b_engine_kernel_launches(const c4b_engine *e);
 

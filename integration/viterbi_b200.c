@@ -13,6 +13,8 @@
  */
 #include <string.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <time.h>
 
 #include "viterbi.h"
 #include "ungapped.h"
@@ -50,6 +52,67 @@ c4b_engine *exonerate_b200_engine(void){
             g_error("libc4b200: %s", c4b_last_error());
         }
     return engine;
+    }
+
+/* EXONERATE_B200_STATS=1: one line on stderr at exit */
+static glong stat_calls = 0, stat_cache_miss = 0;
+static gdouble stat_total = 0, stat_prepare = 0, stat_engine = 0;
+static gdouble now_seconds(void){
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9*ts.tv_nsec;
+    }
+static void print_viterbi_stats(void){
+    fprintf(stderr, "exonerate_b200: Viterbi_calculate calls %ld (%.3f s: prepare %.3f s, "
+                    "engine %.3f s), sequence pairs flattened %ld\n",
+            stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss);
+    }
+
+/* Flattened sequences (they are virtual in the reference: revcomp / subseq / translate
+ * views, sequence.c:257-507) and the four splice-site arrays intron_init_func prepares
+ * (intron.c:259-293) of the CURRENT comparison.  BSDP asks for thousands of region fills
+ * on the same (query, target): flatten once per pair, not once per fill.  The Sequences
+ * are shared (pinned) while cached, so the pointers cannot be recycled under the key. */
+static struct {
+    Sequence *query, *target;
+    gchar *qseq, *tseq;
+    gint32 *splice;
+} pair_cache = {NULL, NULL, NULL, NULL, NULL};
+
+static void pair_cache_fetch(Ungapped_Data *ud, gboolean need_splice){
+    register Intron_ArgumentSet *ias;
+    register gint tlen = ud->target->len;
+    if((pair_cache.query != ud->query) || (pair_cache.target != ud->target)){
+        if(pair_cache.query){
+            c4b_engine_forget_buffers(get_engine()); /* device copies are keyed by these addresses */
+            Sequence_destroy(pair_cache.query);
+            Sequence_destroy(pair_cache.target);
+            g_free(pair_cache.qseq);
+            g_free(pair_cache.tseq);
+            g_free(pair_cache.splice);
+            }
+        pair_cache.query = Sequence_share(ud->query);
+        pair_cache.target = Sequence_share(ud->target);
+        pair_cache.qseq = g_new(gchar, ud->query->len+4);
+        pair_cache.tseq = g_new(gchar, tlen+4);
+        Sequence_strncpy(ud->query, 0, ud->query->len, pair_cache.qseq);
+        Sequence_strncpy(ud->target, 0, tlen, pair_cache.tseq);
+        pair_cache.splice = NULL;
+        stat_cache_miss++;
+        }
+    if(need_splice && !pair_cache.splice){
+        ias = Intron_ArgumentSet_create(NULL);
+        pair_cache.splice = g_new(gint32, 4*((gsize)tlen+1));
+        SplicePredictor_predict_array_int(ias->sps->ss5_forward, pair_cache.tseq,
+            tlen, 0, tlen, pair_cache.splice);
+        SplicePredictor_predict_array_int(ias->sps->ss3_forward, pair_cache.tseq,
+            tlen, 0, tlen, pair_cache.splice+tlen);
+        SplicePredictor_predict_array_int(ias->sps->ss5_reverse, pair_cache.tseq,
+            tlen, 0, tlen, pair_cache.splice+2*(gsize)tlen);
+        SplicePredictor_predict_array_int(ias->sps->ss3_reverse, pair_cache.tseq,
+            tlen, 0, tlen, pair_cache.splice+3*(gsize)tlen);
+        }
+    return;
     }
 
 typedef struct B200_Tables {
@@ -335,10 +398,11 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     register SubOpt_Index_Row *soir;
     register gchar *qseq, *tseq;
     register gint i, j, n_blocked = 0, mode = 0;
-    register gint32 *bq = NULL, *bt = NULL, *splice = NULL;
+    register gint32 *bq = NULL, *bt = NULL;
     register gint64 ops_capacity;
     register B200_Path *path = NULL;
-    register Intron_ArgumentSet *ias;
+    register gdouble t_begin = now_seconds(), t_prepared, t_done;
+    static gboolean stats_registered = FALSE;
     c4b_scoring scoring;
     c4b_pair pair;
     c4b_result result;
@@ -385,11 +449,14 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         case Viterbi_Mode_FIND_REGION: mode = 2; break;
         default: g_error("libc4b200: bad mode"); break;
         }
-    /* sequences are virtual in the reference (revcomp/subseq views): flatten */
-    qseq = g_new(gchar, ud->query->len+4);
-    tseq = g_new(gchar, ud->target->len+4);
-    Sequence_strncpy(ud->query, 0, ud->query->len, qseq);
-    Sequence_strncpy(ud->target, 0, ud->target->len, tseq);
+    if(!stats_registered){
+        stats_registered = TRUE;
+        if(g_getenv("EXONERATE_B200_STATS"))
+            atexit(print_viterbi_stats);
+        }
+    pair_cache_fetch(ud, model_has_splice(tables));
+    qseq = pair_cache.qseq;
+    tseq = pair_cache.tseq;
     memset(&pair, 0, sizeof(pair));
     pair.query = (const uint8_t*)qseq;
     pair.target = (const uint8_t*)tseq;
@@ -399,21 +466,11 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     pair.target_start = region->target_start;
     pair.query_length = region->query_length;
     pair.target_length = region->target_length;
+    pair.reserved = C4B_PAIR_BUFFERS_STABLE; /* pair_cache owns them until the next comparison */
     fill_scoring(ud, &scoring);
-    if(model_has_splice(tables)){ /* what intron_init_func prepares (intron.c:259-293) */
-        ias = Intron_ArgumentSet_create(NULL);
-        splice = g_new(gint32, 4*(ud->target->len+1));
-        SplicePredictor_predict_array_int(ias->sps->ss5_forward, tseq,
-            ud->target->len, 0, ud->target->len, splice);
-        SplicePredictor_predict_array_int(ias->sps->ss3_forward, tseq,
-            ud->target->len, 0, ud->target->len, splice+ud->target->len);
-        SplicePredictor_predict_array_int(ias->sps->ss5_reverse, tseq,
-            ud->target->len, 0, ud->target->len, splice+2*ud->target->len);
-        SplicePredictor_predict_array_int(ias->sps->ss3_reverse, tseq,
-            ud->target->len, 0, ud->target->len, splice+3*ud->target->len);
+    if(model_has_splice(tables))
         for(i = 0; i < 4; i++)
-            pair.splice[i] = splice + i*ud->target->len;
-        }
+            pair.splice[i] = pair_cache.splice + (gsize)i*ud->target->len;
     if(subopt)
         soi = SubOpt_Index_create(subopt, region);
     if(soi){ /* rows are sorted by target_pos, positions by query_pos (subopt.c:250-338) */
@@ -438,6 +495,7 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         pair.blocked_target_pos = bt;
         pair.n_blocked = n_blocked;
         }
+    t_prepared = now_seconds();
     ops_capacity = (gint64)region->query_length + region->target_length + 8;
     if(mode == 1){
         path = g_new0(B200_Path, 1);
@@ -488,6 +546,7 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     } else if(c4b_viterbi_calculate(get_engine(), tables, &scoring, &pair, mode,
                              &result, path?path->ops:NULL, ops_capacity))
         g_error("libc4b200: %s", c4b_last_error());
+    stat_engine += now_seconds() - t_prepared;
     /* what a Viterbi_DP_Func leaves in vd (viterbi.c:464-478,633-653) */
     vd->curr_query_end = result.query_end - region->query_start;
     vd->curr_target_end = result.target_end - region->target_start;
@@ -511,9 +570,10 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         SubOpt_Index_destroy(soi);
     g_free(bq);
     g_free(bt);
-    g_free(splice);
-    g_free(qseq);
-    g_free(tseq);
+    t_done = now_seconds();
+    stat_calls++;
+    stat_total += t_done - t_begin;
+    stat_prepare += t_prepared - t_begin;
     return result.score;
     }
 

@@ -54,3 +54,26 @@ def test_cli_heuristic_runs_extend_hsps_on_the_device(name):
                   got.stderr)
     assert m, got.stderr[-500:]
     assert int(m.group(1)) >= 1 and int(m.group(2)) >= 1 and int(m.group(3)) == 0
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")
+@pytest.mark.parametrize("name", ["bsdp_protein2genome", "bsdp_est2genome"])
+def test_cli_heuristic_runs_on_specialised_kernels(name, tmp_path):
+    """BSDP through the run-time SPECIALISED kernels: every derived model (terminal, join, span
+    with its START / END cell tables, SubOpt blocking) is compiled for sm_100a on first use and
+    kept in a disk cache; the second process must find all of them there.  Output byte-identical
+    to the reference both times."""
+    want = open(os.path.join(CLI, name + ".out")).read()
+    cache = tmp_path / "jit"
+    cache.mkdir()
+    env = dict(os.environ, C4B_JIT_CACHE_DIR=str(cache), EXONERATE_B200_STATS="1")
+    for attempt in range(2):
+        got = subprocess.run([BIN] + COMMANDS[name], cwd=CLI, capture_output=True, text=True, timeout=900, env=env)
+        assert got.returncode == 0, got.stderr[-2000:]
+        assert got.stdout == want
+        assert "interpreter kernel" not in got.stderr  # no specialisation failed
+        if attempt == 0:
+            cubins = sorted(os.listdir(cache))
+            assert len(cubins) >= 3
+        else:
+            assert sorted(os.listdir(cache)) == cubins
