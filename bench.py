@@ -48,6 +48,18 @@ WORKLOADS = {
                 "rows in registers, writes 28 B/row checkpoints every 1024 columns and 2 B/cell records only "
                 "inside the refilled windows, so frac>1 is expected; see DESIGN.md. peak ",
     },
+    # the table-driven path (any closed model), specialised per model at run time
+    "protein2genome": {
+        "metric": "GCUPS protein2genome find_path (score+region+ops, bit-exact), 450 aa x 20 kbp genomic batch",
+        "b_alg": 104, "pairs": 592, "cpu_pairs": 1, "qlen": 450, "tlen": 20000, "query_is_protein": True,
+        "workload": "protein2genome --exhaustive, %d aa protein x %d bp genomic pairs (4 exons, GT..AG introns)",
+        "kernel": "c4b_jit_fill (closed model compiled for sm_100a at run time: region pass + path pass in the "
+                  "alignment box, lattice ring in shared memory) + walk",
+        "traffic_key": "c4b_jit_fill<protein2genome>",
+        "note": "B_alg=104 B/cell (SURVEY 8d: 4 B x 13 states x C=2, reference row layout); the kernel keeps the "
+                "lattice ring in shared memory and writes 13 B/cell only inside the alignment box, so the HBM "
+                "roofline does not bind it (it is issue/latency bound, profiles/r01d_generic_jit.md). peak ",
+    },
 }
 
 
@@ -104,6 +116,44 @@ def make_batch_e2g(seed, n, qlen, tlen, n_exons=5, rate=0.02):
                 targets[k, pos + 2 + intron:pos + 4 + intron] = np.frombuffer(b"AG", dtype=np.uint8)
                 pos += intron + 4
     return queries, targets
+
+
+CODON = {"A": "GCT", "R": "CGT", "N": "AAC", "D": "GAC", "C": "TGC", "Q": "CAG", "E": "GAG", "G": "GGT",
+         "H": "CAC", "I": "ATC", "L": "CTG", "K": "AAG", "M": "ATG", "F": "TTC", "P": "CCG", "S": "TCT",
+         "T": "ACC", "W": "TGG", "Y": "TAC", "V": "GTT"}
+
+
+def make_batch_p2g(seed, n, aa, tlen, n_exons=4, rate=0.03):
+    """SURVEY.md 8d config 4 shape: random proteins; genomic = random sequence with the
+    back-translated protein planted as n_exons exons (cut at codon boundaries), GT...AG introns."""
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer("".join(CODON).encode(), dtype=np.uint8)
+    table = np.zeros((256, 3), dtype=np.uint8)
+    for a, c in CODON.items():
+        table[ord(a)] = np.frombuffer(c.encode(), dtype=np.uint8)
+    queries = letters[rng.integers(0, 20, size=(n, aa))]
+    targets = ACGT[rng.integers(0, 4, size=(n, tlen), dtype=np.uint8)]
+    intron = max(60, (tlen // 2 - 3 * aa) // max(1, n_exons - 1))
+    body_len = 3 * aa + (n_exons - 1) * (intron + 4)
+    assert body_len <= tlen
+    for k in range(n):
+        cds = table[queries[k]].reshape(-1).copy()
+        sub = rng.random(cds.size) < rate
+        cds[sub] = ACGT[rng.integers(0, 4, size=int(sub.sum()))]
+        cuts = [0] + sorted(3 * int(c) for c in rng.choice(np.arange(10, aa - 10), n_exons - 1, replace=False)) + [3 * aa]
+        pos = int(rng.integers(0, tlen - body_len + 1))
+        for e in range(n_exons):
+            ex = cds[cuts[e]:cuts[e + 1]]
+            targets[k, pos:pos + ex.size] = ex
+            pos += ex.size
+            if e + 1 < n_exons:
+                targets[k, pos:pos + 2] = np.frombuffer(b"GT", dtype=np.uint8)
+                targets[k, pos + 2 + intron:pos + 4 + intron] = np.frombuffer(b"AG", dtype=np.uint8)
+                pos += intron + 4
+    return queries, targets
+
+
+GENERATORS = {"affine:local": make_batch, "est2genome": make_batch_e2g, "protein2genome": make_batch_p2g}
 
 
 def clocks_sampler(stop, out, index):
@@ -182,7 +232,8 @@ def _cpu_worker(kind, conn, model_name="affine:local"):
         from oracle import refdrv
 
         def fn(lib):
-            m = refdrv.RefModel(lib, model_name, 0, 0, compiled=True)
+            m = refdrv.RefModel(lib, model_name, int(WORKLOADS[model_name].get("query_is_protein", False)), 0,
+                                compiled=True)
 
             def align(q, t):
                 p = m.pair(q, t)
@@ -200,7 +251,7 @@ def _cpu_worker(kind, conn, model_name="affine:local"):
 
         def align(q, t):
             sp = None
-            if model_name == "est2genome":
+            if model_name in ("est2genome", "protein2genome"):
                 from exonerate_b200.models import splice_arrays
                 sp = splice_arrays(t)
             return helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t, splice=sp),
@@ -262,7 +313,7 @@ def reference_arm(args):
     procs = max(1, min(os.cpu_count() or 1, 64))
     W = WORKLOADS[args.model]
     n = procs  # one pair per host process per step: a bounded sample of the workload
-    gen = make_batch if args.model == "affine:local" else make_batch_e2g
+    gen = GENERATORS[args.model]
     queries, targets = gen(1000, n, args.qlen, args.tlen)  # same generator/seed as rank 0 of our arm
     cells = n * queries.shape[1] * targets.shape[1]
     pool = CpuPool(kind, procs, args.model)
@@ -308,15 +359,16 @@ def ours(args):
     params = helpers.load_params()
     scoring = helpers.load_scoring(params)   # the reference's Submat tables (tests/golden/scoring.json)
     W = WORKLOADS[args.model]
-    model, _ = host_model(args.model)        # closed by the host C layer (csrc/host)
+    # closed by the host C layer (csrc/host)
+    model, _ = host_model(args.model, query_is_protein=W.get("query_is_protein", False))
     n = args.pairs or W["pairs"]
-    if args.model == "affine:local":
-        queries, targets = make_batch(1000 + rank, n, args.qlen, args.tlen)
-        splice = None
-    else:
+    queries, targets = GENERATORS[args.model](1000 + rank, n, args.qlen, args.tlen)
+    splice = None
+    if args.model != "affine:local":
         from exonerate_b200.models import splice_arrays
-        queries, targets = make_batch_e2g(1000 + rank, n, args.qlen, args.tlen)
         splice = [splice_arrays(targets[k]) for k in range(n)]   # host C splice predictor (csrc/host/splice.c)
+    if args.model == "protein2genome":
+        os.environ.setdefault("C4B_GENERIC_JIT", "1")  # the batch is below the auto-specialise size
     pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)], splice=splice)
     cells = pairs.cells
 
@@ -439,13 +491,15 @@ def main():
     ap.add_argument("--model", default="affine:local", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0,
                     help="pairs per GPU per step (default: 10k affine:local, 1k est2genome -- BASELINE configs)")
-    ap.add_argument("--qlen", type=int, default=1000)
-    ap.add_argument("--tlen", type=int, default=100000)
+    ap.add_argument("--qlen", type=int, default=0, help="query length (default: the workload's, 1000)")
+    ap.add_argument("--tlen", type=int, default=0, help="target length (default: the workload's, 100000)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fill-timing", action="store_true", help="read the fill-kernel events every step")
     args = ap.parse_args()
+    args.qlen = args.qlen or WORKLOADS[args.model].get("qlen", 1000)
+    args.tlen = args.tlen or WORKLOADS[args.model].get("tlen", 100000)
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)

@@ -372,7 +372,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     size_t budget = 256ull << 20;  // small jobs (BSDP region fills) never need to ask the driver
     {
         size_t all = 0;
-        for (int p = 0; p < n; ++p) all += align_up((size_t)(box[p].Q + 1) * (box[p].T + 1) * S, 16);
+        for (int p = 0; p < n; ++p) all += align_up(GEN_TB_BYTES(box[p].Q, box[p].T, S), 16);
         if (all > budget) {
             size_t free_b = 0, total_b = 0;
             C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -386,7 +386,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     int64_t ops_cursor = 0;
     int begin = 0;
     for (int p = 0; p < n; ++p) {
-        const size_t need = align_up((size_t)(box[p].Q + 1) * (box[p].T + 1) * S, 16);
+        const size_t need = align_up(GEN_TB_BYTES(box[p].Q, box[p].T, S), 16);
         if (need > budget) {
             set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget");
             return -1;

@@ -342,7 +342,7 @@ c4b_jit_fill(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *_
                     }
                 }
                 if constexpr (JIT_MODE == GEN_PATH) {
-                    unsigned char *tbc = P.tb + ((size_t)i * (T + 1) + j) * S;
+                    unsigned char *tbc = P.tb + GEN_TB_CELL(i, j, Q, S);
 #pragma unroll
                     for (int k = 0; k < S; ++k)
                         if (win[k] != 0xFF) tbc[k] = win[k];

@@ -36,4 +36,11 @@ struct GenTables {
 
 enum { GEN_SCORE = 0, GEN_PATH = 1, GEN_REGION = 2 };
 
+// PATH traceback bytes (winning transition id per state per cell, viterbi.c:220-227 keeps
+// pointers) are laid out by ANTI-DIAGONAL: cell (i,j) at [(i+j)*(Q+1) + i][S].  The fill walks
+// diagonals with one thread per row, so a warp's stores land in consecutive S-byte groups
+// (row-major cells would put every thread in its own 32-byte sector: 32x the write traffic).
+#define GEN_TB_CELL(i, j, Q, S) (((size_t)((i) + (j)) * (size_t)((Q) + 1) + (size_t)(i)) * (size_t)(S))
+#define GEN_TB_BYTES(Q, T, S) ((size_t)((Q) + (T) + 1) * (size_t)((Q) + 1) * (size_t)(S))
+
 }  // namespace c4b

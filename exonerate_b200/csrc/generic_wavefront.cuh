@@ -196,7 +196,7 @@ generic_fill_kernel(const GenPair *__restrict__ pairs, int n_pairs, GenOut *__re
                         if (qid >= 0) dst[qid] = si;
                         if (tid >= 0) dst[tid] = sj;
                     }
-                    if (mode == GEN_PATH) P.tb[((size_t)i * (T + 1) + j) * S + tr.output] = (uint8_t)k;
+                    if (mode == GEN_PATH) P.tb[GEN_TB_CELL(i, j, Q, S) + tr.output] = (uint8_t)k;
                 }
                 if ((set >> m.end_state) & 1u) {  // viterbi.c:778-791
                     const int32_t *ec = cell + m.end_state * C;
@@ -262,7 +262,7 @@ __global__ void generic_plan_box_kernel(const GenPair *__restrict__ full, const 
 
 __global__ void generic_clear_tb_kernel(const GenPair *__restrict__ pairs, int n, int S) {
     const GenPair P = pairs[blockIdx.y];
-    const size_t total = (size_t)(P.Q + 1) * (P.T + 1) * S;
+    const size_t total = GEN_TB_BYTES(P.Q, P.T, S);
     uint32_t *w = reinterpret_cast<uint32_t *>(P.tb);
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < (total + 3) / 4;
          k += (size_t)gridDim.x * blockDim.x)
@@ -301,7 +301,7 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
     int32_t *out = ops + 2 * J.ops_off;
     int n_runs = 0, last_t = -1, i = o.end_i, j = o.end_j;
     if (res.status == 0) {
-        int tr = P.tb[((size_t)i * (P.T + 1) + j) * S + m.end_state];
+        int tr = P.tb[GEN_TB_CELL(i, j, P.Q, S) + m.end_state];
         while (tr != 0xFF) {
             if (tr == last_t) out[2 * (n_runs - 1) + 1] += 1;
             else if (n_runs < J.ops_cap) { out[2 * n_runs] = tr; out[2 * n_runs + 1] = 1; ++n_runs; last_t = tr; }
@@ -310,7 +310,7 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
             j -= m.transitions[tr].advance_target;
             if (m.transitions[tr].input == m.start_state) break;
             if (i < 0 || j < 0) { res.status = 4; break; }
-            tr = P.tb[((size_t)i * (P.T + 1) + j) * S + m.transitions[tr].input];
+            tr = P.tb[GEN_TB_CELL(i, j, P.Q, S) + m.transitions[tr].input];
         }
         for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
             const int t0 = out[2 * a], l0 = out[2 * a + 1];
