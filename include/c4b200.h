@@ -207,7 +207,8 @@ void c4b_engine_destroy(c4b_engine *e);
  * own; lets a host framework order our launches with its copies. */
 int c4b_engine_set_stream(c4b_engine *e, void *cuda_stream);
 /* Drop every device copy kept under C4B_PAIR_BUFFERS_STABLE (call before freeing or
- * rewriting such a buffer).  Waits for the engine's stream. */
+ * rewriting such a buffer; batches created from such pairs must be destroyed first).
+ * Waits for the engine's stream. */
 void c4b_engine_forget_buffers(c4b_engine *e);
 /* Counters since engine creation: kernels launched by this library. */
 int64_t c4b_engine_kernel_launches(const c4b_engine *e);
