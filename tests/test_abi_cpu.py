@@ -95,3 +95,21 @@ def test_every_shipped_model_specialises_for_sm100a(name, q_protein):
         assert size.value > 10000
     assert lib.c4b_model_specialise(C.byref(model), 7, 256, None) == -1
     assert lib.c4b_model_specialise(C.byref(model), 0, 100, None) == -1
+
+
+def test_every_scope_combination_specialises():
+    """BSDP derives sub-models with every start / end scope (C4_DerivedModel_create,
+    heuristic.c:242-325,445-528): the specialised kernel has a compile-time branch per scope
+    and per REGION start-slot layout, so compile them all (est2genome: shadows + splice calcs)."""
+    from exonerate_b200 import load_library
+    from exonerate_b200.models import host_model
+    lib = load_library()
+    base, _ = host_model("est2genome")
+    combos = [(s, abi.SCOPE_ANYWHERE) for s in range(5)] + [(abi.SCOPE_ANYWHERE, e) for e in range(1, 5)] + \
+             [(abi.SCOPE_CORNER, abi.SCOPE_CORNER)]
+    for start, end in combos:
+        m = type(base).from_buffer_copy(base)
+        m.start_scope, m.end_scope = start, end
+        for mode in (0, 1, 2):
+            rc = lib.c4b_model_specialise(C.byref(m), mode, 128, None)
+            assert rc == 0, (start, end, mode, lib.c4b_last_error().decode()[:1500])
