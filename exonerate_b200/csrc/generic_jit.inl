@@ -191,6 +191,53 @@ static std::string jit_cache_path(const std::string &src) {
     return std::string(dir) + name;
 }
 
+// cubin -> loaded kernel with its launch limits; nullptr + log on failure
+static JitKernel *jit_load(const std::vector<char> &cubin, int threads, bool smem_ring, std::string *log) {
+    JitKernel *jk = new JitKernel();
+    jk->threads = threads;
+    bool ok = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+              cudaLibraryGetKernel(&jk->kern, jk->lib, "c4b_jit_fill") == cudaSuccess;
+    if (!ok) *log = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    if (ok && smem_ring) {
+        jk->blocks_per_sm = 1;  // the ring takes the SM's shared memory
+        ok = cudaFuncSetAttribute((const void *)jk->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kJitSmemRingBytes) == cudaSuccess;
+        if (!ok)
+            *log = std::string("opting in to the shared-memory ring failed: ") +
+                   cudaGetErrorString(cudaGetLastError());
+    } else if (ok) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)jk->kern, threads, 0) != cudaSuccess ||
+            nb < 1) {
+            cudaGetLastError();
+            nb = 1;
+        }
+        jk->blocks_per_sm = nb;
+    }
+    if (!ok) {
+        if (jk->lib) cudaLibraryUnload(jk->lib);
+        delete jk;
+        return nullptr;
+    }
+    return jk;
+}
+
+static bool read_file(const std::string &path, std::vector<char> *out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = sz > 0;
+    if (ok) {
+        out->resize((size_t)sz);
+        ok = fread(out->data(), 1, (size_t)sz, f) == (size_t)sz;
+    }
+    fclose(f);
+    if (!ok) out->clear();
+    return ok;
+}
+
 // nullptr = no specialised kernel (reason on stderr once per program)
 static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_ring, bool pack_start) {
     static std::mutex mu;
@@ -203,20 +250,13 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
     std::vector<char> cubin;
     std::string log;
     const std::string path = jit_cache_path(src);
-    if (!path.empty())
-        if (FILE *f = fopen(path.c_str(), "rb")) {
-            fseek(f, 0, SEEK_END);
-            const long sz = ftell(f);
-            fseek(f, 0, SEEK_SET);
-            if (sz > 0) {
-                cubin.resize((size_t)sz);
-                if (fread(cubin.data(), 1, (size_t)sz, f) != (size_t)sz) cubin.clear();
-            }
-            fclose(f);
-        }
-    const bool from_disk = !cubin.empty();
-    if (from_disk || jit_compile(src, &cubin, &log)) {
-        if (!from_disk && !path.empty()) {
+    // a cubin on disk that no longer loads (another toolkit / a torn write) is replaced, not trusted
+    if (!path.empty() && read_file(path, &cubin) && !(jk = jit_load(cubin, threads, smem_ring, &log))) {
+        remove(path.c_str());
+        cubin.clear();
+    }
+    if (!jk && jit_compile(src, &cubin, &log)) {
+        if (!path.empty()) {
             const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
             if (FILE *f = fopen(tmp.c_str(), "wb")) {
                 const bool w = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
@@ -224,33 +264,7 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
                 if (!w || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
             }
         }
-        jk = new JitKernel();
-        jk->threads = threads;
-        if (cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-            cudaLibraryGetKernel(&jk->kern, jk->lib, "c4b_jit_fill") != cudaSuccess) {
-            log = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(cudaGetLastError());
-            if (jk->lib) cudaLibraryUnload(jk->lib);
-            delete jk;
-            jk = nullptr;
-        } else if (smem_ring) {
-            jk->blocks_per_sm = 1;  // the ring takes the SM's shared memory
-            if (cudaFuncSetAttribute((const void *)jk->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kJitSmemRingBytes) != cudaSuccess) {
-                log = std::string("opting in to the shared-memory ring failed: ") +
-                      cudaGetErrorString(cudaGetLastError());
-                cudaLibraryUnload(jk->lib);
-                delete jk;
-                jk = nullptr;
-            }
-        } else {
-            int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)jk->kern, threads, 0) != cudaSuccess ||
-                nb < 1) {
-                cudaGetLastError();
-                nb = 1;
-            }
-            jk->blocks_per_sm = nb;
-        }
+        jk = jit_load(cubin, threads, smem_ring, &log);
     }
     if (!jk)
         fprintf(stderr, "libc4b200: model specialisation unavailable, using the interpreter kernel: %s\n",

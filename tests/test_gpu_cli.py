@@ -61,13 +61,13 @@ def test_cli_heuristic_runs_extend_hsps_on_the_device(name):
 def test_cli_heuristic_runs_on_specialised_kernels(name, tmp_path):
     """BSDP through the run-time SPECIALISED kernels: every derived model (terminal, join, span
     with its START / END cell tables, SubOpt blocking) is compiled for sm_100a on first use and
-    kept in a disk cache; the second process must find all of them there.  Output byte-identical
-    to the reference both times."""
+    kept in a disk cache; the second process must find all of them there, the third one finds one
+    entry corrupted and replaces it.  Output byte-identical to the reference every time."""
     want = open(os.path.join(CLI, name + ".out")).read()
     cache = tmp_path / "jit"
     cache.mkdir()
     env = dict(os.environ, C4B_JIT_CACHE_DIR=str(cache), EXONERATE_B200_STATS="1")
-    for attempt in range(2):
+    for attempt in range(3):
         got = subprocess.run([BIN] + COMMANDS[name], cwd=CLI, capture_output=True, text=True, timeout=900, env=env)
         assert got.returncode == 0, got.stderr[-2000:]
         assert got.stdout == want
@@ -77,3 +77,7 @@ def test_cli_heuristic_runs_on_specialised_kernels(name, tmp_path):
             assert len(cubins) >= 3
         else:
             assert sorted(os.listdir(cache)) == cubins
+        if attempt == 1:  # a cache entry that no longer loads is recompiled, not trusted
+            with open(cache / cubins[0], "wb") as f:
+                f.write(b"not a cubin")
+    assert os.path.getsize(cache / cubins[0]) > 1000
