@@ -230,10 +230,17 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     g->ring_stride = align_up((size_t)depth * (maxQ + 1) * m.n_states * g->cmax, 4);
     rc |= g->d_ring.alloc(g->ring_stride * g->ring_ctas);
     if (rc) { delete g; return -1; }
-    std::vector<uint8_t> hs(sbytes + 64, 0);
-    for (auto &kv : smap) memcpy(hs.data() + kv.second, kv.first.first, (size_t)kv.first.second);
-    std::vector<int32_t> hi(ints + 4, 0);
-    for (auto &kv : imap) memcpy(hi.data() + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t));
+    // small jobs: gather into one host block, one copy each; large batches: clear on the device and
+    // copy every buffer straight from where the caller holds it (no second pass over 100s of MB)
+    const bool direct = sbytes + ints * sizeof(int32_t) > ((size_t)1 << 20);
+    std::vector<uint8_t> hs;
+    std::vector<int32_t> hi;
+    if (!direct) {
+        hs.assign(sbytes + 64, 0);
+        for (auto &kv : smap) memcpy(hs.data() + kv.second, kv.first.first, (size_t)kv.first.second);
+        hi.assign(ints + 4, 0);
+        for (auto &kv : imap) memcpy(hi.data() + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t));
+    }
     g->h_full.resize(n);
     for (int p = 0; p < n; ++p) {
         const c4b_pair &pp = pairs[p];
@@ -274,9 +281,22 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
             return -1;
         }
     }
-    if (cudaMemcpyAsync(g->d_tables.p, &g->tables, sizeof(GenTables), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-        cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-        cudaMemcpyAsync(g->d_ints.p, hi.data(), (ints + 4) * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+    bool staged = true;
+    if (direct) {
+        staged = cudaMemsetAsync(g->d_seq.p, 0, sbytes + 64, stream) == cudaSuccess &&
+                 cudaMemsetAsync(g->d_ints.p, 0, (ints + 4) * sizeof(int32_t), stream) == cudaSuccess;
+        for (auto &kv : smap)
+            staged = staged && cudaMemcpyAsync(g->d_seq.p + kv.second, kv.first.first, (size_t)kv.first.second,
+                                               cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        for (auto &kv : imap)
+            staged = staged && cudaMemcpyAsync(g->d_ints.p + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t),
+                                               cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    } else {
+        staged = cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+                 cudaMemcpyAsync(g->d_ints.p, hi.data(), (ints + 4) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+    }
+    if (!staged ||
+        cudaMemcpyAsync(g->d_tables.p, &g->tables, sizeof(GenTables), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
         cudaMemcpyAsync(g->d_full.p, g->h_full.data(), n * sizeof(GenPair), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
         cudaStreamSynchronize(stream) != cudaSuccess) {
         set_error("staging the generic batch failed");

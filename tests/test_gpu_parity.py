@@ -122,6 +122,33 @@ def test_specialised_kernel_matches_interpreter_at_size(eng, params, scoring, mo
             assert a["score"] == b["score"] and a["region"] == b["region"] and a["ops"] == b["ops"], name
 
 
+def test_est2genome_packed_kernel_vs_specialised_table_driven(eng, params, scoring, monkeypatch):
+    """Two independent device implementations of est2genome on lattices too large for the
+    oracle to check in seconds (20 genes of 600 bp x 20 kbp): the packed 16-bit kernel with
+    checkpoint windows against the run-time specialised table-driven kernel, op for op.  The
+    batch is big enough (> 1 MB of sequences + splice arrays) for the direct staging path."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    import bench
+    model, _ = helpers.load_model("est2genome", params)
+    queries, targets = bench.make_batch_e2g(77, 20, 600, 20000)
+    qs = [bytes(q).decode() for q in queries]
+    ts = [bytes(t).decode() for t in targets]
+    pairs = PairSet(qs, ts, splice=[splice_arrays(t) for t in ts])
+    opt = Optimal(eng, model, scoring)
+    packed = opt.find_path(pairs)
+    monkeypatch.setenv("C4B_NO_E2G", "1")
+    monkeypatch.setenv("C4B_GENERIC_JIT", "1")
+    b = Batch(eng, model, scoring, pairs, want_path=True)
+    b.run()
+    assert b.kernel_name == "generic_jit"
+    b.close()
+    generic = Optimal(eng, model, scoring).find_path(pairs)
+    for k, (a, g) in enumerate(zip(packed, generic)):
+        assert a["score"] == g["score"] and a["region"] == g["region"] and a["ops"] == g["ops"], k
+        assert a["score"] > 2000  # the planted gene was found
+
+
 def oracle_path(model, scoring, q, t):
     return helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t), abi.MODE_FIND_PATH,
                                   max_ops=len(q) + len(t) + 8)
