@@ -24,6 +24,7 @@
 #include "e2g_systolic.cuh"
 #include "e2g_packed16.cuh"
 #include "hsp_extend.cuh"
+#include "span_integrate.cuh"
 
 namespace c4b {
 static thread_local std::string g_error;
@@ -1381,6 +1382,50 @@ int c4b_viterbi_calculate_cells(c4b_engine *e, const c4b_model *model, const c4b
         }
     }
     generic_batch_destroy(g);
+    return rc;
+}
+
+int c4b_span_integrate(c4b_engine *e, const c4b_score *src_scores, const int32_t *src_region,
+                       const int32_t *dst_region, const int32_t *span, int32_t *positions) {
+    if (!e || !src_scores || !src_region || !dst_region || !span || !positions || src_region[2] < 0 ||
+        src_region[3] < 0 || dst_region[2] < 0 || dst_region[3] < 0) {
+        set_error("c4b_span_integrate: bad arguments");
+        return -1;
+    }
+    C4B_CUDA(cudaSetDevice(e->device));
+    tl_pool_stream = e->stream;
+    const size_t n_src = ((size_t)src_region[2] + 1) * ((size_t)src_region[3] + 1);
+    const size_t n_dst = ((size_t)dst_region[2] + 1) * ((size_t)dst_region[3] + 1);
+    if (n_src > ((size_t)1 << 30) || n_dst > ((size_t)1 << 29)) {
+        set_error("c4b_span_integrate: region too large");
+        return -1;
+    }
+    DevBuf<int32_t> d_src, d_pos;
+    int rc = 0;
+    if (d_src.alloc(n_src) || d_pos.alloc(2 * n_dst)) rc = -1;
+    if (!rc) {
+        SpanArgs a;
+        a.sqs = src_region[0]; a.sts = src_region[1]; a.sql = src_region[2]; a.stl = src_region[3];
+        a.dqs = dst_region[0]; a.dts = dst_region[1]; a.dql = dst_region[2]; a.dtl = dst_region[3];
+        a.min_q = span[0]; a.max_q = span[1]; a.min_t = span[2]; a.max_t = span[3];
+        const int threads = 128;
+        const int grid = (int)std::min<size_t>((n_dst + threads - 1) / threads, (size_t)e->sm_count * 16);
+        if (cudaMemcpyAsync(d_src.p, src_scores, n_src * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream) !=
+            cudaSuccess)
+            rc = -1;
+        if (!rc) {
+            span_integrate_kernel<<<std::max(grid, 1), threads, 0, e->stream>>>(d_src.p, a, d_pos.p);
+            e->launches++;
+            if (cudaGetLastError() != cudaSuccess ||
+                cudaMemcpyAsync(positions, d_pos.p, 2 * n_dst * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream) !=
+                    cudaSuccess ||
+                cudaStreamSynchronize(e->stream) != cudaSuccess)
+                rc = -1;
+        }
+        if (rc) set_error(std::string("c4b_span_integrate: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    d_src.release();
+    d_pos.release();
     return rc;
 }
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
-    "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise",
+    "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise", "c4b_span_integrate",
 ]
 
 _lib = None
@@ -64,6 +64,8 @@ def load_library():
     lib.c4b_viterbi_calculate_cells.restype = C.c_int
     lib.c4b_model_specialise.argtypes = [P(abi.Model), C.c_int32, C.c_int32, P(C.c_int64)]
     lib.c4b_model_specialise.restype = C.c_int
+    lib.c4b_span_integrate.argtypes = [C.c_void_p] + [P(C.c_int32)] * 5
+    lib.c4b_span_integrate.restype = C.c_int
     lib.c4b_engine_forget_buffers.argtypes = [C.c_void_p]
     lib.c4b_engine_forget_buffers.restype = None
     lib.c4b_hsp_extend_batch.argtypes = [C.c_void_p, P(abi.Scoring), P(abi.HspParam), C.c_void_p, C.c_int32,
@@ -331,3 +333,21 @@ class HSPset:
                 h = ext[k]
                 self.hsp_list.append([h.query_start, h.target_start, h.length, h.score, h.cobs])
         return self.hsp_list
+
+
+def span_integrate(engine, src_scores, src_region, dst_region, span):
+    """c4b_span_integrate: Heuristic_Span_integrate's scan (src/bsdp/heuristic.c:589-678) on the
+    device.  src_scores: (src_ql+1)*(src_tl+1) ints; regions {q_start,t_start,q_len,t_len};
+    span {min_q,max_q,min_t,max_t}.  Returns the flat list of (query_pos, target_pos) per dst cell."""
+    import numpy as np
+    lib = engine.lib
+    I = C.POINTER(C.c_int32)
+    sc = np.ascontiguousarray(src_scores, dtype=np.int32)
+    src = np.asarray(src_region, dtype=np.int32)
+    dst = np.asarray(dst_region, dtype=np.int32)
+    sp = np.asarray(span, dtype=np.int32)
+    out = np.full(2 * (int(dst[2]) + 1) * (int(dst[3]) + 1), -7, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(I)
+    _check(lib, lib.c4b_span_integrate(engine.h, p(sc), p(src), p(dst), p(sp), p(out)), "c4b_span_integrate")
+    return out.tolist()
+

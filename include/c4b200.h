@@ -320,6 +320,18 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
                          const uint8_t *target, int32_t target_len, const uint8_t *target_mask,
                          int32_t n_seeds, const c4b_hsp_seed *seeds, c4b_hsp *out);
 
+/* ---- BSDP span integration -----------------------------
+ * Replaces the scan of Heuristic_Span_integrate (src/bsdp/heuristic.c:589-678): for every cell
+ * of the dst region, the position of the best src-region START-side score a span of
+ * [min_query,max_query] x [min_target,max_target] symbols can bridge, first in (query, target)
+ * order on ties (:638), or (-1,-1).  src_scores = src_integration_matrix[x][y][0] as
+ * (src_ql+1) x (src_tl+1) ints; regions are {query_start, target_start, query_length,
+ * target_length} (region.h:26-32); span = {min_query, max_query, min_target, max_target}
+ * (C4_Span, c4.h:160-170); positions = (dst_ql+1) x (dst_tl+1) x {query_pos, target_pos}
+ * (Heuristic_Span_Cell, heuristic.h:75-78).  One synchronous call. */
+int c4b_span_integrate(c4b_engine *e, const c4b_score *src_scores, const int32_t *src_region,
+                       const int32_t *dst_region, const int32_t *span, int32_t *positions);
+
 /* ---- model specialisation ---------------------------------------------------
  * Device counterpart of the reference's per-model code generation (Viterbi_compile /
  * Codegen, src/c4/viterbi.c:1638-1727, src/c4/codegen.c; archived by the bootstrapper,

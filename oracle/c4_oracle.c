@@ -585,3 +585,40 @@ int c4o_hspset_replay(const c4b_hsp_param *p, int ql, int n_seeds, const c4b_hsp
     free(horizon);
     return n;
 }
+
+/* ---- Heuristic_Span_integrate (src/bsdp/heuristic.c:589-678) ------------------------------
+ * For every cell (i,j) of the dst region: the src-region cell with the best START-side score
+ * among those a span of [min_query,max_query] x [min_target,max_target] symbols can bridge,
+ * first in (query, target) scan order on ties (strict '<', :638), or (-1,-1) when the window is
+ * empty.  Heuristic_Span_score is the constant 0 (:362-366), so the reference's re-use of the
+ * previous cell's answer when the window did not move (:618-621) changes nothing but time; it
+ * is restated anyway so that the walk is the reference's. */
+void c4o_span_integrate(const int32_t *src_scores, const int32_t *src_region, const int32_t *dst_region,
+                        const int32_t *span, int32_t *out) {
+    const int sqs = src_region[0], sts = src_region[1], sql = src_region[2], stl = src_region[3];
+    const int dqs = dst_region[0], dts = dst_region[1], dql = dst_region[2], dtl = dst_region[3];
+    int prev_iq = -1, prev_fq = -1, prev_it = -1, prev_ft = -1;
+    int top_q = -1, top_t = -1;
+    int32_t top = 0;
+    for (int i = 0; i <= dql; i++)
+        for (int j = 0; j <= dtl; j++) {
+            int iq = dqs + i - span[1], it = dts + j - span[3];
+            int fq = dqs + i - span[0], ft = dts + j - span[2];
+            if (iq < sqs) iq = sqs;
+            if (it < sts) it = sts;
+            if (fq > sqs + sql) fq = sqs + sql;
+            if (ft > sts + stl) ft = sts + stl;
+            if (iq != prev_iq || it != prev_it || fq != prev_fq || ft != prev_ft) {
+                top = C4B_IMPOSSIBLY_LOW_SCORE;
+                top_q = top_t = -1;
+                for (int x = iq; x <= fq; x++)
+                    for (int y = it; y <= ft; y++) {
+                        const int32_t cand = src_scores[(size_t)(x - sqs) * (stl + 1) + (y - sts)];
+                        if (top < cand) { top = cand; top_q = x; top_t = y; }
+                    }
+            }
+            out[2 * ((size_t)i * (dtl + 1) + j)] = top_q;
+            out[2 * ((size_t)i * (dtl + 1) + j) + 1] = top_t;
+            prev_iq = iq; prev_it = it; prev_fq = fq; prev_ft = ft;
+        }
+}

@@ -426,3 +426,48 @@ int c4ref_hspset(int match_type, const char *qseq, const char *tseq, int softmas
     Alphabet_destroy(ta);
     return n;
 }
+
+/* ---- Heuristic_Span_integrate (src/bsdp/heuristic.c:589-678) on caller-supplied matrices ----
+ * The reference function reads only span->{min,max}_{query,target}, src_integration_matrix
+ * [x][y][0] and the two regions, and writes dst_integration_matrix[i][j].{query,target}_pos:
+ * a Heuristic_Span holding just those is enough to run the UNMODIFIED function.
+ * src_scores: (src_ql+1) x (src_tl+1) ints; regions {q_start, t_start, q_len, t_len};
+ * span {min_query, max_query, min_target, max_target};
+ * out: (dst_ql+1) x (dst_tl+1) x {query_pos, target_pos}. */
+void c4ref_span_integrate(const int *src_scores, const int *src_region, const int *dst_region,
+                          const int *span, int *out) {
+    Heuristic_Span hs;
+    C4_Span sp;
+    Region *src = Region_create(src_region[0], src_region[1], src_region[2], src_region[3]);
+    Region *dst = Region_create(dst_region[0], dst_region[1], dst_region[2], dst_region[3]);
+    int i, j, sql = src_region[2], stl = src_region[3], dql = dst_region[2], dtl = dst_region[3];
+    memset(&hs, 0, sizeof(hs));
+    memset(&sp, 0, sizeof(sp));
+    sp.min_query = span[0]; sp.max_query = span[1]; sp.min_target = span[2]; sp.max_target = span[3];
+    hs.span = &sp;
+    hs.src_integration_matrix = g_new(C4_Score **, sql + 1);
+    for (i = 0; i <= sql; i++) {
+        hs.src_integration_matrix[i] = g_new(C4_Score *, stl + 1);
+        for (j = 0; j <= stl; j++) {
+            hs.src_integration_matrix[i][j] = g_new(C4_Score, 1);
+            hs.src_integration_matrix[i][j][0] = src_scores[i * (stl + 1) + j];
+        }
+    }
+    hs.dst_integration_matrix = g_new(Heuristic_Span_Cell *, dql + 1);
+    for (i = 0; i <= dql; i++) hs.dst_integration_matrix[i] = g_new0(Heuristic_Span_Cell, dtl + 1);
+    Heuristic_Span_integrate(&hs, src, dst);
+    for (i = 0; i <= dql; i++)
+        for (j = 0; j <= dtl; j++) {
+            out[2 * (i * (dtl + 1) + j)] = hs.dst_integration_matrix[i][j].query_pos;
+            out[2 * (i * (dtl + 1) + j) + 1] = hs.dst_integration_matrix[i][j].target_pos;
+        }
+    for (i = 0; i <= sql; i++) {
+        for (j = 0; j <= stl; j++) g_free(hs.src_integration_matrix[i][j]);
+        g_free(hs.src_integration_matrix[i]);
+    }
+    g_free(hs.src_integration_matrix);
+    for (i = 0; i <= dql; i++) g_free(hs.dst_integration_matrix[i]);
+    g_free(hs.dst_integration_matrix);
+    Region_destroy(src);
+    Region_destroy(dst);
+}

@@ -794,3 +794,33 @@ def test_cell_callback_tables_vs_oracle(eng, params, scoring, name):
         plain = viterbi_calculate_cells(eng, model, scoring, pairs, abi.MODE_FIND_PATH)
         ref = helpers.oracle_viterbi(model, scoring, pb, abi.MODE_FIND_PATH)
         assert plain["score"] == ref["score"] and plain["ops"] == ref["ops"]
+
+
+def test_span_integrate_golden(eng):
+    """c4b_span_integrate against the vectors the unmodified Heuristic_Span_integrate produced
+    (tests/golden/make_span_golden.py): every dst cell's source position, ties and empty
+    windows included -- SURVEY 8f row 1."""
+    import json
+    import os
+    from exonerate_b200.engine import span_integrate
+    cases = json.load(open(os.path.join(helpers.GOLDEN, "span_cases.json")))
+    assert len(cases) >= 30
+    for c in cases:
+        got = span_integrate(eng, c["src_scores"], c["src_region"], c["dst_region"], c["span"])
+        assert got == c["positions"], c["name"]
+
+
+def test_span_integrate_large_vs_oracle(eng):
+    """BSDP-sized and larger regions (48 x 144 and 96 x 288 cells), random and sparse score
+    matrices, against the oracle restatement."""
+    import test_span_oracle
+    from exonerate_b200.engine import span_integrate
+    rng = random.Random(5)
+    for ql, tl in ((48, 144), (96, 288)):
+        n = (ql + 1) * (tl + 1)
+        sc = [abi.IMPOSSIBLY_LOW_SCORE if rng.random() < 0.7 else rng.randrange(0, 500) for _ in range(n)]
+        case = {"src_scores": sc, "src_region": [100, 5000, ql, tl],
+                "dst_region": [100 + ql // 2, 5000 + tl + 300, ql, tl], "span": [0, ql, 30, 200000]}
+        assert span_integrate(eng, sc, case["src_region"], case["dst_region"], case["span"]) == \
+            test_span_oracle.oracle_span_integrate(case)
+
