@@ -1275,10 +1275,17 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
     if (check_model(*model)) return -1;
     std::vector<char> cubin;
     std::string log;
-    for (int variant = 0; variant < 2; ++variant)  // both lattice-ring placements / start-slot layouts
-        if (!jit_compile(jit_program_source(*model, mode, cta_threads, variant != 0, variant != 0), &cubin, &log)) {
-            set_error("model specialisation failed: " + log);
-            return -1;
+    // every variant the launcher can ask for: lattice ring in shared memory or L2, and for
+    // FIND_REGION the one-slot / two-slot start cell; with C4B_JIT_CACHE_DIR set they are left
+    // in the disk cache under the names the batch entry points look up
+    for (int smem_ring = 0; smem_ring < 2; ++smem_ring)
+        for (int pack_start = 0; pack_start < (mode == GEN_REGION ? 2 : 1); ++pack_start) {
+            const std::string src = jit_program_source(*model, mode, cta_threads, smem_ring != 0, pack_start != 0);
+            if (!jit_compile(src, &cubin, &log)) {
+                set_error("model specialisation failed: " + log);
+                return -1;
+            }
+            jit_store(jit_cache_path(src), cubin);
         }
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;

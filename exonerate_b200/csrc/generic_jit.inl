@@ -238,6 +238,17 @@ static bool read_file(const std::string &path, std::vector<char> *out) {
     return ok;
 }
 
+// write-then-rename, so a concurrent reader (another rank, another process) never sees half a cubin
+static void jit_store(const std::string &path, const std::vector<char> &cubin) {
+    if (path.empty()) return;
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    if (FILE *f = fopen(tmp.c_str(), "wb")) {
+        const bool w = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+        fclose(f);
+        if (!w || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+    }
+}
+
 // nullptr = no specialised kernel (reason on stderr once per program)
 static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_ring, bool pack_start) {
     static std::mutex mu;
@@ -256,14 +267,7 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
         cubin.clear();
     }
     if (!jk && jit_compile(src, &cubin, &log)) {
-        if (!path.empty()) {
-            const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
-            if (FILE *f = fopen(tmp.c_str(), "wb")) {
-                const bool w = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
-                fclose(f);
-                if (!w || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
-            }
-        }
+        jit_store(path, cubin);
         jk = jit_load(cubin, threads, smem_ring, &log);
     }
     if (!jk)

@@ -337,8 +337,10 @@ int c4b_span_integrate(c4b_engine *e, const c4b_score *src_scores, const int32_t
  * Codegen, src/c4/viterbi.c:1638-1727, src/c4/codegen.c; archived by the bootstrapper,
  * src/c4/bootstrapper.c): the table-driven fill is compiled for ONE closed model at run
  * time (NVRTC, sm_100a) and cached.  The batch entry points do this themselves for large
- * batches (env C4B_GENERIC_JIT: 0 never, 1 always); this call only compiles, so a host
- * can warm the cache -- or check that a model specialises -- without a GPU.
+ * batches (env C4B_GENERIC_JIT: 0 never, 1 always); this call only compiles -- every variant
+ * the launcher can ask for -- and, when C4B_JIT_CACHE_DIR is set, leaves the cubins there: a
+ * host can fill the cache (the reference's "bootstrapper" step) or check that a model
+ * specialises without a GPU.
  * mode: 0 FIND_SCORE, 1 FIND_PATH, 2 FIND_REGION; cta_threads: 128, 256 or 512.
  * Returns 0 and the cubin size, or -1 with c4b_last_error(). */
 int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threads, int64_t *cubin_bytes);

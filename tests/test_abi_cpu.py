@@ -110,6 +110,26 @@ def test_every_scope_combination_specialises():
     for start, end in combos:
         m = type(base).from_buffer_copy(base)
         m.start_scope, m.end_scope = start, end
-        for mode in (0, 1, 2):
+        for mode in (0, 2):  # FIND_PATH differs from FIND_SCORE only by its traceback stores
             rc = lib.c4b_model_specialise(C.byref(m), mode, 128, None)
             assert rc == 0, (start, end, mode, lib.c4b_last_error().decode()[:1500])
+
+
+def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
+    """With C4B_JIT_CACHE_DIR set, c4b_model_specialise leaves every variant's cubin in the cache
+    (ring in shared memory / L2, and both start-slot layouts for FIND_REGION) -- the device
+    analogue of running the reference's bootstrapper once -- and a second call rewrites the same
+    files (names are a hash of the generated source)."""
+    from exonerate_b200 import load_library
+    from exonerate_b200.models import host_model
+    lib = load_library()
+    monkeypatch.setenv("C4B_JIT_CACHE_DIR", str(tmp_path))
+    model, _ = host_model("coding2coding")
+    assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
+    first = sorted(os.listdir(tmp_path))
+    assert len(first) == 2 and all(f.startswith("c4bjit_") and f.endswith(".cubin") for f in first)
+    assert lib.c4b_model_specialise(C.byref(model), 2, 128, None) == 0
+    assert len(os.listdir(tmp_path)) == 2 + 4
+    assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
+    assert len(os.listdir(tmp_path)) == 6
+    assert all(os.path.getsize(tmp_path / f) > 10000 for f in os.listdir(tmp_path))
