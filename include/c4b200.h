@@ -200,7 +200,11 @@ typedef struct c4b_batch c4b_batch;
 /* ---- engine ------------------------------------------------------------ */
 int c4b_abi_version(void);
 const char *c4b_last_error(void);
-/* device = CUDA ordinal. Fails (no fallback) when no CUDA device is usable. */
+/* device = CUDA ordinal. Fails (no fallback) when no CUDA device is usable.
+ * Threading: the reference's host side is single-threaded (no USE_PTHREADS; module-level
+ * statics in match.c / argument.c), and so is an engine: use it, and the batches made from
+ * it, from one host thread at a time; engines on different devices (one process per GPU, or
+ * one thread per engine) are independent.  c4b_last_error() is per thread. */
 int c4b_engine_create(int device, c4b_engine **out);
 void c4b_engine_destroy(c4b_engine *e);
 /* Use an existing CUDA stream (cudaStream_t as void*) instead of the engine's
