@@ -239,7 +239,7 @@ def _cpu_worker(kind, conn, model_name="affine:local"):
                 p = m.pair(q, t)
                 r = p.path(max_ops=1 << 15)
                 p.close()
-                return r["score"]
+                return (r["score"], r["region"], r["ops"])
             return serve(align)
         refdrv.session(fn)
     else:
@@ -254,8 +254,9 @@ def _cpu_worker(kind, conn, model_name="affine:local"):
             if model_name in ("est2genome", "protein2genome"):
                 from exonerate_b200.models import splice_arrays
                 sp = splice_arrays(t)
-            return helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t, splice=sp),
-                                            region_threshold_cells=0, max_ops=len(q) + len(t) + 8)["score"]
+            r = helpers.oracle_find_path(model, scoring, helpers.PairBuf(q, t, splice=sp),
+                                         region_threshold_cells=0, max_ops=len(q) + len(t) + 8)
+            return (r["score"], r["region"], r["ops"])
         serve(align)
 
 
@@ -277,8 +278,9 @@ class CpuPool:
             pr.start()
             self.workers.append((pr, parent))
 
-    def run(self, queries, targets):
-        """Wall time for all pairs, dealt round-robin to the processes."""
+    def run(self, queries, targets, full=False):
+        """Wall time for all pairs, dealt round-robin to the processes.  Answers are scores, or
+        (score, region, ops) with full=True."""
         n, w = len(queries), len(self.workers)
         tasks = [[] for _ in range(w)]
         for k in range(n):
@@ -292,7 +294,7 @@ class CpuPool:
         scores = [None] * n
         for wi, (_, sc) in enumerate(res):
             for j, s in enumerate(sc):
-                scores[wi + j * w] = s
+                scores[wi + j * w] = s if full else s[0]
         return wall, scores
 
     def close(self):
@@ -338,53 +340,86 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------
-def ours(args):
-    import torch
-    import torch.distributed as dist
+# ALU-issue roofline of the dominant kernels: warp-instructions per lattice cell from ncu
+# (smsp__inst_executed.sum / cells of the same launch; profiles/traffic.json) against the issue
+# rate of the chip, SMs x 4 schedulers x SM clock -- the bound that actually limits kernels
+# that keep the lattice in registers (pipe_alu 79 %, issue 76 %).
+def alu_roofline(cells, ms, key, sm_count, sm_mhz):
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        ipc = rec["warp_inst"] / rec["cells"]
+    except (OSError, KeyError, ValueError):
+        return None
+    peak = sm_count * 4 * (sm_mhz or 1965.0) * 1e6 / 1e9
+    achieved = ipc * cells / (ms * 1e-3) / 1e9
+    return {"bound": "alu-issue", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s",
+            "frac": achieved / peak, "warp_inst_per_cell": ipc,
+            "source": "ncu smsp__inst_executed.sum / cells of %s (%s); pipe_alu %.1f %%, issue_active %.1f %% in "
+                      "that capture; peak = %d SMs x 4 schedulers x %.0f MHz" % (
+                          key, rec.get("profile", "profiles/"), rec.get("pipe_alu_pct", 0),
+                          rec.get("issue_active_pct", 0), sm_count, sm_mhz or 1965.0)}
+
+
+class Job:
+    """rank / world / timing plumbing shared by every workload of one bench process"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the C4 fill has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        # host-side staging threads of the engine: the ranks of one box share its cores
+        os.environ.setdefault("C4B_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 16) // self.world))))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.sm_count = torch.cuda.get_device_properties(self.local).multi_processor_count
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+
+def run_workload(job, eng, model_name, n, qlen, tlen, steps, warmup, sample_clocks=False, want_e2e=True):
+    """One workload on this rank's shard of n pairs: device-resident steps (CUDA events on the
+    launching stream) and end-to-end steps through c4b_find_path_batch with host buffers.
+    Returns a dict of per-job numbers (max over ranks for times, sum for cells)."""
+    torch = job.torch
     import helpers
-    from exonerate_b200 import Batch, Engine, Optimal, PairSet, abi
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the C4 fill has no CPU fallback)")
-    torch.cuda.set_device(local)
-    # host-side staging threads of the engine: the ranks of one box share its cores
-    os.environ.setdefault("C4B_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 16) // world))))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+    from exonerate_b200 import Batch, Optimal, PairSet, abi
     from exonerate_b200.models import host_model
+    from exonerate_b200.sharding import gather_records
+    W = WORKLOADS[model_name]
     params = helpers.load_params()
     scoring = helpers.load_scoring(params)   # the reference's Submat tables (tests/golden/scoring.json)
-    W = WORKLOADS[args.model]
-    # closed by the host C layer (csrc/host)
-    model, _ = host_model(args.model, query_is_protein=W.get("query_is_protein", False))
-    n = args.pairs or W["pairs"]
-    queries, targets = GENERATORS[args.model](1000 + rank, n, args.qlen, args.tlen)
+    model, _ = host_model(model_name, query_is_protein=W.get("query_is_protein", False))  # closed by csrc/host
+    queries, targets = GENERATORS[model_name](1000 + job.rank, n, qlen, tlen)
     splice = None
-    if args.model != "affine:local":
+    if model_name != "affine:local":
         from exonerate_b200.models import splice_arrays
         splice = [splice_arrays(targets[k]) for k in range(n)]   # host C splice predictor (csrc/host/splice.c)
-    if args.model == "protein2genome":
+    if model_name == "protein2genome":
         os.environ.setdefault("C4B_GENERIC_JIT", "1")  # the batch is below the auto-specialise size
     pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)], splice=splice)
-    cells = pairs.cells
-
-    eng = Engine(local)
-    stream = torch.cuda.current_stream()
-    eng.lib.c4b_engine_set_stream(eng.h, stream.cuda_stream)
     opt = Optimal(eng, model, scoring)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    from exonerate_b200.sharding import gather_records
-    # weak scaling: rank r owns pairs [r*n, (r+1)*n) of the job's pair list
-    shards = [np.arange(r * n, (r + 1) * n) for r in range(world)]
+    shards = [np.arange(r * n, (r + 1) * n) for r in range(job.world)]
 
     # ---- device-resident arm: inputs staged in HBM before the timed region ----
     batch = Batch(eng, model, scoring, pairs, want_path=True)
@@ -393,92 +428,236 @@ def ours(args):
 
     def step_resident():
         batch.run()
-        if world > 1:  # per-pair result records gathered over NCCL/NVLink (north_star)
-            gather_records(dev_results, shards, rank, world)
-    for _ in range(args.warmup):
+        if job.world > 1:  # per-pair result records gathered over NCCL/NVLink (north_star)
+            gather_records(dev_results, shards, job.rank, job.world)
+    for _ in range(warmup):
         step_resident()
-    barrier()
-    stop, lines = threading.Event(), []
-    sampler = threading.Thread(target=clocks_sampler, args=(stop, lines, local), daemon=True)
-    sampler.start()
+    job.barrier()
+    stop, lines, sampler = threading.Event(), [], None
+    if sample_clocks:
+        sampler = threading.Thread(target=clocks_sampler, args=(stop, lines, job.local), daemon=True)
+        sampler.start()
     launches0 = eng.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fill_ms = []
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident()
-        if args.fill_timing:
-            fill_ms.append(batch.last_fill_ms())
+        fill_ms.append(batch.last_fill_ms())   # fill-kernel events of THIS step (syncs the stream)
     e1.record()
-    barrier()
+    job.barrier()
     launches = eng.kernel_launches() - launches0
-    dev_ms = e0.elapsed_time(e1) / args.steps
-    if not fill_ms:
-        fill_ms.append(batch.last_fill_ms())
+    dev_ms = e0.elapsed_time(e1) / steps
     stop.set()
-    sampler.join(timeout=3)
-    results, ops = batch.fetch(ops_capacity=n * 4096)
-    n_ops_total = sum(results[k].n_ops for k in range(n))
+    if sampler:
+        sampler.join(timeout=3)
+    need = batch.ops_needed()
+    results, ops = batch.fetch(ops_capacity=need)
+    kernel_name, route = batch.kernel_name, batch.description
     batch.close()
+    out = {"n": n, "cells": pairs.cells, "dev_ms": dev_ms, "fill_ms": float(np.mean(fill_ms)), "launches": launches,
+           "clock_lines": lines, "results": results, "ops": ops, "queries": queries, "targets": targets,
+           "pairs": pairs, "n_ops_total": int(need), "kernel_name": kernel_name, "route": route, "e2e_ms": None}
 
     # ---- end-to-end arm: host buffers in, host results out, every step ----
-    out = ((abi.Result * n)(), np.empty(2 * n * 4096, dtype=np.int32))  # host result buffers, reused
-    host_scores = torch.zeros((n, 10), dtype=torch.int32, device="cuda")
-    for _ in range(min(args.warmup, 2)):
-        opt.find_path_raw(pairs, out=out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        got, _ = opt.find_path_raw(pairs, out=out)
-        if world > 1:
-            host_scores.copy_(torch.from_numpy(np.frombuffer(got, dtype=np.int32).reshape(n, 10)))
-            gather_records(host_scores, shards, rank, world)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    assert all(got[k].score == results[k].score and got[k].n_ops == results[k].n_ops for k in range(n))
+    if want_e2e:
+        hout = ((abi.Result * n)(), np.empty(2 * max(int(need), 1) + 2, dtype=np.int32))  # reused host buffers
+        host_scores = torch.zeros((n, 10), dtype=torch.int32, device="cuda")
+        for _ in range(min(warmup, 2)):
+            opt.find_path_raw(pairs, out=hout)
+        job.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            got, _ = opt.find_path_raw(pairs, out=hout)
+            if job.world > 1:
+                host_scores.copy_(torch.from_numpy(np.frombuffer(got, dtype=np.int32).reshape(n, 10)))
+                gather_records(host_scores, shards, job.rank, job.world)
+        job.barrier()
+        out["e2e_ms"] = (time.perf_counter() - t0) / steps * 1e3
+        for k in range(n):   # the two arms agree record for record
+            a, b_ = got[k], results[k]
+            assert (a.score, a.query_start, a.target_start, a.query_end, a.target_end, a.n_ops) == \
+                   (b_.score, b_.query_start, b_.target_start, b_.query_end, b_.target_end, b_.n_ops), k
+    dev_ms, e2e_ms = job.max_over_ranks([out["dev_ms"], out["e2e_ms"] or 0.0])
+    (total_cells,) = job.sum_over_ranks([float(pairs.cells)])
+    out.update(dev_ms=dev_ms, e2e_ms=e2e_ms if want_e2e else None, total_cells=total_cells,
+               value=total_cells / (dev_ms * 1e-3) / 1e9,
+               e2e_value=(total_cells / (e2e_ms * 1e-3) / 1e9) if want_e2e else None)
+    return out
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    total_cells = cells * world
-    value = total_cells / (dev_ms * 1e-3) / 1e9
-    e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
+
+def check_against_reference(model_name, w, k):
+    """the first k pairs of the batch on the reference's own CPU implementation (one host
+    core): score, alignment region AND operation list must equal the GPU's"""
+    kind = cpu_arm_available()
+    pool = CpuPool(kind, 1, model_name)
+    wall, cpu = pool.run(w["queries"][:k], w["targets"][:k], full=True)
+    pool.close()
+    for i in range(k):
+        r = w["results"][i]
+        o = int(r.ops_offset)
+        gpu = (r.score, [r.query_start, r.target_start, r.query_end - r.query_start, r.target_end - r.target_start],
+               [(int(w["ops"][2 * (o + j)]), int(w["ops"][2 * (o + j) + 1])) for j in range(r.n_ops)])
+        assert cpu[i][0] == gpu[0], "CPU baseline score differs for pair %d: %r vs %r" % (i, cpu[i][0], gpu[0])
+        if cpu[i][1] is not None:   # (the oracle port returns regions and ops too)
+            assert list(cpu[i][1]) == gpu[1], "CPU baseline region differs for pair %d" % i
+            assert [tuple(x) for x in cpu[i][2]] == gpu[2], "CPU baseline ops differ for pair %d" % i
+    q, t = w["queries"].shape[1], w["targets"].shape[1]
+    return {"value": k * q * t / wall / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
+            "sample": "first %d pair(s) of the batch, single-threaded, %.1f s; score, region and ops equal the GPU's"
+                      % (k, wall)}
+
+
+def cli_leg(n_queries=100, n_targets=100, check_queries=1, check_targets=3):
+    """The shipped binary: integration/_build/exonerate_b200 (the unmodified reference with our
+    viterbi.o + the batch hook gam_b200.o) on a FASTA of n_queries x n_targets 1 kbp x 100 kbp
+    sequences, wall clock of the whole process; a subsample is run through the reference's own
+    binary (oracle/_ref/exonerate_c, compiled models) and must print the same bytes."""
+    import re
+    import tempfile
+    import cli_workload
+    exe = os.path.join(ROOT, "integration", "_build", "exonerate_b200")
+    ref = os.path.join(ROOT, "oracle", "_ref", "exonerate_c")
+    if not os.path.exists(exe):
+        return {"unavailable": "integration/_build/exonerate_b200 not built (needs the reference sources)"}
+    flags = ["--model", "affine:local", "--exhaustive", "yes", "--subopt", "no", "--revcomp", "no", "--score", "0"]
+    with tempfile.TemporaryDirectory() as d:
+        rng = np.random.default_rng(77)
+        qs, ts = make_batch(77, max(n_queries, n_targets), 1000, 100000)
+        qrec = [("q%d" % k, bytes(qs[k]).decode()) for k in range(n_queries)]
+        trec = [("t%d" % k, bytes(ts[k]).decode()) for k in range(n_targets)]   # t_k holds a copy of q_k
+        q, t = os.path.join(d, "q.fa"), os.path.join(d, "t.fa")
+        cli_workload.write_fasta(q, qrec)
+        cli_workload.write_fasta(t, trec)
+        env = dict(os.environ, EXONERATE_B200_STATS="1")
+        t0 = time.perf_counter()
+        got = subprocess.run([exe, q, t] + flags + cli_workload.COMMON, capture_output=True, text=True, env=env)
+        wall = time.perf_counter() - t0
+        if got.returncode != 0:
+            return {"error": got.stderr[-500:]}
+        cells = n_queries * n_targets * 1000 * 100000
+        res = {"binary": "integration/_build/exonerate_b200", "pairs": n_queries * n_targets,
+               "flags": " ".join(flags), "wall_s": wall, "value": cells / wall / 1e9, "unit": "GCUPS",
+               "alignments": got.stdout.count("vulgar:")}
+        m = re.search(r"flatten ([\d.]+) s, splice arrays ([\d.]+) s, device ([\d.]+) s \(([\d.]+) GCUPS\), replay ([\d.]+) s",
+                      got.stderr)
+        if m:
+            res.update(flatten_s=float(m.group(1)), device_s=float(m.group(3)), device_gcups=float(m.group(4)),
+                       replay_s=float(m.group(5)),
+                       other_s=wall - float(m.group(1)) - float(m.group(3)) - float(m.group(5)),
+                       note="other_s = the reference's own FASTA parsing (fastapipe re-reads every target per "
+                            "query), process and CUDA start-up, printing")
+        if os.path.exists(ref) and check_queries:
+            sq, st = os.path.join(d, "sq.fa"), os.path.join(d, "st.fa")
+            cli_workload.write_fasta(sq, qrec[:check_queries])
+            cli_workload.write_fasta(st, trec[:check_targets])
+            t0 = time.perf_counter()
+            want = subprocess.run([ref, sq, st] + flags + cli_workload.COMMON, capture_output=True, text=True).stdout
+            ref_wall = time.perf_counter() - t0
+            mine = subprocess.run([exe, sq, st] + flags + cli_workload.COMMON, capture_output=True, text=True,
+                                  env=env).stdout
+            assert want == mine and want.count("vulgar:") >= 1, "CLI output differs from the reference binary"
+            # ... and the same records inside the big run
+            for line in want.splitlines():
+                if line.startswith(("vulgar:", "cigar:")):
+                    assert line in got.stdout, "subsample line missing from the batch run: " + line[:80]
+            res["checked"] = "%d x %d pairs byte-identical to oracle/_ref/exonerate_c (%.1f s, %.3f GCUPS)" % (
+                check_queries, check_targets, ref_wall, check_queries * check_targets * 1e8 / ref_wall / 1e9)
+        return res
+
+
+def ours(args):
+    from exonerate_b200 import Engine
+    job = Job()
+    torch = job.torch
+    rank, world = job.rank, job.world
+    W = WORKLOADS[args.model]
+    strong = args.scaling == "strong"
+    total_pairs = args.pairs or W["pairs"]
+    n = max(1, total_pairs // world) if strong else total_pairs
+
+    eng = Engine(job.local)
+    eng.lib.c4b_engine_set_stream(eng.h, torch.cuda.current_stream().cuda_stream)
+    w = run_workload(job, eng, args.model, n, args.qlen, args.tlen, args.steps, args.warmup, sample_clocks=True)
+
+    extra, strong_block = {}, {}
+    if not args.only_main:
+        # north_star's other workloads in the same driver-run line (fewer steps: they are context)
+        for name in ("est2genome", "protein2genome"):
+            if name == args.model:
+                continue
+            WW = WORKLOADS[name]
+            x = run_workload(job, eng, name, WW["pairs"], WW.get("qlen", 1000), WW.get("tlen", 100000),
+                             steps=3, warmup=2)
+            extra[name] = {"metric": WW["metric"], "value": x["value"], "unit": "GCUPS", "ms_per_step": x["dev_ms"],
+                           "e2e": x["e2e_value"], "pairs_per_gpu": WW["pairs"], "scaling": "weak",
+                           "kernel": x["kernel_name"], "b_alg_bytes_per_cell": WW["b_alg"],
+                           "hbm_roofline_gcups_per_gpu": measured_peak()[0] / WW["b_alg"]}
+        # strong scaling: north_star's FIXED batches split over the ranks
+        for name, tot in (("affine:local", 10000), ("est2genome", 1000)):
+            WW = WORKLOADS[name]
+            x = run_workload(job, eng, name, max(1, tot // world), WW.get("qlen", 1000), WW.get("tlen", 100000),
+                             steps=3, warmup=2)
+            strong_block[name] = {"pairs_total": (tot // world) * world, "pairs_per_gpu": tot // world,
+                                  "value": x["value"], "e2e": x["e2e_value"], "unit": "GCUPS",
+                                  "ms_per_step": x["dev_ms"]}
+
+    int32_value = None
+    if args.model == "affine:local" and not args.only_main:
+        # the same batch on the int32 kernels: what a lattice outside the 16-bit bound gets
+        # (an N in the query, a protein, global / bestfit / overlap scopes, Q > 6399, SubOpt)
+        os.environ["C4B_AFFINE_PACK16"] = "0"
+        os.environ["C4B_AFFINE_TB16"] = "0"
+        x = run_workload(job, eng, args.model, n, args.qlen, args.tlen, steps=3, warmup=2, want_e2e=False)
+        del os.environ["C4B_AFFINE_PACK16"], os.environ["C4B_AFFINE_TB16"]
+        int32_value = x["value"]
+        assert all(x["results"][k].score == w["results"][k].score and x["results"][k].n_ops == w["results"][k].n_ops
+                   for k in range(n)), "int32 and packed kernels disagree"
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        kfill = float(np.mean(fill_ms))
-        achieved = cells * W["b_alg"] / (kfill * 1e-3) / 1e9
+        clocks = summarise_clocks(w["clock_lines"])
+        achieved = w["cells"] * W["b_alg"] / (w["fill_ms"] * 1e-3) / 1e9
+        q, t = w["queries"].shape[1], w["targets"].shape[1]
         line = {
-            "metric": W["metric"], "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+            "metric": W["metric"], "value": w["value"], "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": w["dev_ms"], "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": W["workload"] % (queries.shape[1], targets.shape[1]),
-                       "pairs_per_gpu": n, "cells_per_step": total_cells, "seed": 1000,
-                       "l2": "inputs (%d MB per GPU) exceed the 126 MB L2" % (pairs.h2d_bytes >> 20),
-                       "kernel": W["kernel"]},
+            "config": {"workload": W["workload"] % (q, t),
+                       "pairs_per_gpu": n, "cells_per_step": w["total_cells"], "seed": 1000,
+                       "l2": "inputs (%d MB per GPU) exceed the 126 MB L2" % (w["pairs"].h2d_bytes >> 20),
+                       "kernel": W["kernel"],
+                       "route": w["route"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(cells, W["traffic_key"]),
-                         "note": W["note"] + peak_src, "fill_kernel_ms": kfill},
-            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": pairs.h2d_bytes * world,
-                    "d2h_bytes_per_step": (n * 40 + n_ops_total * 8) * world},
-            "gpu_launches": int(launches),
-            "clocks": summarise_clocks(lines),
+                         "frac": achieved / peak, "traffic": measured_traffic(w["cells"], W["traffic_key"]),
+                         "note": W["note"] + peak_src, "fill_kernel_ms": w["fill_ms"],
+                         "fill_kernel_ms_is": "mean over the %d timed steps (CUDA events on the launching streams)"
+                                              % args.steps},
+            "roofline_alu": alu_roofline(w["cells"], w["fill_ms"], W["traffic_key"], job.sm_count,
+                                         clocks.get("sm_mhz")),
+            "e2e": {"value": w["e2e_value"], "unit": "GCUPS", "h2d_bytes_per_step": w["pairs"].h2d_bytes * world,
+                    "d2h_bytes_per_step": (n * 40 + w["n_ops_total"] * 8) * world, "steps": args.steps},
+            "gpu_launches": int(w["launches"]),
+            "clocks": clocks,
         }
+        if int32_value is not None:
+            line["config"]["int32_kernel_value"] = int32_value
+            line["config"]["dtype_note"] = ("dtype int32 = the arithmetic the results are defined in; lattices inside "
+                                            "the host-checked 16-bit bound run two per register (route), all others "
+                                            "on the int32 kernels at int32_kernel_value GCUPS on this same batch")
+        if extra:
+            line["workloads"] = extra
+        if strong_block:
+            line["strong_scaling"] = strong_block
         if world == 1 and not args.no_cpu_baseline:
-            kind = cpu_arm_available()
-            k = max(1, args.cpu_pairs or W["cpu_pairs"])
-            pool = CpuPool(kind, 1, args.model)
-            wall, cpu_scores = pool.run(queries[:k], targets[:k])
-            pool.close()
-            assert cpu_scores == [results[i].score for i in range(k)], "CPU baseline disagrees with the GPU scores"
-            line["cpu_baseline"] = {"value": k * queries.shape[1] * targets.shape[1] / wall / 1e9, "unit": "GCUPS", "cores": 1,
-                                    "kind": kind,
-                                    "sample": "first %d pair(s) of the batch, single-threaded, %.1f s" % (k, wall)}
+            line["cpu_baseline"] = check_against_reference(args.model, w, max(1, args.cpu_pairs or W["cpu_pairs"]))
+        if world == 1 and not args.no_cli and args.model == "affine:local":
+            line["cli"] = cli_leg()
         print(json.dumps(line))
     eng.close()
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
     return 0
 
 
@@ -493,10 +672,12 @@ def main():
                     help="pairs per GPU per step (default: 10k affine:local, 1k est2genome -- BASELINE configs)")
     ap.add_argument("--qlen", type=int, default=0, help="query length (default: the workload's, 1000)")
     ap.add_argument("--tlen", type=int, default=0, help="target length (default: the workload's, 100000)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fill-timing", action="store_true", help="read the fill-kernel events every step")
+    ap.add_argument("--no-cli", action="store_true", help="skip the exonerate_b200 CLI leg (N=1 only)")
+    ap.add_argument("--only-main", action="store_true", help="skip the other workloads / strong-scaling blocks")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --pairs (default: the workload's batch) is the JOB's total, split over the ranks")
     args = ap.parse_args()
     args.qlen = args.qlen or WORKLOADS[args.model].get("qlen", 1000)
     args.tlen = args.tlen or WORKLOADS[args.model].get("tlen", 100000)

@@ -630,11 +630,13 @@ __device__ __forceinline__ void affine_fill16u_body(const AffPair *__restrict__ 
     }
 }
 
-// long queries: up to 8 warps per pair of lattices, sweeps pipelined
-__global__ void __maxnreg__(168)   // 3 CTAs of 4 warps, or 1 of 8, per SM
+// long queries (R = 32), or small batches that take fewer rows per lane to occupy the GPU
+// (R = 16 / 8, host: affine_create): up to 8 warps per pair of lattices, sweeps pipelined
+template <int R>
+__global__ void __maxnreg__(168)   // R = 32: 3 CTAs of 4 warps, or 1 of 8, per SM
 affine_fill16u_multi_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
                             const AffModel mdl, const void *__restrict__ score_table) {
-    affine_fill16u_body<32, true>(pairs, outs, n, mdl, score_table);
+    affine_fill16u_body<R, true>(pairs, outs, n, mdl, score_table);
 }
 
 // -----------------------------------------------------------------------------

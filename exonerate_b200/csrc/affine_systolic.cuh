@@ -65,7 +65,13 @@ __device__ __forceinline__ int add_open(int m, int one, int open) {
 // whose queries fit one sweep.
 constexpr int kAffMaxWarps = 8;
 
-template <int R, bool TB, int ENDMODE, int SM>
+// BLK = true: some lattice of the launch carries SubOpt blocked cells (src/c4/subopt.h:77-80):
+// at a blocked DESTINATION cell the MATCH-labelled transition (T4) is skipped
+// (viterbi.c:701-704).  The host turns each lattice's list into {column, row mask} entries
+// per lane strip, sorted by column (AffPair::blk / blk_off); a lane walks its strip's entries
+// with one cursor, and only the steps on which some lane meets a blocked column run the
+// masked copy of phase A (the diagonal candidate becomes "not reachable").
+template <int R, bool TB, int ENDMODE, int SM, bool BLK = false>
 __global__ void __launch_bounds__(32 * kAffMaxWarps)
 affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                    const AffModel mdl, const void *__restrict__ score_table) {
@@ -171,6 +177,20 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
         }
         uint32_t *tbp = nullptr;
         if (TB) tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * WPL;
+        // SubOpt: cursor into my strip's blocked columns (columns are relative to P.blk_j0,
+        // the band origin of a traceback refill)
+        int blk_cur = 0, blk_end = 0, blk_next = INT32_MAX;
+        if (BLK && P.blk_off) {
+            blk_cur = P.blk_off[sweep * 32 + lane];
+            blk_end = P.blk_off[sweep * 32 + lane + 1];
+            int lo = blk_cur, hi = blk_end;      // first entry at or after the band origin
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (P.blk[mid].x < P.blk_j0) lo = mid + 1; else hi = mid;
+            }
+            blk_cur = lo;
+            if (blk_cur < blk_end) blk_next = P.blk[blk_cur].x - P.blk_j0;
+        }
 
         // END_ANYWHERE: the column maximum of a step is examined at the top of the
         // NEXT step, when the column's values sit in their loop-carried registers
@@ -215,6 +235,12 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 code0 = kTargetNone;
             }
             int botM = NEGK, botI = NEGK;
+            uint32_t bmask = 0;   // rows of my strip whose cell in this column is blocked
+            if (BLK && j == blk_next) {
+                bmask = (uint32_t)P.blk[blk_cur].y;
+                ++blk_cur;
+                blk_next = (blk_cur < blk_end) ? P.blk[blk_cur].x - P.blk_j0 : INT32_MAX;
+            }
             if (all_active || (j >= 0 && j <= T)) {
                 uint2 X = make_uint2(0, 0);
                 const int32_t *subcol = nullptr;
@@ -235,29 +261,35 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 // the register of the previous column's value it replaces (row r needs
                 // the old M of row r-1 as its diagonal, which is still untouched), so the
                 // loop-carried arrays are updated in place with no register copies.
+                auto phase_a = [&](auto MASKED) {
+                    constexpr bool masked = decltype(MASKED)::value;
 #pragma unroll
-                for (int r = R - 1; r >= 0; --r) {
-                    int sc;
-                    if (SM == SCORE_PRMT) sc = prmt_sx(X.x, X.y, sel[r]);
-                    else sc = subcol[sel[r]];
-                    const int diag = (r == 0) ? topMprev : Mp[r - 1];
-                    if (!TB) {
-                        Dp[r] = __viaddmax_s32(Dp[r], extD, Mp[r]);
-                        Mp[r] = __viaddmax_s32(diag, sc, Dp[r]);   // max(match, D); START and I follow
-                    } else {
-                        // D: T0 extend (tag 4) first, T2 open (tag 0) replaces only if strictly greater
-                        const int Dt = __viaddmax_s32(Dp[r], extD8t, Mp[r]);
-                        const int dm = (Dt & ~7) | 1;
-                        // START candidate (T5): 0 where START is in scope
-                        int sv = LOCAL ? 0 : sv_col;
-                        if (!LOCAL && r == 0 && first_row_lane && (start_row0 || j == 0)) sv = 0;
-                        // M without I: T4 match|3, T5 start|2, T6 from D|1
-                        const int mt = __vimax3_s32(diag + (sc * 8 + 3), sv + 2, dm);
-                        Dp[r] = dm;
-                        Mp[r] = mt;
-                        w[r / 8] |= (uint32_t)((mt & 3) | (Dt & 4)) << (4 * (r % 8));
+                    for (int r = R - 1; r >= 0; --r) {
+                        int sc;
+                        if (SM == SCORE_PRMT) sc = prmt_sx(X.x, X.y, sel[r]);
+                        else sc = subcol[sel[r]];
+                        int diag = (r == 0) ? topMprev : Mp[r - 1];
+                        if (masked && ((bmask >> r) & 1u)) diag = NEGK;   // T4 skipped at a blocked cell
+                        if (!TB) {
+                            Dp[r] = __viaddmax_s32(Dp[r], extD, Mp[r]);
+                            Mp[r] = __viaddmax_s32(diag, sc, Dp[r]);   // max(match, D); START and I follow
+                        } else {
+                            // D: T0 extend (tag 4) first, T2 open (tag 0) replaces only if strictly greater
+                            const int Dt = __viaddmax_s32(Dp[r], extD8t, Mp[r]);
+                            const int dm = (Dt & ~7) | 1;
+                            // START candidate (T5): 0 where START is in scope
+                            int sv = LOCAL ? 0 : sv_col;
+                            if (!LOCAL && r == 0 && first_row_lane && (start_row0 || j == 0)) sv = 0;
+                            // M without I: T4 match|3, T5 start|2, T6 from D|1
+                            const int mt = __vimax3_s32(diag + (sc * 8 + 3), sv + 2, dm);
+                            Dp[r] = dm;
+                            Mp[r] = mt;
+                            w[r / 8] |= (uint32_t)((mt & 3) | (Dt & 4)) << (4 * (r % 8));
+                        }
                     }
-                }
+                };
+                if (BLK && bmask) phase_a(std::true_type{});
+                else phase_a(std::false_type{});
                 // Phase B, rows TOP-DOWN: the vertical chain I -> M -> G.
                 int upM = topM, upI = topI;
 #pragma unroll

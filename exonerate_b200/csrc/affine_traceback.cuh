@@ -45,6 +45,7 @@ __global__ void affine_plan_band_kernel(const AffPair *__restrict__ full, const 
     int64_t j0 = (int64_t)o.end_j - W;
     if (j0 < 0) j0 = 0;
     P.t = P.t + j0;
+    P.blk_j0 = (int32_t)j0;   // SubOpt lists stay in full-lattice columns
     P.T = o.end_j - (int32_t)j0;
     P.Q = o.end_i;
     band[p] = P;

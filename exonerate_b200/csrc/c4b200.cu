@@ -257,6 +257,7 @@ struct c4b_batch {
     c4b_scoring scoring;
     int64_t cells = 0;
     const char *kernel_name = "none";
+    std::string description;   // which lattices took which kernels (c4b_batch_description)
     bool ran = false;
 
     // ---- affine path ----
@@ -266,6 +267,10 @@ struct c4b_batch {
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
     bool p16_multi = false;     // some packed lattice needs more than one sweep
+    // rows per lane / warps per lattice PAIR of the packed score pass.  Normally R16 = R and one
+    // sweep; a batch too small to fill the GPU with one warp per pair takes a smaller R16, so
+    // that every query becomes several sweeps that run as pipelined warps of one CTA
+    int R16 = 32, fill_warps16 = 1;
     bool tb16_band = false, tb16_direct = false;  // traceback pass on affine_fill16tb_kernel
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
@@ -279,6 +284,9 @@ struct c4b_batch {
     DevBuf<TbJob> d_jobs_band, d_jobs_direct;
     DevBuf<uint32_t> d_tb;
     DevBuf<int2> d_top;
+    DevBuf<int2> d_blk;             // SubOpt blocked cells as {column, row mask} per lane strip
+    DevBuf<int32_t> d_blk_off;
+    bool any_blocked = false;       // some lattice has blocked cells: int32 launches use the BLK kernels
     DevBuf<c4b_result> d_results;
     DevBuf<int32_t> d_ops_slots, d_ops_packed;
     DevBuf<int64_t> d_new_off;  // n + 1 (last = total)
@@ -311,7 +319,7 @@ struct c4b_batch {
         d_out1.release(); d_out2.release(); d_outd.release();
         d_band_j0.release(); d_qorg.release(); d_torg.release();
         d_jobs_band.release(); d_jobs_direct.release();
-        d_tb.release(); d_top.release(); d_results.release();
+        d_tb.release(); d_top.release(); d_blk.release(); d_blk_off.release(); d_results.release();
         d_ops_slots.release(); d_ops_packed.release(); d_new_off.release();
         for (auto &ev : fill_events) {
             if (ev.a) cudaEventDestroy(ev.a);
@@ -333,6 +341,13 @@ namespace {
 template <int R, bool TB, int ENDMODE>
 void launch_fill_sm(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
     const int threads = 32 * b->fill_warps;  // warps per lattice = concurrent sweeps (affine_systolic.cuh)
+    if (b->any_blocked) {   // SubOpt: the variant that masks T4 at blocked cells
+        if (b->score_mode == SCORE_PRMT)
+            affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT, true><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+        else
+            affine_fill_kernel<R, TB, ENDMODE, SCORE_SMEM, true><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+        return;
+    }
     if (b->score_mode == SCORE_PRMT)
         affine_fill_kernel<R, TB, ENDMODE, SCORE_PRMT><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
     else
@@ -382,14 +397,18 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
     if (!count) return 0;
     const int blocks = (count + 1) / 2;
     // the offset-binary variant sweeps long queries with up to 8 pipelined warps per CTA
-    const int threads = (b->p16_unsigned && b->p16_multi) ? 32 * b->fill_warps : 32;
+    const int threads = (b->p16_unsigned && b->p16_multi) ? 32 * b->fill_warps16 : 32;
     auto go = [&](auto kernel) -> int {
         kernel<<<blocks, threads, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
         return 0;
     };
     int rc;
-    if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep (R is 32 then)
-        rc = go(affine_fill16u_multi_kernel);
+    if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep of 32 R16 rows
+        switch (b->R16) {
+        case 8: rc = go(affine_fill16u_multi_kernel<8>); break;
+        case 16: rc = go(affine_fill16u_multi_kernel<16>); break;
+        default: rc = go(affine_fill16u_multi_kernel<32>); break;
+        }
     } else if (b->p16_unsigned) {
         switch (b->R) {
         case 8: rc = go(affine_fill16u_kernel<8>); break;
@@ -494,15 +513,16 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         for (int p = 0; p < n; ++p) {
             const c4b_pair &pp = pairs[p];
             if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
-                pp.query_start + pp.query_length > pp.query_len ||
-                pp.target_start + pp.target_length > pp.target_len) {
+                (int64_t)pp.query_start + pp.query_length > pp.query_len ||
+                (int64_t)pp.target_start + pp.target_length > pp.target_len) {
                 set_error("pair " + std::to_string(p) + ": region outside the sequences");
                 return -1;
             }
-            if (pp.n_blocked) {
-                set_error("affine systolic path does not take SubOpt blocked cells");
-                return -2;
+            if (pp.n_blocked < 0 || (pp.n_blocked && (!pp.blocked_query_pos || !pp.blocked_target_pos))) {
+                set_error("pair " + std::to_string(p) + ": bad SubOpt blocked-cell list");
+                return -1;
             }
+            b->any_blocked = b->any_blocked || pp.n_blocked > 0;
             const SeqKey qk(pp.query + pp.query_start, pp.query_length);
             if (seen.insert(qk).second) distinct_q.push_back(qk);
             maxQ = std::max(maxQ, pp.query_length);
@@ -662,13 +682,29 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
             const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
             // per lattice: a query of primary symbols only (classes 0..3), values in 15 bits
             // (the signed variant: one sweep only)
-            return model_ok && !query_wide[p] && (b->p16_unsigned || Q + 1 <= 32 * b->R) &&
+            // (lattices with SubOpt blocked cells take the int32 kernel, which has the masked variant)
+            return model_ok && !query_wide[p] && !pairs[p].n_blocked && (b->p16_unsigned || Q + 1 <= 32 * b->R) &&
                    (int64_t)max_sub * (std::min(Q, T) + 1) <= 32000;
         };
         auto mid = std::stable_partition(b->score_list.begin(), b->score_list.end(), fits16);
         b->n16 = (int)(mid - b->score_list.begin());
-        for (int k = 0; k < b->n16; ++k)
-            b->p16_multi = b->p16_multi || pairs[b->score_list[k]].query_length + 1 > 32 * b->R;
+        // Rows per lane of the packed score pass.  Fewer rows per lane (a 1 kbp query as 2 or 4
+        // pipelined sweeps on the warps of affine_fill16u_multi_kernel) would put more warps on a
+        // GPU that a small batch leaves under-filled, but measured on the B200 it never pays:
+        // 1250 pairs 2301 / 2299 / 1663 GCUPS at 32 / 16 / 8 rows per lane, 2500 pairs 3226 /
+        // 2833 / 2135 (profiles/r02_strong_sweep.md) -- the per-step hand-off through L2 costs more
+        // than the extra warps bring.  So R16 = R unless C4B_P16_R says otherwise (tuning aid).
+        b->R16 = b->R;
+        int maxQ16 = 0;
+        for (int k = 0; k < b->n16; ++k) maxQ16 = std::max(maxQ16, pairs[b->score_list[k]].query_length);
+        if (b->p16_unsigned && b->n16 > 0) {
+            if (const char *env = getenv("C4B_P16_R")) {
+                const int r = atoi(env);
+                if ((r == 8 || r == 16 || r == 32) && r <= b->R) b->R16 = r;
+            }
+        }
+        b->fill_warps16 = std::max(1, std::min(kAffMaxWarps, (maxQ16 + 1 + 32 * b->R16 - 1) / (32 * b->R16)));
+        b->p16_multi = b->p16_unsigned && maxQ16 + 1 > 32 * b->R16;
         // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
         const char *tv = getenv("C4B_AFFINE_TB16");
         const bool tb_ok = model_ok && nonneg && b->aff.openI <= b->aff.extI && b->aff.openD >= -24 &&
@@ -676,7 +712,8 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                            !(tv && atoi(tv) == 0);
         auto fits_tb16 = [&](int p) {
             const int64_t Q = pairs[p].query_length, T = pairs[p].target_length;
-            return !query_wide[p] && Q + 1 <= 32 * b->R && 8 * (int64_t)max_sub * (std::min(Q, T) + 1) + 2048 < 65000;
+            return !query_wide[p] && !pairs[p].n_blocked && Q + 1 <= 32 * b->R &&
+                   8 * (int64_t)max_sub * (std::min(Q, T) + 1) + 2048 < 65000;
         };
         b->tb16_band = tb_ok && b->want_path && !b->score_list.empty() && b->n16 == (int)b->score_list.size() &&
                        std::all_of(b->score_list.begin(), b->score_list.end(), fits_tb16);
@@ -835,9 +872,9 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     std::vector<size_t> top_off(n, (size_t)-1), top_len(n, 0);
     for (int p = 0; p < n; ++p)
         if (pairs[p].query_length + 1 > 32 * b->R) top_len[p] = (size_t)pairs[p].target_length + 1;
-    for (int k = 0; k + 1 < b->n16; k += 2) {
-        const int pa = b->score_list[k], pb = b->score_list[k + 1];
-        if (std::max(pairs[pa].query_length, pairs[pb].query_length) + 1 > 32 * b->R)
+    for (int k = 0; k < b->n16; k += 2) {
+        const int pa = b->score_list[k], pb = b->score_list[std::min(k + 1, b->n16 - 1)];
+        if (std::max(pairs[pa].query_length, pairs[pb].query_length) + 1 > 32 * b->R16)
             top_len[pa] = std::max(top_len[pa], (size_t)std::max(pairs[pa].target_length, pairs[pb].target_length) + 1);
     }
     size_t top_elems = 0;
@@ -848,8 +885,52 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         }
     if (b->d_top.alloc(top_elems)) return -1;
 
+    // ---- SubOpt blocked cells (src/c4/subopt.c:250-338: region coordinates of the DESTINATION
+    // cell, sorted by target then query position) -> per lane strip {column, row mask}, by column
+    std::vector<int2> h_blk;
+    std::vector<int32_t> h_blk_off;
+    std::vector<size_t> blk_seg(n, (size_t)-1);
+    if (b->any_blocked) {
+        std::vector<std::array<int32_t, 3>> cells;   // (strip, column, row in strip)
+        for (int p = 0; p < n; ++p) {
+            const c4b_pair &pp = pairs[p];
+            if (!pp.n_blocked) continue;
+            const int nstrips = 32 * ((pp.query_length + 1 + 32 * b->R - 1) / (32 * b->R));
+            cells.clear();
+            for (int k = 0; k < pp.n_blocked; ++k) {
+                const int i = pp.blocked_query_pos[k], j = pp.blocked_target_pos[k];
+                if (i < 0 || i > pp.query_length || j < 0 || j > pp.target_length) continue;  // never looked at
+                cells.push_back({i / b->R, j, i % b->R});
+            }
+            std::sort(cells.begin(), cells.end());
+            blk_seg[p] = h_blk_off.size();
+            size_t c = 0;
+            for (int strip = 0; strip < nstrips; ++strip) {
+                h_blk_off.push_back((int32_t)h_blk.size());
+                while (c < cells.size() && cells[c][0] == strip) {
+                    const int j = cells[c][1];
+                    uint32_t mask = 0;
+                    for (; c < cells.size() && cells[c][0] == strip && cells[c][1] == j; ++c) mask |= 1u << cells[c][2];
+                    h_blk.push_back(make_int2(j, (int)mask));
+                }
+            }
+            h_blk_off.push_back((int32_t)h_blk.size());
+            if (h_blk.size() > (size_t)INT32_MAX / 2) {
+                set_error("too many SubOpt blocked cells in one batch");
+                return -1;
+            }
+        }
+        if (b->d_blk.alloc(h_blk.size() + 1) || b->d_blk_off.alloc(h_blk_off.size() + 1)) return -1;
+    }
+
     // ---- tables, lattice descriptors and traceback jobs go up first (small)
     cudaStream_t st = e->stream;
+    if (!h_blk_off.empty()) {
+        if (!h_blk.empty())
+            C4B_CUDA(cudaMemcpyAsync(b->d_blk.p, h_blk.data(), h_blk.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        C4B_CUDA(cudaMemcpyAsync(b->d_blk_off.p, h_blk_off.data(), h_blk_off.size() * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, st));
+    }
     C4B_CUDA(cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemcpyAsync(b->d_score_table.p, table.data(), table.size(), cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), st));
@@ -870,6 +951,10 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
             a.top1 = a.top0 + top_len[p];
         }
         a.out_index = slot;
+        a.blk = b->d_blk.p;
+        a.blk_off = (blk_seg[p] != (size_t)-1) ? b->d_blk_off.p + blk_seg[p] : nullptr;
+        a.blk_j0 = 0;
+        a.blk_pad = 0;
         return a;
     };
     auto make_job = [&](int p, int slot, bool band) {
@@ -993,6 +1078,20 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
     C4B_CUDA(cudaEventRecord(e->stage_free, cs));
     b->kernel_name = "affine_systolic";
+    {
+        char buf[512];
+        int nblk = 0;
+        for (int p = 0; p < n; ++p) nblk += pairs[p].n_blocked > 0;
+        snprintf(buf, sizeof buf,
+                 "affine: %d lattices; score pass: %d packed 16-bit (%s, %d rows/lane, %d warp(s) per lattice pair), "
+                 "%d int32 (%d rows/lane, %d warp(s) per lattice%s); traceback: %d banded (%s), %d single-pass (%s); "
+                 "%d with SubOpt blocked cells",
+                 n, b->n16, b->p16_unsigned ? "offset-binary" : "signed", b->p16_multi ? b->R16 : b->R,
+                 b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R, b->fill_warps,
+                 b->any_blocked ? ", BLK variant" : "", b->want_path ? ns : 0, b->tb16_band ? "packed 16-bit" : "int32",
+                 b->want_path ? nd : 0, b->tb16_direct ? "packed 16-bit" : "int32", nblk);
+        b->description = buf;
+    }
     return 0;
 }
 
@@ -1182,9 +1281,11 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
     b->model = *model;
     b->scoring = *scoring;
     int match_kind = 0;
-    bool any_blocked = false;
-    for (int p = 0; p < n; ++p) any_blocked |= pairs[p].n_blocked > 0;
     int rc;
+    if (check_model(*model)) {   // every path: the specialised kernels index the same tables
+        delete b;
+        return -1;
+    }
     if (n == 0) {
         *out = b;  // an empty batch runs and fetches nothing
         return 0;
@@ -1192,7 +1293,7 @@ int c4b_batch_create(c4b_engine *e, const c4b_model *model, const c4b_scoring *s
     const bool force_generic = getenv("C4B_FORCE_GENERIC") != nullptr;  // testing: every model through the table-driven path
     if (force_generic) {
         rc = 1;
-    } else if (!any_blocked && analyze_affine(*model, &b->aff, &match_kind)) {
+    } else if (analyze_affine(*model, &b->aff, &match_kind)) {
         b->affine = true;
         rc = affine_create(b, pairs, match_kind);
     } else {
@@ -1239,6 +1340,26 @@ int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops, int64_t ops
     if (b->affine) return affine_fetch(b, results, ops, ops_capacity);
     if (b->e2g) return e2g_batch_fetch(b->e2g, results, ops, ops_capacity);
     return generic_batch_fetch(b->generic, results, ops, ops_capacity);
+}
+
+int64_t c4b_batch_ops_needed(c4b_batch *b) {
+    if (!b || !b->ran) {
+        set_error("c4b_batch_ops_needed before c4b_batch_run");
+        return -1;
+    }
+    if (b->n == 0 || !b->want_path) return 0;
+    cudaSetDevice(b->e->device);
+    const int64_t *d_total = b->affine ? b->d_new_off.p + b->n
+                             : b->e2g  ? b->e2g->d_new_off.p + b->n
+                                       : b->generic->d_new_off.p + b->n;
+    cudaStream_t st = b->affine ? b->e->stream : b->e2g ? b->e2g->stream : b->generic->stream;
+    int64_t total = 0;
+    if (cudaMemcpyAsync(&total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(std::string("c4b_batch_ops_needed: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return total;
 }
 
 const void *c4b_batch_device_results(const c4b_batch *b) {
@@ -1293,6 +1414,11 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
 
 const char *c4b_batch_kernel_name(const c4b_batch *b) {
     return b->generic ? b->generic->kernel_used : b->kernel_name;
+}
+
+const char *c4b_batch_description(const c4b_batch *b) {
+    if (!b->description.empty()) return b->description.c_str();
+    return c4b_batch_kernel_name(b);
 }
 
 void c4b_batch_destroy(c4b_batch *b) { delete b; }

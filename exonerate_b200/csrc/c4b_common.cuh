@@ -39,6 +39,12 @@ struct AffPair {
     uint32_t *tb;      // traceback nibbles, skewed layout [sweep][step][lane][R/8]; may be null
     int2 *top0, *top1; // sweep hand-off rows {M,I}[T+1], ping-pong; null when one sweep
     int64_t out_index; // which result slot this lattice reports into
+    // SubOpt blocked cells (int32 fill only): entries {column, row mask} of lane strip k are
+    // blk[blk_off[k] .. blk_off[k+1]), sorted by column; blk_off null = nothing blocked;
+    // blk_j0 = lattice column 0 in the list's coordinates (non-zero for a banded refill)
+    const int2 *blk;
+    const int32_t *blk_off;
+    int32_t blk_j0, blk_pad;
 };
 
 struct AffOut {

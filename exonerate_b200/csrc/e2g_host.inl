@@ -163,7 +163,7 @@ struct E2gBatch {
 // returns 0 ok, 1 "not eligible, use the generic path", <0 error
 static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                             const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
-                            E2gBatch **out) {
+                            E2gBatch **out, bool allow_packed = true) {
     E2gModel mdl;
     if (!analyze_est2genome(*model, *scoring, &mdl)) return 1;
     int maxQ = 0;
@@ -172,7 +172,8 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         const c4b_pair &pp = pairs[p];
         if (pp.n_blocked) return 1;
         if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
-            pp.query_start + pp.query_length > pp.query_len || pp.target_start + pp.target_length > pp.target_len) {
+            (int64_t)pp.query_start + pp.query_length > pp.query_len ||
+            (int64_t)pp.target_start + pp.target_length > pp.target_len) {
             set_error("pair " + std::to_string(p) + ": region outside the sequences");
             return -1;
         }
@@ -215,7 +216,7 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
             for (int c = 0; c < 24 && used[a]; ++c) max_sub = std::max(max_sub, scoring->dna_matrix[a * 24 + c]);
         const char *env = getenv("C4B_E2G_PACK16");
         const int64_t top_score = (int64_t)max_sub * (std::min(maxQ, maxT) + 1) + 400;
-        packed = !(env && atoi(env) == 0) && top_score <= 30000 && mdl.open > -1000 && mdl.ext > -1000 &&
+        packed = allow_packed && !(env && atoi(env) == 0) && top_score <= 30000 && mdl.open > -1000 && mdl.ext > -1000 &&
                  mdl.intron_open > -4000 && mdl.intron_open < 1000 && mdl.min_intron - 2 <= 32000 &&
                  (int64_t)mdl.max_intron >= (int64_t)maxT + 2;
     }
@@ -279,6 +280,10 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         }
         memset(hseq + qbytes + tbytes, tfill, 64);
         std::atomic<bool> out_of_range(false);
+        // the 16-bit value bound assumes an intron never GAINS score: intron_open + 5'ss + 3'ss <= 0
+        // on either strand (true for the default --intronpenalty -30; with e.g. 0, introns chain
+        // without consuming query and the score grows with their number: halfword adds would wrap)
+        std::atomic<int> max_gain(INT32_MIN);
         parallel_for((int)tlist.size(), [&](int k) {
             const size_t off = tlist[k].second, len = (size_t)tlist[k].first.second, slot = align_up(len, 16) + 16;
             memcpy(hseq + qbytes + off, tlist[k].first.first, len);
@@ -288,18 +293,29 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
             const int32_t *s2 = pp.splice[2] + pp.target_start, *s3 = pp.splice[3] + pp.target_start;
             uint32_t *dst = hsp + off;
             bool bad = false;
+            int32_t m0 = INT32_MIN, m1 = INT32_MIN, m2 = INT32_MIN, m3 = INT32_MIN;
             for (size_t j = 0; j < len; ++j) {
                 const int32_t a = s0[j], c = s1[j], d = s2[j], e = s3[j];
+                m0 = std::max(m0, a); m1 = std::max(m1, c); m2 = std::max(m2, d); m3 = std::max(m3, e);
                 bad |= (uint32_t)(a + 127) > 254u || (uint32_t)(c + 127) > 254u || (uint32_t)(d + 127) > 254u ||
                        (uint32_t)(e + 127) > 254u;
                 dst[j] = (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)c << 8) | ((uint32_t)(uint8_t)d << 16) |
                          ((uint32_t)(uint8_t)e << 24);
             }
             if (bad) out_of_range = true;
+            if (len) {
+                const int g = std::max(m0 + m1, m2 + m3);
+                int cur = max_gain.load();
+                while (g > cur && !max_gain.compare_exchange_weak(cur, g)) {}
+            }
         });
         if (out_of_range) {
             delete b;
             return 1;
+        }
+        if (packed && max_gain.load() != INT32_MIN && (int64_t)mdl.intron_open + max_gain.load() > 0) {
+            delete b;   // values are unbounded: the int32 kernel (or the table-driven one) takes the batch
+            return e2g_batch_create(stream, launch_counter, model, scoring, n, pairs, want_path, out, false);
         }
     }
     std::vector<uint2> xt(25);

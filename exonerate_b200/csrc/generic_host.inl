@@ -59,10 +59,29 @@ static int check_model(const c4b_model &m) {
         set_error("model tables out of range");
         return -1;
     }
+    if (m.start_state < 0 || m.start_state >= m.n_states || m.end_state < 0 || m.end_state >= m.n_states ||
+        m.start_scope < C4B_SCOPE_ANYWHERE || m.start_scope > C4B_SCOPE_CORNER ||
+        m.end_scope < C4B_SCOPE_ANYWHERE || m.end_scope > C4B_SCOPE_CORNER) {
+        set_error("model START / END state or scope out of range");
+        return -1;
+    }
+    for (int k = 0; k < m.n_calcs; ++k) {
+        const c4b_calc &c = m.calcs[k];
+        if ((c.kind == C4B_CALC_SPLICE_PRE || c.kind == C4B_CALC_SPLICE_POST) &&
+            (c.param[1] < 0 || c.param[1] >= C4B_SPLICE_TOTAL)) {
+            set_error("calc " + std::to_string(k) + ": splice array index out of range");
+            return -1;
+        }
+        if (c.kind >= C4B_CALC_SPLICE_POST && c.kind < C4B_CALC_KIND_TOTAL &&
+            (c.param[2] < 0 || c.param[2] >= m.n_shadow_slots)) {
+            set_error("calc " + std::to_string(k) + ": shadow slot out of range");
+            return -1;
+        }
+    }
     for (int k = 0; k < m.n_transitions; ++k) {
         const c4b_transition &t = m.transitions[k];
         if (t.input < 0 || t.input >= m.n_states || t.output < 0 || t.output >= m.n_states ||
-            t.advance_query < 0 || t.advance_target < 0 || t.calc >= m.n_calcs ||
+            t.advance_query < 0 || t.advance_target < 0 || t.calc >= m.n_calcs || t.calc < -1 ||
             t.advance_query > m.max_query_advance || t.advance_target > m.max_target_advance) {
             set_error("transition " + std::to_string(k) + " is malformed");
             return -1;
@@ -143,7 +162,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
 
     // ---- stage sequences (dedupe by host pointer), splice arrays, blocked lists
     std::map<std::pair<const uint8_t *, int>, size_t> smap;
-    std::map<const int32_t *, size_t> imap;
+    std::map<std::pair<const int32_t *, size_t>, size_t> imap;   // (address, length): one pointer may back lists of several lengths
     size_t sbytes = 0, ints = 0;
     int maxQ = 0;
     std::vector<size_t> qo(n), to(n);
@@ -161,19 +180,20 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         return off;
     };
     auto place_ints = [&](const int32_t *p, size_t len) {
-        auto it = imap.find(p);
+        const auto key = std::make_pair(p, len);
+        auto it = imap.find(key);
         if (it != imap.end()) return it->second;
         const size_t off = ints;
-        imap[p] = off;
+        imap[key] = off;
         ints += align_up(len, 4);
         return off;
     };
-    std::map<const int32_t *, size_t> ilen;
     for (int p = 0; p < n; ++p) {
         const c4b_pair &pp = pairs[p];
         if (pp.query_length < 0 || pp.target_length < 0 || pp.query_start < 0 || pp.target_start < 0 ||
-            pp.query_start + pp.query_length > pp.query_len ||
-            pp.target_start + pp.target_length > pp.target_len) {
+            (int64_t)pp.query_start + pp.query_length > pp.query_len ||
+            (int64_t)pp.target_start + pp.target_length > pp.target_len || pp.n_blocked < 0 ||
+            (pp.n_blocked && (!pp.blocked_query_pos || !pp.blocked_target_pos))) {
             set_error("pair " + std::to_string(p) + ": region outside the sequences");
             delete g;
             return -1;
@@ -197,12 +217,10 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
                                                                       (size_t)pp.target_len * sizeof(int32_t), 16);
                 if (spdev[4 * p + k]) continue;
                 sp[4 * p + k] = place_ints(pp.splice[k], (size_t)pp.target_len);
-                ilen[pp.splice[k]] = (size_t)pp.target_len;
             }
         if (pp.n_blocked) {
             bq[p] = place_ints(pp.blocked_query_pos, (size_t)pp.n_blocked);
             bt[p] = place_ints(pp.blocked_target_pos, (size_t)pp.n_blocked);
-            ilen[pp.blocked_query_pos] = ilen[pp.blocked_target_pos] = (size_t)pp.n_blocked;
         }
         maxQ = std::max(maxQ, pp.query_length);
         g->max_t = std::max(g->max_t, pp.target_length);
@@ -239,7 +257,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         hs.assign(sbytes + 64, 0);
         for (auto &kv : smap) memcpy(hs.data() + kv.second, kv.first.first, (size_t)kv.first.second);
         hi.assign(ints + 4, 0);
-        for (auto &kv : imap) memcpy(hi.data() + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t));
+        for (auto &kv : imap) memcpy(hi.data() + kv.second, kv.first.first, kv.first.second * sizeof(int32_t));
     }
     g->h_full.resize(n);
     for (int p = 0; p < n; ++p) {
@@ -289,7 +307,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
             staged = staged && cudaMemcpyAsync(g->d_seq.p + kv.second, kv.first.first, (size_t)kv.first.second,
                                                cudaMemcpyHostToDevice, stream) == cudaSuccess;
         for (auto &kv : imap)
-            staged = staged && cudaMemcpyAsync(g->d_ints.p + kv.second, kv.first, ilen[kv.first] * sizeof(int32_t),
+            staged = staged && cudaMemcpyAsync(g->d_ints.p + kv.second, kv.first.first, kv.first.second * sizeof(int32_t),
                                                cudaMemcpyHostToDevice, stream) == cudaSuccess;
     } else {
         staged = cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
@@ -333,6 +351,14 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
             g->kernel_used = "generic_jit";
             return 0;
         }
+        // The specialised kernel was asked for and is not available (no NVRTC, compile or load
+        // failure): that is a 10x performance cliff, so it is an error unless the caller opted in
+        // to the interpreter kernel (still a device kernel; C4B_JIT_FALLBACK=1).
+        if (!getenv("C4B_JIT_FALLBACK")) {
+            set_error("model specialisation failed (reason on stderr); set C4B_JIT_FALLBACK=1 to run the "
+                      "interpreter kernel instead, or C4B_GENERIC_JIT=0 to never specialise");
+            return -1;
+        }
         g->use_jit = false;
     }
     const int grid = std::min(g->grid, count);
@@ -342,14 +368,9 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
     const size_t ring_bytes = g->ring_stride * sizeof(int32_t);
     // (taken when it does not cost residency: few lattices, or a ring small enough for 4 CTAs per SM)
     const bool smem_ring = ring_bytes <= kSmemRingMax && (count <= g->sm_count || ring_bytes <= 20 * 1024);
-    if (smem_ring) {
-        static bool opted_in = false;
-        if (!opted_in) {
-            C4B_CUDA(cudaFuncSetAttribute(generic_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kSmemRingMax));
-            opted_in = true;
-        }
-    }
+    if (smem_ring)   // per device and cheap: set on every launch that needs it (engines on several devices)
+        C4B_CUDA(cudaFuncSetAttribute(generic_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemRingMax));
     generic_fill_kernel<<<grid, g->threads, smem_ring ? ring_bytes : 0, g->stream>>>(
         pairs, count, outs, g->d_tables.p, mode, g->d_ring.p, g->ring_stride, g->d_cursor.p, smem_ring ? 1 : 0);
     C4B_CUDA(cudaGetLastError());

@@ -254,8 +254,13 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
     static std::mutex mu;
     static std::map<std::string, JitKernel *> cache;
     const std::string src = jit_program_source(m, mode, threads, smem_ring, pack_start);
+    // loaded kernels carry per-device state (the shared-memory opt-in, the occupancy answer):
+    // one entry per (device, program)
+    int device = 0;
+    cudaGetDevice(&device);
+    const std::string key = std::to_string(device) + ":" + src;
     std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find(src);
+    auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     JitKernel *jk = nullptr;
     std::vector<char> cubin;
@@ -271,9 +276,8 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
         jk = jit_load(cubin, threads, smem_ring, &log);
     }
     if (!jk)
-        fprintf(stderr, "libc4b200: model specialisation unavailable, using the interpreter kernel: %s\n",
-                log.c_str());
-    cache[src] = jk;
+        fprintf(stderr, "libc4b200: model specialisation unavailable: %s\n", log.c_str());
+    cache[key] = jk;
     return jk;
 }
 

@@ -19,7 +19,7 @@ EXPORTS = [
     "c4b_abi_version", "c4b_last_error", "c4b_engine_create", "c4b_engine_destroy",
     "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
-    "c4b_batch_cells", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_destroy",
+    "c4b_batch_cells", "c4b_batch_ops_needed", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_description", "c4b_batch_destroy",
     "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise", "c4b_span_integrate",
 ]
 
@@ -57,6 +57,8 @@ def load_library():
     lib.c4b_batch_fetch.argtypes = [C.c_void_p, P(abi.Result), C.c_void_p, C.c_int64]
     lib.c4b_batch_device_results.argtypes = [C.c_void_p]
     lib.c4b_batch_device_results.restype = C.c_void_p
+    lib.c4b_batch_ops_needed.argtypes = [C.c_void_p]
+    lib.c4b_batch_ops_needed.restype = C.c_int64
     lib.c4b_batch_cells.argtypes = [C.c_void_p]
     lib.c4b_batch_cells.restype = C.c_int64
     lib.c4b_viterbi_calculate_cells.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), P(abi.Pair), C.c_int,
@@ -76,6 +78,8 @@ def load_library():
     lib.c4b_batch_last_fill_ms.restype = C.c_double
     lib.c4b_batch_kernel_name.argtypes = [C.c_void_p]
     lib.c4b_batch_kernel_name.restype = C.c_char_p
+    lib.c4b_batch_description.argtypes = [C.c_void_p]
+    lib.c4b_batch_description.restype = C.c_char_p
     lib.c4b_batch_destroy.argtypes = [C.c_void_p]
     lib.c4b_viterbi_calculate.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), P(abi.Pair), C.c_int,
                                           P(abi.Result), C.c_void_p, C.c_int64]
@@ -181,9 +185,19 @@ class Batch:
     def cells(self):
         return self.lib.c4b_batch_cells(self.h)
 
+    def ops_needed(self):
+        n = self.lib.c4b_batch_ops_needed(self.h)
+        if n < 0:
+            raise C4BError("c4b_batch_ops_needed: " + self.lib.c4b_last_error().decode())
+        return n
+
     @property
     def kernel_name(self):
         return self.lib.c4b_batch_kernel_name(self.h).decode()
+
+    @property
+    def description(self):
+        return self.lib.c4b_batch_description(self.h).decode()
 
     def last_fill_ms(self):
         return self.lib.c4b_batch_last_fill_ms(self.h)
@@ -323,11 +337,11 @@ class HSPset:
         horizon = {}
         self.hsp_list = []
         for k, (qs, ts) in enumerate(self.seeds):
-            if ext[k].status != 0:   # the reference aborts here (hspset.c:740-743)
-                raise C4BError("Initial HSP score less than zero for seed (%d, %d)" % (qs, ts))
             key = ((ts * qadv - qs * tadv + ql) % ql, qs % qadv, ts % tadv)
-            if ts < horizon.get(key, 0):
+            if ts < horizon.get(key, 0):   # skipped before HSP_init ever sees it (hspset.c:960-972)
                 continue
+            if ext[k].status != 0:   # the reference aborts here (HSP_init, hspset.c:740-743)
+                raise C4BError("Initial HSP score less than zero for seed (%d, %d)" % (qs, ts))
             horizon[key] = ext[k].target_end
             if ext[k].stored:
                 h = ext[k]

@@ -242,6 +242,11 @@ int c4b_batch_run(c4b_batch *b, c4b_score threshold);
 /* Wait, then copy results (and ops when want_path) to the host. */
 int c4b_batch_fetch(c4b_batch *b, c4b_result *results, int32_t *ops,
                     int64_t ops_capacity);
+/* Number of (transition,length) pairs the paths of the last run hold in total = the
+ * ops_capacity c4b_batch_fetch needs (an Alignment's operation_list lengths summed,
+ * src/c4/alignment.h:34-50).  Waits for the run; -1 on error.  Lets a host size the ops
+ * buffer exactly instead of for the worst case (query_length + target_length per lattice). */
+int64_t c4b_batch_ops_needed(c4b_batch *b);
 /* Device pointer to the c4b_result[n] array of the last run (pair order), valid
  * until the batch is destroyed; for device-side consumers such as an NCCL
  * gather of the per-pair records.  NULL for score-only batches before a run. */
@@ -253,6 +258,9 @@ int64_t c4b_batch_cells(const c4b_batch *b);
 double c4b_batch_last_fill_ms(c4b_batch *b);
 /* Name of the kernel path chosen for this batch ("affine_systolic", "generic"). */
 const char *c4b_batch_kernel_name(const c4b_batch *b);
+/* One line on how the batch was routed: how many lattices took the packed 16-bit, int32 and
+ * table-driven kernels, rows per lane, warps per lattice (diagnostics; bench.py prints it). */
+const char *c4b_batch_description(const c4b_batch *b);
 void c4b_batch_destroy(c4b_batch *b);
 
 /* ---- single-lattice Viterbi_DP_Func shape ------------------------------ */

@@ -12,7 +12,7 @@
  * reference's own HSPset_add_known_hsp (HSP_init + HSP_store: threshold, --hspfilter
  * queues, hsp_list) -- so everything downstream of the extension is still the reference.
  * Every Match_Type (DNA2DNA, PROTEIN2PROTEIN, DNA2PROTEIN, PROTEIN2DNA, CODON2CODON) has a
- * device form; an unknown one would be passed straight to the reference's function. */
+ * device form; an unknown one is a g_error (there is no CPU fallback). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -67,11 +67,9 @@ static gint device_match_kind(Match *match){
 
 void HSPset_seed_hsp(HSPset *hsp_set, guint query_start, guint target_start){
     register B200_Pending *p;
-    if(device_match_kind(hsp_set->param->match) < 0){
-        count(&stat_passthrough, 1);
-        c4bref_HSPset_seed_hsp(hsp_set, query_start, target_start);
-        return;
-        }
+    if(device_match_kind(hsp_set->param->match) < 0) /* no CPU fallback: hard error */
+        g_error("libc4b200: Match_Type [%d] has no device form for HSP extension",
+                hsp_set->param->match->type);
     for(p = pending_list; p; p = p->next)
         if(p->hsp_set == hsp_set)
             break;

@@ -24,6 +24,7 @@
 #include "match.h"
 #include "splice.h"
 #include "c4b200.h"
+#include "b200_binding.h"
 
 /* ---- options (viterbi.c:27-38): -D/--dpmemory is accepted and ignored -------- */
 Viterbi_ArgumentSet *Viterbi_ArgumentSet_create(Argument *arg){
@@ -42,8 +43,10 @@ Viterbi_ArgumentSet *Viterbi_ArgumentSet_create(Argument *arg){
 /* ---- engine + per-Viterbi tables --------------------------------------------- */
 static c4b_engine *engine = NULL;
 
-c4b_engine *exonerate_b200_engine(void); /* shared with hspset_b200.c */
-#define get_engine exonerate_b200_engine
+#define get_engine exonerate_b200_engine /* shared with hspset_b200.c, gam_b200.c */
+
+B200_Replay *b200_replay = NULL;
+glong b200_stat_prefetch_hits = 0, b200_stat_prefetch_misses = 0;
 
 c4b_engine *exonerate_b200_engine(void){
     if(!engine){
@@ -64,8 +67,10 @@ static gdouble now_seconds(void){
     }
 static void print_viterbi_stats(void){
     fprintf(stderr, "exonerate_b200: Viterbi_calculate calls %ld (%.3f s: prepare %.3f s, "
-                    "engine %.3f s), sequence pairs flattened %ld\n",
-            stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss);
+                    "engine %.3f s), sequence pairs flattened %ld, answered from the batch "
+                    "prefetch %ld (prefetched but not usable %ld)\n",
+            stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss,
+            b200_stat_prefetch_hits, b200_stat_prefetch_misses);
     }
 
 /* Flattened sequences (they are virtual in the reference: revcomp / subseq / translate
@@ -79,8 +84,19 @@ static struct {
     gint32 *splice;
 } pair_cache = {NULL, NULL, NULL, NULL, NULL};
 
+gint32 *b200_splice_arrays(gchar *tseq, gint tlen){
+    register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
+    register gint32 *splice = g_new(gint32, 4*((gsize)tlen+1));
+    SplicePredictor_predict_array_int(ias->sps->ss5_forward, tseq, tlen, 0, tlen, splice);
+    SplicePredictor_predict_array_int(ias->sps->ss3_forward, tseq, tlen, 0, tlen, splice+tlen);
+    SplicePredictor_predict_array_int(ias->sps->ss5_reverse, tseq, tlen, 0, tlen,
+                                      splice+2*(gsize)tlen);
+    SplicePredictor_predict_array_int(ias->sps->ss3_reverse, tseq, tlen, 0, tlen,
+                                      splice+3*(gsize)tlen);
+    return splice;
+    }
+
 static void pair_cache_fetch(Ungapped_Data *ud, gboolean need_splice){
-    register Intron_ArgumentSet *ias;
     register gint tlen = ud->target->len;
     if((pair_cache.query != ud->query) || (pair_cache.target != ud->target)){
         if(pair_cache.query){
@@ -100,18 +116,8 @@ static void pair_cache_fetch(Ungapped_Data *ud, gboolean need_splice){
         pair_cache.splice = NULL;
         stat_cache_miss++;
         }
-    if(need_splice && !pair_cache.splice){
-        ias = Intron_ArgumentSet_create(NULL);
-        pair_cache.splice = g_new(gint32, 4*((gsize)tlen+1));
-        SplicePredictor_predict_array_int(ias->sps->ss5_forward, pair_cache.tseq,
-            tlen, 0, tlen, pair_cache.splice);
-        SplicePredictor_predict_array_int(ias->sps->ss3_forward, pair_cache.tseq,
-            tlen, 0, tlen, pair_cache.splice+tlen);
-        SplicePredictor_predict_array_int(ias->sps->ss5_reverse, pair_cache.tseq,
-            tlen, 0, tlen, pair_cache.splice+2*(gsize)tlen);
-        SplicePredictor_predict_array_int(ias->sps->ss3_reverse, pair_cache.tseq,
-            tlen, 0, tlen, pair_cache.splice+3*(gsize)tlen);
-        }
+    if(need_splice && !pair_cache.splice)
+        pair_cache.splice = b200_splice_arrays(pair_cache.tseq, tlen);
     return;
     }
 
@@ -248,7 +254,7 @@ static void flatten_model(C4_Model *model, c4b_model *out){
     return;
     }
 
-static c4b_model *tables_for(Viterbi *viterbi){
+c4b_model *b200_tables_for(Viterbi *viterbi){
     register B200_Tables *bt;
     for(bt = tables_list; bt; bt = bt->next)
         if(bt->viterbi == viterbi)
@@ -357,20 +363,20 @@ Codegen *Viterbi_make_Codegen(Viterbi *viterbi){
     }
 
 /* ---- the call: Viterbi_calculate (viterbi.c:846-865) ----------------------------- */
-static void fill_scoring(Ungapped_Data *ud, c4b_scoring *sc){
+void b200_fill_scoring(Match_ArgumentSet *mas, c4b_scoring *sc){
     register gint i, j;
     register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
-    register Translate *t = ud->mas->translate;
+    register Translate *t = mas->translate;
     memset(sc, 0, sizeof(c4b_scoring));
     for(i = 0; i < SUBMAT_ALPHABETSIZE; i++)
         for(j = 0; j < SUBMAT_ALPHABETSIZE; j++){
-            sc->dna_matrix[i*C4B_SUBMAT_N+j] = ud->mas->dna_submat->matrix[i][j];
+            sc->dna_matrix[i*C4B_SUBMAT_N+j] = mas->dna_submat->matrix[i][j];
             sc->protein_matrix[i*C4B_SUBMAT_N+j]
-                = ud->mas->protein_submat->matrix[i][j];
+                = mas->protein_submat->matrix[i][j];
             }
     for(i = 0; i < 256; i++){
-        sc->dna_index[i] = ud->mas->dna_submat->index[i];
-        sc->protein_index[i] = ud->mas->protein_submat->index[i];
+        sc->dna_index[i] = mas->dna_submat->index[i];
+        sc->protein_index[i] = mas->protein_submat->index[i];
         sc->nt2d[i] = t->nt2d[i];
         }
     for(i = 0; i < 4096; i++)
@@ -380,7 +386,7 @@ static void fill_scoring(Ungapped_Data *ud, c4b_scoring *sc){
     return;
     }
 
-static gboolean model_has_splice(c4b_model *m){
+gboolean b200_model_has_splice(c4b_model *m){
     register gint i;
     for(i = 0; i < m->n_calcs; i++)
         if((m->calcs[i].kind == C4B_CALC_SPLICE_PRE)
@@ -389,16 +395,102 @@ static gboolean model_has_splice(c4b_model *m){
     return FALSE;
     }
 
+gint b200_blocked_list(SubOpt *subopt, Region *region, gint32 **bq, gint32 **bt){
+    register SubOpt_Index *soi = subopt?SubOpt_Index_create(subopt, region):NULL;
+    register SubOpt_Index_Row *soir;
+    register gint i, j, n_blocked = 0;
+    (*bq) = (*bt) = NULL;
+    if(!soi)
+        return 0;
+    /* rows are sorted by target_pos, positions by query_pos (subopt.c:250-338) */
+    for(i = 0; i < soi->row_list->len; i++){
+        soir = soi->row_list->pdata[i];
+        if(soir != soi->blank_row)
+            n_blocked += soir->total;
+        }
+    (*bq) = g_new(gint32, n_blocked+1);
+    (*bt) = g_new(gint32, n_blocked+1);
+    n_blocked = 0;
+    for(i = 0; i < soi->row_list->len; i++){
+        soir = soi->row_list->pdata[i];
+        if(soir == soi->blank_row)
+            continue;
+        for(j = 0; j < soir->total; j++){
+            (*bq)[n_blocked] = soir->query_pos[j];
+            (*bt)[n_blocked++] = soir->target_pos;
+            }
+        }
+    SubOpt_Index_destroy(soi);
+    return n_blocked;
+    }
+
+/* what a Viterbi_DP_Func leaves in vd (viterbi.c:464-478,633-653) */
+static void vd_set_result(Viterbi_Data *vd, Region *region, c4b_result *result,
+                          B200_Path *path){
+    vd->curr_query_end = result->query_end - region->query_start;
+    vd->curr_target_end = result->target_end - region->target_start;
+    vd->curr_query_start = result->query_start - region->query_start;
+    vd->curr_target_start = result->target_start - region->target_start;
+    if(vd->alignment_region){
+        vd->alignment_region->query_start = result->query_start;
+        vd->alignment_region->target_start = result->target_start;
+        vd->alignment_region->query_length = result->query_end - result->query_start;
+        vd->alignment_region->target_length = result->target_end - result->target_start;
+        }
+    if(path){
+        path->result = (*result);
+        if(vd->traceback){
+            g_free(((B200_Path*)vd->traceback)->ops);
+            g_free(vd->traceback);
+            }
+        vd->traceback = (C4_Transition****)path;
+        }
+    return;
+    }
+
+/* The batch hook (gam_b200.c) computed this call's answer ahead of time?  Only if it is
+ * exactly the call the answer was computed for. */
+static gboolean prefetch_lookup(Viterbi *viterbi, Region *region, Viterbi_Data *vd,
+                                Ungapped_Data *ud, gint n_blocked, gint32 *bq, gint32 *bt,
+                                C4_Score *score){
+    register B200_Replay *rp = b200_replay;
+    register B200_Round *round;
+    register B200_Path *path;
+    if(!rp || (rp->cursor >= rp->n_rounds))
+        return FALSE;
+    round = &rp->rounds[rp->cursor];
+    if((rp->viterbi != viterbi) || (viterbi->mode != Viterbi_Mode_FIND_PATH)
+    || (rp->query != ud->query) || (rp->target != ud->target)
+    || region->query_start || region->target_start
+    || (region->query_length != ud->query->len)
+    || (region->target_length != ud->target->len)
+    || (round->n_blocked != n_blocked)
+    || (n_blocked && (memcmp(round->bq, bq, n_blocked*sizeof(gint32))
+                   || memcmp(round->bt, bt, n_blocked*sizeof(gint32))))){
+        rp->cursor = rp->n_rounds; /* the series diverged: nothing later can match */
+        b200_stat_prefetch_misses++;
+        return FALSE;
+        }
+    rp->cursor++;
+    path = g_new0(B200_Path, 1);
+    path->ops = g_new(gint32, 2*round->result.n_ops+2);
+    memcpy(path->ops, round->ops, 2*round->result.n_ops*sizeof(gint32));
+    vd_set_result(vd, region, &round->result, path);
+    path->result.ops_offset = 0;
+    (*score) = round->result.score;
+    b200_stat_prefetch_hits++;
+    return TRUE;
+    }
+
 C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
                            Viterbi_Data *vd, gpointer user_data,
                            SubOpt *subopt){
     register Ungapped_Data *ud = user_data; /* every shipped *_Data inherits it */
-    register c4b_model *tables = tables_for(viterbi);
-    register SubOpt_Index *soi = NULL;
-    register SubOpt_Index_Row *soir;
+    register c4b_model *tables = b200_tables_for(viterbi);
     register gchar *qseq, *tseq;
     register gint i, j, n_blocked = 0, mode = 0;
-    register gint32 *bq = NULL, *bt = NULL;
+    gint32 *bq = NULL, *bt = NULL;
+    C4_Score prefetched_score;
     register gint64 ops_capacity;
     register B200_Path *path = NULL;
     register gdouble t_begin = now_seconds(), t_prepared, t_done;
@@ -454,7 +546,16 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         if(g_getenv("EXONERATE_B200_STATS"))
             atexit(print_viterbi_stats);
         }
-    pair_cache_fetch(ud, model_has_splice(tables));
+    n_blocked = b200_blocked_list(subopt, region, &bq, &bt);
+    if(b200_replay && prefetch_lookup(viterbi, region, vd, ud, n_blocked, bq, bt,
+                                      &prefetched_score)){
+        g_free(bq);
+        g_free(bt);
+        stat_calls++;
+        stat_total += now_seconds() - t_begin;
+        return prefetched_score;
+        }
+    pair_cache_fetch(ud, b200_model_has_splice(tables));
     qseq = pair_cache.qseq;
     tseq = pair_cache.tseq;
     memset(&pair, 0, sizeof(pair));
@@ -467,30 +568,11 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     pair.query_length = region->query_length;
     pair.target_length = region->target_length;
     pair.reserved = C4B_PAIR_BUFFERS_STABLE; /* pair_cache owns them until the next comparison */
-    fill_scoring(ud, &scoring);
-    if(model_has_splice(tables))
+    b200_fill_scoring(ud->mas, &scoring);
+    if(b200_model_has_splice(tables))
         for(i = 0; i < 4; i++)
             pair.splice[i] = pair_cache.splice + (gsize)i*ud->target->len;
-    if(subopt)
-        soi = SubOpt_Index_create(subopt, region);
-    if(soi){ /* rows are sorted by target_pos, positions by query_pos (subopt.c:250-338) */
-        for(i = 0; i < soi->row_list->len; i++){
-            soir = soi->row_list->pdata[i];
-            if(soir != soi->blank_row)
-                n_blocked += soir->total;
-            }
-        bq = g_new(gint32, n_blocked+1);
-        bt = g_new(gint32, n_blocked+1);
-        n_blocked = 0;
-        for(i = 0; i < soi->row_list->len; i++){
-            soir = soi->row_list->pdata[i];
-            if(soir == soi->blank_row)
-                continue;
-            for(j = 0; j < soir->total; j++){
-                bq[n_blocked] = soir->query_pos[j];
-                bt[n_blocked++] = soir->target_pos;
-                }
-            }
+    if(n_blocked){
         pair.blocked_query_pos = bq;
         pair.blocked_target_pos = bt;
         pair.n_blocked = n_blocked;
@@ -547,27 +629,7 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
                              &result, path?path->ops:NULL, ops_capacity))
         g_error("libc4b200: %s", c4b_last_error());
     stat_engine += now_seconds() - t_prepared;
-    /* what a Viterbi_DP_Func leaves in vd (viterbi.c:464-478,633-653) */
-    vd->curr_query_end = result.query_end - region->query_start;
-    vd->curr_target_end = result.target_end - region->target_start;
-    vd->curr_query_start = result.query_start - region->query_start;
-    vd->curr_target_start = result.target_start - region->target_start;
-    if(vd->alignment_region){
-        vd->alignment_region->query_start = result.query_start;
-        vd->alignment_region->target_start = result.target_start;
-        vd->alignment_region->query_length = result.query_end - result.query_start;
-        vd->alignment_region->target_length = result.target_end - result.target_start;
-        }
-    if(path){
-        path->result = result;
-        if(vd->traceback){
-            g_free(((B200_Path*)vd->traceback)->ops);
-            g_free(vd->traceback);
-            }
-        vd->traceback = (C4_Transition****)path;
-        }
-    if(soi)
-        SubOpt_Index_destroy(soi);
+    vd_set_result(vd, region, &result, path);
     g_free(bq);
     g_free(bt);
     t_done = now_seconds();

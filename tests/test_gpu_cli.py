@@ -81,3 +81,53 @@ def test_cli_heuristic_runs_on_specialised_kernels(name, tmp_path):
             with open(cache / cubins[0], "wb") as f:
                 f.write(b"not a cubin")
     assert os.path.getsize(cache / cubins[0]) > 1000
+
+
+# ---- the batch hook (integration/gam_b200.c) at the metric shape -------------------------
+import cli_workload  # noqa: E402
+
+BATCH_GOLDEN = os.path.join(helpers.GOLDEN, "cli_batch")
+
+
+def _run_batch_cli(tmp_path, name, extra_env=None):
+    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name]
+    q, t = cli_workload.write_workload(str(tmp_path), kind, nq, nt)
+    env = dict(os.environ, EXONERATE_B200_STATS="1", **(extra_env or {}))
+    return subprocess.run([BIN, q, t] + flags + cli_workload.COMMON, capture_output=True, text=True, timeout=900,
+                          env=env)
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")
+@pytest.mark.parametrize("name", sorted(cli_workload.BATCH_COMMANDS))
+def test_cli_batch_hook_metric_shape(name, tmp_path):
+    """`exonerate --exhaustive` on 1 kbp x 100 kbp FASTA input through the batch hook: the queued
+    pairs are answered by batched device rounds and replayed through the reference's own
+    GAM_Result_exhaustive_create; stdout byte-identical to the reference binary (compiled models)."""
+    import re
+    want = open(os.path.join(BATCH_GOLDEN, name + ".out")).read()
+    got = _run_batch_cli(tmp_path, name)
+    assert got.returncode == 0, got.stderr[-2000:]
+    assert got.stdout == want
+    assert len(want.splitlines()) >= 4
+    m = re.search(r"batch hook: (\d+) pair\(s\) in (\d+) flush\(es\), (\d+) device round", got.stderr)
+    assert m, got.stderr[-800:]
+    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name]
+    strands = 1 if "--revcomp" in flags else 2   # --revcomp defaults to yes: every query twice
+    assert int(m.group(1)) == nq * nt * strands and int(m.group(2)) == 1
+    m = re.search(r"answered from the batch prefetch (\d+) \(prefetched but not usable (\d+)\)", got.stderr)
+    assert m and int(m.group(1)) >= nq * nt * strands and int(m.group(2)) == 0, got.stderr[-800:]
+    if "--bestn" not in flags:   # every Viterbi_calculate of the run was answered from a batch
+        m = re.search(r"Viterbi_calculate calls (\d+) .* answered from the batch prefetch (\d+)", got.stderr)
+        assert m and m.group(1) == m.group(2), got.stderr[-800:]
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")
+def test_cli_batch_hook_small_queue_and_off(tmp_path):
+    """a queue bound of 5 pairs (several flushes) and batching switched off print the same bytes"""
+    name = "metric_affine_local"
+    want = open(os.path.join(BATCH_GOLDEN, name + ".out")).read()
+    got = _run_batch_cli(tmp_path, name, {"EXONERATE_B200_BATCH_PAIRS": "5"})
+    assert got.returncode == 0 and got.stdout == want, got.stderr[-2000:]
+    assert "in 5 flush(es)" in got.stderr
+    got = _run_batch_cli(tmp_path, name, {"EXONERATE_B200_BATCH": "0"})
+    assert got.returncode == 0 and got.stdout == want, got.stderr[-2000:]

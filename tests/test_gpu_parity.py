@@ -468,13 +468,14 @@ def test_regions_sub_lattices(eng, params, scoring):
 
 
 def blocked_points(model, alignments):
-    pts = []
+    pts, seen = [], set()
     for a in alignments:
         qp, tp = a["region"][0], a["region"][1]
         for tid, length in a["ops"]:
             tr = model.transitions[tid]
             for _ in range(length):
-                if tr.label == abi.LABEL_MATCH and (qp, tp) not in pts:
+                if tr.label == abi.LABEL_MATCH and (qp, tp) not in seen:
+                    seen.add((qp, tp))
                     pts.append((qp, tp))
                 qp += tr.advance_query
                 tp += tr.advance_target
@@ -500,6 +501,75 @@ def test_subopt_blocking(eng, params, scoring):
             done.append(ref)
             n += 1
     assert n >= 6
+
+
+def _subopt_series(opt, model, scoring, q, t, rounds, region=None):
+    """the --subopt loop of GAM_Result_exhaustive_create (src/hub/gam.c:1160-1172) against the
+    oracle: every iteration blocks the match cells of all earlier paths"""
+    from exonerate_b200 import PairSet
+    done = []
+    for _ in range(rounds):
+        pts = blocked_points(model, done)
+        if region:   # blocked lists are in REGION coordinates (src/c4/subopt.c:250-338)
+            pts = [(a - region[0], b - region[1]) for a, b in pts
+                   if 0 <= a - region[0] <= region[2] and 0 <= b - region[1] <= region[3]]
+        want = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, blocked=pts, region=region),
+                                      abi.MODE_FIND_PATH, max_ops=len(q) + len(t) + 8)
+        got = opt.find_path(PairSet([q], [t], blocked=[pts], regions=[region] if region else None))[0]
+        assert got["score"] == want["score"] and got["region"] == want["region"], (got["score"], want["score"])
+        assert got["ops"] == want["ops"]
+        if not want["ops"]:
+            break
+        done.append(want)
+    return done
+
+
+@pytest.mark.parametrize("name,shape", [("affine_local_dna", (300, 900)), ("affine_local_dna", (1000, 20000)),
+                                        ("affine_local_dna", (1500, 1700)), ("affine_global_dna", (120, 150)),
+                                        ("affine_bestfit_dna", (90, 400)), ("affine_overlap_dna", (200, 260)),
+                                        ("affine_local_protein", (250, 600))])
+def test_subopt_on_the_affine_kernels(eng, params, scoring, name, shape):
+    """SubOpt blocked cells stay on the affine kernels (per-lattice routing; the int32 kernel's
+    BLK variant masks T4 at blocked destination cells, viterbi.c:701-704): four iterations of the
+    sub-optimal series, single pass and banded two-pass, one and several sweeps, all scopes."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    model, _ = helpers.load_model(name, params)
+    opt = Optimal(eng, model, scoring)
+    if name.endswith("protein"):
+        q, t = helpers.protein_pair(7100, *shape)
+    else:
+        q, t = helpers.dna_pair(7100 + shape[0], *shape)
+    done = _subopt_series(opt, model, scoring, q, t, 4)
+    assert len(done) >= 2
+    b = Batch(eng, model, scoring, PairSet([q], [t], blocked=[blocked_points(model, done[:1])]))
+    assert b.kernel_name == "affine_systolic"
+    b.close()
+
+
+def test_subopt_mixed_batch_and_regions(eng, params, scoring):
+    """blocked and unblocked lattices in ONE batch: the unblocked ones keep the packed 16-bit
+    kernels, the blocked ones take the int32 BLK kernel; a sub-region with its own list"""
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    qs, ts, blocked, want = [], [], [], []
+    for k in range(24):
+        q, t = helpers.dna_pair(7300 + k, 200 + 37 * k, 3000 + 811 * k)
+        first = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t), abi.MODE_FIND_PATH,
+                                       max_ops=len(q) + len(t) + 8)
+        pts = blocked_points(model, [first]) if k % 3 else []
+        qs.append(q)
+        ts.append(t)
+        blocked.append(pts)
+        want.append(helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, blocked=pts), abi.MODE_FIND_PATH,
+                                           max_ops=len(q) + len(t) + 8))
+    got = opt.find_path(PairSet(qs, ts, blocked=blocked))
+    scores = opt.find_score(PairSet(qs, ts, blocked=blocked))
+    for k in range(24):
+        assert got[k]["score"] == want[k]["score"] == scores[k], k
+        assert got[k]["region"] == want[k]["region"] and got[k]["ops"] == want[k]["ops"], k
+    q, t = helpers.dna_pair(7400, 400, 5000)
+    _subopt_series(opt, model, scoring, q, t, 3, region=(20, 300, 350, 4500))
 
 
 def test_threshold_and_errors(eng, params, scoring):
