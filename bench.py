@@ -653,6 +653,8 @@ def ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = check_against_reference(args.model, w, max(1, args.cpu_pairs or W["cpu_pairs"]))
         if world == 1 and not args.no_cli and args.model == "affine:local":
+            eng.close()   # the CLI is its own process: give it the GPU (pool memory, context time slices)
+            torch.cuda.empty_cache()
             line["cli"] = cli_leg()
         print(json.dumps(line))
     eng.close()

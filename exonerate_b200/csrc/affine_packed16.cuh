@@ -640,6 +640,174 @@ affine_fill16u_multi_kernel(const AffPair *__restrict__ pairs, AffOut *__restric
 }
 
 // -----------------------------------------------------------------------------
+// affine_fill16f_kernel: the score pass FOLDED -- ONE lattice per warp, both halves of the
+// registers working on it.  For batches too small to fill the GPU with one warp per PAIR of
+// lattices (a shard of a fixed batch split over several GPUs: 1250 pairs are 625 warps on 592
+// schedulers).  The low halves hold lattice rows [lane R, lane R + R), the high halves rows
+// [32 R + lane R, ...), and the high halves run 32 columns behind the low ones: at step s lane l
+// works on column s - l (low) and s - l - 32 (high).  Row 32 R - 1 (lane 31, low) therefore
+// produced column j one step before row 32 R (lane 0, high) needs it, and the hand-off is the
+// same single shuffle as between neighbouring lanes, rotated: lane 0 takes its HIGH top row and
+// column symbol from lane 31's LOW bottom row.  Same instructions per step as
+// affine_fill16u_kernel, half the rows per lane (shorter dependent chain), twice the warps.
+// Exactness: as affine_fill16u_kernel (values of one LOCAL lattice in 15 bits, offset binary).
+// Columns before 0 (high halves, first 32 steps) and after T (low halves, last 32) are computed
+// on the "no symbol" column: they hold START-level values only (local model), never feed a real
+// cell with anything a real cell would not have, and are excluded from the END bookkeeping.
+template <int R>
+__global__ void __launch_bounds__(32)
+affine_fill16f_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs, const int n,
+                      const AffModel mdl, const void *__restrict__ score_table) {
+    __shared__ uint32_t xt4[25];
+    const int lane = threadIdx.x;
+    const AffPair P = pairs[blockIdx.x];
+    const int Q = P.Q, T = P.T;
+    if (lane < 25) xt4[lane] = reinterpret_cast<const uint2 *>(score_table)[lane].x;  // classes 0..3, all >= 0
+    __syncwarp();
+
+    const int open = mdl.openD, one = mdl.one;
+    const uint32_t openK = (uint32_t)(open * 0x10001), extDK = (uint32_t)(mdl.extD * 0x10001);
+    const uint32_t extI2 = pack16(mdl.extI);
+    constexpr int H = 32 * R;                 // rows per half
+    const int nsteps = T + 1 + 31 + 32;
+    const int rowL = lane * R, rowH = H + lane * R;
+
+    uint32_t sel[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int il = rowL + r, ih = rowH + r;
+        uint32_t sa = 0x88u, sb = 0xCCu;  // padding rows: sign of a (non-negative) pool byte = 0
+        if (il >= 1 && il <= Q) { const uint32_t c = P.q[il - 1]; sa = c | ((c | 8u) << 4); }
+        if (ih >= 1 && ih <= Q) { const uint32_t c = 4u + P.q[ih - 1]; sb = c | ((c | 8u) << 4); }
+        sel[r] = sa | (sb << 8);
+    }
+    uint32_t Mp[R], Dp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        Mp[r] = kNegU16x2;
+        Dp[r] = kNegU16x2;
+    }
+    uint32_t topM = kNegU16x2, topI = kNegU16x2, topMprev = kNegU16x2;
+    uint32_t in_code = kTargetNone | (kTargetNone << 8), code0 = kTargetNone;
+
+    uint32_t best2 = 0u;  // below every stored value
+    int bjL = 0, biL = 0, bjH = 0, biH = 0;
+    uint32_t pend = 0u;
+    int pend_j = 0;   // column of the LOW halves; the high halves are at pend_j - 32
+    auto settle_pending = [&]() {
+        const uint32_t nb = __vmaxu2(best2, pend);
+        if (nb != best2) {  // some half improved strictly (within a half columns arrive in increasing j)
+            if ((pend & 0xFFFFu) > (best2 & 0xFFFFu)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) & 0xFFFFu) == 0) { bi = rowL + r; found = true; }
+                biL = bi;
+                bjL = pend_j;
+            }
+            if ((pend >> 16) > (best2 >> 16)) {
+                int bi = 0;
+                bool found = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!found && ((Mp[r] ^ pend) >> 16) == 0) { bi = rowH + r; found = true; }
+                biH = bi;
+                bjH = pend_j - 32;
+            }
+            best2 = nb;
+        }
+        pend = 0u;
+    };
+
+    auto step = [&](const int s, auto ALL) {
+        constexpr bool all_real = decltype(ALL)::value;   // every lane: both halves inside [0, T]
+        const int j = s - lane;
+        settle_pending();
+        // lane 0: the low column symbol comes from the target, the high one came round from lane 31
+        const uint32_t code = (lane == 0) ? (code0 | (in_code & 0xFF00u)) : in_code;
+        code0 = (s + 1 <= T) ? (uint32_t)P.t[s] : (uint32_t)kTargetNone;
+        const uint32_t Xa = xt4[code & 0xFFu], Xb = xt4[code >> 8];
+        uint32_t cm = 0u;
+        // phase A, bottom-up, rows independent: D, then G~ = max(match, D, START) + open
+#pragma unroll
+        for (int r = R - 1; r >= 0; --r) {
+            uint32_t sc;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(Xa), "r"(Xb), "r"(sel[r]));
+            const uint32_t diag = (r == 0) ? topMprev : Mp[r - 1];
+            Dp[r] = __vmaxu2(imad_add(Dp[r], one, extDK), Mp[r]);
+            const uint32_t x = __vimax3_u16x2(imad_add(diag, one, sc), Dp[r], kBias16x2);
+            Mp[r] = imad_add(x, one, openK);
+        }
+        // phase B, top-down: I chain (one op per row), G = max(G~, I + open) off the chain
+        uint32_t Iv = __viaddmax_u16x2(topI, extI2, topM);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t gt = Mp[r];
+            const uint32_t Gv = __vmaxu2(gt, imad_add(Iv, one, openK));
+            Mp[r] = Gv;
+            if (r & 1) cm = __vimax3_u16x2(cm, Gv, Mp[r - 1]);
+            if (r + 1 < R) Iv = __viaddmax_u16x2(Iv, extI2, gt);
+        }
+        const uint32_t botM = Mp[R - 1], botI = Iv;
+        topMprev = topM;
+        if (!all_real) {   // END candidates only from real columns
+            if (j < 0 || j > T) cm &= 0xFFFF0000u;
+            if (j - 32 < 0 || j - 32 > T) cm &= 0x0000FFFFu;
+        }
+        pend = cm;
+        pend_j = j;
+        // rotate by one lane: lane l > 0 takes both halves from lane l - 1; lane 0 takes its HIGH
+        // half from lane 31's LOW half (row 32 R follows row 32 R - 1) and has no row above its low half
+        const int src = (lane + 31) & 31;
+        const uint32_t nM = __shfl_sync(0xffffffffu, botM, src);
+        const uint32_t nI = __shfl_sync(0xffffffffu, botI, src);
+        const uint32_t nC = __shfl_sync(0xffffffffu, code, src);
+        if (lane > 0) {
+            topM = nM;
+            topI = nI;
+            in_code = nC;
+        } else {
+            topM = __byte_perm(nM, kNegU16x2, 0x1054);   // {low: not reachable, high: lane 31's low}
+            topI = __byte_perm(nI, kNegU16x2, 0x1054);
+            in_code = (nC & 0xFFu) << 8;
+        }
+    };
+
+    const int fill_end = min(63, nsteps);
+    const int steady_end = max(fill_end, min(T + 1, nsteps));
+    int s = 0;
+    for (; s < fill_end; ++s) step(s, std::false_type{});
+    for (; s < steady_end; ++s) step(s, std::true_type{});
+    for (; s < nsteps; ++s) step(s, std::false_type{});
+    settle_pending();
+    __syncwarp();
+
+    // one lattice: the better of the two halves (max score, then min j, then min i), then over lanes
+    int b = (int)(best2 & 0xFFFFu), bj = bjL, bi = biL;
+    {
+        const int ob = (int)(best2 >> 16);
+        if ((ob > b) || (ob == b && (bjH < bj || (bjH == bj && biH < bi)))) { b = ob; bj = bjH; bi = biH; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, b, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if ((ob > b) || (ob == b && (oj < bj || (oj == bj && oi < bi)))) { b = ob; bj = oj; bi = oi; }
+    }
+    if (lane == 0) {
+        AffOut o;
+        o.best = b - (int)kBias16 - open;  // tracked as G = M + open, offset binary
+        o.end_i = bi;
+        o.end_j = bj;
+        o.flags = 0;
+        outs[P.out_index] = o;
+    }
+    (void)n;
+}
+
+// -----------------------------------------------------------------------------
 // affine_fill16tb_kernel: the TRACEBACK pass with two lattices per warp.  Used for
 // the banded refill of long targets and for the single pass of short ones (e.g.
 // 1 kbp x 1 kbp) when every lattice of the launch qualifies.

@@ -271,6 +271,9 @@ struct c4b_batch {
     // sweep; a batch too small to fill the GPU with one warp per pair takes a smaller R16, so
     // that every query becomes several sweeps that run as pipelined warps of one CTA
     int R16 = 32, fill_warps16 = 1;
+    // small batches: ONE lattice per warp, the two register halves on the two halves of its rows
+    // (affine_fill16f_kernel), so that a batch of n lattices is n warps instead of n / 2
+    bool p16_fold = false;
     bool tb16_band = false, tb16_direct = false;  // traceback pass on affine_fill16tb_kernel
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
@@ -403,7 +406,13 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
         return 0;
     };
     int rc;
-    if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep of 32 R16 rows
+    if (b->p16_fold) {
+        auto gof = [&](auto kernel) -> int {
+            kernel<<<count, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
+            return 0;
+        };
+        rc = (b->R == 32) ? gof(affine_fill16f_kernel<16>) : gof(affine_fill16f_kernel<8>);
+    } else if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep of 32 R16 rows
         switch (b->R16) {
         case 8: rc = go(affine_fill16u_multi_kernel<8>); break;
         case 16: rc = go(affine_fill16u_multi_kernel<16>); break;
@@ -705,6 +714,15 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         }
         b->fill_warps16 = std::max(1, std::min(kAffMaxWarps, (maxQ16 + 1 + 32 * b->R16 - 1) / (32 * b->R16)));
         b->p16_multi = b->p16_unsigned && maxQ16 + 1 > 32 * b->R16;
+        // fold: one warp per lattice instead of one per PAIR while the batch is small enough that
+        // the finer grain wins (fewer empty warp slots, a smaller tail wave).  Measured on the B200
+        // (profiles/r02_strong_sweep.md, 1 kbp x 100 kbp, score pass GCUPS packed -> folded):
+        // 1250 lattices 2302 -> 2847, 2500 3227 -> 3525, 3552 3646 -> 4135, 5000 3352 -> 3860,
+        // 7104 3678 -> 4020, 10000 4417 -> 4282: folded up to 2.4 full waves of packed CTAs.
+        b->p16_fold = b->p16_unsigned && !b->p16_multi && b->R >= 16 && b->n16 > 0 &&
+                      (int64_t)(b->n16 + 1) / 2 * 10 < (int64_t)e->sm_count * 12 * 24;
+        if (const char *env = getenv("C4B_P16_FOLD"))
+            b->p16_fold = b->p16_unsigned && !b->p16_multi && b->R >= 16 && b->n16 > 0 && atoi(env) != 0;
         // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
         const char *tv = getenv("C4B_AFFINE_TB16");
         const bool tb_ok = model_ok && nonneg && b->aff.openI <= b->aff.extI && b->aff.openD >= -24 &&
@@ -1086,7 +1104,8 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                  "affine: %d lattices; score pass: %d packed 16-bit (%s, %d rows/lane, %d warp(s) per lattice pair), "
                  "%d int32 (%d rows/lane, %d warp(s) per lattice%s); traceback: %d banded (%s), %d single-pass (%s); "
                  "%d with SubOpt blocked cells",
-                 n, b->n16, b->p16_unsigned ? "offset-binary" : "signed", b->p16_multi ? b->R16 : b->R,
+                 n, b->n16, b->p16_fold ? "offset-binary, folded: one lattice per warp" : b->p16_unsigned ? "offset-binary" : "signed",
+                 b->p16_fold ? b->R / 2 : b->p16_multi ? b->R16 : b->R,
                  b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R, b->fill_warps,
                  b->any_blocked ? ", BLK variant" : "", b->want_path ? ns : 0, b->tb16_band ? "packed 16-bit" : "int32",
                  b->want_path ? nd : 0, b->tb16_direct ? "packed 16-bit" : "int32", nblk);
@@ -1247,6 +1266,10 @@ int c4b_engine_create(int device, c4b_engine **out) {
 void c4b_engine_destroy(c4b_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
+    {   // give the cached pool memory back to the driver (other processes may share the GPU)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, e->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     for (auto &kv : e->resident.map) cudaFree(kv.second);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->stage_free) cudaEventDestroy(e->stage_free);

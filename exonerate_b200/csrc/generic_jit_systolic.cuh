@@ -1,0 +1,390 @@
+// generic_jit_systolic.cuh -- the table-driven lattice fill as a SYSTOLIC kernel,
+// specialised to one closed C4 model at run time (NVRTC; never seen by nvcc).
+//
+// generic_jit_kernel.cuh gives every lattice row a thread and walks anti-diagonals
+// with a CTA-wide barrier per diagonal, the lattice in a shared-memory ring: 635
+// warp-instructions per warp-cell for protein2genome, a third of them ring
+// addressing (profiles/r01d_generic_jit.md).  This file is the mapping the
+// hand-written affine / est2genome kernels use (affine_systolic.cuh), generated for
+// ANY closed model:
+//   * a lane owns R consecutive lattice rows; lanes are skewed by one column (lane l
+//     works on column step - l), so the warp is the anti-diagonal wavefront;
+//   * the lattice lives in REGISTERS: per row, the states that are ever read at a
+//     non-zero advance keep their last advance_target + 1 columns (V[row][...], shifted
+//     once per step); nothing of the lattice touches shared memory or HBM;
+//   * the rows above a lane's strip (as many as the model's largest advance_query) are
+//     "virtual rows" of the same register file, fed by one warp shuffle per carried word
+//     per step from the lane above; queries longer than 32 R rows are swept in strips
+//     by the W warps of the CTA, pipelined, the strip hand-off row in L2 exactly as in
+//     affine_fill_kernel (monotone counter in shared memory, no __syncthreads);
+//   * shadow slots are carried only by the states that lie between a shadow's start and
+//     the transitions that read it (kNeed, computed on the host from the closed model).
+// Cell semantics are those of Viterbi_interpreted (src/c4/viterbi.c:655-837): per cell
+// every state starts unset, transitions are tried in closed-model order, the first valid
+// one assigns, later ones replace only if strictly greater (:766-775); END is the first
+// strict maximum in (target outer, query inner) order (:778-791).  calc_score<> and the
+// scope tests are the ones of generic_jit_kernel.cuh (included in front of this file).
+//
+// Not handled here (the host keeps generic_jit_kernel.cuh for them): SubOpt blocked
+// cells, START / END cell tables of BSDP's derived models.
+//
+// Expected in front of this file, after generic_jit_kernel.cuh's own tables:
+//   JIT_SYS_R (rows per lane), namespace c4bjit { AQ (largest advance_query), VW (words
+//   per row), kNW[S] (words a state carries), kVD[S] (columns kept - 1; -1: never stored),
+//   kVOff[S], kNeed[S * C4B_MAX_SHADOW_SLOTS], NSEND (words handed down per step) }.
+
+namespace c4bjit {
+
+constexpr int SR = JIT_SYS_R;
+constexpr int NROWS = AQ + SR;        // virtual rows above the strip first
+constexpr int kSysMaxWarps = 8;
+// word index of shadow slot l / of the packed START cell inside a state's carried words
+__device__ constexpr int word_of_slot(int s, int l) {
+    int w = 1;
+    for (int k = 0; k < l; ++k) w += kNeed[s * C4B_MAX_SHADOW_SLOTS + k] ? 1 : 0;
+    return kNeed[s * C4B_MAX_SHADOW_SLOTS + l] ? w : -1;
+}
+__device__ constexpr int word_of_start(int s) {
+    int w = 1;
+    for (int k = 0; k < NSH; ++k) w += kNeed[s * C4B_MAX_SHADOW_SLOTS + k] ? 1 : 0;
+    return kRegion ? w : -1;
+}
+static_assert(!kRegion || kPackStart, "the systolic kernel carries the START cell in one packed word");
+
+// one cell's working set: every state's score + all possible words (dead ones fold away)
+constexpr int CWMAX = 1 + NSH + 1;
+struct Cell {
+    int v[S][CWMAX];   // [0] score, [1 + l] shadow slot l, [1 + NSH] packed start cell
+    bool set[S];
+    unsigned char win[S];
+};
+
+struct SysCtx {
+    Ctx X;
+    int row0;          // lattice row of real row 0 of this lane
+    bool has_up;       // some lattice row lies above my strip
+    int j;             // my column this step
+    bool colok;        // 0 <= j <= T
+};
+
+template <int K, int ROW>
+__device__ __forceinline__ void sys_precalc(const SysCtx &Z, const int (&V)[NROWS][VW], int (&cs)[TN]) {
+    if constexpr (K < TN) {
+        if constexpr (calc_hoisted<K>()) {
+            constexpr int calc = kTrCalc[K];
+            constexpr int slot = calc_shadow_slot<calc>();
+            constexpr int in = kTrIn[K], aq = kTrAq[K], at = kTrAt[K];
+            const int si = max(Z.row0 + ROW - aq, 0), sj = max(Z.j - at, 0);
+            int shadow = 0;
+            if constexpr (slot >= 0 && word_of_slot(in, slot >= 0 ? slot : 0) >= 0)
+                shadow = V[AQ + ROW - aq][kVOff[in] + at * kNW[in] + word_of_slot(in, slot >= 0 ? slot : 0)];
+            cs[K] = calc_score<calc>(Z.X, Z.X.q_start + si, Z.X.t_start + min(sj, Z.X.T), shadow);
+        }
+        sys_precalc<K + 1, ROW>(Z, V, cs);
+    }
+}
+
+template <int K, int ROW>
+__device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[NROWS][VW], const int (&cs)[TN],
+                                                bool rowok, Cell &c) {
+    if constexpr (K < TN) {
+        constexpr int in = kTrIn[K], out = kTrOut[K], aq = kTrAq[K], at = kTrAt[K];
+        constexpr int calc = kTrCalc[K];
+        constexpr bool from_start = (in == START);
+        const int i = Z.row0 + ROW, j = Z.j;
+        const int si = i - aq, sj = j - at;
+        bool valid = rowok && state_active<in>(si, sj, Z.X.Q, Z.X.T) && state_active<out>(i, j, Z.X.Q, Z.X.T);
+        if constexpr (at > 0) valid = valid && sj >= 0;
+        if constexpr (aq > ROW) valid = valid && (Z.has_up && si >= 0);
+        int src[CWMAX];
+#pragma unroll
+        for (int l = 0; l < CWMAX; ++l) src[l] = 0;
+        if constexpr (from_start) {
+            // START's cell is all zero (no cell_start_func tables on this kernel)
+        } else if constexpr (aq + at > 0) {
+            constexpr int base = kVOff[in] + at * kNW[in];
+            src[0] = V[AQ + ROW - aq][base];
+#pragma unroll
+            for (int l = 0; l < NSH; ++l)
+                if constexpr (word_of_slot(in, l) >= 0) src[1 + l] = V[AQ + ROW - aq][base + word_of_slot(in, l)];
+            if constexpr (kRegion) src[1 + NSH] = V[AQ + ROW - aq][base + word_of_start(in)];
+        } else {
+#pragma unroll
+            for (int l = 0; l < CWMAX; ++l) src[l] = c.v[in][l];
+        }
+        int t = src[0];
+        if constexpr (calc >= 0) {
+            if constexpr (calc_hoisted<K>()) {
+                t += cs[K];
+            } else {  // shadow-reading calc on a silent transition: its slot is only known now
+                constexpr int slot = calc_shadow_slot<calc>();
+                t += calc_score<calc>(Z.X, Z.X.q_start + max(si, 0), Z.X.t_start + max(sj, 0), src[1 + (slot >= 0 ? slot : 0)]);
+            }
+            if constexpr ((kCalcProt[calc >= 0 ? calc : 0] & C4B_PROTECT_UNDERFLOW) != 0) t = max(t, LOWV);
+            if constexpr ((kCalcProt[calc >= 0 ? calc : 0] & C4B_PROTECT_OVERFLOW) != 0)
+                t = min(t, C4B_IMPOSSIBLY_HIGH_SCORE);
+        }
+        const bool take = valid && (!c.set[out] || c.v[out][0] < t);
+        c.set[out] = c.set[out] || valid;
+        // Viterbi_Data_assign (viterbi.c:445-462); stamps go on the transported copy
+        c.v[out][0] = take ? t : c.v[out][0];
+#pragma unroll
+        for (int l = 0; l < NSH; ++l) {
+            if constexpr (word_of_slot(out, l) >= 0) {
+                constexpr int stamp = kShadow[in * C4B_MAX_SHADOW_SLOTS + l];
+                int nv = src[1 + l];
+                if constexpr (stamp == 1) nv = Z.X.t_start + sj;
+                if constexpr (stamp == 2) nv = Z.X.q_start + si;
+                c.v[out][1 + l] = take ? nv : c.v[out][1 + l];
+            }
+        }
+        if constexpr (kRegion) {
+            int nv = src[1 + NSH];
+            if constexpr (from_start) nv = si * (Z.X.T + 1) + sj;
+            c.v[out][1 + NSH] = take ? nv : c.v[out][1 + NSH];
+        }
+        if constexpr (JIT_MODE == GEN_PATH) c.win[out] = take ? (unsigned char)K : c.win[out];
+        sys_transitions<K + 1, ROW>(Z, V, cs, rowok, c);
+    }
+}
+
+// what a lane hands to the lane below per step: for every virtual-row distance d (1..AQ) the
+// carried words of the states some transition reads at advance_query >= d, current column
+__device__ constexpr bool state_sent(int s, int d) {
+    for (int k = 0; k < TN; ++k)
+        if (kTrIn[k] == s && kTrIn[k] != START && kTrAq[k] >= d) return true;
+    return false;
+}
+
+template <int D, int ST, int W_, typename F>
+__device__ __forceinline__ void for_each_sent(F &&f) {   // f(d, state, word, running index)
+    // plain nested loops with compile-time bounds; `idx` counts the words in a fixed order
+    int idx = 0;
+#pragma unroll
+    for (int d = 1; d <= AQ; ++d)
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (state_sent(s, d) && kVD[s] >= 0)
+#pragma unroll
+                for (int w = 0; w < kNW[s]; ++w) f(d, s, w, idx++);
+}
+
+}  // namespace c4bjit
+
+// one CTA per lattice; blockDim.x = 32 W, the W warps take the strips of 32 R rows round-robin
+extern "C" __global__ void __launch_bounds__(32 * c4bjit::kSysMaxWarps)
+c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__restrict__ outs,
+            const c4b::GenTables *__restrict__ tables, int32_t *top_base, size_t top_stride) {
+    using namespace c4bjit;
+    __shared__ c4b_scoring s_scoring;
+    __shared__ volatile long long vprog[kSysMaxWarps];
+    __shared__ int red[kSysMaxWarps][4];
+    {
+        const int *src = reinterpret_cast<const int *>(&tables->scoring);
+        int *dst = reinterpret_cast<int *>(&s_scoring);
+        for (int k = threadIdx.x; k < (int)(sizeof(c4b_scoring) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    if (threadIdx.x < kSysMaxWarps) vprog[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int pi = blockIdx.x;
+    if (pi >= n_pairs) return;
+    const GenPair P = pairs[pi];
+    SysCtx Z;
+    Z.X.sc = &s_scoring;
+    Z.X.q = P.q; Z.X.t = P.t;
+    for (int k = 0; k < 4; ++k) Z.X.splice[k] = P.splice[k];
+    Z.X.start_cells = nullptr;
+    Z.X.blk_q = nullptr; Z.X.blk_t = nullptr;
+    Z.X.n_blocked = 0; Z.X.blk_dq = 0; Z.X.blk_dt = 0;
+    Z.X.q_start = P.q_start; Z.X.t_start = P.t_start; Z.X.Q = P.Q; Z.X.T = P.T;
+    const int Q = P.Q, T = P.T;
+    constexpr int rows_per_sweep = 32 * SR;
+    const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    const int nsteps = T + 1 + 31;
+    // sweep hand-off rows in L2: two buffers of (T + 1) x NSEND words per lattice, ping-pong
+    int32_t *top0 = top_base + (size_t)pi * top_stride;
+    int32_t *top1 = top0 + (size_t)(T + 1) * (NSEND > 0 ? NSEND : 1);
+
+    int best = INT_MIN, best_i = 0, best_j = 0, best_start = 0;
+
+    for (int sweep = warp; sweep < nsweeps; sweep += W) {
+        Z.row0 = sweep * rows_per_sweep + lane * SR;
+        Z.has_up = !(sweep == 0 && lane == 0);
+        const bool later_sweep = sweep > 0;
+        const int32_t *top_in = (sweep & 1) ? top0 : top1;   // written by sweep - 1
+        int32_t *top_out = (sweep & 1) ? top1 : top0;
+        const bool write_top = (sweep + 1 < nsweeps) && lane == 31;
+        const bool piped = later_sweep && W > 1;
+        const int wp = (sweep - 1) % W;
+        const long long in_base = (long long)(sweep - 1) * (T + 1);
+        long long avail = 0;
+        auto wait_column = [&](int col) {   // until column `col` of the sweep above is published
+            const long long need = in_base + col + 1;
+            if (avail < need) {
+                while ((avail = vprog[wp]) < need) __nanosleep(40);
+                __threadfence_block();
+            }
+        };
+        // the register lattice: V[row][state block: column k = 0 (current) .. kVD][carried word]
+        int V[NROWS][VW];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if constexpr (true) {
+                    if (kVD[s] >= 0) {
+#pragma unroll
+                        for (int k = 0; k <= (kVD[s] >= 0 ? kVD[s] : 0); ++k)
+#pragma unroll
+                            for (int w = 0; w < kNW[s]; ++w) V[r][kVOff[s] + k * kNW[s] + w] = (w == 0) ? LOWV : 0;
+                    }
+                }
+        // lane 0 of a later sweep: column 0 of the row(s) above comes from the hand-off buffer
+        int upin[NSEND > 0 ? NSEND : 1];
+        auto load_top = [&](int col) {
+#pragma unroll
+            for (int w = 0; w < NSEND; ++w) upin[w] = __ldcg(top_in + (size_t)col * NSEND + w);
+        };
+        auto place_up = [&](const int (&vals)[NSEND > 0 ? NSEND : 1]) {   // received words -> virtual rows, column 0
+            for_each_sent<0, 0, 0>([&](int d, int s, int w, int idx) { V[AQ - d][kVOff[s] + w] = vals[idx]; });
+        };
+        if (later_sweep) {
+            if (piped) wait_column(0);
+            load_top(0);
+            if (lane == 0) place_up(upin);
+        }
+        unsigned char *tbp = nullptr;
+        constexpr int TBCH = ((SR * S + 15) / 16) * 16;   // traceback bytes per lane per step, 16-byte chunks
+        if constexpr (JIT_MODE == GEN_PATH)
+            tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * TBCH;
+
+        for (int s = 0; s < nsteps; ++s) {
+            const int j = s - lane;
+            Z.j = j;
+            Z.colok = (j >= 0 && j <= T);
+            // the next column of the sweep above, fetched early with warp-uniform addresses
+            if (later_sweep && s + 1 <= T) {
+                if (piped) wait_column(s + 1);
+                load_top(s + 1);
+            }
+            uint32_t tbw[TBCH / 4];
+#pragma unroll
+            for (int k = 0; k < TBCH / 4; ++k) tbw[k] = 0xFFFFFFFFu;
+            // rows of my strip, top-down (a row reads the CURRENT column of the rows above it)
+            auto do_row = [&](auto ROWC) {
+                constexpr int ROW = decltype(ROWC)::value;
+                const int i = Z.row0 + ROW;
+                const bool rowok = Z.colok && i <= Q;
+                int cs[TN];
+                sys_precalc<0, ROW>(Z, V, cs);
+                Cell c;
+#pragma unroll
+                for (int st = 0; st < S; ++st) {
+#pragma unroll
+                    for (int l = 0; l < CWMAX; ++l) c.v[st][l] = (l == 0) ? LOWV : 0;   // viterbi.c:691-694
+                    c.set[st] = false;
+                    c.win[st] = 0xFF;
+                }
+                sys_transitions<0, ROW>(Z, V, cs, rowok, c);
+                if (c.set[END]) {   // viterbi.c:778-791; within a thread cells arrive in scan order
+                    const int v = c.v[END][0];
+                    if (v > best) {
+                        best = v; best_i = i; best_j = j;
+                        if constexpr (kRegion) best_start = c.v[END][1 + NSH];
+                    }
+                }
+                if constexpr (JIT_MODE == GEN_PATH) {
+#pragma unroll
+                    for (int st = 0; st < S; ++st) {
+                        constexpr int dummy = 0;
+                        const int byte = ROW * S + st;
+                        tbw[byte / 4] = (tbw[byte / 4] & ~(0xFFu << (8 * (byte % 4)))) |
+                                        ((uint32_t)c.win[st] << (8 * (byte % 4)));
+                        (void)dummy;
+                    }
+                }
+                // current column of the states that are read later
+#pragma unroll
+                for (int st = 0; st < S; ++st)
+                    if (kVD[st] >= 0) {
+                        V[AQ + ROW][kVOff[st]] = c.v[st][0];
+#pragma unroll
+                        for (int l = 0; l < NSH; ++l)
+                            if (word_of_slot(st, l) >= 0) V[AQ + ROW][kVOff[st] + word_of_slot(st, l)] = c.v[st][1 + l];
+                        if (kRegion) V[AQ + ROW][kVOff[st] + (word_of_start(st) >= 0 ? word_of_start(st) : 0)] = c.v[st][1 + NSH];
+                    }
+            };
+            [&]<int... RS>(c4b_seq<RS...>) { (do_row(c4b_int<RS>{}), ...); }(c4b_make_seq<SR>{});
+
+            if constexpr (JIT_MODE == GEN_PATH) {
+                if (Z.colok) {
+#pragma unroll
+                    for (int k = 0; k < TBCH / 16; ++k)
+                        reinterpret_cast<uint4 *>(tbp)[k] = make_uint4(tbw[4 * k], tbw[4 * k + 1], tbw[4 * k + 2], tbw[4 * k + 3]);
+                }
+                tbp += 32 * TBCH;
+            }
+            // hand the bottom rows' current column to the lane below / the next sweep
+            int send[NSEND > 0 ? NSEND : 1];
+            for_each_sent<0, 0, 0>([&](int d, int st, int w, int idx) { send[idx] = V[AQ + SR - d][kVOff[st] + w]; });
+            if (write_top && Z.colok) {
+#pragma unroll
+                for (int w = 0; w < NSEND; ++w) top_out[(size_t)j * NSEND + w] = send[w];
+                if (W > 1) {
+                    __threadfence_block();   // the row is written before the counter moves
+                    vprog[warp] = (long long)sweep * (T + 1) + j + 1;
+                }
+            }
+            int recv[NSEND > 0 ? NSEND : 1];
+#pragma unroll
+            for (int w = 0; w < NSEND; ++w) {
+                recv[w] = __shfl_up_sync(0xffffffffu, send[w], 1);
+                if (lane == 0) recv[w] = upin[w];   // column s + 1 of the sweep above (unused in sweep 0)
+            }
+            // every kept column moves one place back; column 0 of the virtual rows is what arrived
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+                for (int st = 0; st < S; ++st)
+                    if (kVD[st] >= 1) {
+#pragma unroll
+                        for (int k = (kVD[st] >= 1 ? kVD[st] : 1); k >= 1; --k)
+#pragma unroll
+                            for (int w = 0; w < kNW[st]; ++w)
+                                V[r][kVOff[st] + k * kNW[st] + w] = V[r][kVOff[st] + (k - 1) * kNW[st] + w];
+                    }
+            place_up(recv);
+        }
+        __syncwarp();
+    }
+    // lexicographic reduction: max score, then min j, then min i
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        const int os = __shfl_xor_sync(0xffffffffu, best_start, off);
+        const bool take = (ob > best) || (ob == best && (oj < best_j || (oj == best_j && oi < best_i)));
+        if (take) { best = ob; best_j = oj; best_i = oi; best_start = os; }
+    }
+    if (W > 1) {
+        if (lane == 0) { red[warp][0] = best; red[warp][1] = best_j; red[warp][2] = best_i; red[warp][3] = best_start; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w < W; ++w) {
+                const int ob = red[w][0], oj = red[w][1], oi = red[w][2];
+                if ((ob > best) || (ob == best && (oj < best_j || (oj == best_j && oi < best_i)))) {
+                    best = ob; best_j = oj; best_i = oi; best_start = red[w][3];
+                }
+            }
+    }
+    if (threadIdx.x == 0) {
+        GenOut o;
+        o.score = best; o.end_i = best_i; o.end_j = best_j;
+        o.start_i = kRegion ? best_start / (T + 1) : 0;
+        o.start_j = kRegion ? best_start % (T + 1) : 0;
+        o.flags = (best == INT_MIN) ? 1 : 0;
+        outs[P.out_index] = o;
+    }
+}

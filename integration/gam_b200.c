@@ -366,8 +366,12 @@ GAM_Result *b200_GAM_Result_exhaustive_create(GAM *gam, Sequence *query, Sequenc
     register B200_Job *job;
     if(enabled < 0){
         enabled = env_long("EXONERATE_B200_BATCH", 1)?1:0;
-        max_pairs = env_long("EXONERATE_B200_BATCH_PAIRS", 16384);
-        max_bytes = env_long("EXONERATE_B200_BATCH_MB", 4096) << 20;
+        /* defaults: a flush of 4096 pairs keeps the GPU busy for ~0.1 s at the metric shape while
+         * the queued Sequences (the reference re-reads every target per query) stay cache- and
+         * page-friendly: 10k pairs of 1 kbp x 100 kbp ran in 4.85 s with flushes of 2000 pairs
+         * and 5.62 s as one flush (profiles/r02_cli.md) */
+        max_pairs = env_long("EXONERATE_B200_BATCH_PAIRS", 4096);
+        max_bytes = env_long("EXONERATE_B200_BATCH_MB", 1024) << 20;
         max_cells = (gint64)env_long("EXONERATE_B200_BATCH_GCELLS", 4000) * 1000000000ll;
         if(g_getenv("EXONERATE_B200_STATS"))
             atexit(print_stats);

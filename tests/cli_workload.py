@@ -85,7 +85,9 @@ def est2genome_metric(n_queries, n_targets, tlen=100000, seed=2):
     return qs, ts
 
 
-def write_workload(directory, kind, n_queries, n_targets, **kw):
+def write_workload(directory, kind, n_queries, n_targets, *rest, **kw):
+    if rest:   # BATCH_COMMANDS entries may carry generator keywords as a fifth element
+        kw = dict(rest[0], **kw) if isinstance(rest[0], dict) else kw
     qs, ts = (affine_metric if kind == "affine" else est2genome_metric)(n_queries, n_targets, **kw)
     os.makedirs(directory, exist_ok=True)
     q, t = os.path.join(directory, "q_%s.fa" % kind), os.path.join(directory, "t_%s.fa" % kind)
@@ -101,7 +103,9 @@ BATCH_COMMANDS = {
     "metric_affine_local": ("affine", 4, 6, ["--model", "affine:local", "--exhaustive", "yes", "--subopt", "no",
                                              "--revcomp", "no", "--score", "0"]),
     # CLI defaults: --subopt yes (sub-optimal series, batched in rounds), both strands, --score 100
-    "metric_affine_local_defaults": ("affine", 3, 4, ["--model", "affine:local", "--exhaustive", "yes"]),
+    # (20 kbp targets: the reference spends minutes per 100 kbp lattice on a sub-optimal series)
+    "metric_affine_local_defaults": ("affine", 3, 4, ["--model", "affine:local", "--exhaustive", "yes"],
+                                     {"tlen": 20000}),
     # --bestn changes the threshold as results are submitted: the replay order matters
     "metric_affine_local_bestn": ("affine", 3, 4, ["--model", "affine:local", "--exhaustive", "yes", "--bestn", "1",
                                                    "--subopt", "no"]),

@@ -23,9 +23,9 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "exonerate_c")
 
 
 def make(name):
-    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name]
+    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name][:4]
     with tempfile.TemporaryDirectory() as d:
-        q, t = cli_workload.write_workload(d, kind, nq, nt)
+        q, t = cli_workload.write_workload(d, kind, nq, nt, *cli_workload.BATCH_COMMANDS[name][4:])
         out = subprocess.run([REF_BIN, q, t] + flags + cli_workload.COMMON, capture_output=True, text=True,
                              check=True).stdout
     with open(os.path.join(OUT, name + ".out"), "w") as f:

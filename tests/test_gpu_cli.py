@@ -90,8 +90,8 @@ BATCH_GOLDEN = os.path.join(helpers.GOLDEN, "cli_batch")
 
 
 def _run_batch_cli(tmp_path, name, extra_env=None):
-    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name]
-    q, t = cli_workload.write_workload(str(tmp_path), kind, nq, nt)
+    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name][:4]
+    q, t = cli_workload.write_workload(str(tmp_path), kind, nq, nt, *cli_workload.BATCH_COMMANDS[name][4:])
     env = dict(os.environ, EXONERATE_B200_STATS="1", **(extra_env or {}))
     return subprocess.run([BIN, q, t] + flags + cli_workload.COMMON, capture_output=True, text=True, timeout=900,
                           env=env)
@@ -111,7 +111,7 @@ def test_cli_batch_hook_metric_shape(name, tmp_path):
     assert len(want.splitlines()) >= 4
     m = re.search(r"batch hook: (\d+) pair\(s\) in (\d+) flush\(es\), (\d+) device round", got.stderr)
     assert m, got.stderr[-800:]
-    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name]
+    kind, nq, nt, flags = cli_workload.BATCH_COMMANDS[name][:4]
     strands = 1 if "--revcomp" in flags else 2   # --revcomp defaults to yes: every query twice
     assert int(m.group(1)) == nq * nt * strands and int(m.group(2)) == 1
     m = re.search(r"answered from the batch prefetch (\d+) \(prefetched but not usable (\d+)\)", got.stderr)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Small-batch occupancy of the packed score pass (tuning aid, not a bench number): one
-GPU's shard of the fixed 10k-pair batch at N = 8 / 4 / 2 / 1 GPUs, with 32 / 16 / 8 rows per
-lane (C4B_P16_R; 16 and 8 turn a 1 kbp query into 2 / 4 pipelined warps per lattice pair).
+GPU's shard of the fixed 10k-pair batch at N = 8 / 4 / 2 / 1 GPUs, packed two lattices per warp
+(C4B_P16_FOLD=0) against folded one lattice per warp (C4B_P16_FOLD=1); C4B_P16_R=16 / 8 turn a
+1 kbp query into 2 / 4 pipelined warps per lattice pair (measured slower, profiles/r02_strong_sweep.md).
 usage: python tools/strong_sweep.py [model=affine:local]   (run in a fresh process per R: env)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,14 +28,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         for _ in range(3):
             b.run()
         e1.record(); torch.cuda.synchronize()
-        print("P16_R=%-4s pairs=%5d path=%d GCUPS=%.0f" % (os.environ.get("C4B_P16_R", "auto"), n, want_path,
+        print("FOLD=%-4s P16_R=%-4s pairs=%5d path=%d GCUPS=%.0f" % (os.environ.get("C4B_P16_FOLD", "auto"), os.environ.get("C4B_P16_R", "auto"), n, want_path,
               pairs.cells / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e9), flush=True)
         b.close()
     sys.exit(0)
 
-for n in (1250, 2500, 5000, 10000):
-    for r in ("32", "16", "8", None):
+for n in (1250, 2500, 3552, 5000, 7104, 10000):
+    for fold in ("0", "1", None):
         env = dict(os.environ)
-        if r: env["C4B_P16_R"] = r
-        else: env.pop("C4B_P16_R", None)
+        if fold: env["C4B_P16_FOLD"] = fold
+        else: env.pop("C4B_P16_FOLD", None)
         subprocess.run([sys.executable, __file__, "--one", str(n)], env=env)
