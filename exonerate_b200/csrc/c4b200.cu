@@ -1431,6 +1431,22 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
             }
             jit_store(jit_cache_path(src), cubin);
         }
+    // ... and the systolic specialisation the launcher prefers for lattices without SubOpt
+    // blocked cells / cell-callback tables (cta_threads does not apply: one warp per strip)
+    {
+        const char *env = getenv("C4B_JIT_SYSTOLIC");
+        const SysLayout L = jit_sys_layout(*model, mode, mode == GEN_REGION);
+        if (L.ok && !(env && atoi(env) == 0)) {
+            // (for the strip counts of queries that fill cta_threads rows of the thread-per-row kernel)
+            const std::string src = jit_sys_program_source(*model, mode, mode == GEN_REGION, L,
+                                                           jit_sys_warps(L, cta_threads - 1));
+            if (!jit_compile(src, &cubin, &log)) {
+                set_error("systolic model specialisation failed: " + log);
+                return -1;
+            }
+            jit_store(jit_cache_path(src), cubin);
+        }
+    }
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
 }

@@ -17,6 +17,12 @@ struct GenericBatch {
     int ring_ctas = 0;     // CTAs the lattice ring was sized for
     int max_q = 0, max_t = 0;
     const char *kernel_used = "generic_wavefront";
+    // the systolic specialisation (generic_jit_systolic.cuh): lattices without SubOpt blocked cells
+    // or cell-callback tables; layouts per fill mode, hand-off rows of the strip sweeps
+    bool plain = true;
+    SysLayout sys_score, sys_region, sys_path;
+    DevBuf<int32_t> d_top;
+    size_t top_stride = 0;
     std::vector<c4b_pair> host_pairs;
     std::vector<GenPair> h_full;
     DevBuf<GenTables> d_tables;
@@ -36,7 +42,7 @@ struct GenericBatch {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     double fill_ms = -1;
     ~GenericBatch() {
-        d_endm.release(); d_startc.release();
+        d_endm.release(); d_startc.release(); d_top.release();
         d_tables.release(); d_seq.release(); d_ints.release(); d_full.release(); d_box.release();
         d_out_a.release(); d_out_b.release(); d_jobs.release(); d_ring.release(); d_cursor.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
@@ -242,6 +248,29 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     g->use_jit = policy == 1 || (policy == 2 && g->cells >= ((int64_t)1 << 31));
     g->jit_threads = jit_threads_for(maxQ);
     g->max_q = maxQ;
+    {
+        const char *env = getenv("C4B_JIT_SYSTOLIC");
+        g->plain = !start_cells && !end_cells;   // (set here: the descriptors are filled in below)
+        for (int p = 0; p < n; ++p) g->plain = g->plain && pairs[p].n_blocked == 0;
+        if (g->use_jit && g->plain && !(env && atoi(env) == 0)) {
+            const bool pack_start = ((int64_t)maxQ + 1) * ((int64_t)g->max_t + 1) < ((int64_t)1 << 31);
+            g->sys_score = jit_sys_layout(m, GEN_SCORE, false);
+            g->sys_region = jit_sys_layout(m, GEN_REGION, pack_start);
+            g->sys_path = jit_sys_layout(m, GEN_PATH, false);
+            // The REGION pass exists to keep the PATH records small (optimal.c:368-413).  When the
+            // records of the FULL lattices fit comfortably (a third of free memory), one PATH pass
+            // over everything is cheaper than REGION + PATH-in-the-box, and gives the same path.
+            if (g->use_region && g->sys_path.ok) {
+                size_t all = 0, free_b = 0, total_b = 0;
+                for (int p = 0; p < n; ++p)
+                    all += align_up(GEN_TBS_BYTES(pairs[p].query_length, pairs[p].target_length, g->sys_path.R,
+                                                  g->sys_path.chunk), 16);
+                const char *d = getenv("C4B_GENERIC_DIRECT_PATH");
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (d ? atoi(d) != 0 : all < free_b / 3))
+                    g->use_region = false;
+            }
+        }
+    }
     g->ring_ctas = g->grid;
     if (g->use_jit) g->ring_ctas = std::max(g->ring_ctas, std::min(n, g->sm_count * (2048 / g->jit_threads)));
     const int depth = m.max_target_advance + m.max_query_advance + 1;
@@ -277,6 +306,8 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         G.start_cells = nullptr;
         G.end_cells = nullptr;
         G.out_index = p;
+        G.tb_rows = 0;
+        G.tb_chunk = 0;
     }
     if ((start_cells || end_cells) && n == 1) {
         const size_t cells = ((size_t)pairs[0].query_length + 1) * ((size_t)pairs[0].target_length + 1) *
@@ -331,6 +362,36 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
 static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode) {
     if (!count) return 0;
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
+    const SysLayout &SL = mode == GEN_SCORE ? g->sys_score : (mode == GEN_REGION ? g->sys_region : g->sys_path);
+    if (g->use_jit && SL.ok) {
+        const bool pack_start = mode == GEN_REGION;
+        // one CTA per lattice, one warp per strip of 32 R rows (up to 8, then round-robin);
+        // strips hand their bottom rows over through L2: 2 x (T + 1) x NSEND words per lattice
+        int maxQ = 0, maxT = 0;
+        for (int p = 0; p < g->n; ++p) { maxQ = std::max(maxQ, g->h_full[p].Q); maxT = std::max(maxT, g->h_full[p].T); }
+        const int nsweeps = (maxQ + 32 * SL.R) / (32 * SL.R);
+        const int warps = jit_sys_warps(SL, maxQ);
+        if (JitKernel *jk = jit_get_sys(g->tables.model, mode, pack_start, SL, warps)) {
+            const size_t nsend = std::max<size_t>(1, SL.sendD.size());
+            const size_t stride = nsweeps > 1 ? align_up(2 * ((size_t)maxT + 1) * nsend, 4) : 0;
+            if (stride * (size_t)count > g->d_top.n) {
+                g->d_top.release();
+                if (g->d_top.alloc(stride * (size_t)count + 4)) return -1;
+            }
+            int32_t *top = g->d_top.p;
+            void *args[] = {(void *)&pairs, (void *)&count, (void *)&outs, (void *)&g->d_tables.p, (void *)&top,
+                            (void *)&stride};
+            C4B_CUDA(cudaLaunchKernel((const void *)jk->kern, dim3(count), dim3(32 * warps), args, 0, g->stream));
+            (*g->launches)++;
+            g->kernel_used = "generic_jit_systolic";
+            return 0;
+        }
+        if (!getenv("C4B_JIT_FALLBACK")) {
+            set_error("systolic model specialisation failed (reason on stderr); set C4B_JIT_SYSTOLIC=0 to use the "
+                      "thread-per-row specialisation");
+            return -1;
+        }
+    }
     if (g->use_jit) {
         // the lattice ring goes to shared memory when DEPTH columns of the longest query fit
         const bool pack_start = mode == GEN_REGION && ((int64_t)g->max_q + 1) * ((int64_t)g->max_t + 1) < ((int64_t)1 << 31);
@@ -410,10 +471,17 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         }
     }
     // 2) PATH fill inside the boxes, chunked to the traceback arena
+    const bool sys_tb = g->use_jit && g->sys_path.ok;   // the systolic kernel's record layout
+    auto tb_bytes = [&](int p) {
+        return sys_tb ? GEN_TBS_BYTES(box[p].Q, box[p].T, g->sys_path.R, g->sys_path.chunk)
+                      : GEN_TB_BYTES(box[p].Q, box[p].T, S);
+    };
+    if (sys_tb)
+        for (int p = 0; p < n; ++p) { box[p].tb_rows = g->sys_path.R; box[p].tb_chunk = g->sys_path.chunk; }
     size_t budget = 256ull << 20;  // small jobs (BSDP region fills) never need to ask the driver
     {
         size_t all = 0;
-        for (int p = 0; p < n; ++p) all += align_up(GEN_TB_BYTES(box[p].Q, box[p].T, S), 16);
+        for (int p = 0; p < n; ++p) all += align_up(tb_bytes(p), 16);
         if (all > budget) {
             size_t free_b = 0, total_b = 0;
             C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -427,7 +495,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     int64_t ops_cursor = 0;
     int begin = 0;
     for (int p = 0; p < n; ++p) {
-        const size_t need = align_up(GEN_TB_BYTES(box[p].Q, box[p].T, S), 16);
+        const size_t need = align_up(tb_bytes(p), 16);
         if (need > budget) {
             set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget");
             return -1;

@@ -147,6 +147,153 @@ static std::string jit_program_source(const c4b_model &m, int mode, int threads,
     return o.str();
 }
 
+// ---- the systolic specialisation (generic_jit_systolic.cuh) -----------------------------
+// Register layout of one lattice row, derived from the closed model.
+struct SysLayout {
+    bool ok = false;
+    int R = 1;            // lattice rows per lane
+    int AQ = 0;           // largest advance_query of a transition that reads the lattice
+    int VW = 0;           // words per row
+    int chunk = 16;       // PATH bytes per lane per step
+    std::vector<int> NW, VD, VOff;          // per state
+    std::vector<int> need;                  // [S * C4B_MAX_SHADOW_SLOTS]
+    std::vector<int> sendD, sendOff;        // hand-off words
+    // PATH record: per cell, per state, WHICH of the transitions that enter the state won, as its
+    // 1-based rank among them in closed-model order (0 = state unset): ceil(log2(n_in + 1)) bits
+    // instead of the reference's pointer (viterbi.c:220-227) or a byte per state
+    std::vector<int> tbCode, tbBits, tbBitOff;   // per transition / per state / per state
+    int rowBits = 0;
+};
+
+static void jit_tb_bits(const c4b_model &m, std::vector<int> *code, std::vector<int> *bits, std::vector<int> *off,
+                        int *row_bits) {
+    const int S = m.n_states, TN = m.n_transitions;
+    std::vector<int> n_in(S, 0);
+    code->assign(TN, 0);
+    for (int k = 0; k < TN; ++k) (*code)[k] = ++n_in[m.transitions[k].output];
+    bits->assign(S, 0);
+    off->assign(S, 0);
+    *row_bits = 0;
+    for (int s = 0; s < S; ++s) {
+        int b = 0;
+        while ((1 << b) < n_in[s] + 1) ++b;
+        (*bits)[s] = b;
+        (*off)[s] = *row_bits;
+        *row_bits += b;
+    }
+}
+
+static SysLayout jit_sys_layout(const c4b_model &m, int mode, bool pack_start) {
+    SysLayout L;
+    const int S = m.n_states, TN = m.n_transitions, NSH = m.n_shadow_slots;
+    const bool region = mode == GEN_REGION && m.start_scope != C4B_SCOPE_CORNER;
+    // REGION carries the START cell as ONE packed word: needs both coordinates free and < 2^31 cells
+    if (region && !(pack_start && m.start_scope != C4B_SCOPE_QUERY && m.start_scope != C4B_SCOPE_TARGET)) return L;
+    L.need.assign((size_t)S * C4B_MAX_SHADOW_SLOTS, 0);
+    for (int l = 0; l < NSH; ++l) {
+        // F: states a stamped value can reach; B: states whose slot value can still be read.
+        // Every transition LEAVING a stamping state overwrites the slot (viterbi.c:413-422).
+        std::vector<char> F(S, 0), B(S, 0);
+        for (bool grow = true; grow;) {
+            grow = false;
+            for (int k = 0; k < TN; ++k) {
+                const c4b_transition &t = m.transitions[k];
+                if ((m.shadow_start[t.input][l] || F[t.input]) && !F[t.output]) { F[t.output] = 1; grow = true; }
+            }
+        }
+        for (int k = 0; k < TN; ++k) {
+            const c4b_transition &t = m.transitions[k];
+            if (t.calc >= 0 && m.calcs[t.calc].kind >= C4B_CALC_SPLICE_POST && m.calcs[t.calc].param[2] == l)
+                B[t.input] = 1;
+        }
+        for (bool grow = true; grow;) {
+            grow = false;
+            for (int k = 0; k < TN; ++k) {
+                const c4b_transition &t = m.transitions[k];
+                if (B[t.output] && !m.shadow_start[t.input][l] && !B[t.input]) { B[t.input] = 1; grow = true; }
+            }
+        }
+        for (int s = 0; s < S; ++s) L.need[(size_t)s * C4B_MAX_SHADOW_SLOTS + l] = F[s] && B[s];
+    }
+    L.NW.assign(S, 1);
+    L.VD.assign(S, -1);
+    L.VOff.assign(S, 0);
+    for (int s = 0; s < S; ++s) {
+        for (int l = 0; l < NSH; ++l) L.NW[s] += L.need[(size_t)s * C4B_MAX_SHADOW_SLOTS + l];
+        if (region) L.NW[s] += 1;
+    }
+    for (int k = 0; k < TN; ++k) {
+        const c4b_transition &t = m.transitions[k];
+        if (t.input == m.start_state || t.advance_query + t.advance_target == 0) continue;
+        L.VD[t.input] = std::max(L.VD[t.input], t.advance_target);
+        L.AQ = std::max(L.AQ, t.advance_query);
+    }
+    for (int s = 0; s < S; ++s) {
+        L.VOff[s] = L.VW;
+        if (L.VD[s] >= 0) L.VW += L.NW[s] * (L.VD[s] + 1);
+    }
+    if (L.AQ < 1 || L.VW < 1) return L;   // nothing advances the query: not a lattice this mapping helps
+    for (int d = 1; d <= L.AQ; ++d)
+        for (int s = 0; s < S; ++s) {
+            bool sent = false;
+            for (int k = 0; k < TN; ++k)
+                sent = sent || (m.transitions[k].input == s && s != m.start_state && m.transitions[k].advance_query >= d);
+            if (!sent || L.VD[s] < 0) continue;
+            for (int w = 0; w < L.NW[s]; ++w) { L.sendD.push_back(d); L.sendOff.push_back(L.VOff[s] + w); }
+        }
+    // rows per lane from the register budget: (AQ + R) rows of VW words next to ~70 registers of
+    // working set; more rows amortise the per-step hand-off, fewer keep more warps resident
+    int budget = 150;
+    if (const char *env = getenv("C4B_JIT_SYS_REGS")) budget = std::max(32, atoi(env));
+    L.R = std::max(1, std::min(8, budget / L.VW - L.AQ));
+    if (const char *env = getenv("C4B_JIT_SYS_R")) L.R = std::max(1, std::min(16, atoi(env)));
+    jit_tb_bits(m, &L.tbCode, &L.tbBits, &L.tbBitOff, &L.rowBits);
+    L.chunk = std::max(4, (L.R * L.rowBits + 31) / 32 * 4);
+    L.ok = (L.AQ + L.R) * L.VW <= 230 && (int)L.sendD.size() <= 64;
+    return L;
+}
+
+// warps per CTA (= strips of one lattice in flight) for queries of up to max_q symbols
+static int jit_sys_warps(const SysLayout &L, int max_q) {
+    int max_warps = 8;
+    if (const char *env = getenv("C4B_JIT_SYS_WARPS")) max_warps = std::max(1, std::min(8, atoi(env)));
+    return std::max(1, std::min(max_warps, (max_q + 32 * L.R) / (32 * L.R)));
+}
+
+static std::string jit_sys_program_source(const c4b_model &m, int mode, bool pack_start, const SysLayout &L,
+                                          int warps) {
+    // the tables of the thread-per-row kernel first (its calc / scope code is shared), then ours
+    std::string base = jit_program_source(m, mode, 128, false, pack_start);
+    const size_t cut = base.find(kJitSrc_generic_jit_kernel_cuh);
+    std::ostringstream o;
+    o << base.substr(0, cut);
+    // resident CTAs per SM the register allocation must allow: 16 warps per SM (128 registers)
+    int minb = std::max(1, 16 / warps);
+    if (const char *env = getenv("C4B_JIT_SYS_MINB")) minb = std::max(1, std::min(16, atoi(env)));
+    o << "#define JIT_SYSTOLIC 1\n#define JIT_SYS_R " << L.R << "\n#define JIT_SYS_MINB " << minb
+      << "\n#define JIT_SYS_WARPS " << warps << "\n";
+    o << "namespace c4bjit {\n";
+    o << "constexpr int AQ = " << L.AQ << ", VW = " << L.VW << ", NSEND = " << L.sendD.size() << ";\n";
+    auto arr = [&](const char *name, const std::vector<int> &v, size_t n) {
+        o << "constexpr int " << name << "[" << std::max<size_t>(1, n) << "] = {";
+        for (size_t k = 0; k < std::max<size_t>(1, n); ++k) o << (k ? "," : "") << (k < v.size() ? v[k] : 0);
+        o << "};\n";
+    };
+    arr("kNW", L.NW, L.NW.size());
+    arr("kVD", L.VD, L.VD.size());
+    arr("kVOff", L.VOff, L.VOff.size());
+    arr("kNeed", L.need, L.need.size());
+    arr("kSendD", L.sendD, L.sendD.size());
+    arr("kSendOff", L.sendOff, L.sendOff.size());
+    arr("kTbCode", L.tbCode, L.tbCode.size());
+    arr("kTbBits", L.tbBits, L.tbBits.size());
+    arr("kTbBitOff", L.tbBitOff, L.tbBitOff.size());
+    o << "constexpr int TB_ROW_BITS = " << L.rowBits << ", TB_CHUNK = " << L.chunk << ";\n";
+    o << "}  // namespace c4bjit\n";
+    o << kJitSrc_generic_jit_kernel_cuh << "\n" << kJitSrc_generic_jit_systolic_cuh;
+    return o.str();
+}
+
 static uint64_t fnv1a(const std::string &s) {
     uint64_t h = 1469598103934665603ull;
     for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
@@ -192,11 +339,12 @@ static std::string jit_cache_path(const std::string &src) {
 }
 
 // cubin -> loaded kernel with its launch limits; nullptr + log on failure
-static JitKernel *jit_load(const std::vector<char> &cubin, int threads, bool smem_ring, std::string *log) {
+static JitKernel *jit_load(const std::vector<char> &cubin, int threads, bool smem_ring, std::string *log,
+                           const char *entry = "c4b_jit_fill") {
     JitKernel *jk = new JitKernel();
     jk->threads = threads;
     bool ok = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-              cudaLibraryGetKernel(&jk->kern, jk->lib, "c4b_jit_fill") == cudaSuccess;
+              cudaLibraryGetKernel(&jk->kern, jk->lib, entry) == cudaSuccess;
     if (!ok) *log = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(cudaGetLastError());
     if (ok && smem_ring) {
         jk->blocks_per_sm = 1;  // the ring takes the SM's shared memory
@@ -277,6 +425,34 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
     }
     if (!jk)
         fprintf(stderr, "libc4b200: model specialisation unavailable: %s\n", log.c_str());
+    cache[key] = jk;
+    return jk;
+}
+
+// the systolic specialisation of (model, mode); nullptr = not available (reason on stderr once)
+static JitKernel *jit_get_sys(const c4b_model &m, int mode, bool pack_start, const SysLayout &L, int warps) {
+    static std::mutex mu;
+    static std::map<std::string, JitKernel *> cache;
+    const std::string src = jit_sys_program_source(m, mode, pack_start, L, warps);
+    int device = 0;
+    cudaGetDevice(&device);
+    const std::string key = std::to_string(device) + ":" + src;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    JitKernel *jk = nullptr;
+    std::vector<char> cubin;
+    std::string log;
+    const std::string path = jit_cache_path(src);
+    if (!path.empty() && read_file(path, &cubin) && !(jk = jit_load(cubin, 32, false, &log, "c4b_jit_sys"))) {
+        remove(path.c_str());
+        cubin.clear();
+    }
+    if (!jk && jit_compile(src, &cubin, &log)) {
+        jit_store(path, cubin);
+        jk = jit_load(cubin, 32, false, &log, "c4b_jit_sys");
+    }
+    if (!jk) fprintf(stderr, "libc4b200: systolic model specialisation unavailable: %s\n", log.c_str());
     cache[key] = jk;
     return jk;
 }

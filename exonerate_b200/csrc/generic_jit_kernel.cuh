@@ -266,6 +266,7 @@ __device__ constexpr bool model_has_match_label() {
 
 }  // namespace c4bjit
 
+#ifndef JIT_SYSTOLIC   // generic_jit_systolic.cuh follows instead and defines its own kernel
 // grid = resident CTAs; each loops over lattices through an atomic cursor.
 extern "C" __global__ void __launch_bounds__(JIT_THREADS, JIT_MIN_CTAS)
 c4b_jit_fill(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__restrict__ outs,
@@ -385,3 +386,4 @@ c4b_jit_fill(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *_
         __syncthreads();
     }
 }
+#endif  // JIT_SYSTOLIC

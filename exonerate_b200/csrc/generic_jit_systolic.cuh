@@ -31,7 +31,9 @@
 // Expected in front of this file, after generic_jit_kernel.cuh's own tables:
 //   JIT_SYS_R (rows per lane), namespace c4bjit { AQ (largest advance_query), VW (words
 //   per row), kNW[S] (words a state carries), kVD[S] (columns kept - 1; -1: never stored),
-//   kVOff[S], kNeed[S * C4B_MAX_SHADOW_SLOTS], NSEND (words handed down per step) }.
+//   kVOff[S], kNeed[S * C4B_MAX_SHADOW_SLOTS], NSEND (words handed down per step),
+//   kSendD[NSEND], kSendOff[NSEND], kTbCode[TN], kTbBits[S], kTbBitOff[S], TB_ROW_BITS,
+//   TB_CHUNK (PATH record, see the host's SysLayout) }.
 
 namespace c4bjit {
 
@@ -106,8 +108,8 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
             src[0] = V[AQ + ROW - aq][base];
 #pragma unroll
             for (int l = 0; l < NSH; ++l)
-                if constexpr (word_of_slot(in, l) >= 0) src[1 + l] = V[AQ + ROW - aq][base + word_of_slot(in, l)];
-            if constexpr (kRegion) src[1 + NSH] = V[AQ + ROW - aq][base + word_of_start(in)];
+                if (word_of_slot(in, l) >= 0) src[1 + l] = V[AQ + ROW - aq][base + max(word_of_slot(in, l), 0)];
+            if constexpr (kRegion) src[1 + NSH] = V[AQ + ROW - aq][base + max(word_of_start(in), 0)];
         } else {
 #pragma unroll
             for (int l = 0; l < CWMAX; ++l) src[l] = c.v[in][l];
@@ -130,11 +132,11 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
         c.v[out][0] = take ? t : c.v[out][0];
 #pragma unroll
         for (int l = 0; l < NSH; ++l) {
-            if constexpr (word_of_slot(out, l) >= 0) {
-                constexpr int stamp = kShadow[in * C4B_MAX_SHADOW_SLOTS + l];
+            if (word_of_slot(out, l) >= 0) {   // (folds per unrolled l: dead slots cost nothing)
+                const int stamp = kShadow[in * C4B_MAX_SHADOW_SLOTS + l];
                 int nv = src[1 + l];
-                if constexpr (stamp == 1) nv = Z.X.t_start + sj;
-                if constexpr (stamp == 2) nv = Z.X.q_start + si;
+                if (stamp == 1) nv = Z.X.t_start + sj;
+                if (stamp == 2) nv = Z.X.q_start + si;
                 c.v[out][1 + l] = take ? nv : c.v[out][1 + l];
             }
         }
@@ -143,36 +145,81 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
             if constexpr (from_start) nv = si * (Z.X.T + 1) + sj;
             c.v[out][1 + NSH] = take ? nv : c.v[out][1 + NSH];
         }
-        if constexpr (JIT_MODE == GEN_PATH) c.win[out] = take ? (unsigned char)K : c.win[out];
+        if constexpr (JIT_MODE == GEN_PATH) c.win[out] = take ? (unsigned char)kTbCode[K] : c.win[out];
         sys_transitions<K + 1, ROW>(Z, V, cs, rowok, c);
     }
 }
 
-// what a lane hands to the lane below per step: for every virtual-row distance d (1..AQ) the
-// carried words of the states some transition reads at advance_query >= d, current column
-__device__ constexpr bool state_sent(int s, int d) {
-    for (int k = 0; k < TN; ++k)
-        if (kTrIn[k] == s && kTrIn[k] != START && kTrAq[k] >= d) return true;
-    return false;
+// What a lane hands to the lane below per step (host-generated): word w of the hand-off is
+// V[AQ + SR - kSendD[w]][kSendOff[w]] of the sender (current column of the row at distance
+// kSendD[w] above the receiver's row 0) and lands in V[AQ - kSendD[w]][kSendOff[w]] of the
+// receiver -- the carried words of every state some transition reads at advance_query >= d.
+
+// ---- one lattice row of the lane's strip at the lane's column -----------------------
+struct SysBest {
+    int score, i, j, start;
+};
+
+template <int ROW>
+__device__ __forceinline__ void sys_row(const SysCtx &Z, int (&V)[NROWS][VW], SysBest &best,
+                                        uint32_t (&tbw)[TB_CHUNK / 4]) {
+    const int i = Z.row0 + ROW;
+    const bool rowok = Z.colok && i <= Z.X.Q;
+    int cs[TN];
+    sys_precalc<0, ROW>(Z, V, cs);
+    Cell c;
+#pragma unroll
+    for (int st = 0; st < S; ++st) {
+#pragma unroll
+        for (int l = 0; l < CWMAX; ++l) c.v[st][l] = (l == 0) ? LOWV : 0;   // viterbi.c:691-694
+        c.set[st] = false;
+        c.win[st] = 0;
+    }
+    sys_transitions<0, ROW>(Z, V, cs, rowok, c);
+    if (c.set[END]) {   // viterbi.c:778-791; within a thread cells arrive in scan order
+        const int v = c.v[END][0];
+        if (v > best.score) {
+            best.score = v; best.i = i; best.j = Z.j;
+            if constexpr (kRegion) best.start = c.v[END][1 + NSH];
+        }
+    }
+    if constexpr (JIT_MODE == GEN_PATH) {
+        // the record: per state the rank of the winner among the transitions entering it (0 = unset)
+#pragma unroll
+        for (int st = 0; st < S; ++st)
+            if (kTbBits[st] > 0) {
+                const int pos = ROW * TB_ROW_BITS + kTbBitOff[st];
+                tbw[pos / 32] |= (uint32_t)c.win[st] << (pos % 32);
+                if (pos % 32 + kTbBits[st] > 32) tbw[pos / 32 + 1] |= (uint32_t)c.win[st] >> (32 - pos % 32);
+            }
+    }
+    // current column of the states that are read later
+#pragma unroll
+    for (int st = 0; st < S; ++st)
+        if (kVD[st] >= 0) {
+            V[AQ + ROW][kVOff[st]] = c.v[st][0];
+#pragma unroll
+            for (int l = 0; l < NSH; ++l)
+                if (word_of_slot(st, l) >= 0) V[AQ + ROW][kVOff[st] + max(word_of_slot(st, l), 0)] = c.v[st][1 + l];
+            if (kRegion) V[AQ + ROW][kVOff[st] + max(word_of_start(st), 0)] = c.v[st][1 + NSH];
+        }
 }
 
-template <int D, int ST, int W_, typename F>
-__device__ __forceinline__ void for_each_sent(F &&f) {   // f(d, state, word, running index)
-    // plain nested loops with compile-time bounds; `idx` counts the words in a fixed order
-    int idx = 0;
-#pragma unroll
-    for (int d = 1; d <= AQ; ++d)
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-            if (state_sent(s, d) && kVD[s] >= 0)
-#pragma unroll
-                for (int w = 0; w < kNW[s]; ++w) f(d, s, w, idx++);
+template <int ROW>
+__device__ __forceinline__ void sys_rows(const SysCtx &Z, int (&V)[NROWS][VW], SysBest &best,
+                                         uint32_t (&tbw)[TB_CHUNK / 4]) {
+    if constexpr (ROW < SR) {   // top-down: a row reads the CURRENT column of the rows above it
+        sys_row<ROW>(Z, V, best, tbw);
+        sys_rows<ROW + 1>(Z, V, best, tbw);
+    }
 }
 
 }  // namespace c4bjit
 
 // one CTA per lattice; blockDim.x = 32 W, the W warps take the strips of 32 R rows round-robin
-extern "C" __global__ void __launch_bounds__(32 * c4bjit::kSysMaxWarps)
+// JIT_SYS_WARPS = warps per CTA the host launches (strips in flight per lattice), JIT_SYS_MINB =
+// resident CTAs per SM the register allocation must allow (the host aims at 16 warps per SM)
+extern "C" __global__ void __launch_bounds__(32 * JIT_SYS_WARPS, JIT_SYS_MINB)
 c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__restrict__ outs,
             const c4b::GenTables *__restrict__ tables, int32_t *top_base, size_t top_stride) {
     using namespace c4bjit;
@@ -206,7 +253,8 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
     int32_t *top0 = top_base + (size_t)pi * top_stride;
     int32_t *top1 = top0 + (size_t)(T + 1) * (NSEND > 0 ? NSEND : 1);
 
-    int best = INT_MIN, best_i = 0, best_j = 0, best_start = 0;
+    SysBest bst;
+    bst.score = INT_MIN; bst.i = 0; bst.j = 0; bst.start = 0;
 
     for (int sweep = warp; sweep < nsweeps; sweep += W) {
         Z.row0 = sweep * rows_per_sweep + lane * SR;
@@ -231,23 +279,24 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
 #pragma unroll
         for (int r = 0; r < NROWS; ++r)
 #pragma unroll
-            for (int s = 0; s < S; ++s)
-                if constexpr (true) {
-                    if (kVD[s] >= 0) {
+            for (int st = 0; st < S; ++st)
+                if (kVD[st] >= 0) {
 #pragma unroll
-                        for (int k = 0; k <= (kVD[s] >= 0 ? kVD[s] : 0); ++k)
+                    for (int k = 0; k <= (kVD[st] >= 0 ? kVD[st] : 0); ++k)
 #pragma unroll
-                            for (int w = 0; w < kNW[s]; ++w) V[r][kVOff[s] + k * kNW[s] + w] = (w == 0) ? LOWV : 0;
-                    }
+                        for (int w = 0; w < kNW[st]; ++w) V[r][kVOff[st] + k * kNW[st] + w] = (w == 0) ? LOWV : 0;
                 }
         // lane 0 of a later sweep: column 0 of the row(s) above comes from the hand-off buffer
         int upin[NSEND > 0 ? NSEND : 1];
+#pragma unroll
+        for (int w = 0; w < (NSEND > 0 ? NSEND : 1); ++w) upin[w] = 0;
         auto load_top = [&](int col) {
 #pragma unroll
             for (int w = 0; w < NSEND; ++w) upin[w] = __ldcg(top_in + (size_t)col * NSEND + w);
         };
         auto place_up = [&](const int (&vals)[NSEND > 0 ? NSEND : 1]) {   // received words -> virtual rows, column 0
-            for_each_sent<0, 0, 0>([&](int d, int s, int w, int idx) { V[AQ - d][kVOff[s] + w] = vals[idx]; });
+#pragma unroll
+            for (int w = 0; w < NSEND; ++w) V[AQ - kSendD[w]][kSendOff[w]] = vals[w];
         };
         if (later_sweep) {
             if (piped) wait_column(0);
@@ -255,7 +304,7 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             if (lane == 0) place_up(upin);
         }
         unsigned char *tbp = nullptr;
-        constexpr int TBCH = ((SR * S + 15) / 16) * 16;   // traceback bytes per lane per step, 16-byte chunks
+        constexpr int TBCH = TB_CHUNK;   // traceback bytes per lane per step
         if constexpr (JIT_MODE == GEN_PATH)
             tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * TBCH;
 
@@ -270,69 +319,27 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             }
             uint32_t tbw[TBCH / 4];
 #pragma unroll
-            for (int k = 0; k < TBCH / 4; ++k) tbw[k] = 0xFFFFFFFFu;
-            // rows of my strip, top-down (a row reads the CURRENT column of the rows above it)
-            auto do_row = [&](auto ROWC) {
-                constexpr int ROW = decltype(ROWC)::value;
-                const int i = Z.row0 + ROW;
-                const bool rowok = Z.colok && i <= Q;
-                int cs[TN];
-                sys_precalc<0, ROW>(Z, V, cs);
-                Cell c;
-#pragma unroll
-                for (int st = 0; st < S; ++st) {
-#pragma unroll
-                    for (int l = 0; l < CWMAX; ++l) c.v[st][l] = (l == 0) ? LOWV : 0;   // viterbi.c:691-694
-                    c.set[st] = false;
-                    c.win[st] = 0xFF;
-                }
-                sys_transitions<0, ROW>(Z, V, cs, rowok, c);
-                if (c.set[END]) {   // viterbi.c:778-791; within a thread cells arrive in scan order
-                    const int v = c.v[END][0];
-                    if (v > best) {
-                        best = v; best_i = i; best_j = j;
-                        if constexpr (kRegion) best_start = c.v[END][1 + NSH];
-                    }
-                }
-                if constexpr (JIT_MODE == GEN_PATH) {
-#pragma unroll
-                    for (int st = 0; st < S; ++st) {
-                        constexpr int dummy = 0;
-                        const int byte = ROW * S + st;
-                        tbw[byte / 4] = (tbw[byte / 4] & ~(0xFFu << (8 * (byte % 4)))) |
-                                        ((uint32_t)c.win[st] << (8 * (byte % 4)));
-                        (void)dummy;
-                    }
-                }
-                // current column of the states that are read later
-#pragma unroll
-                for (int st = 0; st < S; ++st)
-                    if (kVD[st] >= 0) {
-                        V[AQ + ROW][kVOff[st]] = c.v[st][0];
-#pragma unroll
-                        for (int l = 0; l < NSH; ++l)
-                            if (word_of_slot(st, l) >= 0) V[AQ + ROW][kVOff[st] + word_of_slot(st, l)] = c.v[st][1 + l];
-                        if (kRegion) V[AQ + ROW][kVOff[st] + (word_of_start(st) >= 0 ? word_of_start(st) : 0)] = c.v[st][1 + NSH];
-                    }
-            };
-            [&]<int... RS>(c4b_seq<RS...>) { (do_row(c4b_int<RS>{}), ...); }(c4b_make_seq<SR>{});
+            for (int k = 0; k < TBCH / 4; ++k) tbw[k] = 0u;
+            sys_rows<0>(Z, V, bst, tbw);
 
             if constexpr (JIT_MODE == GEN_PATH) {
                 if (Z.colok) {
 #pragma unroll
-                    for (int k = 0; k < TBCH / 16; ++k)
-                        reinterpret_cast<uint4 *>(tbp)[k] = make_uint4(tbw[4 * k], tbw[4 * k + 1], tbw[4 * k + 2], tbw[4 * k + 3]);
+                    for (int k = 0; k < TBCH / 4; ++k) reinterpret_cast<uint32_t *>(tbp)[k] = tbw[k];
                 }
                 tbp += 32 * TBCH;
             }
             // hand the bottom rows' current column to the lane below / the next sweep
             int send[NSEND > 0 ? NSEND : 1];
-            for_each_sent<0, 0, 0>([&](int d, int st, int w, int idx) { send[idx] = V[AQ + SR - d][kVOff[st] + w]; });
+#pragma unroll
+            for (int w = 0; w < NSEND; ++w) send[w] = V[AQ + SR - kSendD[w]][kSendOff[w]];
             if (write_top && Z.colok) {
 #pragma unroll
                 for (int w = 0; w < NSEND; ++w) top_out[(size_t)j * NSEND + w] = send[w];
-                if (W > 1) {
-                    __threadfence_block();   // the row is written before the counter moves
+                // publish in groups of 8 columns: the fence costs far more than the stores, and the
+                // consumer runs at least 32 columns behind anyway
+                if (W > 1 && ((j & 7) == 7 || j == T)) {
+                    __threadfence_block();   // the rows are written before the counter moves
                     vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                 }
             }
@@ -358,6 +365,7 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
         }
         __syncwarp();
     }
+    int best = bst.score, best_i = bst.i, best_j = bst.j, best_start = bst.start;
     // lexicographic reduction: max score, then min j, then min i
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -23,6 +23,9 @@ struct GenPair {
     const int32_t *start_cells;      // what cell_start_func returns per cell (viterbi.c:727-741), or null
     int32_t *end_cells;              // END's cell wherever END is reached (cell_end_func's input), or null
     int64_t out_index;
+    // PATH record layout: 0 = by anti-diagonal, one byte per state (GEN_TB_CELL); r > 0 = the systolic
+    // kernel's skewed bit-packed layout with r rows per lane (GEN_TBS_CHUNK)
+    int32_t tb_rows, tb_chunk;
 };
 
 struct GenOut {
@@ -42,5 +45,14 @@ enum { GEN_SCORE = 0, GEN_PATH = 1, GEN_REGION = 2 };
 // (row-major cells would put every thread in its own 32-byte sector: 32x the write traffic).
 #define GEN_TB_CELL(i, j, Q, S) (((size_t)((i) + (j)) * (size_t)((Q) + 1) + (size_t)(i)) * (size_t)(S))
 #define GEN_TB_BYTES(Q, T, S) ((size_t)((Q) + (T) + 1) * (size_t)((Q) + 1) * (size_t)(S))
+// the systolic layout (generic_jit_systolic.cuh): [strip][step][lane][CH bytes], CH bytes = the R
+// rows of a lane at one column, row r at bit r * row_bits, state s at its bit offset inside the row:
+// the 1-based rank of the winning transition among those entering s (0 = unset).  Chunk of cell
+// (i, j) in a lattice with T target positions:
+#define GEN_TBS_CHUNK(i, j, T, R, CH)                                                                    \
+    ((((size_t)((i) / (32 * (R))) * (size_t)((T) + 32) + (size_t)((j) + ((i) / (R)) % 32)) * 32 +        \
+      (size_t)(((i) / (R)) % 32)) * (size_t)(CH))
+#define GEN_TBS_BYTES(Q, T, R, CH) \
+    ((size_t)(((Q) + 32 * (R)) / (32 * (R))) * (size_t)((T) + 32) * 32 * (size_t)(CH))
 
 }  // namespace c4b

@@ -301,7 +301,31 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
     int32_t *out = ops + 2 * J.ops_off;
     int n_runs = 0, last_t = -1, i = o.end_i, j = o.end_j;
     if (res.status == 0) {
-        int tr = P.tb[GEN_TB_CELL(i, j, P.Q, S) + m.end_state];
+        // systolic record (GEN_TBS_CHUNK): per state the rank of the winner among the transitions
+        // entering it, bit-packed; bit offsets follow from the model exactly as the host laid them out
+        int bit_off[C4B_MAX_STATES], bit_n[C4B_MAX_STATES], row_bits = 0;
+        if (P.tb_rows) {
+            for (int s = 0; s < S; ++s) {
+                int n_in = 0, b = 0;
+                for (int k = 0; k < m.n_transitions; ++k) n_in += m.transitions[k].output == s;
+                while ((1 << b) < n_in + 1) ++b;
+                bit_off[s] = row_bits; bit_n[s] = b; row_bits += b;
+            }
+        }
+        auto winner = [&](int ci, int cj, int state) -> int {   // transition id, 0xFF = unset
+            if (!P.tb_rows) return P.tb[GEN_TB_CELL(ci, cj, P.Q, S) + state];
+            if (bit_n[state] == 0) return 0xFF;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(P.tb + GEN_TBS_CHUNK(ci, cj, P.T, P.tb_rows, P.tb_chunk));
+            const int pos = (ci % P.tb_rows) * row_bits + bit_off[state];
+            uint64_t v = w[pos / 32];
+            if (pos % 32 + bit_n[state] > 32) v |= (uint64_t)w[pos / 32 + 1] << 32;
+            int code = (int)((v >> (pos % 32)) & ((1u << bit_n[state]) - 1u));
+            if (code == 0) return 0xFF;
+            for (int k = 0; k < m.n_transitions; ++k)
+                if (m.transitions[k].output == state && --code == 0) return k;
+            return 0xFF;
+        };
+        int tr = winner(i, j, m.end_state);
         while (tr != 0xFF) {
             if (tr == last_t) out[2 * (n_runs - 1) + 1] += 1;
             else if (n_runs < J.ops_cap) { out[2 * n_runs] = tr; out[2 * n_runs + 1] = 1; ++n_runs; last_t = tr; }
@@ -310,7 +334,7 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
             j -= m.transitions[tr].advance_target;
             if (m.transitions[tr].input == m.start_state) break;
             if (i < 0 || j < 0) { res.status = 4; break; }
-            tr = P.tb[GEN_TB_CELL(i, j, P.Q, S) + m.transitions[tr].input];
+            tr = winner(i, j, m.transitions[tr].input);
         }
         for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
             const int t0 = out[2 * a], l0 = out[2 * a + 1];

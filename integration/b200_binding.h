@@ -42,6 +42,15 @@ typedef struct {
     gint n_rounds, cursor;
 } B200_Replay;
 
+/* ---- BSDP prefetch (bsdp_b200.c): FIND_SCORE answers of a comparison's SAR fills ----
+ * b200_prefetch_scores() runs `n` region fills of ONE Viterbi (a terminal or join model of the
+ * heuristic, src/bsdp/heuristic.c:242-325) on the current (query, target) as one device batch
+ * and keeps the answers; Viterbi_calculate returns a kept answer only for exactly the same call
+ * (same Viterbi, sequences, region and SubOpt blocked cells).  Dropped when the comparison changes. */
+void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer user_data,
+                          SubOpt *subopt);
+extern glong b200_stat_score_hits, b200_stat_score_prefetched, b200_stat_score_batches;
+
 extern B200_Replay *b200_replay;
 extern glong b200_stat_prefetch_hits, b200_stat_prefetch_misses;
 

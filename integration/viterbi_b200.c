@@ -47,6 +47,8 @@ static c4b_engine *engine = NULL;
 
 B200_Replay *b200_replay = NULL;
 glong b200_stat_prefetch_hits = 0, b200_stat_prefetch_misses = 0;
+glong b200_stat_score_hits = 0, b200_stat_score_prefetched = 0, b200_stat_score_batches = 0;
+static void score_cache_clear(void);
 
 c4b_engine *exonerate_b200_engine(void){
     if(!engine){
@@ -65,12 +67,26 @@ static gdouble now_seconds(void){
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec + 1e-9*ts.tv_nsec;
     }
+/* EXONERATE_B200_TRACE=1: one line per Viterbi_calculate on stderr (debugging aid: diff two runs) */
+static void trace_call(Viterbi *viterbi, Region *region, const gchar *how, C4_Score score){
+    static gint on = -1;
+    if(on < 0)
+        on = g_getenv("EXONERATE_B200_TRACE")?1:0;
+    if(on)
+        fprintf(stderr, "b200-trace %s mode %d [%s] region %d %d %d %d -> %d\n", how,
+                (gint)viterbi->mode, viterbi->name, region->query_start, region->target_start,
+                region->query_length, region->target_length, score);
+    return;
+    }
+
 static void print_viterbi_stats(void){
     fprintf(stderr, "exonerate_b200: Viterbi_calculate calls %ld (%.3f s: prepare %.3f s, "
                     "engine %.3f s), sequence pairs flattened %ld, answered from the batch "
-                    "prefetch %ld (prefetched but not usable %ld)\n",
+                    "prefetch %ld (prefetched but not usable %ld); BSDP region fills prefetched %ld "
+                    "in %ld batch(es), answered from them %ld\n",
             stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss,
-            b200_stat_prefetch_hits, b200_stat_prefetch_misses);
+            b200_stat_prefetch_hits, b200_stat_prefetch_misses,
+            b200_stat_score_prefetched, b200_stat_score_batches, b200_stat_score_hits);
     }
 
 /* Flattened sequences (they are virtual in the reference: revcomp / subseq / translate
@@ -99,6 +115,7 @@ gint32 *b200_splice_arrays(gchar *tseq, gint tlen){
 static void pair_cache_fetch(Ungapped_Data *ud, gboolean need_splice){
     register gint tlen = ud->target->len;
     if((pair_cache.query != ud->query) || (pair_cache.target != ud->target)){
+        score_cache_clear(); /* prefetched BSDP fills belong to the previous comparison */
         if(pair_cache.query){
             c4b_engine_forget_buffers(get_engine()); /* device copies are keyed by these addresses */
             Sequence_destroy(pair_cache.query);
@@ -482,6 +499,137 @@ static gboolean prefetch_lookup(Viterbi *viterbi, Region *region, Viterbi_Data *
     return TRUE;
     }
 
+/* ---- BSDP prefetch: kept FIND_SCORE answers of the current comparison ------------------ */
+typedef struct B200_ScoreEntry {
+    Viterbi *viterbi;
+    gint qs, ts, ql, tl;
+    gint n_blocked;
+    gint32 *bq, *bt;
+    c4b_result result;
+    struct B200_ScoreEntry *next;
+} B200_ScoreEntry;
+#define SCORE_BUCKETS 4096
+static B200_ScoreEntry *score_table[SCORE_BUCKETS];
+static gint score_entries = 0;
+
+static guint score_hash(Viterbi *viterbi, Region *region){
+    register guint64 h = (guint64)(gsize)viterbi * 0x9E3779B97F4A7C15ull;
+    h ^= ((guint64)(guint)region->query_start << 32) | (guint)region->target_start;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= ((guint64)(guint)region->query_length << 32) | (guint)region->target_length;
+    h *= 0xC4CEB9FE1A85EC53ull;
+    return (guint)(h >> 40) & (SCORE_BUCKETS-1);
+    }
+
+static void score_cache_clear(void){
+    register gint i;
+    register B200_ScoreEntry *e, *next;
+    if(!score_entries)
+        return;
+    for(i = 0; i < SCORE_BUCKETS; i++){
+        for(e = score_table[i]; e; e = next){
+            next = e->next;
+            g_free(e->bq);
+            g_free(e->bt);
+            g_free(e);
+            }
+        score_table[i] = NULL;
+        }
+    score_entries = 0;
+    return;
+    }
+
+static B200_ScoreEntry *score_cache_find(Viterbi *viterbi, Region *region,
+                                         gint n_blocked, gint32 *bq, gint32 *bt){
+    register B200_ScoreEntry *e;
+    if(!score_entries)
+        return NULL;
+    for(e = score_table[score_hash(viterbi, region)]; e; e = e->next)
+        if((e->viterbi == viterbi) && (e->qs == region->query_start)
+        && (e->ts == region->target_start) && (e->ql == region->query_length)
+        && (e->tl == region->target_length) && (e->n_blocked == n_blocked)
+        && (!n_blocked || (!memcmp(e->bq, bq, n_blocked*sizeof(gint32))
+                        && !memcmp(e->bt, bt, n_blocked*sizeof(gint32)))))
+            return e;
+    return NULL;
+    }
+
+void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer user_data,
+                          SubOpt *subopt){
+    register Ungapped_Data *ud = user_data;
+    register c4b_model *tables = b200_tables_for(viterbi);
+    register gboolean with_splice = b200_model_has_splice(tables);
+    register c4b_pair *pairs;
+    register c4b_result *results;
+    register B200_ScoreEntry **entry;
+    register gint i, k, m = 0;
+    register guint h;
+    gint32 *bq, *bt;
+    gint nb;
+    c4b_batch *batch = NULL;
+    c4b_scoring scoring;
+    if((n <= 0) || (viterbi->mode != Viterbi_Mode_FIND_SCORE) || model_is_bound(viterbi->model)
+    || viterbi->model->start_state->cell_start_func || viterbi->model->end_state->cell_end_func)
+        return;
+    pair_cache_fetch(ud, with_splice);
+    b200_fill_scoring(ud->mas, &scoring);
+    pairs = g_new0(c4b_pair, n);
+    results = g_new0(c4b_result, n);
+    entry = g_new0(B200_ScoreEntry*, n);
+    for(i = 0; i < n; i++){
+        nb = b200_blocked_list((subopt && subopt->path_count)?subopt:NULL, regions[i], &bq, &bt);
+        if(score_cache_find(viterbi, regions[i], nb, bq, bt)){ /* asked for twice */
+            g_free(bq);
+            g_free(bt);
+            continue;
+            }
+        entry[m] = g_new0(B200_ScoreEntry, 1);
+        entry[m]->viterbi = viterbi;
+        entry[m]->qs = regions[i]->query_start;
+        entry[m]->ts = regions[i]->target_start;
+        entry[m]->ql = regions[i]->query_length;
+        entry[m]->tl = regions[i]->target_length;
+        entry[m]->n_blocked = nb;
+        entry[m]->bq = bq;
+        entry[m]->bt = bt;
+        h = score_hash(viterbi, regions[i]); /* visible to the duplicate test of later regions */
+        entry[m]->next = score_table[h];
+        score_table[h] = entry[m];
+        score_entries++;
+        pairs[m].query = (const uint8_t*)pair_cache.qseq;
+        pairs[m].target = (const uint8_t*)pair_cache.tseq;
+        pairs[m].query_len = ud->query->len;
+        pairs[m].target_len = ud->target->len;
+        pairs[m].query_start = regions[i]->query_start;
+        pairs[m].target_start = regions[i]->target_start;
+        pairs[m].query_length = regions[i]->query_length;
+        pairs[m].target_length = regions[i]->target_length;
+        pairs[m].blocked_query_pos = bq;
+        pairs[m].blocked_target_pos = bt;
+        pairs[m].n_blocked = nb;
+        pairs[m].reserved = C4B_PAIR_BUFFERS_STABLE;
+        if(with_splice)
+            for(k = 0; k < 4; k++)
+                pairs[m].splice[k] = pair_cache.splice + (gsize)k*ud->target->len;
+        m++;
+        }
+    if(m){
+        if(c4b_batch_create(get_engine(), tables, &scoring, m, pairs, 0, &batch)
+        || c4b_batch_run(batch, C4B_IMPOSSIBLY_LOW_SCORE)
+        || c4b_batch_fetch(batch, results, NULL, 0))
+            g_error("libc4b200: %s", c4b_last_error());
+        c4b_batch_destroy(batch);
+        for(i = 0; i < m; i++)
+            entry[i]->result = results[i];
+        b200_stat_score_prefetched += m;
+        b200_stat_score_batches++;
+        }
+    g_free(entry);
+    g_free(results);
+    g_free(pairs);
+    return;
+    }
+
 C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
                            Viterbi_Data *vd, gpointer user_data,
                            SubOpt *subopt){
@@ -533,6 +681,15 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         g_free(tseq);
         vd->curr_query_end = result.query_end - region->query_start;
         vd->curr_target_end = result.target_end - region->target_start;
+        if(g_getenv("EXONERATE_B200_TRACE")){
+            register gint64 sum = 0;
+            for(i = 0; i <= Q; i++)
+                for(j = 0; j <= T; j++)
+                    sum += matrix[region->query_start+i][region->target_start+j];
+            fprintf(stderr, "b200-trace bound matrix sum %ld corner %d\n", (glong)sum,
+                    matrix[region->query_start+Q][region->target_start+T]);
+            }
+        trace_call(viterbi, region, "bound", result.score);
         return result.score;
         }
     switch(viterbi->mode){
@@ -553,7 +710,22 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
         g_free(bt);
         stat_calls++;
         stat_total += now_seconds() - t_begin;
+        trace_call(viterbi, region, "replay", prefetched_score);
         return prefetched_score;
+        }
+    if((mode == 0) && score_entries && (pair_cache.query == ud->query)
+    && (pair_cache.target == ud->target)){
+        register B200_ScoreEntry *se = score_cache_find(viterbi, region, n_blocked, bq, bt);
+        if(se){ /* this very fill was part of the comparison's prefetched batch */
+            vd_set_result(vd, region, &se->result, NULL);
+            g_free(bq);
+            g_free(bt);
+            b200_stat_score_hits++;
+            stat_calls++;
+            stat_total += now_seconds() - t_begin;
+            trace_call(viterbi, region, "prefetched", se->result.score);
+            return se->result.score;
+            }
         }
     pair_cache_fetch(ud, b200_model_has_splice(tables));
     qseq = pair_cache.qseq;
@@ -636,6 +808,7 @@ C4_Score Viterbi_calculate(Viterbi *viterbi, Region *region,
     stat_calls++;
     stat_total += t_done - t_begin;
     stat_prepare += t_prepared - t_begin;
+    trace_call(viterbi, region, "device", result.score);
     return result.score;
     }
 

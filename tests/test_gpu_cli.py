@@ -116,9 +116,12 @@ def test_cli_batch_hook_metric_shape(name, tmp_path):
     assert int(m.group(1)) == nq * nt * strands and int(m.group(2)) == 1
     m = re.search(r"answered from the batch prefetch (\d+) \(prefetched but not usable (\d+)\)", got.stderr)
     assert m and int(m.group(1)) >= nq * nt * strands and int(m.group(2)) == 0, got.stderr[-800:]
-    if "--bestn" not in flags:   # every Viterbi_calculate of the run was answered from a batch
-        m = re.search(r"Viterbi_calculate calls (\d+) .* answered from the batch prefetch (\d+)", got.stderr)
-        assert m and m.group(1) == m.group(2), got.stderr[-800:]
+    m = re.search(r"Viterbi_calculate calls (\d+) .* answered from the batch prefetch (\d+)", got.stderr)
+    assert m, got.stderr[-800:]
+    if "--bestn" not in flags and "--subopt" in flags:   # every Viterbi_calculate of the run came from a batch
+        assert m.group(1) == m.group(2), got.stderr[-800:]
+    elif "--bestn" not in flags:   # sub-optimal series deeper than the 16 prefetched rounds run on synchronously
+        assert int(m.group(2)) >= 0.95 * int(m.group(1)), got.stderr[-800:]
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="integration binary not built (needs the reference sources)")

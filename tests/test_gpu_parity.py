@@ -64,21 +64,24 @@ def test_golden_vectors(eng, name, params, scoring):
         assert helpers.report_line("cigar", model, "qy", "tg", *strands(name), r) == ref["cigar"]
 
 
+@pytest.mark.parametrize("systolic", ["1", "0"])
 @pytest.mark.parametrize("name", AFFINE + GENERIC)
-def test_golden_vectors_specialised_kernel(eng, name, params, scoring, monkeypatch):
-    """The same golden cases through the run-time SPECIALISED table-driven kernel
-    (generic_jit_kernel.cuh compiled for this model by NVRTC): every model, the affine
-    and est2genome families included, forced off their own kernels."""
+def test_golden_vectors_specialised_kernel(eng, name, params, scoring, monkeypatch, systolic):
+    """The same golden cases through the run-time SPECIALISED table-driven kernels, compiled
+    for this model by NVRTC: the systolic one (generic_jit_systolic.cuh: lattice in registers,
+    lanes skewed by a column) and the thread-per-row one (generic_jit_kernel.cuh); every model,
+    the affine and est2genome families included, forced off their own kernels."""
     from exonerate_b200 import Batch, Optimal, PairSet
     monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
     monkeypatch.setenv("C4B_GENERIC_JIT", "1")
+    monkeypatch.setenv("C4B_JIT_SYSTOLIC", systolic)
     model, _ = helpers.load_model(name, params)
     cases = helpers.load_cases(name)
     pairs = PairSet([c["q"] for c in cases], [c["t"] for c in cases],
                     splice=[splice_for(name, c) for c in cases])
     b = Batch(eng, model, scoring, pairs, want_path=True)
     b.run()
-    assert b.kernel_name == "generic_jit"
+    assert b.kernel_name == ("generic_jit_systolic" if systolic == "1" else "generic_jit")
     b.close()
     opt = Optimal(eng, model, scoring)
     scores = opt.find_score(pairs)
@@ -112,14 +115,23 @@ def test_specialised_kernel_matches_interpreter_at_size(eng, params, scoring, mo
             sp.append(splice_arrays(t) if name != "coding2coding" else None)
         pairs = PairSet(qs, ts, splice=sp)
         got = {}
-        for jit in ("0", "1"):
+        # interpreter, thread-per-row specialisation, systolic specialisation (REGION + box and
+        # one PATH pass over the full lattices), systolic with one row per lane (more strips)
+        for jit, env in (("0", {}), ("1", {"C4B_JIT_SYSTOLIC": "0"}),
+                         ("sys", {"C4B_GENERIC_DIRECT_PATH": "0"}), ("sys-direct", {"C4B_GENERIC_DIRECT_PATH": "1"}),
+                         ("sys-r1", {"C4B_JIT_SYS_R": "1"})):
             monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
-            monkeypatch.setenv("C4B_GENERIC_JIT", jit)
+            monkeypatch.setenv("C4B_GENERIC_JIT", "0" if jit == "0" else "1")
+            for k in ("C4B_JIT_SYSTOLIC", "C4B_GENERIC_DIRECT_PATH", "C4B_JIT_SYS_R"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
             opt = Optimal(eng, model, scoring)
             got[jit] = (opt.find_score(pairs), opt.find_path(pairs))
-        assert got["0"][0] == got["1"][0], name
-        for a, b in zip(got["0"][1], got["1"][1]):
-            assert a["score"] == b["score"] and a["region"] == b["region"] and a["ops"] == b["ops"], name
+        for jit in got:
+            assert got["0"][0] == got[jit][0], (name, jit)
+            for a, b in zip(got["0"][1], got[jit][1]):
+                assert a["score"] == b["score"] and a["region"] == b["region"] and a["ops"] == b["ops"], (name, jit)
 
 
 def test_est2genome_packed_kernel_vs_specialised_table_driven(eng, params, scoring, monkeypatch):
@@ -141,7 +153,7 @@ def test_est2genome_packed_kernel_vs_specialised_table_driven(eng, params, scori
     monkeypatch.setenv("C4B_GENERIC_JIT", "1")
     b = Batch(eng, model, scoring, pairs, want_path=True)
     b.run()
-    assert b.kernel_name == "generic_jit"
+    assert b.kernel_name == "generic_jit_systolic"
     b.close()
     generic = Optimal(eng, model, scoring).find_path(pairs)
     for k, (a, g) in enumerate(zip(packed, generic)):
