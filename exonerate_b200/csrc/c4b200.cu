@@ -1495,6 +1495,172 @@ int c4b_find_path_batch(c4b_engine *e, const c4b_model *model, const c4b_scoring
     return rc;
 }
 
+// ---- device groups -----------------------------------------------------------------------
+}  // extern "C"
+
+struct c4b_group {
+    std::vector<c4b_engine *> engines;
+};
+
+namespace {
+
+// LPT: lattices by cost, largest first, each to the device with the least work so far
+std::vector<std::vector<int>> group_shards(int n_dev, int n, const c4b_pair *pairs) {
+    std::vector<int> order(n);
+    for (int k = 0; k < n; ++k) order[k] = k;
+    auto cost = [&](int k) { return (int64_t)pairs[k].query_length * pairs[k].target_length; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    std::vector<std::vector<int>> shard(n_dev);
+    std::vector<int64_t> load(n_dev, 0);
+    for (int k : order) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[d].push_back(k);
+        load[d] += cost(k) + 1;
+    }
+    for (auto &s : shard) std::sort(s.begin(), s.end());   // pair order inside a shard
+    return shard;
+}
+
+// one worker per device; the first error (if any) is handed to the calling thread
+template <typename Work>
+int group_run(c4b_group *g, const std::vector<std::vector<int>> &shard, Work work) {
+    const int nd = (int)g->engines.size();
+    std::vector<int> rc(nd, 0);
+    std::vector<std::string> err(nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d)
+        th.emplace_back([&, d] {
+            if (shard[d].empty()) return;
+            rc[d] = work(d);
+            if (rc[d]) err[d] = c4b::g_error;   // thread-local in the worker
+        });
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; ++d)
+        if (rc[d]) {
+            set_error("device " + std::to_string(g->engines[d]->device) + ": " + err[d]);
+            return rc[d];
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int c4b_group_create(int n_devices, const int *devices, c4b_group **out) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no CUDA device (libc4b200 has no CPU fallback)");
+        return -1;
+    }
+    std::vector<int> dev;
+    if (n_devices <= 0)
+        for (int d = 0; d < count; ++d) dev.push_back(d);
+    else
+        dev.assign(devices, devices + n_devices);
+    c4b_group *g = new c4b_group();
+    for (int d : dev) {
+        c4b_engine *e = nullptr;
+        if (c4b_engine_create(d, &e)) {
+            c4b_group_destroy(g);
+            return -1;
+        }
+        g->engines.push_back(e);
+    }
+    *out = g;
+    return 0;
+}
+
+void c4b_group_destroy(c4b_group *g) {
+    if (!g) return;
+    for (c4b_engine *e : g->engines) c4b_engine_destroy(e);
+    delete g;
+}
+
+int c4b_group_size(const c4b_group *g) { return g ? (int)g->engines.size() : 0; }
+
+int64_t c4b_group_kernel_launches(const c4b_group *g) {
+    int64_t n = 0;
+    for (c4b_engine *e : g->engines) n += e->launches;
+    return n;
+}
+
+void c4b_free(void *p) { free(p); }
+
+int c4b_group_find_score_batch(c4b_group *g, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
+                               const c4b_pair *pairs, c4b_score *scores) {
+    if (!g || g->engines.empty() || n < 0 || (n && (!pairs || !scores))) {
+        set_error("c4b_group_find_score_batch: bad arguments");
+        return -1;
+    }
+    const auto shard = group_shards((int)g->engines.size(), n, pairs);
+    return group_run(g, shard, [&](int d) -> int {
+        const std::vector<int> &idx = shard[d];
+        std::vector<c4b_pair> mine(idx.size());
+        for (size_t k = 0; k < idx.size(); ++k) mine[k] = pairs[idx[k]];
+        std::vector<c4b_score> sc(idx.size());
+        const int rc = c4b_find_score_batch(g->engines[d], model, scoring, (int32_t)mine.size(), mine.data(), sc.data());
+        if (!rc)
+            for (size_t k = 0; k < idx.size(); ++k) scores[idx[k]] = sc[k];
+        return rc;
+    });
+}
+
+int c4b_group_find_path_batch(c4b_group *g, const c4b_model *model, const c4b_scoring *scoring, int32_t n,
+                              const c4b_pair *pairs, c4b_score threshold, c4b_result *results, int32_t **ops_out,
+                              int64_t *n_ops_out) {
+    if (!g || g->engines.empty() || n < 0 || (n && (!pairs || !results)) || !ops_out || !n_ops_out) {
+        set_error("c4b_group_find_path_batch: bad arguments");
+        return -1;
+    }
+    *ops_out = nullptr;
+    *n_ops_out = 0;
+    const int nd = (int)g->engines.size();
+    const auto shard = group_shards(nd, n, pairs);
+    std::vector<std::vector<c4b_result>> res(nd);
+    std::vector<std::vector<int32_t>> ops(nd);
+    int rc = group_run(g, shard, [&](int d) -> int {
+        const std::vector<int> &idx = shard[d];
+        std::vector<c4b_pair> mine(idx.size());
+        for (size_t k = 0; k < idx.size(); ++k) mine[k] = pairs[idx[k]];
+        c4b_batch *b = nullptr;
+        int r = c4b_batch_create(g->engines[d], model, scoring, (int32_t)mine.size(), mine.data(), 1, &b);
+        if (r) return r;
+        r = c4b_batch_run(b, threshold);
+        int64_t need = r ? -1 : c4b_batch_ops_needed(b);
+        if (!r && need < 0) r = -1;
+        if (!r) {
+            res[d].resize(idx.size());
+            ops[d].resize(2 * (size_t)need + 2);
+            r = c4b_batch_fetch(b, res[d].data(), ops[d].data(), need);
+            ops[d].resize(2 * (size_t)need);
+        }
+        c4b_batch_destroy(b);
+        return r;
+    });
+    if (rc) return rc;
+    int64_t total = 0;
+    for (int d = 0; d < nd; ++d) total += (int64_t)ops[d].size() / 2;
+    int32_t *all = (int32_t *)malloc(sizeof(int32_t) * (2 * (size_t)total + 2));
+    if (!all) {
+        set_error("c4b_group_find_path_batch: out of host memory");
+        return -1;
+    }
+    int64_t base = 0;
+    for (int d = 0; d < nd; ++d) {   // shard op lists one after the other; offsets rebased
+        if (!ops[d].empty()) memcpy(all + 2 * base, ops[d].data(), ops[d].size() * sizeof(int32_t));
+        for (size_t k = 0; k < shard[d].size(); ++k) {
+            c4b_result r = res[d][k];
+            r.ops_offset += base;
+            results[shard[d][k]] = r;
+        }
+        base += (int64_t)ops[d].size() / 2;
+    }
+    *ops_out = all;
+    *n_ops_out = total;
+    return 0;
+}
+
 int c4b_viterbi_calculate(c4b_engine *e, const c4b_model *model, const c4b_scoring *scoring,
                           const c4b_pair *pair, int mode, c4b_result *result, int32_t *ops,
                           int64_t ops_capacity) {

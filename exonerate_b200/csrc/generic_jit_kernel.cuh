@@ -114,9 +114,12 @@ __device__ __forceinline__ int calc_score(const Ctx &X, int qp, int tp, int shad
                           translate(s, SEQ(t, tp), SEQ(t, tp + 1), SEQ(t, tp + 2)));
         else if constexpr (kind == C4B_CALC_SPLICE_PRE) return p0 + __ldg(X.splice[p1] + tp);
         else if constexpr (kind == C4B_CALC_SPLICE_POST) {
+            // min_intron <= len <= max_intron (intron.c:151-159) as ONE unsigned compare
             const int len = tp - shadow + 2;
             const int v = __ldg(X.splice[p1] + tp);
-            return (len < s.min_intron || len > s.max_intron) ? LOWV : v;
+            const bool bad = (s.max_intron < s.min_intron) |
+                             ((unsigned)(len - s.min_intron) > (unsigned)(s.max_intron - s.min_intron));
+            return bad ? LOWV : v;
         } else if constexpr (kind == C4B_CALC_PHASE1_POST) {
             const int sh = max(shadow, 1);
             const int v = submat(s.protein_matrix, s.protein_index, SEQ(q, qp),

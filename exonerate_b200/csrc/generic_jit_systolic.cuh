@@ -55,9 +55,18 @@ static_assert(!kRegion || kPackStart, "the systolic kernel carries the START cel
 
 // one cell's working set: every state's score + all possible words (dead ones fold away)
 constexpr int CWMAX = 1 + NSH + 1;
+constexpr int UNSET = INT_MIN;   // a state no transition has reached yet in this cell
+// LOCAL models (START and END in scope everywhere: END is reachable with a score >= 0 from every
+// cell) run RELAXED: only the transitions that leave START are tested for validity.  A transition
+// whose source cell does not exist (row or column < 0) reads a register that holds <= LOWV (the
+// reset value, viterbi.c:691-694) and offers LOWV-ish garbage, which no value that descends from
+// START can lose against -- so every REACHABLE value, every winner on a path from START and the
+// END maximum are exactly the reference's; only cells the reference leaves unset differ, and
+// those are clamped back to LOWV when stored.  Models with restricted scopes (BSDP's derived
+// models, global / bestfit / overlap), where an unreachable END must stay unset, keep every test.
+constexpr bool kRelaxed = START_SCOPE == C4B_SCOPE_ANYWHERE && END_SCOPE == C4B_SCOPE_ANYWHERE;
 struct Cell {
-    int v[S][CWMAX];   // [0] score, [1 + l] shadow slot l, [1 + NSH] packed start cell
-    bool set[S];
+    int v[S][CWMAX];   // [0] score (UNSET until assigned), [1 + l] shadow slot l, [1 + NSH] packed start cell
     unsigned char win[S];
 };
 
@@ -95,9 +104,13 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
         constexpr bool from_start = (in == START);
         const int i = Z.row0 + ROW, j = Z.j;
         const int si = i - aq, sj = j - at;
-        bool valid = rowok && state_active<in>(si, sj, Z.X.Q, Z.X.T) && state_active<out>(i, j, Z.X.Q, Z.X.T);
-        if constexpr (at > 0) valid = valid && sj >= 0;
-        if constexpr (aq > ROW) valid = valid && (Z.has_up && si >= 0);
+        constexpr bool tested = !kRelaxed || from_start;
+        bool valid = true;
+        if constexpr (tested) {
+            valid = rowok && state_active<in>(si, sj, Z.X.Q, Z.X.T) && state_active<out>(i, j, Z.X.Q, Z.X.T);
+            if constexpr (at > 0) valid = valid && sj >= 0;
+            if constexpr (aq > ROW) valid = valid && (Z.has_up && si >= 0);
+        }
         int src[CWMAX];
 #pragma unroll
         for (int l = 0; l < CWMAX; ++l) src[l] = 0;
@@ -115,6 +128,10 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
             for (int l = 0; l < CWMAX; ++l) src[l] = c.v[in][l];
         }
         int t = src[0];
+        if constexpr (!from_start && aq + at == 0) {   // an unset state reads as reset (viterbi.c:691-694)
+            if constexpr (kRelaxed) t = max(t, LOWV);
+            else t = (t == UNSET) ? LOWV : t;
+        }
         if constexpr (calc >= 0) {
             if constexpr (calc_hoisted<K>()) {
                 t += cs[K];
@@ -126,26 +143,32 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
             if constexpr ((kCalcProt[calc >= 0 ? calc : 0] & C4B_PROTECT_OVERFLOW) != 0)
                 t = min(t, C4B_IMPOSSIBLY_HIGH_SCORE);
         }
-        const bool take = valid && (!c.set[out] || c.v[out][0] < t);
-        c.set[out] = c.set[out] || valid;
-        // Viterbi_Data_assign (viterbi.c:445-462); stamps go on the transported copy
-        c.v[out][0] = take ? t : c.v[out][0];
+        // "first valid transition assigns, later ones replace only if strictly greater"
+        // (viterbi.c:766-775) as a max: an unset state holds UNSET, below every candidate, and an
+        // invalid transition offers UNSET.  (t is never UNSET: scores stay above 2 * LOWV.)
+        const int teff = tested ? (valid ? t : UNSET) : t;
+        constexpr bool carries = (JIT_MODE == GEN_PATH) || kRegion || (kNW[out] > 1);
+        if constexpr (carries) {
+            const bool take = teff > c.v[out][0];
+            // Viterbi_Data_assign (viterbi.c:445-462); stamps go on the transported copy
 #pragma unroll
-        for (int l = 0; l < NSH; ++l) {
-            if (word_of_slot(out, l) >= 0) {   // (folds per unrolled l: dead slots cost nothing)
-                const int stamp = kShadow[in * C4B_MAX_SHADOW_SLOTS + l];
-                int nv = src[1 + l];
-                if (stamp == 1) nv = Z.X.t_start + sj;
-                if (stamp == 2) nv = Z.X.q_start + si;
-                c.v[out][1 + l] = take ? nv : c.v[out][1 + l];
+            for (int l = 0; l < NSH; ++l) {
+                if (word_of_slot(out, l) >= 0) {   // (folds per unrolled l: dead slots cost nothing)
+                    const int stamp = kShadow[in * C4B_MAX_SHADOW_SLOTS + l];
+                    int nv = src[1 + l];
+                    if (stamp == 1) nv = Z.X.t_start + sj;
+                    if (stamp == 2) nv = Z.X.q_start + si;
+                    c.v[out][1 + l] = take ? nv : c.v[out][1 + l];
+                }
             }
+            if constexpr (kRegion) {
+                int nv = src[1 + NSH];
+                if constexpr (from_start) nv = si * (Z.X.T + 1) + sj;
+                c.v[out][1 + NSH] = take ? nv : c.v[out][1 + NSH];
+            }
+            if constexpr (JIT_MODE == GEN_PATH) c.win[out] = take ? (unsigned char)kTbCode[K] : c.win[out];
         }
-        if constexpr (kRegion) {
-            int nv = src[1 + NSH];
-            if constexpr (from_start) nv = si * (Z.X.T + 1) + sj;
-            c.v[out][1 + NSH] = take ? nv : c.v[out][1 + NSH];
-        }
-        if constexpr (JIT_MODE == GEN_PATH) c.win[out] = take ? (unsigned char)kTbCode[K] : c.win[out];
+        c.v[out][0] = max(c.v[out][0], teff);
         sys_transitions<K + 1, ROW>(Z, V, cs, rowok, c);
     }
 }
@@ -171,14 +194,13 @@ __device__ __forceinline__ void sys_row(const SysCtx &Z, int (&V)[NROWS][VW], Sy
 #pragma unroll
     for (int st = 0; st < S; ++st) {
 #pragma unroll
-        for (int l = 0; l < CWMAX; ++l) c.v[st][l] = (l == 0) ? LOWV : 0;   // viterbi.c:691-694
-        c.set[st] = false;
+        for (int l = 0; l < CWMAX; ++l) c.v[st][l] = (l == 0) ? UNSET : 0;
         c.win[st] = 0;
     }
     sys_transitions<0, ROW>(Z, V, cs, rowok, c);
-    if (c.set[END]) {   // viterbi.c:778-791; within a thread cells arrive in scan order
+    {   // viterbi.c:778-791; within a thread cells arrive in scan order; UNSET never beats a score
         const int v = c.v[END][0];
-        if (v > best.score) {
+        if ((!kRelaxed || rowok) && v > best.score) {
             best.score = v; best.i = i; best.j = Z.j;
             if constexpr (kRegion) best.start = c.v[END][1 + NSH];
         }
@@ -193,11 +215,11 @@ __device__ __forceinline__ void sys_row(const SysCtx &Z, int (&V)[NROWS][VW], Sy
                 if (pos % 32 + kTbBits[st] > 32) tbw[pos / 32 + 1] |= (uint32_t)c.win[st] >> (32 - pos % 32);
             }
     }
-    // current column of the states that are read later
+    // current column of the states that are read later (an unset state is stored as the reset value)
 #pragma unroll
     for (int st = 0; st < S; ++st)
         if (kVD[st] >= 0) {
-            V[AQ + ROW][kVOff[st]] = c.v[st][0];
+            V[AQ + ROW][kVOff[st]] = kRelaxed ? max(c.v[st][0], LOWV) : ((c.v[st][0] == UNSET) ? LOWV : c.v[st][0]);
 #pragma unroll
             for (int l = 0; l < NSH; ++l)
                 if (word_of_slot(st, l) >= 0) V[AQ + ROW][kVOff[st] + max(word_of_slot(st, l), 0)] = c.v[st][1 + l];
@@ -289,7 +311,7 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
         // lane 0 of a later sweep: column 0 of the row(s) above comes from the hand-off buffer
         int upin[NSEND > 0 ? NSEND : 1];
 #pragma unroll
-        for (int w = 0; w < (NSEND > 0 ? NSEND : 1); ++w) upin[w] = 0;
+        for (int w = 0; w < (NSEND > 0 ? NSEND : 1); ++w) upin[w] = LOWV;   // "no row above": reads as reset
         auto load_top = [&](int col) {
 #pragma unroll
             for (int w = 0; w < NSEND; ++w) upin[w] = __ldcg(top_in + (size_t)col * NSEND + w);

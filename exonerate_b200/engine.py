@@ -20,6 +20,8 @@ EXPORTS = [
     "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_ops_needed", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_description", "c4b_batch_destroy",
+    "c4b_group_create", "c4b_group_destroy", "c4b_group_size", "c4b_group_find_score_batch",
+    "c4b_group_find_path_batch", "c4b_group_kernel_launches", "c4b_free",
     "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise", "c4b_span_integrate",
 ]
 
@@ -78,6 +80,16 @@ def load_library():
     lib.c4b_batch_last_fill_ms.restype = C.c_double
     lib.c4b_batch_kernel_name.argtypes = [C.c_void_p]
     lib.c4b_batch_kernel_name.restype = C.c_char_p
+    lib.c4b_group_create.argtypes = [C.c_int, P(C.c_int), P(C.c_void_p)]
+    lib.c4b_group_destroy.argtypes = [C.c_void_p]
+    lib.c4b_group_size.argtypes = [C.c_void_p]
+    lib.c4b_group_kernel_launches.argtypes = [C.c_void_p]
+    lib.c4b_group_kernel_launches.restype = C.c_int64
+    lib.c4b_group_find_score_batch.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), C.c_int32, P(abi.Pair),
+                                               C.c_void_p]
+    lib.c4b_group_find_path_batch.argtypes = [C.c_void_p, P(abi.Model), P(abi.Scoring), C.c_int32, P(abi.Pair),
+                                              C.c_int32, P(abi.Result), P(C.c_void_p), P(C.c_int64)]
+    lib.c4b_free.argtypes = [C.c_void_p]
     lib.c4b_batch_description.argtypes = [C.c_void_p]
     lib.c4b_batch_description.restype = C.c_char_p
     lib.c4b_batch_destroy.argtypes = [C.c_void_p]
@@ -241,6 +253,52 @@ class Engine:
     def close(self):
         if self.h:
             self.lib.c4b_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Group:
+    """c4b_group: one batch sharded over several GPUs of one box inside the C library (one engine and
+    one host thread per device, lattices dealt by cost); same results as one Engine."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        devs = list(devices) if devices else []
+        arr = (C.c_int * max(1, len(devs)))(*devs)
+        _check(self.lib, self.lib.c4b_group_create(len(devs), arr, C.byref(self.h)), "c4b_group_create")
+
+    @property
+    def size(self):
+        return self.lib.c4b_group_size(self.h)
+
+    def kernel_launches(self):
+        return self.lib.c4b_group_kernel_launches(self.h)
+
+    def find_score(self, model, scoring, pairs):
+        scores = np.zeros(max(pairs.n, 1), dtype=np.int32)
+        _check(self.lib, self.lib.c4b_group_find_score_batch(self.h, C.byref(model), C.byref(scoring), pairs.n,
+                                                             pairs.array, scores.ctypes.data),
+               "c4b_group_find_score_batch")
+        return [int(x) for x in scores[:pairs.n]]
+
+    def find_path_raw(self, model, scoring, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE):
+        """(c4b_result array, int32 ops array copied out of the library's buffer)"""
+        results = (abi.Result * max(pairs.n, 1))()
+        ops_p, n_ops = C.c_void_p(), C.c_int64()
+        _check(self.lib, self.lib.c4b_group_find_path_batch(self.h, C.byref(model), C.byref(scoring), pairs.n,
+                                                            pairs.array, threshold, results, C.byref(ops_p),
+                                                            C.byref(n_ops)), "c4b_group_find_path_batch")
+        ops = np.ctypeslib.as_array(C.cast(ops_p, C.POINTER(C.c_int32)), shape=(2 * max(n_ops.value, 1),)).copy()
+        self.lib.c4b_free(ops_p)
+        return results, ops
+
+    def find_path(self, model, scoring, pairs, threshold=abi.IMPOSSIBLY_LOW_SCORE):
+        results, ops = self.find_path_raw(model, scoring, pairs, threshold)
+        return results_to_list(results, ops, pairs.n)
+
+    def close(self):
+        if self.h:
+            self.lib.c4b_group_destroy(self.h)
             self.h = C.c_void_p()
 
 

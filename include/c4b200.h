@@ -263,6 +263,31 @@ const char *c4b_batch_kernel_name(const c4b_batch *b);
 const char *c4b_batch_description(const c4b_batch *b);
 void c4b_batch_destroy(c4b_batch *b);
 
+/* ---- device groups: one batch over several GPUs of one box ----------------
+ * Pairs are independent (GAM_Result_exhaustive_create touches per-pair state only,
+ * src/hub/gam.c:1140-1180), so a batch shards with no exchange step inside the DP: the group owns
+ * one engine and one host thread per device, deals the lattices to the devices by cost
+ * (query_length x target_length, largest first, to the least loaded device), runs the shards
+ * concurrently -- each device is sent only its own shard's sequences -- and merges results and
+ * op lists back into pair order.  Results are identical to c4b_find_path_batch on one device.
+ * A single lattice is never split across devices.  devices = CUDA ordinals; n_devices = 0 means
+ * every visible device.  Same single-host-thread rule as an engine. */
+typedef struct c4b_group c4b_group;
+int c4b_group_create(int n_devices, const int *devices, c4b_group **out);
+void c4b_group_destroy(c4b_group *g);
+int c4b_group_size(const c4b_group *g);
+/* Optimal_find_score / Optimal_find_path over n lattices, sharded.  The path variant returns the
+ * op list in a buffer of exactly the needed size, allocated by the library (release it with
+ * c4b_free); results[k].ops_offset index into it. */
+int c4b_group_find_score_batch(c4b_group *g, const c4b_model *model, const c4b_scoring *scoring,
+                               int32_t n, const c4b_pair *pairs, c4b_score *scores);
+int c4b_group_find_path_batch(c4b_group *g, const c4b_model *model, const c4b_scoring *scoring,
+                              int32_t n, const c4b_pair *pairs, c4b_score threshold,
+                              c4b_result *results, int32_t **ops_out, int64_t *n_ops_out);
+void c4b_free(void *p);
+/* kernels launched by all engines of the group since creation */
+int64_t c4b_group_kernel_launches(const c4b_group *g);
+
 /* ---- single-lattice Viterbi_DP_Func shape ------------------------------ */
 /* mode: 0 FIND_SCORE, 1 FIND_PATH, 2 FIND_REGION (src/c4/viterbi.h:104-109).
  * One synchronous lattice; what Bootstrapper_lookup()'s trampolines call. */

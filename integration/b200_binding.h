@@ -11,6 +11,10 @@
 /* the process-wide engine (EXONERATE_B200_DEVICE selects the CUDA ordinal) */
 c4b_engine *exonerate_b200_engine(void);
 
+/* EXONERATE_B200_DEVICES=all | 0,1,2,...: the exhaustive batches of the CLI are sharded over
+ * these GPUs (c4b_group); NULL when unset (one device) */
+c4b_group *exonerate_b200_group(void);
+
 /* closed C4_Model of a Viterbi -> flat tables (built once per Viterbi) */
 c4b_model *b200_tables_for(Viterbi *viterbi);
 gboolean b200_model_has_splice(c4b_model *m);

@@ -171,12 +171,13 @@ static void flat_table_clear(void){
 static void run_round(GAM *gam, gint round, gint *active, gint n_active){
     register Viterbi *viterbi = gam->optimal->find_path;
     register c4b_model *tables = b200_tables_for(viterbi);
-    register c4b_engine *engine = exonerate_b200_engine();
+    register c4b_group *group = exonerate_b200_group(); /* several GPUs: EXONERATE_B200_DEVICES */
+    register c4b_engine *engine = group?NULL:exonerate_b200_engine();
     register c4b_pair *pairs = g_new0(c4b_pair, n_active);
     register c4b_result *results = g_new0(c4b_result, n_active);
-    register gint32 *ops = NULL;
+    gint32 *ops = NULL;
     register gint k, i;
-    register gint64 need;
+    gint64 need;
     register gboolean with_splice = b200_model_has_splice(tables);
     register B200_Job *job;
     register B200_Round *rd;
@@ -212,16 +213,22 @@ static void run_round(GAM *gam, gint round, gint *active, gint n_active){
     t0 = now_seconds();
     /* create / run / size the op buffer exactly / fetch: the worst-case op count
      * (query + target per lattice) of a 10k-pair batch would be gigabytes */
-    if(c4b_batch_create(engine, tables, &scoring, n_active, pairs, 1, &batch)
-    || c4b_batch_run(batch, C4B_IMPOSSIBLY_LOW_SCORE))
-        g_error("libc4b200: %s", c4b_last_error());
-    need = c4b_batch_ops_needed(batch);
-    if(need < 0)
-        g_error("libc4b200: %s", c4b_last_error());
-    ops = g_new(gint32, 2*need+2);
-    if(c4b_batch_fetch(batch, results, ops, need))
-        g_error("libc4b200: %s", c4b_last_error());
-    c4b_batch_destroy(batch);
+    if(group){ /* lattices dealt to the devices by cost, shards run concurrently, merged in pair order */
+        if(c4b_group_find_path_batch(group, tables, &scoring, n_active, pairs,
+                                     C4B_IMPOSSIBLY_LOW_SCORE, results, &ops, &need))
+            g_error("libc4b200: %s", c4b_last_error());
+    } else {
+        if(c4b_batch_create(engine, tables, &scoring, n_active, pairs, 1, &batch)
+        || c4b_batch_run(batch, C4B_IMPOSSIBLY_LOW_SCORE))
+            g_error("libc4b200: %s", c4b_last_error());
+        need = c4b_batch_ops_needed(batch);
+        if(need < 0)
+            g_error("libc4b200: %s", c4b_last_error());
+        ops = g_new(gint32, 2*need+2);
+        if(c4b_batch_fetch(batch, results, ops, need))
+            g_error("libc4b200: %s", c4b_last_error());
+        c4b_batch_destroy(batch);
+        }
     stat_device += now_seconds() - t0;
     for(k = 0; k < n_active; k++){
         job = &queue.job[active[k]];
@@ -234,7 +241,10 @@ static void run_round(GAM *gam, gint round, gint *active, gint n_active){
         }
     stat_rounds++;
     stat_lattices += n_active;
-    g_free(ops);
+    if(group)
+        c4b_free(ops);
+    else
+        g_free(ops);
     g_free(results);
     g_free(pairs);
     return;

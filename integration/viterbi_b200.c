@@ -59,6 +59,25 @@ c4b_engine *exonerate_b200_engine(void){
     return engine;
     }
 
+c4b_group *exonerate_b200_group(void){
+    static c4b_group *group = NULL;
+    static gboolean tried = FALSE;
+    register const gchar *spec = g_getenv("EXONERATE_B200_DEVICES");
+    int devices[64], n = 0;
+    if(tried || !spec || !spec[0])
+        return group;
+    tried = TRUE;
+    if(strcmp(spec, "all")){
+        register gchar **part = g_strsplit(spec, ",", 64);
+        for(n = 0; part[n] && (n < 64); n++)
+            devices[n] = atoi(part[n]);
+        g_strfreev(part);
+        }
+    if(c4b_group_create(n, devices, &group))
+        g_error("libc4b200: %s", c4b_last_error());
+    return group;
+    }
+
 /* EXONERATE_B200_STATS=1: one line on stderr at exit */
 static glong stat_calls = 0, stat_cache_miss = 0;
 static gdouble stat_total = 0, stat_prepare = 0, stat_engine = 0;

@@ -117,9 +117,10 @@ def test_every_scope_combination_specialises():
 
 def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
     """With C4B_JIT_CACHE_DIR set, c4b_model_specialise leaves every variant's cubin in the cache
-    (ring in shared memory / L2, and both start-slot layouts for FIND_REGION) -- the device
-    analogue of running the reference's bootstrapper once -- and a second call rewrites the same
-    files (names are a hash of the generated source)."""
+    (thread-per-row kernel: ring in shared memory / L2, and both start-slot layouts for FIND_REGION;
+    plus the systolic kernel of the mode) -- the device analogue of running the reference's
+    bootstrapper once -- and a second call rewrites the same files (names are a hash of the
+    generated source)."""
     from exonerate_b200 import load_library
     from exonerate_b200.models import host_model
     lib = load_library()
@@ -127,9 +128,16 @@ def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
     model, _ = host_model("coding2coding")
     assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
     first = sorted(os.listdir(tmp_path))
-    assert len(first) == 2 and all(f.startswith("c4bjit_") and f.endswith(".cubin") for f in first)
+    assert len(first) == 3 and all(f.startswith("c4bjit_") and f.endswith(".cubin") for f in first)
     assert lib.c4b_model_specialise(C.byref(model), 2, 128, None) == 0
-    assert len(os.listdir(tmp_path)) == 2 + 4
+    assert len(os.listdir(tmp_path)) == 3 + 5
     assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
-    assert len(os.listdir(tmp_path)) == 6
-    assert all(os.path.getsize(tmp_path / f) > 10000 for f in os.listdir(tmp_path))
+    assert len(os.listdir(tmp_path)) == 8
+    monkeypatch.setenv("C4B_JIT_SYSTOLIC", "0")   # the thread-per-row variants alone
+    other = tmp_path / "no_systolic"
+    other.mkdir()
+    monkeypatch.setenv("C4B_JIT_CACHE_DIR", str(other))
+    assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
+    assert len(os.listdir(other)) == 2
+    monkeypatch.setenv("C4B_JIT_CACHE_DIR", str(tmp_path))
+    assert all(os.path.getsize(tmp_path / f) > 10000 for f in os.listdir(tmp_path) if f.endswith(".cubin"))

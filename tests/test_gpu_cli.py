@@ -134,3 +134,6 @@ def test_cli_batch_hook_small_queue_and_off(tmp_path):
     assert "in 5 flush(es)" in got.stderr
     got = _run_batch_cli(tmp_path, name, {"EXONERATE_B200_BATCH": "0"})
     assert got.returncode == 0 and got.stdout == want, got.stderr[-2000:]
+    # the flushes sharded over a device group inside the C library (two engines on GPU 0 here)
+    got = _run_batch_cli(tmp_path, name, {"EXONERATE_B200_DEVICES": "0,0"})
+    assert got.returncode == 0 and got.stdout == want, got.stderr[-2000:]

@@ -584,6 +584,36 @@ def test_subopt_mixed_batch_and_regions(eng, params, scoring):
     _subopt_series(opt, model, scoring, q, t, 3, region=(20, 300, 350, 4500))
 
 
+def test_device_group_shards_and_merges(eng, params, scoring):
+    """c4b_group: the batch is dealt to the group's engines by cost, the shards run on one host
+    thread per engine, results and op lists come back in pair order -- identical to one engine.
+    (Two engines on device 0 here: the sharding / merging logic does not care which GPU.)"""
+    from exonerate_b200 import Group, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    grp = Group([0, 0, 0])
+    assert grp.size == 3
+    for name in ("affine_local_dna", "est2genome", "coding2coding"):
+        model, _ = helpers.load_model(name, params)
+        qs, ts = [], []
+        for k in range(17):
+            if name == "est2genome":
+                q, t = helpers.gene_pair(8100 + k, 100 + 40 * k, 2000 + 300 * k, n_exons=1 + k % 3)
+            else:
+                q, t = helpers.dna_pair(8100 + k, 90 + 31 * k, 700 + 517 * k)
+            qs.append(q)
+            ts.append(t)
+        sp = [splice_arrays(t) for t in ts] if name == "est2genome" else None
+        pairs = PairSet(qs, ts, splice=sp)
+        want = Optimal(eng, model, scoring).find_path(pairs)
+        got = grp.find_path(model, scoring, pairs)
+        assert got == want, name
+        assert grp.find_score(model, scoring, pairs) == [w["score"] for w in want], name
+        assert grp.find_path(model, scoring, pairs, threshold=10 ** 6)[0]["status"] == 1
+    assert grp.find_path(model, scoring, PairSet([], [])) == []
+    assert grp.kernel_launches() > 0
+    grp.close()
+
+
 def test_threshold_and_errors(eng, params, scoring):
     from exonerate_b200 import C4BError, Optimal, PairSet
     model, _ = helpers.load_model("affine_local_dna", params)
