@@ -1776,6 +1776,22 @@ void c4b_engine_forget_buffers(c4b_engine *e) {
     e->resident.bytes = 0;
 }
 
+void c4b_engine_forget_buffer(c4b_engine *e, const void *host) {
+    if (!e || !host) return;
+    cudaSetDevice(e->device);
+    bool synced = false;
+    for (auto it = e->resident.map.begin(); it != e->resident.map.end();) {
+        if (it->first.first == host) {
+            if (!synced) { cudaStreamSynchronize(e->stream); synced = true; }
+            cudaFree(it->second);
+            e->resident.bytes -= std::min(e->resident.bytes, it->first.second);
+            it = e->resident.map.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
 int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hsp_param *param,
                          const uint8_t *query, int32_t query_len, const uint8_t *query_mask,
                          const uint8_t *target, int32_t target_len, const uint8_t *target_mask,

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("C4B_LIB", os.path.join(_HERE, "libc4b200.so"))  # ove
 
 EXPORTS = [
     "c4b_abi_version", "c4b_last_error", "c4b_engine_create", "c4b_engine_destroy",
-    "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_kernel_launches", "c4b_find_score_batch",
+    "c4b_engine_set_stream", "c4b_engine_forget_buffers", "c4b_engine_forget_buffer", "c4b_engine_kernel_launches", "c4b_find_score_batch",
     "c4b_find_path_batch", "c4b_batch_create", "c4b_batch_run", "c4b_batch_fetch",
     "c4b_batch_cells", "c4b_batch_ops_needed", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_description", "c4b_batch_destroy",
     "c4b_group_create", "c4b_group_destroy", "c4b_group_size", "c4b_group_find_score_batch",

@@ -214,6 +214,9 @@ int c4b_engine_set_stream(c4b_engine *e, void *cuda_stream);
  * rewriting such a buffer; batches created from such pairs must be destroyed first).
  * Waits for the engine's stream. */
 void c4b_engine_forget_buffers(c4b_engine *e);
+/* The same for the copies of ONE host buffer (by address), e.g. when a host keeps a target and
+ * its splice arrays across comparisons and only the query changes. */
+void c4b_engine_forget_buffer(c4b_engine *e, const void *host);
 /* Counters since engine creation: kernels launched by this library. */
 int64_t c4b_engine_kernel_launches(const c4b_engine *e);
 

@@ -100,7 +100,7 @@ static void trace_call(Viterbi *viterbi, Region *region, const gchar *how, C4_Sc
 
 static void print_viterbi_stats(void){
     fprintf(stderr, "exonerate_b200: Viterbi_calculate calls %ld (%.3f s: prepare %.3f s, "
-                    "engine %.3f s), sequence pairs flattened %ld, answered from the batch "
+                    "engine %.3f s), targets flattened %ld, answered from the batch "
                     "prefetch %ld (prefetched but not usable %ld); BSDP region fills prefetched %ld "
                     "in %ld batch(es), answered from them %ld\n",
             stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss,
@@ -112,12 +112,105 @@ static void print_viterbi_stats(void){
  * views, sequence.c:257-507) and the four splice-site arrays intron_init_func prepares
  * (intron.c:259-293) of the CURRENT comparison.  BSDP asks for thousands of region fills
  * on the same (query, target): flatten once per pair, not once per fill.  The Sequences
- * are shared (pinned) while cached, so the pointers cannot be recycled under the key. */
+ * are shared (pinned) while cached, so the pointers cannot be recycled under the key.
+ * TARGETS are kept across comparisons, by content: the usual run compares many queries (and
+ * their reverse complements) with the same genomic targets, which the reference re-reads --
+ * as new Sequence objects -- for every query (src/database/fastapipe.c:106-137).  Flattening a
+ * 6 Mbp target and predicting its four splice arrays per comparison cost 134 s of a 242 s run
+ * (profiles/r02_bsdp.md); kept, they are computed once, and the engine's device copies
+ * (C4B_PAIR_BUFFERS_STABLE, keyed by the host address) stay valid with them. */
+typedef struct {
+    guint64 hash;
+    gint len;
+    gchar *tseq;
+    gint32 *splice;
+    glong last_use;
+} B200_Target;
+#define TARGET_SLOTS 8
+static B200_Target target_cache[TARGET_SLOTS];
+static glong target_clock = 0;
+static gsize target_cache_bytes = 0;
+
 static struct {
     Sequence *query, *target;
     gchar *qseq, *tseq;
     gint32 *splice;
-} pair_cache = {NULL, NULL, NULL, NULL, NULL};
+    B200_Target *entry;
+} pair_cache = {NULL, NULL, NULL, NULL, NULL, NULL};
+
+static guint64 content_hash(const gchar *s, gint len){
+    register guint64 h = 0x9E3779B97F4A7C15ull ^ (guint64)len;
+    register gint i;
+    guint64 w;
+    for(i = 0; i+8 <= len; i += 8){
+        memcpy(&w, s+i, 8);
+        h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+        h ^= h >> 32;
+        }
+    for(; i < len; i++)
+        h = (h ^ (guchar)s[i]) * 0x100000001B3ull;
+    return h ^ (h >> 29);
+    }
+
+static void target_entry_drop(B200_Target *e){
+    if(!e->tseq)
+        return;
+    c4b_engine_forget_buffer(get_engine(), e->tseq); /* device copies are keyed by these addresses */
+    if(e->splice){
+        register gint k;
+        for(k = 0; k < 4; k++)
+            c4b_engine_forget_buffer(get_engine(), e->splice + (gsize)k*e->len);
+        target_cache_bytes -= 16*((gsize)e->len+1);
+        }
+    target_cache_bytes -= e->len;
+    g_free(e->tseq);
+    g_free(e->splice);
+    memset(e, 0, sizeof(B200_Target));
+    return;
+    }
+
+static B200_Target *target_fetch(Sequence *target){
+    register gint i, tlen = target->len;
+    register gchar *flat = g_new(gchar, tlen+4);
+    register guint64 h;
+    register B200_Target *e, *victim = NULL;
+    Sequence_strncpy(target, 0, tlen, flat);
+    memset(flat+tlen, 0, 4);
+    h = content_hash(flat, tlen);
+    for(i = 0; i < TARGET_SLOTS; i++){
+        e = &target_cache[i];
+        if(e->tseq && (e->hash == h) && (e->len == tlen) && !memcmp(e->tseq, flat, tlen)){
+            g_free(flat);
+            e->last_use = ++target_clock;
+            return e;
+            }
+        }
+    /* keep at most TARGET_SLOTS targets / 2 GB of sequence + splice arrays: drop the oldest */
+    for(;;){
+        register B200_Target *oldest = NULL;
+        victim = NULL;
+        for(i = 0; i < TARGET_SLOTS; i++){
+            e = &target_cache[i];
+            if(!e->tseq)
+                victim = e;
+            else if((e != pair_cache.entry) && (!oldest || (e->last_use < oldest->last_use)))
+                oldest = e;
+            }
+        if(victim && ((target_cache_bytes + 17*(gsize)tlen <= ((gsize)2 << 30)) || !oldest))
+            break;
+        if(!oldest)
+            g_error("libc4b200: target cache exhausted");
+        target_entry_drop(oldest);
+        }
+    victim->hash = h;
+    victim->len = tlen;
+    victim->tseq = flat;
+    victim->splice = NULL;
+    victim->last_use = ++target_clock;
+    target_cache_bytes += tlen;
+    stat_cache_miss++;
+    return victim;
+    }
 
 gint32 *b200_splice_arrays(gchar *tseq, gint tlen){
     register Intron_ArgumentSet *ias = Intron_ArgumentSet_create(NULL);
@@ -135,25 +228,31 @@ static void pair_cache_fetch(Ungapped_Data *ud, gboolean need_splice){
     register gint tlen = ud->target->len;
     if((pair_cache.query != ud->query) || (pair_cache.target != ud->target)){
         score_cache_clear(); /* prefetched BSDP fills belong to the previous comparison */
-        if(pair_cache.query){
-            c4b_engine_forget_buffers(get_engine()); /* device copies are keyed by these addresses */
-            Sequence_destroy(pair_cache.query);
-            Sequence_destroy(pair_cache.target);
-            g_free(pair_cache.qseq);
-            g_free(pair_cache.tseq);
-            g_free(pair_cache.splice);
+        if(pair_cache.query != ud->query){
+            if(pair_cache.query){
+                c4b_engine_forget_buffer(get_engine(), pair_cache.qseq);
+                Sequence_destroy(pair_cache.query);
+                g_free(pair_cache.qseq);
+                }
+            pair_cache.query = Sequence_share(ud->query);
+            pair_cache.qseq = g_new(gchar, ud->query->len+4);
+            Sequence_strncpy(ud->query, 0, ud->query->len, pair_cache.qseq);
             }
-        pair_cache.query = Sequence_share(ud->query);
-        pair_cache.target = Sequence_share(ud->target);
-        pair_cache.qseq = g_new(gchar, ud->query->len+4);
-        pair_cache.tseq = g_new(gchar, tlen+4);
-        Sequence_strncpy(ud->query, 0, ud->query->len, pair_cache.qseq);
-        Sequence_strncpy(ud->target, 0, tlen, pair_cache.tseq);
-        pair_cache.splice = NULL;
-        stat_cache_miss++;
+        if(pair_cache.target != ud->target){
+            if(pair_cache.target)
+                Sequence_destroy(pair_cache.target);
+            pair_cache.target = Sequence_share(ud->target);
+            pair_cache.entry = NULL;
+            pair_cache.entry = target_fetch(ud->target);
+            pair_cache.tseq = pair_cache.entry->tseq;
+            pair_cache.splice = pair_cache.entry->splice;
+            }
         }
-    if(need_splice && !pair_cache.splice)
-        pair_cache.splice = b200_splice_arrays(pair_cache.tseq, tlen);
+    if(need_splice && !pair_cache.splice){
+        pair_cache.entry->splice = b200_splice_arrays(pair_cache.tseq, tlen);
+        pair_cache.splice = pair_cache.entry->splice;
+        target_cache_bytes += 16*((gsize)tlen+1);
+        }
     return;
     }
 

@@ -587,10 +587,13 @@ def test_subopt_mixed_batch_and_regions(eng, params, scoring):
 def test_device_group_shards_and_merges(eng, params, scoring):
     """c4b_group: the batch is dealt to the group's engines by cost, the shards run on one host
     thread per engine, results and op lists come back in pair order -- identical to one engine.
-    (Two engines on device 0 here: the sharding / merging logic does not care which GPU.)"""
+    (On a one-GPU box all three engines sit on device 0: the sharding / merging logic does not
+    care which GPU; with more GPUs visible the group spans them.)"""
+    import torch
     from exonerate_b200 import Group, Optimal, PairSet
     from exonerate_b200.models import splice_arrays
-    grp = Group([0, 0, 0])
+    nd = max(1, torch.cuda.device_count())
+    grp = Group([0, 1 % nd, 2 % nd])
     assert grp.size == 3
     for name in ("affine_local_dna", "est2genome", "coding2coding"):
         model, _ = helpers.load_model(name, params)
