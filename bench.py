@@ -53,12 +53,12 @@ WORKLOADS = {
         "metric": "GCUPS protein2genome find_path (score+region+ops, bit-exact), 450 aa x 20 kbp genomic batch",
         "b_alg": 104, "pairs": 592, "cpu_pairs": 1, "qlen": 450, "tlen": 20000, "query_is_protein": True,
         "workload": "protein2genome --exhaustive, %d aa protein x %d bp genomic pairs (4 exons, GT..AG introns)",
-        "kernel": "c4b_jit_fill (closed model compiled for sm_100a at run time: region pass + path pass in the "
-                  "alignment box, lattice ring in shared memory) + walk",
-        "traffic_key": "c4b_jit_fill<protein2genome>",
+        "kernel": "c4b_jit_sys (closed model compiled for sm_100a at run time as a systolic kernel: lattice in "
+                  "registers, lanes skewed by a column, one PATH pass with rank-bit records) + walk",
+        "traffic_key": "c4b_jit_sys<protein2genome>",
         "note": "B_alg=104 B/cell (SURVEY 8d: 4 B x 13 states x C=2, reference row layout); the kernel keeps the "
-                "lattice ring in shared memory and writes 13 B/cell only inside the alignment box, so the HBM "
-                "roofline does not bind it (it is issue/latency bound, profiles/r01d_generic_jit.md). peak ",
+                "lattice in registers and writes 4 B/cell of rank-bit traceback records, so the HBM roofline does "
+                "not bind it (ALU-pipe bound, profiles/r02_kernels.md). peak ",
     },
 }
 

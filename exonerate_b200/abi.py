@@ -60,6 +60,10 @@ class Pair(C.Structure):
                 ("n_blocked", C.c_int32), ("reserved", C.c_int32)]
 
 
+class SpanJob(C.Structure):   # c4b_span_job
+    _fields_ = [("src", Pair), ("dst", Pair), ("span", C.c_int32 * 4)]
+
+
 class Result(C.Structure):
     _fields_ = [("score", C.c_int32), ("query_start", C.c_int32), ("target_start", C.c_int32),
                 ("query_end", C.c_int32), ("target_end", C.c_int32), ("n_ops", C.c_int32),

@@ -1767,6 +1767,97 @@ int c4b_span_integrate(c4b_engine *e, const c4b_score *src_scores, const int32_t
     return rc;
 }
 
+int c4b_span_score_batch(c4b_engine *e, const c4b_model *src_model, const c4b_model *dst_model,
+                         const c4b_scoring *scoring, int32_t n, const c4b_span_job *jobs, c4b_score *scores) {
+    if (!e || !src_model || !dst_model || !scoring || n < 0 || (n && (!jobs || !scores))) {
+        set_error("c4b_span_score_batch: bad arguments");
+        return -1;
+    }
+    if (n == 0) return 0;
+    C4B_CUDA(cudaSetDevice(e->device));
+    tl_pool_stream = e->stream;
+    cudaStream_t st = e->stream;
+    const int c_src = 1 + src_model->n_shadow_slots, c_dst = 1 + dst_model->n_shadow_slots;
+    std::vector<c4b_pair> src(n), dst(n);
+    std::vector<size_t> end_off(n), start_off(n);
+    size_t end_ints = 0, start_ints = 0;
+    int max_dst_cells = 1;
+    for (int k = 0; k < n; ++k) {
+        src[k] = jobs[k].src;
+        dst[k] = jobs[k].dst;
+        if (src[k].query_length < 0 || src[k].target_length < 0 || dst[k].query_length < 0 || dst[k].target_length < 0) {
+            set_error("c4b_span_score_batch: job " + std::to_string(k) + " has a negative region extent");
+            return -1;
+        }
+        end_off[k] = end_ints;
+        start_off[k] = start_ints;
+        end_ints += ((size_t)src[k].query_length + 1) * ((size_t)src[k].target_length + 1) * c_src;
+        const size_t dc = ((size_t)dst[k].query_length + 1) * ((size_t)dst[k].target_length + 1);
+        start_ints += dc * c_dst;
+        max_dst_cells = (int)std::max<size_t>(max_dst_cells, std::min<size_t>(dc, 1u << 30));
+    }
+    DevBuf<int32_t> d_end, d_start;
+    DevBuf<SpanJob> d_jobs;
+    GenericBatch *gs = nullptr, *gd = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        if (gs) generic_batch_destroy(gs);
+        if (gd) generic_batch_destroy(gd);
+        d_end.release(); d_start.release(); d_jobs.release();
+    };
+    if (d_end.alloc(end_ints + 4) || d_start.alloc(start_ints + 4) || d_jobs.alloc(n)) { cleanup(); return -1; }
+    // "END not reached": the byte pattern reads as a score far below C4_IMPOSSIBLY_LOW_SCORE
+    if (cudaMemsetAsync(d_end.p, 0x80, end_ints * sizeof(int32_t), st) != cudaSuccess) rc = -1;
+    std::vector<int32_t *> end_ptr(n);
+    std::vector<const int32_t *> start_ptr(n);
+    std::vector<SpanJob> hj(n);
+    for (int k = 0; k < n; ++k) {
+        end_ptr[k] = d_end.p + end_off[k];
+        start_ptr[k] = d_start.p + start_off[k];
+        SpanJob &J = hj[k];
+        J.a.sqs = src[k].query_start; J.a.sts = src[k].target_start;
+        J.a.sql = src[k].query_length; J.a.stl = src[k].target_length;
+        J.a.dqs = dst[k].query_start; J.a.dts = dst[k].target_start;
+        J.a.dql = dst[k].query_length; J.a.dtl = dst[k].target_length;
+        J.a.min_q = jobs[k].span[0]; J.a.max_q = jobs[k].span[1];
+        J.a.min_t = jobs[k].span[2]; J.a.max_t = jobs[k].span[3];
+        J.src_end = end_ptr[k];
+        J.dst_start = d_start.p + start_off[k];
+        J.c_src = c_src;
+        J.c_dst = c_dst;
+    }
+    GenDevTables ts, td;
+    ts.end = end_ptr.data();
+    td.start = start_ptr.data();
+    // 1) src fills: END's cell of every cell that reaches END
+    if (!rc) rc = generic_batch_create(st, &e->launches, src_model, scoring, n, src.data(), false, &gs, nullptr, false,
+                                       e->sm_count, &e->resident, &ts);
+    if (!rc) rc = generic_batch_run(gs, C4B_IMPOSSIBLY_LOW_SCORE);
+    // 2) integrate + START tables of the dst fills
+    if (!rc) {
+        if (cudaMemcpyAsync(d_jobs.p, hj.data(), n * sizeof(SpanJob), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+        const int threads = 128;
+        const dim3 grid((unsigned)std::max(1, std::min((max_dst_cells + threads - 1) / threads, 64)), (unsigned)n);
+        span_start_table_kernel<<<grid, threads, 0, st>>>(d_jobs.p);
+        e->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = -1;
+        if (rc) set_error(std::string("c4b_span_score_batch: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    // 3) dst fills from the tables
+    if (!rc) rc = generic_batch_create(st, &e->launches, dst_model, scoring, n, dst.data(), false, &gd, nullptr, false,
+                                       e->sm_count, &e->resident, &td);
+    if (!rc) rc = generic_batch_run(gd, C4B_IMPOSSIBLY_LOW_SCORE);
+    if (!rc) {
+        std::vector<c4b_result> res(n);
+        rc = generic_batch_fetch(gd, res.data(), nullptr, 0);
+        if (!rc)
+            for (int k = 0; k < n; ++k) scores[k] = res[k].score;
+    }
+    if (rc) cudaStreamSynchronize(st);   // the staging vectors above must outlive the copies
+    cleanup();
+    return rc;
+}
+
 void c4b_engine_forget_buffers(c4b_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);

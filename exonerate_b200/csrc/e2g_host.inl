@@ -135,6 +135,7 @@ struct E2gBatch {
     bool packed = false;              // e2g_packed16.cuh: both strands per register, one warp per lattice
     DevBuf<E2pPair> d_pairs16;
     DevBuf<uint2> d_top;              // sweep hand-off rows (packed path, queries longer than 511)
+    int max_query = 0;
     bool windowed = false;            // find_path by checkpoints + window refills (e2g_packed16.cuh)
     DevBuf<uint32_t> d_ck;
     DevBuf<E2pWalk> d_walk;
@@ -226,6 +227,7 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     b->stream = stream; b->launches = launch_counter; b->n = n; b->want_path = want_path; b->mdl = mdl;
     b->packed = packed;
     b->max_target = maxT;
+    b->max_query = maxQ;
     b->warps = std::max(1, (maxQ + 1 + 32 * kE2gR - 1) / (32 * kE2gR));
     // ---- staging: region slices of query / target, packed splice words ---------------
     std::vector<size_t> qoff(n), toff(n);
@@ -486,11 +488,22 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
     cudaStream_t st = b->stream;
     const int n = b->n;
     const int threads = 32 * b->warps;
+    // packed kernel: small batches run the 512-row sweeps of a lattice on pipelined warps (the
+    // one-warp kernel otherwise: see e2g_packed16.cuh for the measurements; C4B_E2G_WARPS overrides)
+    int warps16 = std::max(1, std::min(kE2pMaxWarps, (b->max_query + 1 + 32 * kE2pR - 1) / (32 * kE2pR)));
+    if (n > 600) warps16 = 1;
+    if (const char *env = getenv("C4B_E2G_WARPS"))
+        warps16 = std::max(1, std::min(std::min(kE2pMaxWarps, (b->max_query + 1 + 32 * kE2pR - 1) / (32 * kE2pR)), atoi(env)));
+    const int threads16 = 32 * warps16;
     C4B_CUDA(cudaEventRecord(b->ev_a, st));
     if (b->packed) {
         if (!b->want_path) {
-            e2g_fill16_kernel<E2P_SCORE><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
-                                                           nullptr, nullptr, 0);
+            if (warps16 > 1)
+                e2g_fill16_kernel<E2P_SCORE, true><<<n, threads16, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl,
+                                                                            b->d_xtab.p, nullptr, nullptr, nullptr, 0);
+            else
+                e2g_fill16_kernel<E2P_SCORE><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
+                                                               nullptr, nullptr, 0);
             C4B_CUDA(cudaGetLastError());
             C4B_CUDA(cudaEventRecord(b->ev_b, st));
             e2g16_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_qorg.p,
@@ -502,8 +515,12 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
         if (b->windowed) {
             // pass 1: END cell + column checkpoints; then rounds of (refill the window under
             // each traceback cursor, walk it) until every cursor has reached START
-            e2g_fill16_kernel<E2P_SCORE_CK><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
-                                                              nullptr, nullptr, nullptr, 0);
+            if (warps16 > 1)
+                e2g_fill16_kernel<E2P_SCORE_CK, true><<<n, threads16, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl,
+                                                                               b->d_xtab.p, nullptr, nullptr, nullptr, 0);
+            else
+                e2g_fill16_kernel<E2P_SCORE_CK><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
+                                                                  nullptr, nullptr, nullptr, 0);
             e2g16_walk_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n, b->mdl,
                                                                    threshold, b->d_walk.p, b->d_ops_slots.p);
             e2g16_walk_rejected_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n,

@@ -73,8 +73,19 @@ enum { E2P_SCORE = 0, E2P_FULL_TB = 1, E2P_SCORE_CK = 2, E2P_WINDOW_TB = 3 };
 // MODE: E2P_SCORE (END cell only), E2P_FULL_TB (records for the whole lattice),
 // E2P_SCORE_CK (END cell + column checkpoints), E2P_WINDOW_TB (records for one window
 // of one lattice, started from a checkpoint; active = list of lattices, walk = cursors).
-template <int MODE>
-__global__ void __launch_bounds__(32)
+// blockDim.x = 32 W (W <= kE2pMaxWarps; W = 1 for E2P_WINDOW_TB): the W warps of a CTA take the
+// sweeps (strips of 512 rows) of ONE lattice round-robin and run them as a pipeline -- sweep k+1
+// follows sweep k at >= 32 columns, reading the hand-off row the moment it is published (monotone
+// counter in shared memory, published every 8 columns; the scheme of affine_fill_kernel) -- so a
+// 1 kbp cDNA occupies two schedulers instead of one: small batches (a shard of the 1k-pair batch on
+// 8 GPUs is 125 lattices) leave most of the GPU idle with one warp per lattice.
+constexpr int kE2pMaxWarps = 4;
+
+// PIPE = false is the one-warp kernel exactly as before (W folds to 1 at compile time): measured on
+// the B200, the pipelined form wins only while the batch leaves warp slots empty (find_path GCUPS,
+// one warp -> pipelined: 125 lattices 86 -> 118, 500 336 -> 350, 1000 487 -> 369, 4000 597 -> 452).
+template <int MODE, bool PIPE = false>
+__global__ void __launch_bounds__(PIPE ? 32 * kE2pMaxWarps : 32)
 e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, const E2gModel mdl,
                   const uint2 *__restrict__ score_table, const int32_t *__restrict__ active,
                   const E2pWalk *__restrict__ walk, uint16_t *__restrict__ winbuf, size_t win_stride) {
@@ -83,12 +94,19 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
     constexpr bool WIN = (MODE == E2P_WINDOW_TB);
     constexpr bool CK = (MODE == E2P_SCORE_CK);
     __shared__ uint2 xtab[25];
-    const int lane = threadIdx.x;
+    __shared__ volatile long long vprog[kE2pMaxWarps];
+    __shared__ int red[kE2pMaxWarps][6];
+    const int lane = threadIdx.x & 31, warp = PIPE ? (int)(threadIdx.x >> 5) : 0, W = PIPE ? (int)(blockDim.x >> 5) : 1;
     const int pidx = WIN ? active[blockIdx.x] : (int)blockIdx.x;
     const E2pPair P = pairs[pidx];
     const int Q = P.Q, T = P.T;
-    if (lane < 25) xtab[lane] = score_table[lane];
-    __syncwarp();
+    if (threadIdx.x < 25) xtab[threadIdx.x] = score_table[threadIdx.x];
+    if (PIPE) {
+        if (threadIdx.x < kE2pMaxWarps) vprog[threadIdx.x] = 0;
+        __syncthreads();
+    } else {
+        __syncwarp();
+    }
 
     const uint32_t open2 = pack16(mdl.open), ext2 = pack16(mdl.ext);
     const uint32_t preK = pack16(mdl.intron_open - mdl.open);  // N opens from G = M + open
@@ -113,10 +131,24 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
     int bestF = INT32_MIN, bjF = 0, biF = 0, bestR = INT32_MIN, bjR = 0, biR = 0;
     uint32_t best2 = kMin16x2;
 
-    for (int sweep = 0; sweep < nsweeps; ++sweep) {
+    for (int sweep = warp; sweep < nsweeps; sweep += W) {
         const int row0 = sweep * rows_per_sweep + lane * R;
         const bool first_row_lane = (sweep == 0 && lane == 0);
         const bool later_sweep = (sweep > 0);
+        // END bookkeeping is per warp: an earlier sweep OF THIS WARP may hold a tie at a larger column
+        const bool later_mine = (sweep != warp);
+        // the sweep above may still be running on another warp
+        const bool piped = PIPE && later_sweep && W > 1;
+        const int wp = (sweep - 1) % W;
+        const long long in_base = (long long)(sweep - 1) * (T + 1);
+        long long avail = 0;
+        auto wait_column = [&](int col) {   // until column `col` of the sweep above is published
+            const long long need = in_base + col + 1;
+            if (avail < need) {
+                while ((avail = vprog[wp]) < need) __nanosleep(40);
+                __threadfence_block();
+            }
+        };
         const int nvalid = min(R, max(0, Q - row0 + 1));  // rows r < nvalid are lattice rows <= Q
         uint32_t sel[R];
 #pragma unroll
@@ -161,7 +193,8 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         if (WIN && ck_in && lane > 0)
             topGprev = ck_in[((size_t)(sweep * 32 + lane - 1) * R + (R - 1)) * kE2pCkWords + 0];
         if (later_sweep) {
-            top0v = top_in[c0];
+            if (piped) wait_column(c0);
+            top0v = PIPE ? __ldcg(top_in + c0) : top_in[c0];
             if (c0 >= 1 && lane == 0) topGprev = top_in[c0 - 1].x;
         }
         uint4 *tbp = nullptr;
@@ -178,7 +211,10 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             if (s + 1 <= T) {
                 code0 = (int)P.t[s];
                 sp0 = (s >= 1) ? P.sp[s - 1] : 0u;   // source column (s+1)-2
-                if (later_sweep) top0v = top_in[s + 1];
+                if (later_sweep) {
+                    if (piped) wait_column(s + 1);
+                    top0v = PIPE ? __ldcg(top_in + s + 1) : top_in[s + 1];
+                }
             } else {
                 code0 = kTargetNone;
                 sp0 = 0u;
@@ -263,7 +299,13 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                     tbp[1] = make_uint4(rec[8] | (rec[9] << 16), rec[10] | (rec[11] << 16),
                                         rec[12] | (rec[13] << 16), rec[14] | (rec[15] << 16));
                 }
-                if (write_top) top_out[j] = make_uint2(botG, botI);
+                if (write_top) {
+                    top_out[j] = make_uint2(botG, botI);
+                    if (PIPE && W > 1 && ((j & 7) == 7 || j == T)) {
+                        __threadfence_block();   // the rows are written before the counter moves
+                        vprog[warp] = (long long)sweep * (T + 1) + j + 1;
+                    }
+                }
                 if (CK && ((j + 1) & (kE2pWin - 1)) == 0 && j < T) {
                     // last column of a window: the state a later window refill starts from
                     uint32_t *c = P.ck + ((size_t)(((j + 1) / kE2pWin - 1) * all_sweeps + sweep) * 32 + lane) * R * kE2pCkWords;
@@ -280,7 +322,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 bool trig = false;
                 if (!WIN) {
                     bool gh, gl;
-                    if (later_sweep) {
+                    if (later_mine) {
                         (void)__vibmax_s16x2(cm, best2, &gh, &gl);   // cm >= best
                         trig = gh || gl;
                     } else {
@@ -343,7 +385,21 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             if (ob > bestR || (ob == bestR && (oj < bjR || (oj == bjR && oi < biR)))) { bestR = ob; bjR = oj; biR = oi; }
         }
     }
-    if (lane == 0) {
+    if (PIPE && W > 1) {   // combine the warps' sweeps (idle warps carry INT32_MIN)
+        if (lane == 0) {
+            red[warp][0] = bestF; red[warp][1] = bjF; red[warp][2] = biF;
+            red[warp][3] = bestR; red[warp][4] = bjR; red[warp][5] = biR;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w < W; ++w) {
+                int ob = red[w][0], oj = red[w][1], oi = red[w][2];
+                if (ob > bestF || (ob == bestF && (oj < bjF || (oj == bjF && oi < biF)))) { bestF = ob; bjF = oj; biF = oi; }
+                ob = red[w][3]; oj = red[w][4]; oi = red[w][5];
+                if (ob > bestR || (ob == bestR && (oj < bjR || (oj == bjR && oi < biR)))) { bestR = ob; bjR = oj; biR = oi; }
+            }
+    }
+    if (threadIdx.x == 0) {
         // the first cell (target outer, query inner) that reaches the overall maximum; in that
         // cell the reverse strand is tried first and the forward one must be strictly greater
         bool fwd;

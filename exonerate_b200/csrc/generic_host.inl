@@ -138,7 +138,7 @@ static void *resident_copy(ResidentBuffers *rb, const void *host, size_t bytes, 
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
                          GenericBatch **out, const int32_t *start_cells, bool end_cells, int sm_count,
-                         ResidentBuffers *resident) {
+                         ResidentBuffers *resident, const GenDevTables *dev) {
     if (check_model(*model)) return -1;
     GenericBatch *g = new GenericBatch();
     g->stream = stream;
@@ -153,7 +153,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     // REGION-then-box is only self-consistent for ANYWHERE starts (see tests/test_oracle_golden.py)
     // (cell-callback tables are indexed by region cell: those lattices take the direct PATH pass)
     g->use_region = want_path && m.start_scope == C4B_SCOPE_ANYWHERE && m.end_scope == C4B_SCOPE_ANYWHERE &&
-                    !start_cells && !end_cells;
+                    !start_cells && !end_cells && !dev;
     g->cmax = 1 + m.n_shadow_slots + (g->use_region ? 2 : 0);
     if (sm_count <= 0) {
         int dev = 0;
@@ -250,7 +250,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     g->max_q = maxQ;
     {
         const char *env = getenv("C4B_JIT_SYSTOLIC");
-        g->plain = !start_cells && !end_cells;   // (set here: the descriptors are filled in below)
+        g->plain = !start_cells && !end_cells && !dev;   // (set here: the descriptors are filled in below)
         for (int p = 0; p < n; ++p) g->plain = g->plain && pairs[p].n_blocked == 0;
         if (g->use_jit && g->plain && !(env && atoi(env) == 0)) {
             const bool pack_start = ((int64_t)maxQ + 1) * ((int64_t)g->max_t + 1) < ((int64_t)1 << 31);
@@ -303,8 +303,8 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         G.Q = pp.query_length; G.T = pp.target_length;
         G.blk_dq = 0; G.blk_dt = 0;
         G.tb = nullptr;
-        G.start_cells = nullptr;
-        G.end_cells = nullptr;
+        G.start_cells = (dev && dev->start) ? dev->start[p] : nullptr;
+        G.end_cells = (dev && dev->end) ? dev->end[p] : nullptr;
         G.out_index = p;
         G.tb_rows = 0;
         G.tb_chunk = 0;

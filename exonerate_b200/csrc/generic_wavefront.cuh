@@ -280,13 +280,37 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
                                          const GenOut *__restrict__ reg_outs, const GenJob *__restrict__ jobs,
                                          int n, const GenTables *__restrict__ tables, int threshold,
                                          c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+    // decode tables of the rank-bit record (GEN_TBS_CHUNK): bit offset / width of every state in a
+    // row's record, and rank -> transition id per state; exactly as the host laid them out
+    __shared__ short s_bit_off[C4B_MAX_STATES], s_bit_n[C4B_MAX_STATES];
+    __shared__ unsigned char s_rank2tr[C4B_MAX_STATES][C4B_MAX_TRANSITIONS + 1];
+    __shared__ unsigned char s_in[C4B_MAX_TRANSITIONS], s_aq[C4B_MAX_TRANSITIONS], s_at[C4B_MAX_TRANSITIONS];
+    __shared__ int s_row_bits;
+    const c4b_model &m = tables->model;
+    const int S = m.n_states;
+    if (threadIdx.x == 0) {
+        int row_bits = 0;
+        for (int s = 0; s < S; ++s) {
+            int n_in = 0, b = 0;
+            for (int k = 0; k < m.n_transitions; ++k)
+                if (m.transitions[k].output == s) s_rank2tr[s][++n_in] = (unsigned char)k;
+            s_rank2tr[s][0] = 0xFF;
+            while ((1 << b) < n_in + 1) ++b;
+            s_bit_off[s] = (short)row_bits; s_bit_n[s] = (short)b; row_bits += b;
+        }
+        s_row_bits = row_bits;
+        for (int k = 0; k < m.n_transitions; ++k) {
+            s_in[k] = (unsigned char)m.transitions[k].input;
+            s_aq[k] = (unsigned char)m.transitions[k].advance_query;
+            s_at[k] = (unsigned char)m.transitions[k].advance_target;
+        }
+    }
+    __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
-    const c4b_model &m = tables->model;
     const GenJob J = jobs[g];
     const GenPair P = pairs[J.pair];
     const GenOut o = outs[P.out_index];
-    const int S = m.n_states;
     c4b_result res;
     res.score = o.score; res.status = 0; res.reserved = 0; res.n_ops = 0; res.ops_offset = J.ops_off;
     res.query_start = P.q_start; res.target_start = P.t_start;
@@ -301,40 +325,59 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
     int32_t *out = ops + 2 * J.ops_off;
     int n_runs = 0, last_t = -1, i = o.end_i, j = o.end_j;
     if (res.status == 0) {
-        // systolic record (GEN_TBS_CHUNK): per state the rank of the winner among the transitions
-        // entering it, bit-packed; bit offsets follow from the model exactly as the host laid them out
-        int bit_off[C4B_MAX_STATES], bit_n[C4B_MAX_STATES], row_bits = 0;
-        if (P.tb_rows) {
-            for (int s = 0; s < S; ++s) {
-                int n_in = 0, b = 0;
-                for (int k = 0; k < m.n_transitions; ++k) n_in += m.transitions[k].output == s;
-                while ((1 << b) < n_in + 1) ++b;
-                bit_off[s] = row_bits; bit_n[s] = b; row_bits += b;
-            }
-        }
+        const int row_bits = s_row_bits;
         auto winner = [&](int ci, int cj, int state) -> int {   // transition id, 0xFF = unset
             if (!P.tb_rows) return P.tb[GEN_TB_CELL(ci, cj, P.Q, S) + state];
-            if (bit_n[state] == 0) return 0xFF;
+            const int nb = s_bit_n[state];
+            if (nb == 0) return 0xFF;
             const uint32_t *w = reinterpret_cast<const uint32_t *>(P.tb + GEN_TBS_CHUNK(ci, cj, P.T, P.tb_rows, P.tb_chunk));
-            const int pos = (ci % P.tb_rows) * row_bits + bit_off[state];
+            const int pos = (ci % P.tb_rows) * row_bits + s_bit_off[state];
             uint64_t v = w[pos / 32];
-            if (pos % 32 + bit_n[state] > 32) v |= (uint64_t)w[pos / 32 + 1] << 32;
-            int code = (int)((v >> (pos % 32)) & ((1u << bit_n[state]) - 1u));
-            if (code == 0) return 0xFF;
-            for (int k = 0; k < m.n_transitions; ++k)
-                if (m.transitions[k].output == state && --code == 0) return k;
-            return 0xFF;
+            if (pos % 32 + nb > 32) v |= (uint64_t)w[pos / 32 + 1] << 32;
+            return s_rank2tr[state][(int)((v >> (pos % 32)) & ((1u << nb) - 1u))];
+        };
+        auto emit = [&](int tr, int count) -> bool {
+            if (tr == last_t) { out[2 * (n_runs - 1) + 1] += count; return true; }
+            if (n_runs >= J.ops_cap) return false;
+            out[2 * n_runs] = tr; out[2 * n_runs + 1] = count; ++n_runs; last_t = tr;
+            return true;
         };
         int tr = winner(i, j, m.end_state);
         while (tr != 0xFF) {
-            if (tr == last_t) out[2 * (n_runs - 1) + 1] += 1;
-            else if (n_runs < J.ops_cap) { out[2 * n_runs] = tr; out[2 * n_runs + 1] = 1; ++n_runs; last_t = tr; }
-            else { res.status = 4; break; }
-            i -= m.transitions[tr].advance_query;
-            j -= m.transitions[tr].advance_target;
-            if (m.transitions[tr].input == m.start_state) break;
+            if (!emit(tr, 1)) { res.status = 4; break; }
+            const int aq = s_aq[tr], at = s_at[tr], in = s_in[tr];
+            i -= aq;
+            j -= at;
+            if (in == m.start_state) break;
             if (i < 0 || j < 0) { res.status = 4; break; }
-            tr = winner(i, j, m.transitions[tr].input);
+            if (m.transitions[tr].output == in && aq + at > 0) {
+                // a self-loop (an intron, a gap run): the walk is a chain of dependent loads, one per
+                // cell, but while the loop goes on the cells to look at are known in advance -- fetch
+                // eight at a time and consume them in order
+                for (;;) {
+                    int nxt[8], kk = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int ci = i - u * aq, cj = j - u * at;
+                        nxt[u] = (ci >= 0 && cj >= 0) ? winner(ci, cj, in) : 0xFF;
+                    }
+                    while (kk < 8 && nxt[kk] == tr) ++kk;
+                    if (kk) {
+                        if (!emit(tr, kk)) { res.status = 4; break; }
+                        i -= kk * aq;
+                        j -= kk * at;
+                    }
+                    if (kk < 8) {
+                        // the loop ended: cell (i, j) holds another winner (or the lattice edge)
+                        tr = (i >= 0 && j >= 0) ? nxt[kk] : 0xFF;
+                        if (i < 0 || j < 0) res.status = 4;
+                        break;
+                    }
+                }
+                if (res.status) break;
+                continue;   // `tr` is the winner of state `in` at the current cell
+            }
+            tr = winner(i, j, in);
         }
         for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
             const int t0 = out[2 * a], l0 = out[2 * a + 1];
@@ -369,10 +412,16 @@ struct ResidentBuffers {
     std::map<std::pair<const void *, size_t>, void *> map;
     size_t bytes = 0;
 };
+// per-lattice START / END cell tables that already live on the device (batched span fills):
+// host arrays of n device pointers, either may be null
+struct GenDevTables {
+    const int32_t *const *start = nullptr;
+    int32_t *const *end = nullptr;
+};
 int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b_model *model,
                          const c4b_scoring *scoring, int n, const c4b_pair *pairs, bool want_path,
                          GenericBatch **out, const int32_t *start_cells = nullptr, bool end_cells = false,
-                         int sm_count = 0, ResidentBuffers *resident = nullptr);
+                         int sm_count = 0, ResidentBuffers *resident = nullptr, const GenDevTables *dev = nullptr);
 int generic_batch_run(GenericBatch *g, c4b_score threshold);
 int generic_batch_fetch(GenericBatch *g, c4b_result *results, int32_t *ops, int64_t ops_capacity);
 int64_t generic_batch_cells(const GenericBatch *g);

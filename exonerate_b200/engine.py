@@ -22,7 +22,7 @@ EXPORTS = [
     "c4b_batch_cells", "c4b_batch_ops_needed", "c4b_batch_device_results", "c4b_batch_last_fill_ms", "c4b_batch_kernel_name", "c4b_batch_description", "c4b_batch_destroy",
     "c4b_group_create", "c4b_group_destroy", "c4b_group_size", "c4b_group_find_score_batch",
     "c4b_group_find_path_batch", "c4b_group_kernel_launches", "c4b_free",
-    "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise", "c4b_span_integrate",
+    "c4b_viterbi_calculate", "c4b_viterbi_calculate_cells", "c4b_hsp_extend_batch", "c4b_model_specialise", "c4b_span_integrate", "c4b_span_score_batch",
 ]
 
 _lib = None
@@ -405,6 +405,27 @@ class HSPset:
                 h = ext[k]
                 self.hsp_list.append([h.query_start, h.target_start, h.length, h.score, h.cobs])
         return self.hsp_list
+
+
+def span_score_batch(engine, src_model, dst_model, scoring, pairs, src_regions, dst_regions, spans):
+    """c4b_span_score_batch: SAR_Span_find_score (src/bsdp/sar.c:898-917) for a list of span edges.
+    pairs: a PairSet whose lattice k carries the sequences / splice arrays of edge k; src_regions /
+    dst_regions: (query_start, target_start, query_length, target_length); spans: (min_q, max_q, min_t, max_t)."""
+    lib = engine.lib
+    n = pairs.n
+    jobs = (abi.SpanJob * max(n, 1))()
+    for k in range(n):
+        for side, reg in ((jobs[k].src, src_regions[k]), (jobs[k].dst, dst_regions[k])):
+            C.memmove(C.byref(side), C.byref(pairs.array[k]), C.sizeof(abi.Pair))
+            side.query_start, side.target_start, side.query_length, side.target_length = reg
+        for l in range(4):
+            jobs[k].span[l] = spans[k][l]
+    scores = np.zeros(max(n, 1), dtype=np.int32)
+    lib.c4b_span_score_batch.argtypes = [C.c_void_p, C.POINTER(abi.Model), C.POINTER(abi.Model), C.POINTER(abi.Scoring),
+                                         C.c_int32, C.POINTER(abi.SpanJob), C.c_void_p]
+    _check(lib, lib.c4b_span_score_batch(engine.h, C.byref(src_model), C.byref(dst_model), C.byref(scoring), n, jobs,
+                                         scores.ctypes.data), "c4b_span_score_batch")
+    return [int(x) for x in scores[:n]]
 
 
 def span_integrate(engine, src_scores, src_region, dst_region, span):

@@ -372,6 +372,21 @@ int c4b_hsp_extend_batch(c4b_engine *e, const c4b_scoring *scoring, const c4b_hs
 int c4b_span_integrate(c4b_engine *e, const c4b_score *src_scores, const int32_t *src_region,
                        const int32_t *dst_region, const int32_t *span, int32_t *positions);
 
+/* ---- BSDP span edges, batched ------------------------------------------
+ * SAR_Span_find_score (src/bsdp/sar.c:898-917) for n span edges of one heuristic comparison in a
+ * few launches: the src fills (src_model: START at the region's corner, END's cell reported from
+ * every cell, heuristic.c:385-410), Heuristic_Span_integrate (:589-678) and the START table of
+ * Heuristic_Span_dst_init_start_func (:412-443) built on the device from the src END cells, the
+ * dst fills (dst_model: START's cell from that table, END at the corner).  scores[k] = what the
+ * dst Optimal_find_score returns (the caller subtracts the SAR components).  span = {min_query,
+ * max_query, min_target, max_target} (C4_Span, c4.h:160-170). */
+typedef struct {
+    c4b_pair src, dst;
+    int32_t span[4];
+} c4b_span_job;
+int c4b_span_score_batch(c4b_engine *e, const c4b_model *src_model, const c4b_model *dst_model,
+                         const c4b_scoring *scoring, int32_t n, const c4b_span_job *jobs, c4b_score *scores);
+
 /* ---- model specialisation ---------------------------------------------------
  * Device counterpart of the reference's per-model code generation (Viterbi_compile /
  * Codegen, src/c4/viterbi.c:1638-1727, src/c4/codegen.c; archived by the bootstrapper,

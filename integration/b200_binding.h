@@ -53,6 +53,12 @@ typedef struct {
  * (same Viterbi, sequences, region and SubOpt blocked cells).  Dropped when the comparison changes. */
 void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer user_data,
                           SubOpt *subopt);
+/* n span edges of ONE Heuristic_Span (src / dst derived models of src/bsdp/heuristic.c:445-528) on
+ * the current (query, target): what SAR_Span_find_score's dst Optimal_find_score would return,
+ * scores[k], from one c4b_span_score_batch call.  bq/bt lists: the SubOpt blocked cells of each
+ * region at this moment (kept by the caller to validate a later use), as b200_blocked_list returns. */
+void b200_span_scores(gpointer heuristic_span, gint n, Region **src_regions, Region **dst_regions,
+                      gpointer user_data, SubOpt *subopt, C4_Score *scores);
 extern glong b200_stat_score_hits, b200_stat_score_prefetched, b200_stat_score_batches;
 
 extern B200_Replay *b200_replay;

@@ -24,6 +24,7 @@
 #include "match.h"
 #include "splice.h"
 #include "c4b200.h"
+#include "heuristic.h"
 #include "b200_binding.h"
 
 /* ---- options (viterbi.c:27-38): -D/--dpmemory is accepted and ignored -------- */
@@ -745,6 +746,63 @@ void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer u
     g_free(entry);
     g_free(results);
     g_free(pairs);
+    return;
+    }
+
+static void fill_pair_region(c4b_pair *pair, Ungapped_Data *ud, Region *region, gboolean with_splice,
+                             SubOpt *subopt, gint32 **bq, gint32 **bt){
+    register gint k;
+    memset(pair, 0, sizeof(c4b_pair));
+    pair->query = (const uint8_t*)pair_cache.qseq;
+    pair->target = (const uint8_t*)pair_cache.tseq;
+    pair->query_len = ud->query->len;
+    pair->target_len = ud->target->len;
+    pair->query_start = region->query_start;
+    pair->target_start = region->target_start;
+    pair->query_length = region->query_length;
+    pair->target_length = region->target_length;
+    pair->reserved = C4B_PAIR_BUFFERS_STABLE;
+    pair->n_blocked = b200_blocked_list((subopt && subopt->path_count)?subopt:NULL, region, bq, bt);
+    pair->blocked_query_pos = (*bq);
+    pair->blocked_target_pos = (*bt);
+    if(with_splice)
+        for(k = 0; k < 4; k++)
+            pair->splice[k] = pair_cache.splice + (gsize)k*ud->target->len;
+    return;
+    }
+
+void b200_span_scores(gpointer heuristic_span, gint n, Region **src_regions, Region **dst_regions,
+                      gpointer user_data, SubOpt *subopt, C4_Score *scores){
+    register Heuristic_Span *hs = heuristic_span;
+    register Ungapped_Data *ud = user_data;
+    register c4b_model *src_tables = b200_tables_for(hs->src_optimal->find_score),
+                       *dst_tables = b200_tables_for(hs->dst_optimal->find_score);
+    register gboolean with_splice = b200_model_has_splice(src_tables)
+                                 || b200_model_has_splice(dst_tables);
+    register c4b_span_job *jobs = g_new0(c4b_span_job, n);
+    register gint32 **lists = g_new0(gint32*, 4*n);
+    register gint i;
+    c4b_scoring scoring;
+    pair_cache_fetch(ud, with_splice);
+    b200_fill_scoring(ud->mas, &scoring);
+    for(i = 0; i < n; i++){
+        fill_pair_region(&jobs[i].src, ud, src_regions[i], with_splice, subopt,
+                         &lists[4*i], &lists[4*i+1]);
+        fill_pair_region(&jobs[i].dst, ud, dst_regions[i], with_splice, subopt,
+                         &lists[4*i+2], &lists[4*i+3]);
+        jobs[i].span[0] = hs->span->min_query;
+        jobs[i].span[1] = hs->span->max_query;
+        jobs[i].span[2] = hs->span->min_target;
+        jobs[i].span[3] = hs->span->max_target;
+        }
+    if(c4b_span_score_batch(get_engine(), src_tables, dst_tables, &scoring, n, jobs, scores))
+        g_error("libc4b200: %s", c4b_last_error());
+    for(i = 0; i < 4*n; i++)
+        g_free(lists[i]);
+    g_free(lists);
+    g_free(jobs);
+    b200_stat_score_prefetched += 2*n;
+    b200_stat_score_batches++;
     return;
     }
 

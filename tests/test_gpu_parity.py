@@ -911,6 +911,59 @@ def test_cell_callback_tables_vs_oracle(eng, params, scoring, name):
         assert plain["score"] == ref["score"] and plain["ops"] == ref["ops"]
 
 
+@pytest.mark.parametrize("name", ["est2genome", "affine_local_dna", "protein2genome"])
+def test_span_score_batch_vs_oracle(eng, params, scoring, name, monkeypatch):
+    """c4b_span_score_batch = SAR_Span_find_score for many span edges at once: src fill with END's
+    cell reported from every cell, Heuristic_Span_integrate, the START table of
+    Heuristic_Span_dst_init_start_func, dst fill -- against the same pipeline on the oracle
+    (c4o_viterbi_cells + c4o_span_integrate), interpreter and specialised kernels."""
+    from exonerate_b200 import PairSet
+    import test_span_oracle
+    from exonerate_b200.engine import span_score_batch
+    from exonerate_b200.models import splice_arrays
+    model, _ = helpers.load_model(name, params)
+    C_ = 1 + model.n_shadow_slots
+    rng = random.Random(41)
+    qs, ts, sp, sreg, dreg, spans, want = [], [], [], [], [], [], []
+    for k in range(14):
+        ql, tl = rng.choice([60, 90, 140]), rng.choice([400, 700, 1200])
+        if name == "protein2genome":
+            q, _t = helpers.protein_pair(6100 + k, ql, 30)
+            t = helpers.rand_dna(random.Random(k), tl)
+        else:
+            q, t = helpers.gene_pair(6000 + k, ql, tl, n_exons=2) if name == "est2genome" else helpers.dna_pair(6000 + k, ql, tl)
+        s_ = splice_arrays(t) if name in ("est2genome", "protein2genome") else None
+        # a src box near the start, a dst box further along the target, overlapping in the query
+        sq, st = rng.randrange(0, 10), rng.randrange(0, 40)
+        sl, stl = rng.randrange(12, 30), rng.randrange(20, 70)
+        dq, dt = sq + rng.randrange(0, sl), st + stl + rng.randrange(0, 200)
+        dl, dtl = rng.randrange(10, min(28, len(q) - dq)), rng.randrange(20, min(70, len(t) - dt))
+        span = (0, rng.choice([0, 0, 5]), rng.choice([0, 20]), rng.choice([100, 200000]))
+        qs.append(q); ts.append(t); sp.append(s_)
+        sreg.append((sq, st, sl, stl)); dreg.append((dq, dt, dl, dtl)); spans.append(span)
+        # the oracle pipeline
+        src_end = np.full(((sl + 1) * (stl + 1), C_), 0, dtype=np.int32)
+        src_end[:, 0] = abi.IMPOSSIBLY_LOW_SCORE     # Heuristic_Span_clear
+        helpers.oracle_viterbi_cells(model, scoring, helpers.PairBuf(q, t, splice=s_, region=sreg[-1]),
+                                     abi.MODE_FIND_SCORE, None, src_end)
+        pos = test_span_oracle.oracle_span_integrate({"src_scores": src_end[:, 0].tolist(), "src_region": sreg[-1],
+                                                      "dst_region": dreg[-1], "span": span})
+        start = np.zeros(((dl + 1) * (dtl + 1), C_), dtype=np.int32)
+        start[:, 0] = abi.IMPOSSIBLY_LOW_SCORE
+        for c in range((dl + 1) * (dtl + 1)):
+            if pos[2 * c] >= 0:
+                start[c] = src_end[(pos[2 * c] - sq) * (stl + 1) + (pos[2 * c + 1] - st)]
+        w = helpers.oracle_viterbi_cells(model, scoring, helpers.PairBuf(q, t, splice=s_, region=dreg[-1]),
+                                         abi.MODE_FIND_SCORE, start, None)
+        want.append(w["score"])
+    pairs = PairSet(qs, ts, splice=sp)
+    for jit in ("0", "1"):
+        monkeypatch.setenv("C4B_GENERIC_JIT", jit)
+        got = span_score_batch(eng, model, model, scoring, pairs, sreg, dreg, spans)
+        assert got == want, (name, jit)
+    assert len(set(want)) > 3
+
+
 def test_span_integrate_golden(eng):
     """c4b_span_integrate against the vectors the unmodified Heuristic_Span_integrate produced
     (tests/golden/make_span_golden.py): every dst cell's source position, ties and empty
