@@ -417,7 +417,12 @@ def run_workload(job, eng, model_name, n, qlen, tlen, steps, warmup, sample_cloc
         splice = [splice_arrays(targets[k]) for k in range(n)]   # host C splice predictor (csrc/host/splice.c)
     if model_name == "protein2genome":
         os.environ.setdefault("C4B_GENERIC_JIT", "1")  # the batch is below the auto-specialise size
-    pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)], splice=splice)
+    # the step's inputs live in pinned host memory (bench contract): the engine DMAs straight from it
+    pin = [torch.empty(a.shape, dtype=torch.uint8, pin_memory=True) for a in (queries, targets)]
+    for t_, a in zip(pin, (queries, targets)):
+        t_.numpy()[...] = a
+    queries, targets = pin[0].numpy(), pin[1].numpy()
+    pairs = PairSet([queries[k] for k in range(n)], [targets[k] for k in range(n)], splice=splice, pinned=True)
     opt = Optimal(eng, model, scoring)
     shards = [np.arange(r * n, (r + 1) * n) for r in range(job.world)]
 
@@ -457,7 +462,7 @@ def run_workload(job, eng, model_name, n, qlen, tlen, steps, warmup, sample_cloc
     batch.close()
     out = {"n": n, "cells": pairs.cells, "dev_ms": dev_ms, "fill_ms": float(np.mean(fill_ms)), "launches": launches,
            "clock_lines": lines, "results": results, "ops": ops, "queries": queries, "targets": targets,
-           "pairs": pairs, "n_ops_total": int(need), "kernel_name": kernel_name, "route": route, "e2e_ms": None}
+           "pairs": pairs, "n_ops_total": int(need), "kernel_name": kernel_name, "route": route, "e2e_ms": None, "_pinned": pin}
 
     # ---- end-to-end arm: host buffers in, host results out, every step ----
     if want_e2e:
@@ -596,8 +601,16 @@ def ours(args):
         # strong scaling: north_star's FIXED batches split over the ranks
         for name, tot in (("affine:local", 10000), ("est2genome", 1000)):
             WW = WORKLOADS[name]
-            x = run_workload(job, eng, name, max(1, tot // world), WW.get("qlen", 1000), WW.get("tlen", 100000),
-                             steps=3, warmup=2)
+            if world == 1 and name == args.model and n == tot and not strong:
+                x = w   # at N=1 the fixed batch IS the main workload: same numbers, not measured twice
+            elif world == 1 and name in extra and WW["pairs"] == tot:
+                strong_block[name] = {"pairs_total": tot, "pairs_per_gpu": tot, "value": extra[name]["value"],
+                                      "e2e": extra[name]["e2e"], "unit": "GCUPS",
+                                      "ms_per_step": extra[name]["ms_per_step"]}
+                continue
+            else:
+                x = run_workload(job, eng, name, max(1, tot // world), WW.get("qlen", 1000), WW.get("tlen", 100000),
+                                 steps=3, warmup=2)
             strong_block[name] = {"pairs_total": (tot // world) * world, "pairs_per_gpu": tot // world,
                                   "value": x["value"], "e2e": x["e2e_value"], "unit": "GCUPS",
                                   "ms_per_step": x["dev_ms"]}

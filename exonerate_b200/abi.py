@@ -50,6 +50,9 @@ class Scoring(C.Structure):
                 ("min_intron", C.c_int32), ("max_intron", C.c_int32)]
 
 
+PAIR_BUFFERS_STABLE, PAIR_BUFFERS_PINNED = 1, 2
+
+
 class Pair(C.Structure):
     _fields_ = [("query", C.c_void_p), ("target", C.c_void_p),
                 ("query_len", C.c_int32), ("target_len", C.c_int32),

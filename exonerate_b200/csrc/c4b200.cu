@@ -719,8 +719,10 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         // (profiles/r02_strong_sweep.md, 1 kbp x 100 kbp, score pass GCUPS packed -> folded):
         // 1250 lattices 2302 -> 2847, 2500 3227 -> 3525, 3552 3646 -> 4135, 5000 3352 -> 3860,
         // 7104 3678 -> 4020, 10000 4417 -> 4282: folded up to 2.4 full waves of packed CTAs.
+        // (queries of up to 511 rows fold to 8 rows per lane, where the per-step overhead weighs more:
+        // folded only below one packed wave -- 512 x 100 kbp, 7812 lattices: 2293 packed vs 2084 folded)
         b->p16_fold = b->p16_unsigned && !b->p16_multi && b->R >= 16 && b->n16 > 0 &&
-                      (int64_t)(b->n16 + 1) / 2 * 10 < (int64_t)e->sm_count * 12 * 24;
+                      (int64_t)(b->n16 + 1) / 2 * 10 < (int64_t)e->sm_count * 12 * (b->R == 32 ? 24 : 10);
         if (const char *env = getenv("C4B_P16_FOLD"))
             b->p16_fold = b->p16_unsigned && !b->p16_multi && b->R >= 16 && b->n16 > 0 && atoi(env) != 0;
         // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
@@ -1034,38 +1036,73 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     // copy, DMA and the fill overlap.
     cudaStream_t cs = e->copy_stream;
     C4B_CUDA(cudaStreamWaitEvent(cs, b->ev_base, 0));
-    if (e->stage_free) C4B_CUDA(cudaEventSynchronize(e->stage_free));  // previous batch done reading
-    if (e->h_stage_cap < stage_bytes) {
-        if (e->h_stage) cudaFreeHost(e->h_stage);
-        e->h_stage = nullptr;
-        e->h_stage_cap = 0;
-        C4B_CUDA(cudaMallocHost(&e->h_stage, stage_bytes + stage_bytes / 8));
-        e->h_stage_cap = stage_bytes + stage_bytes / 8;
+    // Callers whose sequence buffers are page-locked (C4B_PAIR_BUFFERS_PINNED on every pair) skip
+    // the bounce buffer: the DMA reads their memory directly.  Runs of equally long sequences at a
+    // constant stride (rows of one array, the usual case) go as ONE 2-D copy each.
+    bool pinned = n > 0;
+    for (int p = 0; p < n && pinned; ++p) pinned = (pairs[p].reserved & C4B_PAIR_BUFFERS_PINNED) != 0;
+    uint8_t *h_seq = nullptr;
+    if (!pinned) {
+        if (e->stage_free) C4B_CUDA(cudaEventSynchronize(e->stage_free));  // previous batch done reading
+        if (e->h_stage_cap < stage_bytes) {
+            if (e->h_stage) cudaFreeHost(e->h_stage);
+            e->h_stage = nullptr;
+            e->h_stage_cap = 0;
+            C4B_CUDA(cudaMallocHost(&e->h_stage, stage_bytes + stage_bytes / 8));
+            e->h_stage_cap = stage_bytes + stage_bytes / 8;
+        }
+        h_seq = e->h_stage;
+        memset(h_seq + qbytes + tbytes, tfill, 64);
+    } else {
+        C4B_CUDA(cudaMemsetAsync(b->d_seq.p + qbytes + tbytes, tfill, 64, cs));
     }
-    uint8_t *h_seq = e->h_stage;
-    memset(h_seq + qbytes + tbytes, tfill, 64);
     const unsigned hw = host_threads();
     size_t next_group = 0;
     for (size_t si = 0; si < slices.size(); ++si) {
         const Slice &S = slices[si];
         const size_t bytes = S.hi - S.lo;
-        const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
-        auto work = [&](unsigned t) {
-            for (size_t k = S.j0 + t; k < S.j1; k += nt) {
-                const CopyJob &c = jobs[k];
-                memcpy(h_seq + c.dst, c.src, c.len);
-                memset(h_seq + c.dst + c.len, c.fill, c.slot - c.len);
+        if (pinned) {
+            // slot padding first (the encode kernels read whole slots), then the sequences
+            const size_t qhi_ = std::min(S.hi, qbytes), tlo_ = std::max(S.lo, qbytes);
+            if (S.lo < qhi_) C4B_CUDA(cudaMemsetAsync(b->d_seq.p + S.lo, qfill, qhi_ - S.lo, cs));
+            if (tlo_ < S.hi) C4B_CUDA(cudaMemsetAsync(b->d_seq.p + tlo_, tfill, S.hi - tlo_, cs));
+            for (size_t k = S.j0; k < S.j1;) {
+                size_t run = 1;
+                if (k + 1 < S.j1 && jobs[k + 1].len == jobs[k].len && jobs[k + 1].slot == jobs[k].slot &&
+                    jobs[k + 1].src > jobs[k].src) {
+                    const size_t stride = (size_t)(jobs[k + 1].src - jobs[k].src);
+                    while (k + run < S.j1 && jobs[k + run].len == jobs[k].len && jobs[k + run].slot == jobs[k].slot &&
+                           jobs[k + run].src == jobs[k].src + run * stride && jobs[k + run].dst == jobs[k].dst + run * jobs[k].slot)
+                        ++run;
+                    if (run > 1 && stride >= jobs[k].len && jobs[k].len > 0)
+                        C4B_CUDA(cudaMemcpy2DAsync(b->d_seq.p + jobs[k].dst, jobs[k].slot, jobs[k].src, stride, jobs[k].len,
+                                                   run, cudaMemcpyHostToDevice, cs));
+                    else
+                        run = 1;
+                }
+                if (run == 1 && jobs[k].len)
+                    C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + jobs[k].dst, jobs[k].src, jobs[k].len, cudaMemcpyHostToDevice, cs));
+                k += run;
             }
-        };
-        if (nt <= 1) {
-            work(0);
         } else {
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto &x : th) x.join();
+            const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
+            auto work = [&](unsigned t) {
+                for (size_t k = S.j0 + t; k < S.j1; k += nt) {
+                    const CopyJob &c = jobs[k];
+                    memcpy(h_seq + c.dst, c.src, c.len);
+                    memset(h_seq + c.dst + c.len, c.fill, c.slot - c.len);
+                }
+            };
+            if (nt <= 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th) x.join();
+            }
+            C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + S.lo, h_seq + S.lo, bytes, cudaMemcpyHostToDevice, cs));
         }
-        C4B_CUDA(cudaMemcpyAsync(b->d_seq.p + S.lo, h_seq + S.lo, bytes, cudaMemcpyHostToDevice, cs));
         // encode [lo, hi): the part inside the query region with the query LUT, the rest
         // with the target LUT (slots are multiples of 16 bytes, so is every boundary)
         const size_t qhi = std::min(S.hi, qbytes);
@@ -1093,8 +1130,10 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
     }
     b->pass1_inflight = true;
     tmark("create: all slices staged, pass 1 queued");
-    if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
-    C4B_CUDA(cudaEventRecord(e->stage_free, cs));
+    if (!pinned) {
+        if (!e->stage_free) C4B_CUDA(cudaEventCreateWithFlags(&e->stage_free, cudaEventDisableTiming));
+        C4B_CUDA(cudaEventRecord(e->stage_free, cs));
+    }
     b->kernel_name = "affine_systolic";
     {
         char buf[512];

@@ -109,7 +109,10 @@ def _check(lib, rc, what):
 class PairSet:
     """n query x target lattices as a contiguous c4b_pair array (host buffers)."""
 
-    def __init__(self, queries, targets, splice=None, blocked=None, regions=None):
+    def __init__(self, queries, targets, splice=None, blocked=None, regions=None, pinned=False):
+        """pinned=True: the caller guarantees that every sequence buffer (numpy arrays, used in place)
+        lives in page-locked memory -- e.g. rows of torch.empty(..., pin_memory=True).numpy() -- and
+        stays valid until the batch has been fetched (C4B_PAIR_BUFFERS_PINNED)."""
         assert len(queries) == len(targets)
         n = len(queries)
         self.n = n
@@ -136,6 +139,9 @@ class PairSet:
             p.query_len, p.target_len = len(q), len(t)
             reg = regions[k] if regions else (0, 0, len(q), len(t))
             p.query_start, p.target_start, p.query_length, p.target_length = reg
+            if pinned:
+                assert isinstance(queries[k], np.ndarray) and isinstance(targets[k], np.ndarray)
+                p.reserved |= abi.PAIR_BUFFERS_PINNED
             if splice and splice[k] is not None:
                 arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in splice[k]]
                 self._keep.append(arrs)

@@ -175,6 +175,12 @@ typedef struct {
  * thousands of small region fills on one (query, target) (src/bsdp/sar.c): each fill then
  * uploads its own descriptors only.  Blocked-cell lists are per call and never kept. */
 #define C4B_PAIR_BUFFERS_STABLE 1
+/* c4b_pair.reserved bit: the query and target buffers are page-locked host memory (cudaHostAlloc /
+ * cudaHostRegister, e.g. a pinned framework tensor).  When EVERY pair of an affine-family batch
+ * says so, the engine DMAs straight from them instead of copying through its own pinned bounce
+ * buffer (equally long sequences at a constant stride -- rows of one array -- as one 2-D copy).
+ * The buffers must stay valid until the batch has been fetched. */
+#define C4B_PAIR_BUFFERS_PINNED 2
 
 /* Result of one lattice.  Coordinates are SEQUENCE coordinates like
  * Alignment.region (src/c4/alignment.h:39-45); ops index into ops[] buffers as

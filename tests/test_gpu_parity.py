@@ -584,6 +584,32 @@ def test_subopt_mixed_batch_and_regions(eng, params, scoring):
     _subopt_series(opt, model, scoring, q, t, 3, region=(20, 300, 350, 4500))
 
 
+def test_pinned_caller_buffers_skip_the_bounce(eng, params, scoring):
+    """C4B_PAIR_BUFFERS_PINNED: sequences in page-locked caller memory are DMA'd directly -- rows of
+    one array as 2-D copies, ragged buffers one by one -- with the same results as the bounce path."""
+    import torch
+    from exonerate_b200 import Optimal, PairSet
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    n, ql, tl = 40, 300, 5000
+    tq = torch.empty((n, ql), dtype=torch.uint8, pin_memory=True)
+    tt = torch.empty((n, tl), dtype=torch.uint8, pin_memory=True)
+    for k in range(n):
+        q, t = helpers.dna_pair(9500 + k, ql, tl)
+        tq.numpy()[k] = np.frombuffer(q.encode(), dtype=np.uint8)
+        tt.numpy()[k] = np.frombuffer(t.encode(), dtype=np.uint8)
+    rows_q, rows_t = [tq.numpy()[k] for k in range(n)], [tt.numpy()[k] for k in range(n)]
+    want = opt.find_path(PairSet(rows_q, rows_t))
+    assert opt.find_path(PairSet(rows_q, rows_t, pinned=True)) == want
+    # ragged: views of different lengths into the same pinned arrays, shuffled order
+    order = list(range(n))
+    random.Random(3).shuffle(order)
+    rq = [tq.numpy()[k][: 100 + 5 * k] for k in order]
+    rt = [tt.numpy()[k][: 2000 + 70 * k] for k in order]
+    assert opt.find_path(PairSet(rq, rt, pinned=True)) == opt.find_path(PairSet(rq, rt))
+    assert opt.find_score(PairSet(rq, rt, pinned=True)) == [w["score"] for w in opt.find_path(PairSet(rq, rt))]
+
+
 def test_device_group_shards_and_merges(eng, params, scoring):
     """c4b_group: the batch is dealt to the group's engines by cost, the shards run on one host
     thread per engine, results and op lists come back in pair order -- identical to one engine.
@@ -727,6 +753,42 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel
     check(list(range(len(qs))))
     for k in range(len(E2G_SHAPES)):
         check([k])
+
+
+def test_est2genome_intron_gain_leaves_the_packed_kernel(eng, params, scoring):
+    """--intronpenalty 0 (accepted by the reference, intron.c:35): an intron then GAINS score at good
+    splice sites, introns chain without consuming query and values are no longer bounded by the
+    16-bit argument -- the batch must leave the packed kernel and still be exact."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    base, _ = helpers.load_model("est2genome", params)
+    model = type(base).from_buffer_copy(base)
+    n_pre = 0
+    for k in range(model.n_calcs):
+        if model.calcs[k].kind == abi.CALC_SPLICE_PRE:
+            model.calcs[k].param[0] = 0
+            n_pre += 1
+    assert n_pre >= 2
+    qs, ts = [], []
+    for k, (ql, tl) in enumerate([(120, 1500), (300, 2500), (700, 4000)]):
+        q, t = helpers.gene_pair(9100 + k, ql, tl, n_exons=3, rate=0.02, reverse=bool(k & 1))
+        qs.append(q)
+        ts.append(t)
+    sp = [splice_arrays(t) for t in ts]
+    pairs = PairSet(qs, ts, splice=sp)
+    b = Batch(eng, model, scoring, pairs, want_path=True)
+    assert b.kernel_name != "e2g_packed16"
+    b.close()
+    opt = Optimal(eng, model, scoring)
+    scores, paths = opt.find_score(pairs), opt.find_path(pairs)
+    for k in range(pairs.n):
+        want = e2g_oracle(model, scoring, qs[k], ts[k], sp[k])
+        assert scores[k] == want["score"] and paths[k]["score"] == want["score"], k
+        assert paths[k]["region"] == want["region"] and paths[k]["ops"] == want["ops"], k
+    # the default penalty keeps the packed kernel
+    b = Batch(eng, base, scoring, pairs, want_path=True)
+    assert b.kernel_name == "e2g_packed16"
+    b.close()
 
 
 def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkeypatch):
