@@ -1477,13 +1477,17 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
         const SysLayout L = jit_sys_layout(*model, mode, mode == GEN_REGION);
         if (L.ok && !(env && atoi(env) == 0)) {
             // (for the strip counts of queries that fill cta_threads rows of the thread-per-row kernel)
-            const std::string src = jit_sys_program_source(*model, mode, mode == GEN_REGION, L,
-                                                           jit_sys_warps(L, cta_threads - 1));
-            if (!jit_compile(src, &cubin, &log)) {
-                set_error("systolic model specialisation failed: " + log);
-                return -1;
+            // + the column-window variants: checkpointing score pass / PATH over one window
+            for (int win = 0; win < 3; ++win) {
+                if ((win == 1 && mode != GEN_SCORE) || (win == 2 && mode != GEN_PATH)) continue;
+                const std::string src = jit_sys_program_source(*model, mode, mode == GEN_REGION, L,
+                                                               jit_sys_warps(L, cta_threads - 1), win);
+                if (!jit_compile(src, &cubin, &log)) {
+                    set_error("systolic model specialisation failed: " + log);
+                    return -1;
+                }
+                jit_store(jit_cache_path(src), cubin);
             }
-            jit_store(jit_cache_path(src), cubin);
         }
     }
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();

@@ -136,6 +136,7 @@ struct E2gBatch {
     DevBuf<E2pPair> d_pairs16;
     DevBuf<uint2> d_top;              // sweep hand-off rows (packed path, queries longer than 511)
     int max_query = 0;
+    int rows16 = kE2pR;               // rows per lane of the packed kernels (8 for small batches), all layouts
     bool windowed = false;            // find_path by checkpoints + window refills (e2g_packed16.cuh)
     DevBuf<uint32_t> d_ck;
     DevBuf<E2pWalk> d_walk;
@@ -229,6 +230,18 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     b->max_target = maxT;
     b->max_query = maxQ;
     b->warps = std::max(1, (maxQ + 1 + 32 * kE2gR - 1) / (32 * kE2gR));
+    // Rows per lane of the packed kernels.  A batch that cannot give every scheduler a warp at 16 rows
+    // per lane (one warp per 512-row sweep: 125 lattices of a 1 kbp cDNA are 250 warps for 592
+    // schedulers) runs 8 rows per lane instead: twice the sweeps, each on its own pipelined warp.
+    {
+        const int sweeps16 = (maxQ + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+        const int sweeps8 = (maxQ + 1 + 32 * 8 - 1) / (32 * 8);
+        // (measured, 1 kbp x 100 kbp find_path GCUPS, 16 rows one warp -> 8 rows four warps: 125 lattices
+        // 107 -> 183+, 250 210 -> 315+, 500 413 -> 447+, 1000 559 -> 540: profiles/r02_e2g_small.md)
+        b->rows16 = ((int64_t)n * sweeps16 <= 1400 && sweeps8 > sweeps16) ? 8 : kE2pR;
+        if (const char *env = getenv("C4B_E2G_ROWS")) b->rows16 = (atoi(env) == 8) ? 8 : kE2pR;
+    }
+    const int RW = b->rows16;
     // ---- staging: region slices of query / target, packed splice words ---------------
     std::vector<size_t> qoff(n), toff(n);
     size_t qbytes = 0, tbytes = 0;
@@ -350,13 +363,13 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         const char *env = getenv("C4B_E2G_WINDOWS");
         size_t max_sweeps = 1;
         for (int p = 0; p < n; ++p) {
-            const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+            const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * RW - 1) / (32 * RW);
             const size_t nwin = (size_t)pairs[p].target_length / kE2pWin + 1;
             max_sweeps = std::max(max_sweeps, sweeps);
             ck_off[p] = ck_words;
-            ck_words += (nwin - 1) * sweeps * 32 * kE2pR * kE2pCkWords;
+            ck_words += (nwin - 1) * sweeps * 32 * RW * kE2pCkWords;
         }
-        b->win_stride = max_sweeps * kE2pWinSteps * 32 * kE2pR;
+        b->win_stride = max_sweeps * kE2pWinSteps * 32 * RW;
         const size_t need = ck_words * 4 + (size_t)n * b->win_stride * 2;
         b->windowed = !(env && atoi(env) == 0) && need / 2 < budget_hw;
     }
@@ -365,9 +378,9 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         int begin = 0;
         for (int k = 0; k < n; ++k) {
             const c4b_pair &pp = pairs[b->order[k]];
-            const size_t sweeps = ((size_t)pp.query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+            const size_t sweeps = ((size_t)pp.query_length + 1 + 32 * RW - 1) / (32 * RW);
             const size_t hw = b->windowed ? 0
-                              : packed ? align_up(sweeps * (pp.target_length + 32) * 32 * kE2pR, 16)
+                              : packed ? align_up(sweeps * (pp.target_length + 32) * 32 * RW, 16)
                                        : align_up((size_t)b->warps * (pp.target_length + 32) * 32 * kE2gR, 16);
             if (hw > budget_hw) {
                 set_error("traceback of pair " + std::to_string(b->order[k]) + " exceeds the device memory budget");
@@ -399,8 +412,8 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     size_t top_elems = 0;
     if (packed) {
         for (int p = 0; p < n; ++p)
-            if (pairs[p].query_length + 1 > 32 * kE2pR) {
-                const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+            if (pairs[p].query_length + 1 > 32 * RW) {
+                const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * RW - 1) / (32 * RW);
                 top_off[p] = top_elems;
                 top_elems += (sweeps - 1) * ((size_t)pairs[p].target_length + 1);
             }
@@ -484,26 +497,39 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     return 0;
 }
 
+// the packed fill kernel for a batch's rows per lane / warps per lattice
+template <int MODE>
+static void e2p_launch(int rows, int warps, int grid, cudaStream_t st, const E2pPair *pairs, E2gOut *outs,
+                       const E2gModel &mdl, const uint2 *xtab, const int32_t *active, const E2pWalk *walk,
+                       uint16_t *winbuf, size_t win_stride) {
+    const int threads = 32 * warps;
+    if constexpr (MODE == E2P_FULL_TB) warps = 1;   // (the whole-lattice record pass is one warp per lattice)
+    if (rows == 8) {
+        if (warps > 1) e2g_fill16_kernel<MODE, true, 8><<<grid, threads, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+        else e2g_fill16_kernel<MODE, false, 8><<<grid, 32, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+    } else {
+        if (warps > 1) e2g_fill16_kernel<MODE, true, kE2pR><<<grid, threads, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+        else e2g_fill16_kernel<MODE, false, kE2pR><<<grid, 32, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+    }
+}
+
 static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
     cudaStream_t st = b->stream;
     const int n = b->n;
     const int threads = 32 * b->warps;
-    // packed kernel: small batches run the 512-row sweeps of a lattice on pipelined warps (the
-    // one-warp kernel otherwise: see e2g_packed16.cuh for the measurements; C4B_E2G_WARPS overrides)
-    int warps16 = std::max(1, std::min(kE2pMaxWarps, (b->max_query + 1 + 32 * kE2pR - 1) / (32 * kE2pR)));
-    if (n > 600) warps16 = 1;
-    if (const char *env = getenv("C4B_E2G_WARPS"))
-        warps16 = std::max(1, std::min(std::min(kE2pMaxWarps, (b->max_query + 1 + 32 * kE2pR - 1) / (32 * kE2pR)), atoi(env)));
-    const int threads16 = 32 * warps16;
+    // packed kernel: small batches run the sweeps of a lattice on pipelined warps (the one-warp kernel
+    // otherwise: see e2g_packed16.cuh for the measurements; C4B_E2G_WARPS / C4B_E2G_ROWS override)
+    const int RW = b->rows16;
+    const int sweeps16 = (b->max_query + 1 + 32 * RW - 1) / (32 * RW);
+    int warps16 = (RW == 8) ? std::max(1, std::min(kE2pMaxWarps, sweeps16)) : 1;
+    if (const char *env = getenv("C4B_E2G_WARPS")) warps16 = std::max(1, std::min(std::min(kE2pMaxWarps, sweeps16), atoi(env)));
+    // window refills: the sweeps of a refill are independent (hand-off rows kept from pass 1)
+    const int warps_win = (RW == 8) ? warps16 : 1;
     C4B_CUDA(cudaEventRecord(b->ev_a, st));
     if (b->packed) {
         if (!b->want_path) {
-            if (warps16 > 1)
-                e2g_fill16_kernel<E2P_SCORE, true><<<n, threads16, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl,
-                                                                            b->d_xtab.p, nullptr, nullptr, nullptr, 0);
-            else
-                e2g_fill16_kernel<E2P_SCORE><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
-                                                               nullptr, nullptr, 0);
+            e2p_launch<E2P_SCORE>(RW, warps16, n, st, b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr, nullptr,
+                                  nullptr, 0);
             C4B_CUDA(cudaGetLastError());
             C4B_CUDA(cudaEventRecord(b->ev_b, st));
             e2g16_score_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_qorg.p,
@@ -515,12 +541,8 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
         if (b->windowed) {
             // pass 1: END cell + column checkpoints; then rounds of (refill the window under
             // each traceback cursor, walk it) until every cursor has reached START
-            if (warps16 > 1)
-                e2g_fill16_kernel<E2P_SCORE_CK, true><<<n, threads16, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl,
-                                                                               b->d_xtab.p, nullptr, nullptr, nullptr, 0);
-            else
-                e2g_fill16_kernel<E2P_SCORE_CK><<<n, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
-                                                                  nullptr, nullptr, nullptr, 0);
+            e2p_launch<E2P_SCORE_CK>(RW, warps16, n, st, b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
+                                     nullptr, nullptr, 0);
             e2g16_walk_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n, b->mdl,
                                                                    threshold, b->d_walk.p, b->d_ops_slots.p);
             e2g16_walk_rejected_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, n,
@@ -540,12 +562,11 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
                     set_error("internal: est2genome windowed traceback did not terminate");
                     return -1;
                 }
-                e2g_fill16_kernel<E2P_WINDOW_TB><<<cnt, 32, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
-                                                                   b->d_active.p, b->d_walk.p, b->d_win.p,
-                                                                   b->win_stride);
+                e2p_launch<E2P_WINDOW_TB>(RW, warps_win, cnt, st, b->d_pairs16.p, b->d_outs.p, b->mdl, b->d_xtab.p,
+                                          b->d_active.p, b->d_walk.p, b->d_win.p, b->win_stride);
                 e2g16_walk_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p, b->d_active.p,
                                                                  cnt, b->mdl, b->d_walk.p, b->d_win.p, b->win_stride,
-                                                                 b->d_results.p, b->d_ops_slots.p);
+                                                                 b->d_results.p, b->d_ops_slots.p, RW);
                 (*b->launches) += 2;
                 C4B_CUDA(cudaGetLastError());
             }
@@ -559,12 +580,12 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
         }
         for (const Chunk &c : b->chunks) {
             const int cnt = c.end - c.begin;
-            e2g_fill16_kernel<E2P_FULL_TB><<<cnt, 32, 0, st>>>(b->d_pairs16.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p,
-                                                             nullptr, nullptr, nullptr, 0);
+            e2p_launch<E2P_FULL_TB>(RW, 1, cnt, st, b->d_pairs16.p + c.begin, b->d_outs.p, b->mdl, b->d_xtab.p, nullptr,
+                                    nullptr, nullptr, 0);
             C4B_CUDA(cudaGetLastError());
             e2g16_traceback_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(b->d_pairs16.p, b->d_outs.p, b->d_jobs.p + c.begin,
                                                                   cnt, b->mdl, threshold, b->d_results.p,
-                                                                  b->d_ops_slots.p);
+                                                                  b->d_ops_slots.p, RW);
             C4B_CUDA(cudaGetLastError());
             (*b->launches) += 2;
         }

@@ -84,12 +84,19 @@ constexpr int kE2pMaxWarps = 4;
 // PIPE = false is the one-warp kernel exactly as before (W folds to 1 at compile time): measured on
 // the B200, the pipelined form wins only while the batch leaves warp slots empty (find_path GCUPS,
 // one warp -> pipelined: 125 lattices 86 -> 118, 500 336 -> 350, 1000 487 -> 369, 4000 597 -> 452).
-template <int MODE, bool PIPE = false>
+//
+// RR = rows per lane.  16 (512-row sweeps) is the loaded-GPU shape.  8 (256-row sweeps) exists for
+// SMALL batches: a 1 kbp cDNA becomes four sweeps on four pipelined warps, and -- because the sweeps
+// of a window refill read the hand-off rows pass 1 left in L2 -- the window refills of a lattice run
+// on independent warps as well.  All record / checkpoint layouts are [..][lane][RR]: one batch uses
+// one RR throughout (E2gBatch::rows16).
+template <int MODE, bool PIPE = false, int RR = kE2pR>
 __global__ void __launch_bounds__(PIPE ? 32 * kE2pMaxWarps : 32)
 e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, const E2gModel mdl,
                   const uint2 *__restrict__ score_table, const int32_t *__restrict__ active,
                   const E2pWalk *__restrict__ walk, uint16_t *__restrict__ winbuf, size_t win_stride) {
-    constexpr int R = kE2pR;
+    constexpr int R = RR;
+    static_assert(R == 8 || R == 16, "records are stored as uint4 groups of 8 rows");
     constexpr bool TB = (MODE == E2P_FULL_TB || MODE == E2P_WINDOW_TB);
     constexpr bool WIN = (MODE == E2P_WINDOW_TB);
     constexpr bool CK = (MODE == E2P_SCORE_CK);
@@ -138,7 +145,8 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         // END bookkeeping is per warp: an earlier sweep OF THIS WARP may hold a tie at a larger column
         const bool later_mine = (sweep != warp);
         // the sweep above may still be running on another warp
-        const bool piped = PIPE && later_sweep && W > 1;
+        // (a window refill never waits: its hand-off rows are the ones pass 1 kept)
+        const bool piped = PIPE && !WIN && later_sweep && W > 1;
         const int wp = (sweep - 1) % W;
         const long long in_base = (long long)(sweep - 1) * (T + 1);
         long long avail = 0;
@@ -189,12 +197,20 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         int in_code = kTargetNone, code0 = (c0 >= 1) ? (int)P.t[c0 - 1] : kTargetNone;
         uint32_t in_sp = 0u, sp0 = (c0 >= 2) ? P.sp[c0 - 2] : 0u;
         uint2 top0v = make_uint2(kNeg16x2, kNeg16x2);
+        // hand-off columns fetched ahead of their step: a step of 8 rows is shorter than an L2 round
+        // trip, so the 8-row shape keeps the next PF columns in flight (tq = columns s+1 .. s+PF-1)
+        constexpr int PF = (R == 8) ? 4 : 1;
+        uint2 tq[PF > 1 ? PF - 1 : 1];
         // diagonal input of my first row at column c0: G of the row above at column c0-1
         if (WIN && ck_in && lane > 0)
             topGprev = ck_in[((size_t)(sweep * 32 + lane - 1) * R + (R - 1)) * kE2pCkWords + 0];
         if (later_sweep) {
-            if (piped) wait_column(c0);
+            if (piped) wait_column(min(c0 + PF - 1, T));
             top0v = PIPE ? __ldcg(top_in + c0) : top_in[c0];
+#pragma unroll
+            for (int k = 0; k < PF - 1; ++k)
+                tq[k] = (c0 + 1 + k <= T) ? (PIPE ? __ldcg(top_in + c0 + 1 + k) : top_in[c0 + 1 + k])
+                                          : make_uint2(kNeg16x2, kNeg16x2);
             if (c0 >= 1 && lane == 0) topGprev = top_in[c0 - 1].x;
         }
         uint4 *tbp = nullptr;
@@ -212,8 +228,19 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 code0 = (int)P.t[s];
                 sp0 = (s >= 1) ? P.sp[s - 1] : 0u;   // source column (s+1)-2
                 if (later_sweep) {
-                    if (piped) wait_column(s + 1);
-                    top0v = PIPE ? __ldcg(top_in + s + 1) : top_in[s + 1];
+                    uint2 nv = make_uint2(kNeg16x2, kNeg16x2);
+                    if (s + PF <= T) {
+                        if (piped) wait_column(s + PF);
+                        nv = PIPE ? __ldcg(top_in + s + PF) : top_in[s + PF];
+                    }
+                    if constexpr (PF > 1) {
+                        top0v = tq[0];
+#pragma unroll
+                        for (int k = 0; k + 1 < PF - 1; ++k) tq[k] = tq[k + 1];
+                        tq[PF - 2] = nv;
+                    } else {
+                        top0v = nv;
+                    }
                 }
             } else {
                 code0 = kTargetNone;
@@ -294,10 +321,10 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 botI = upI;
                 topGprev = topG;
                 if (TB) {
-                    tbp[0] = make_uint4(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16), rec[4] | (rec[5] << 16),
-                                        rec[6] | (rec[7] << 16));
-                    tbp[1] = make_uint4(rec[8] | (rec[9] << 16), rec[10] | (rec[11] << 16),
-                                        rec[12] | (rec[13] << 16), rec[14] | (rec[15] << 16));
+#pragma unroll
+                    for (int g = 0; g < R / 8; ++g)
+                        tbp[g] = make_uint4(rec[8 * g] | (rec[8 * g + 1] << 16), rec[8 * g + 2] | (rec[8 * g + 3] << 16),
+                                            rec[8 * g + 4] | (rec[8 * g + 5] << 16), rec[8 * g + 6] | (rec[8 * g + 7] << 16));
                 }
                 if (write_top) {
                     top_out[j] = make_uint2(botG, botI);
@@ -345,7 +372,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 }
             }
             if (first_row_lane) { topG = kNeg16x2; topI = kNeg16x2; }
-            if (TB) tbp += 2 * 32;
+            if (TB) tbp += (R / 8) * 32;
             const uint32_t nG = __shfl_up_sync(0xffffffffu, botG, 1);
             const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
             const int nC = __shfl_up_sync(0xffffffffu, code, 1);
@@ -420,7 +447,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
 // Viterbi_Data_create_Alignment (viterbi.c:342-392) over the 15-bit records.
 __global__ void e2g16_traceback_kernel(const E2pPair *__restrict__ pairs, const E2gOut *__restrict__ outs,
                                        const E2gJob *__restrict__ jobs, int n, const E2gModel mdl, int threshold,
-                                       c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+                                       c4b_result *__restrict__ results, int32_t *__restrict__ ops, int R) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const E2gJob J = jobs[g];
@@ -441,8 +468,8 @@ __global__ void e2g16_traceback_kernel(const E2pPair *__restrict__ pairs, const 
         else overflow = true;
     };
     auto record = [&](int ci, int cj) -> uint32_t {
-        const int w = ci / (32 * kE2pR), ln = (ci / kE2pR) & 31, r = ci % kE2pR;
-        return P.tb[(((size_t)w * nsteps + (cj + ln)) * 32 + ln) * kE2pR + r];
+        const int w = ci / (32 * R), ln = (ci / R) & 31, r = ci % R;
+        return P.tb[(((size_t)w * nsteps + (cj + ln)) * 32 + ln) * R + r];
     };
     if (o.best < threshold) {
         res.status = 1;
@@ -515,7 +542,7 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
                                   const E2gJob *__restrict__ jobs, const int32_t *__restrict__ active, int n_active,
                                   const E2gModel mdl, E2pWalk *__restrict__ walk,
                                   const uint16_t *__restrict__ winbuf, size_t win_stride,
-                                  c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+                                  c4b_result *__restrict__ results, int32_t *__restrict__ ops, int R) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_active) return;
     const int pidx = active[slot];
@@ -523,7 +550,7 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
     const E2pPair P = pairs[pidx];
     E2pWalk W = walk[pidx];
     const int c0 = (W.j / kE2pWin) * kE2pWin;
-    const int all_sweeps = (P.Q + 1 + 32 * kE2pR - 1) / (32 * kE2pR);
+    const int all_sweeps = (P.Q + 1 + 32 * R - 1) / (32 * R);
     const uint16_t *rec_base = winbuf + (size_t)slot * win_stride;
     int32_t *out = ops + 2 * J.ops_off;
     int i = W.i, j = W.j, state = W.state, n_runs = W.n_runs, last_t = W.last_t;
@@ -536,8 +563,8 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
         else overflow = true;
     };
     auto record = [&](int ci, int cj) -> uint32_t {
-        const int w = ci / (32 * kE2pR), ln = (ci / kE2pR) & 31, r = ci % kE2pR;
-        return rec_base[(((size_t)w * kE2pWinSteps + (cj - c0 + ln)) * 32 + ln) * kE2pR + r];
+        const int w = ci / (32 * R), ln = (ci / R) & 31, r = ci % R;
+        return rec_base[(((size_t)w * kE2pWinSteps + (cj - c0 + ln)) * 32 + ln) * R + r];
     };
     while (j >= c0) {
         const uint32_t f = (record(i, j) >> (7 * x)) & 127u;
@@ -562,8 +589,8 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
     if (!finished && !overflow && i >= 0 && j >= 0 && state == 3 && c0 > 0) {
         // inside an intron at column j in {c0-1, c0-2}: the checkpoint left of this window
         // holds the intron's age there = j - (column the intron was opened from)
-        const int w = i / (32 * kE2pR), ln = (i / kE2pR) & 31, r = i % kE2pR;
-        const uint32_t *c = P.ck + (((size_t)(c0 / kE2pWin - 1) * all_sweeps + w) * 32 + ln) * kE2pR * kE2pCkWords +
+        const int w = i / (32 * R), ln = (i / R) & 31, r = i % R;
+        const uint32_t *c = P.ck + (((size_t)(c0 / kE2pWin - 1) * all_sweeps + w) * 32 + ln) * R * kE2pCkWords +
                             (size_t)r * kE2pCkWords;
         const uint32_t a2 = (j == c0 - 1) ? c[4] : c[5];
         const int rel = (int)(short)((a2 >> (16 * x)) & 0xFFFFu);   // stored relative to the threshold

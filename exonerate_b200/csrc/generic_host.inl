@@ -39,10 +39,18 @@ struct GenericBatch {
     DevBuf<int32_t> d_ops_slots, d_ops_packed;
     DevBuf<int64_t> d_new_off;
     DevBuf<int32_t> d_endm, d_startc;  // END-cell / START-cell tables of lattice 0 (BSDP cell callbacks), else empty
+    // lattices whose PATH record exceeds the budget: column checkpoints + window refills (JIT_SYS_WIN)
+    DevBuf<GenPair> d_wpairs;
+    DevBuf<GenWin> d_wins;
+    DevBuf<GenWalk> d_wwalk;
+    DevBuf<int32_t> d_wbig, d_wck;
+    DevBuf<uint8_t> d_wtb;
+    int windowed_lattices = 0, window_cols = 0, window_rounds = 0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     double fill_ms = -1;
     ~GenericBatch() {
         d_endm.release(); d_startc.release(); d_top.release();
+        d_wpairs.release(); d_wins.release(); d_wwalk.release(); d_wbig.release(); d_wck.release(); d_wtb.release();
         d_tables.release(); d_seq.release(); d_ints.release(); d_full.release(); d_box.release();
         d_out_a.release(); d_out_b.release(); d_jobs.release(); d_ring.release(); d_cursor.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
@@ -359,10 +367,16 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     return 0;
 }
 
-static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode) {
+// win / wins: the column-window variants of the systolic kernel (JIT_SYS_WIN), one GenWin per lattice
+static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode,
+                               int win = 0, const GenWin *wins = nullptr) {
     if (!count) return 0;
     C4B_CUDA(cudaMemsetAsync(g->d_cursor.p, 0, sizeof(int), g->stream));
     const SysLayout &SL = mode == GEN_SCORE ? g->sys_score : (mode == GEN_REGION ? g->sys_region : g->sys_path);
+    if (win && !(g->use_jit && SL.ok)) {
+        set_error("internal: windowed PATH pass without the systolic specialisation");
+        return -1;
+    }
     if (g->use_jit && SL.ok) {
         const bool pack_start = mode == GEN_REGION;
         // one CTA per lattice, one warp per strip of 32 R rows (up to 8, then round-robin);
@@ -371,7 +385,7 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
         for (int p = 0; p < g->n; ++p) { maxQ = std::max(maxQ, g->h_full[p].Q); maxT = std::max(maxT, g->h_full[p].T); }
         const int nsweeps = (maxQ + 32 * SL.R) / (32 * SL.R);
         const int warps = jit_sys_warps(SL, maxQ);
-        if (JitKernel *jk = jit_get_sys(g->tables.model, mode, pack_start, SL, warps)) {
+        if (JitKernel *jk = jit_get_sys(g->tables.model, mode, pack_start, SL, warps, win)) {
             const size_t nsend = std::max<size_t>(1, SL.sendD.size());
             const size_t stride = nsweeps > 1 ? align_up(2 * ((size_t)maxT + 1) * nsend, 4) : 0;
             if (stride * (size_t)count > g->d_top.n) {
@@ -380,13 +394,13 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
             }
             int32_t *top = g->d_top.p;
             void *args[] = {(void *)&pairs, (void *)&count, (void *)&outs, (void *)&g->d_tables.p, (void *)&top,
-                            (void *)&stride};
+                            (void *)&stride, (void *)&wins};
             C4B_CUDA(cudaLaunchKernel((const void *)jk->kern, dim3(count), dim3(32 * warps), args, 0, g->stream));
             (*g->launches)++;
             g->kernel_used = "generic_jit_systolic";
             return 0;
         }
-        if (!getenv("C4B_JIT_FALLBACK")) {
+        if (win || !getenv("C4B_JIT_FALLBACK")) {
             set_error("systolic model specialisation failed (reason on stderr); set C4B_JIT_SYSTOLIC=0 to use the "
                       "thread-per-row specialisation");
             return -1;
@@ -439,6 +453,106 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
     return 0;
 }
 
+// PATH for lattices whose whole record does not fit `budget`: pass 1 (score) leaves a checkpoint of
+// the systolic register lattice after every `wcols` columns; then rounds of {refill the window under
+// each traceback cursor from the checkpoint to its left, walk it} until every cursor reached START.
+// Memory: checkpoints (T / wcols per strip) + one window of records per lattice.  d_jobs / d_box /
+// d_ops_slots are those of generic_batch_run; results land where the ordinary traceback puts them.
+static int generic_batch_run_windows(GenericBatch *g, const std::vector<GenPair> &box, const std::vector<int32_t> &big,
+                                     size_t budget, c4b_score threshold) {
+    cudaStream_t st = g->stream;
+    const int nb = (int)big.size();
+    const SysLayout &LS = g->sys_score, &LP = g->sys_path;
+    if (LS.R != LP.R || LS.VW != LP.VW || LS.AQ != LP.AQ || LS.VOff != LP.VOff) {
+        set_error("internal: score and PATH specialisations disagree on the register lattice");
+        return -1;
+    }
+    const size_t R = (size_t)LP.R, ckw = (size_t)(LP.AQ + LP.R) * LP.VW;
+    auto sweeps_of = [&](int p) { return ((size_t)box[p].Q + 32 * R) / (32 * R); };
+    auto win_bytes = [&](int p, size_t wc) { return align_up(sweeps_of(p) * (wc + 31) * 32 * (size_t)LP.chunk, 16); };
+    auto ck_words = [&](int p, size_t wc) { return ((size_t)box[p].T / wc) * sweeps_of(p) * ckw * 32; };
+    size_t wcols = 4096;
+    if (const char *env = getenv("C4B_GENERIC_WINDOW_COLS")) wcols = std::max<size_t>(32, (size_t)atoll(env));
+    while (wcols & (wcols - 1)) wcols &= wcols - 1;   // a power of two (the kernel masks with it)
+    auto totals = [&](size_t wc, size_t *wb, size_t *cb) {
+        *wb = 0; *cb = 0;
+        for (int p : big) { *wb += win_bytes(p, wc); *cb += ck_words(p, wc) * 4; }
+    };
+    size_t wb = 0, cb = 0;
+    totals(wcols, &wb, &cb);
+    while (wb > budget / 2 && wcols > 32) { wcols >>= 1; totals(wcols, &wb, &cb); }
+    while (cb > budget / 2 && wb * 2 <= budget / 2) { wcols <<= 1; totals(wcols, &wb, &cb); }
+    if (wb > budget / 2 || cb > budget / 2) {
+        set_error("traceback of pair " + std::to_string(big[0]) + " exceeds the device memory budget even as column "
+                  "windows (" + std::to_string(wb >> 20) + " MB of records + " + std::to_string(cb >> 20) +
+                  " MB of checkpoints)");
+        return -1;
+    }
+    g->windowed_lattices = nb;
+    g->window_cols = (int)wcols;
+    g->d_wpairs.release(); g->d_wins.release(); g->d_wwalk.release(); g->d_wbig.release(); g->d_wck.release();
+    g->d_wtb.release();
+    if (g->d_wpairs.alloc(nb) || g->d_wins.alloc(nb) || g->d_wwalk.alloc(nb) || g->d_wbig.alloc(nb) ||
+        g->d_wck.alloc(cb / 4 + 32) || g->d_wtb.alloc(wb + 16))
+        return -1;
+    std::vector<GenPair> wp(nb);
+    std::vector<GenWin> wins(nb);
+    {
+        size_t tb_cur = 0, ck_cur = 0;
+        for (int k = 0; k < nb; ++k) {
+            const int p = big[k];
+            wp[k] = box[p];
+            wp[k].tb = g->d_wtb.p + tb_cur;
+            wp[k].tb_rows = LP.R; wp[k].tb_chunk = LP.chunk;
+            tb_cur += win_bytes(p, wcols);
+            wins[k].ck = g->d_wck.p + ck_cur;
+            ck_cur += ck_words(p, wcols);
+            wins[k].wcols = (int32_t)wcols; wins[k].c0 = 0; wins[k].c1 = box[p].T; wins[k].nsweeps = 0; wins[k].reserved = 0;
+        }
+    }
+    C4B_CUDA(cudaMemcpyAsync(g->d_wpairs.p, wp.data(), nb * sizeof(GenPair), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(g->d_wins.p, wins.data(), nb * sizeof(GenWin), cudaMemcpyHostToDevice, st));
+    C4B_CUDA(cudaMemcpyAsync(g->d_wbig.p, big.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // pass 1 inside the boxes: END cell (checked against the REGION pass like any box refill) + checkpoints
+    if (generic_launch_fill(g, g->d_wpairs.p, nb, g->d_out_b.p, GEN_SCORE, 1, g->d_wins.p)) return -1;
+    generic_window_walk_init_kernel<<<(nb + 63) / 64, 64, 0, st>>>(g->d_wpairs.p, g->d_out_b.p, g->d_out_a.p, g->d_jobs.p,
+                                                                   g->d_wbig.p, nb, g->d_tables.p, threshold,
+                                                                   g->d_wwalk.p, g->d_results.p);
+    (*g->launches)++;
+    C4B_CUDA(cudaGetLastError());
+    std::vector<GenWalk> walk(nb);
+    int64_t round_cap = 16;
+    for (int p : big) round_cap += 2 * ((int64_t)box[p].T / (int64_t)wcols + 1) + 2 * (int64_t)sweeps_of(p);
+    for (int64_t round = 0;; ++round) {
+        C4B_CUDA(cudaMemcpyAsync(walk.data(), g->d_wwalk.p, nb * sizeof(GenWalk), cudaMemcpyDeviceToHost, st));
+        C4B_CUDA(cudaStreamSynchronize(st));
+        int active = 0;
+        for (int k = 0; k < nb; ++k) {
+            GenWin &w = wins[k];
+            w.nsweeps = 0;
+            if (walk[k].done) continue;
+            ++active;
+            w.c0 = (int32_t)((size_t)walk[k].j / wcols * wcols);
+            w.c1 = walk[k].j;                                         // the path never moves right or down
+            w.nsweeps = (int32_t)((size_t)walk[k].i / (32 * R) + 1);
+        }
+        if (!active) break;
+        if (round >= round_cap) {
+            set_error("internal: windowed traceback did not terminate");
+            return -1;
+        }
+        C4B_CUDA(cudaMemcpyAsync(g->d_wins.p, wins.data(), nb * sizeof(GenWin), cudaMemcpyHostToDevice, st));
+        if (generic_launch_fill(g, g->d_wpairs.p, nb, g->d_out_b.p, GEN_PATH, 2, g->d_wins.p)) return -1;
+        generic_window_walk_kernel<<<(nb + 63) / 64, 64, 0, st>>>(g->d_wpairs.p, g->d_out_b.p, g->d_jobs.p, g->d_wbig.p,
+                                                                  g->d_wins.p, nb, g->d_tables.p, g->d_wwalk.p,
+                                                                  g->d_results.p, g->d_ops_slots.p);
+        (*g->launches)++;
+        C4B_CUDA(cudaGetLastError());
+        g->window_rounds++;
+    }
+    return 0;
+}
+
 int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     cudaStream_t st = g->stream;
     const int n = g->n;
@@ -487,28 +601,43 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
             C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
             if (free_b > (3ull << 30)) budget = (free_b - (2ull << 30)) / 2;
         }
+        if (const char *env = getenv("C4B_GENERIC_TB_BUDGET_KB"))   // testing: force the chunked / windowed routes
+            budget = std::max<size_t>(256, (size_t)atoll(env) << 10);
     }
     std::vector<size_t> tb_off(n);
     std::vector<Chunk> chunks;
     std::vector<GenJob> jobs(n);
+    std::vector<int32_t> big;   // lattices whose record alone exceeds the budget: column windows
     size_t cur = 0, arena = 0;
     int64_t ops_cursor = 0;
     int begin = 0;
     for (int p = 0; p < n; ++p) {
         const size_t need = align_up(tb_bytes(p), 16);
-        if (need > budget) {
-            set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget");
-            return -1;
-        }
-        if (cur + need > budget) { chunks.push_back({begin, p}); begin = p; cur = 0; }
-        tb_off[p] = cur;
-        cur += need;
-        arena = std::max(arena, cur);
         GenJob &J = jobs[p];
         J.pair = p; J.result = p; J.expect = g->use_region ? 1 : 0; J.score_slot = p;
         J.ops_cap = (int32_t)std::min<int64_t>((int64_t)box[p].Q + box[p].T + 4, INT32_MAX);
         J.ops_off = ops_cursor; J.reserved = 0;
         ops_cursor += J.ops_cap;
+        if (need > budget) {
+            // The reference recurses through checkpoint rows here (optimal.c:183-345).  The systolic
+            // kernel checkpoints its register lattice by column instead and refills one window at a
+            // time under the traceback cursor (generic_batch_run_windows).
+            if (!(sys_tb && g->plain && g->sys_score.ok)) {
+                set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget "
+                          "(column windows need the systolic specialisation: no SubOpt blocked cells or cell tables)");
+                return -1;
+            }
+            if (begin < p) chunks.push_back({begin, p});
+            begin = p + 1;
+            cur = 0;
+            tb_off[p] = 0;
+            big.push_back(p);
+            continue;
+        }
+        if (cur + need > budget) { chunks.push_back({begin, p}); begin = p; cur = 0; }
+        tb_off[p] = cur;
+        cur += need;
+        arena = std::max(arena, cur);
     }
     if (begin < n) chunks.push_back({begin, n});
     g->d_tb.release(); g->d_jobs.release(); g->d_ops_slots.release(); g->d_ops_packed.release();
@@ -528,6 +657,8 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         (*g->launches)++;
         C4B_CUDA(cudaGetLastError());
     }
+    // (a budget forced small for testing only decides the route: the windows themselves get real room)
+    if (!big.empty() && generic_batch_run_windows(g, box, big, std::max<size_t>(budget, 256ull << 20), threshold)) return -1;
     C4B_CUDA(cudaEventRecord(g->ev_b, st));
     apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(g->d_results.p, n, threshold);
     ops_scan_kernel<<<1, 1024, 0, st>>>(g->d_results.p, n, g->d_new_off.p, g->d_new_off.p + n);

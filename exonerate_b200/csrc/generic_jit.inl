@@ -260,8 +260,10 @@ static int jit_sys_warps(const SysLayout &L, int max_q) {
     return std::max(1, std::min(max_warps, (max_q + 32 * L.R) / (32 * L.R)));
 }
 
+// win: 0 whole-lattice pass, 1 score pass that leaves column checkpoints, 2 PATH over one column
+// window started from a checkpoint (JIT_SYS_WIN in generic_jit_systolic.cuh)
 static std::string jit_sys_program_source(const c4b_model &m, int mode, bool pack_start, const SysLayout &L,
-                                          int warps) {
+                                          int warps, int win = 0) {
     // the tables of the thread-per-row kernel first (its calc / scope code is shared), then ours
     std::string base = jit_program_source(m, mode, 128, false, pack_start);
     const size_t cut = base.find(kJitSrc_generic_jit_kernel_cuh);
@@ -272,6 +274,7 @@ static std::string jit_sys_program_source(const c4b_model &m, int mode, bool pac
     if (const char *env = getenv("C4B_JIT_SYS_MINB")) minb = std::max(1, std::min(16, atoi(env)));
     o << "#define JIT_SYSTOLIC 1\n#define JIT_SYS_R " << L.R << "\n#define JIT_SYS_MINB " << minb
       << "\n#define JIT_SYS_WARPS " << warps << "\n";
+    if (win) o << "#define JIT_SYS_WIN " << win << "\n";
     o << "namespace c4bjit {\n";
     o << "constexpr int AQ = " << L.AQ << ", VW = " << L.VW << ", NSEND = " << L.sendD.size() << ";\n";
     auto arr = [&](const char *name, const std::vector<int> &v, size_t n) {
@@ -430,10 +433,11 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
 }
 
 // the systolic specialisation of (model, mode); nullptr = not available (reason on stderr once)
-static JitKernel *jit_get_sys(const c4b_model &m, int mode, bool pack_start, const SysLayout &L, int warps) {
+static JitKernel *jit_get_sys(const c4b_model &m, int mode, bool pack_start, const SysLayout &L, int warps,
+                              int win = 0) {
     static std::mutex mu;
     static std::map<std::string, JitKernel *> cache;
-    const std::string src = jit_sys_program_source(m, mode, pack_start, L, warps);
+    const std::string src = jit_sys_program_source(m, mode, pack_start, L, warps, win);
     int device = 0;
     cudaGetDevice(&device);
     const std::string key = std::to_string(device) + ":" + src;

@@ -28,6 +28,17 @@
 // Not handled here (the host keeps generic_jit_kernel.cuh for them): SubOpt blocked
 // cells, START / END cell tables of BSDP's derived models.
 //
+// JIT_SYS_WIN -- a PATH record for lattices whose whole record would not fit device memory (the
+// reference recurses through checkpoint rows for the same reason, src/c4/optimal.c:183-345,
+// src/c4/viterbi.c:515-631; results do not depend on it):
+//   1  whole lattice (score), and every lane saves its complete register lattice V after the last
+//      column of each window of `wcols` columns (a column checkpoint: everything the columns to its
+//      right depend on);
+//   2  PATH over ONE window of columns [c0, c1] and the strips down to the traceback cursor,
+//      started from the checkpoint to its left; records are laid out as a lattice of wcols columns.
+// The host alternates window refills and a resumable walk (generic_window_walk_kernel) from the
+// END cell leftwards: record memory is one window, not the lattice.
+//
 // Expected in front of this file, after generic_jit_kernel.cuh's own tables:
 //   JIT_SYS_R (rows per lane), namespace c4bjit { AQ (largest advance_query), VW (words
 //   per row), kNW[S] (words a state carries), kVD[S] (columns kept - 1; -1: never stored),
@@ -35,8 +46,15 @@
 //   kSendD[NSEND], kSendOff[NSEND], kTbCode[TN], kTbBits[S], kTbBitOff[S], TB_ROW_BITS,
 //   TB_CHUNK (PATH record, see the host's SysLayout) }.
 
+#ifndef JIT_SYS_WIN
+#define JIT_SYS_WIN 0
+#endif
+
 namespace c4bjit {
 
+constexpr int kWinMode = JIT_SYS_WIN;
+static_assert(kWinMode == 0 || (kWinMode == 1 && JIT_MODE == GEN_SCORE) || (kWinMode == 2 && JIT_MODE == GEN_PATH),
+              "checkpoints are written by the score pass and consumed by the PATH pass");
 constexpr int SR = JIT_SYS_R;
 constexpr int NROWS = AQ + SR;        // virtual rows above the strip first
 constexpr int kSysMaxWarps = 8;
@@ -243,7 +261,8 @@ __device__ __forceinline__ void sys_rows(const SysCtx &Z, int (&V)[NROWS][VW], S
 // resident CTAs per SM the register allocation must allow (the host aims at 16 warps per SM)
 extern "C" __global__ void __launch_bounds__(32 * JIT_SYS_WARPS, JIT_SYS_MINB)
 c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__restrict__ outs,
-            const c4b::GenTables *__restrict__ tables, int32_t *top_base, size_t top_stride) {
+            const c4b::GenTables *__restrict__ tables, int32_t *top_base, size_t top_stride,
+            const c4b::GenWin *__restrict__ wins) {
     using namespace c4bjit;
     __shared__ c4b_scoring s_scoring;
     __shared__ volatile long long vprog[kSysMaxWarps];
@@ -269,8 +288,18 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
     Z.X.q_start = P.q_start; Z.X.t_start = P.t_start; Z.X.Q = P.Q; Z.X.T = P.T;
     const int Q = P.Q, T = P.T;
     constexpr int rows_per_sweep = 32 * SR;
-    const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
+    int nsweeps = all_sweeps;
     const int nsteps = T + 1 + 31;
+    // column window [c0, c1] of this launch (the whole lattice unless JIT_SYS_WIN == 2)
+    int c0 = 0, c1 = T, wcols = 0;
+    int32_t *ck = nullptr;
+    constexpr int CKW = NROWS * VW;   // words of one lane's checkpoint
+    if constexpr (kWinMode != 0) {
+        const c4b::GenWin Wn = wins[pi];
+        ck = Wn.ck; wcols = Wn.wcols;
+        if constexpr (kWinMode == 2) { c0 = Wn.c0; c1 = Wn.c1; nsweeps = min(all_sweeps, Wn.nsweeps); }
+    }
     // sweep hand-off rows in L2: two buffers of (T + 1) x NSEND words per lattice, ping-pong
     int32_t *top0 = top_base + (size_t)pi * top_stride;
     int32_t *top1 = top0 + (size_t)(T + 1) * (NSEND > 0 ? NSEND : 1);
@@ -320,32 +349,46 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
 #pragma unroll
             for (int w = 0; w < NSEND; ++w) V[AQ - kSendD[w]][kSendOff[w]] = vals[w];
         };
+        if constexpr (kWinMode == 2) {
+            if (c0 > 0) {   // the state after column c0 - 1: [window boundary][sweep][word][lane]
+                const int32_t *cp = ck + (((size_t)(c0 / wcols - 1) * all_sweeps + sweep) * CKW) * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+                    for (int x = 0; x < VW; ++x) V[r][x] = cp[(size_t)(r * VW + x) * 32];
+            }
+        }
         if (later_sweep) {
-            if (piped) wait_column(0);
-            load_top(0);
+            if (piped) wait_column(c0);
+            load_top(c0);
             if (lane == 0) place_up(upin);
         }
         unsigned char *tbp = nullptr;
         constexpr int TBCH = TB_CHUNK;   // traceback bytes per lane per step
         if constexpr (JIT_MODE == GEN_PATH)
-            tbp = P.tb + ((size_t)sweep * nsteps * 32 + lane) * TBCH;
+            tbp = P.tb + ((size_t)sweep * (kWinMode == 2 ? wcols + 31 : nsteps) * 32 + lane) * TBCH;
 
-        for (int s = 0; s < nsteps; ++s) {
+        for (int s = c0; s < c1 + 32; ++s) {
             const int j = s - lane;
             Z.j = j;
             Z.colok = (j >= 0 && j <= T);
+            // a lane left of its window waits for its first column with the checkpoint untouched (the
+            // first window has no checkpoint: its lanes run in from column -lane like a whole-lattice pass)
+            const bool live = (kWinMode != 2) || c0 == 0 || (j >= c0);
+            const bool inwin = (kWinMode != 2) || (j >= c0 && j <= c1);
             // the next column of the sweep above, fetched early with warp-uniform addresses
-            if (later_sweep && s + 1 <= T) {
+            // (c1 = T outside window refills; a refill's producer never goes past c1)
+            if (later_sweep && s + 1 <= c1) {
                 if (piped) wait_column(s + 1);
                 load_top(s + 1);
             }
             uint32_t tbw[TBCH / 4];
 #pragma unroll
             for (int k = 0; k < TBCH / 4; ++k) tbw[k] = 0u;
-            sys_rows<0>(Z, V, bst, tbw);
+            if (live) sys_rows<0>(Z, V, bst, tbw);
 
             if constexpr (JIT_MODE == GEN_PATH) {
-                if (Z.colok) {
+                if (Z.colok && inwin) {
 #pragma unroll
                     for (int k = 0; k < TBCH / 4; ++k) reinterpret_cast<uint32_t *>(tbp)[k] = tbw[k];
                 }
@@ -355,12 +398,12 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             int send[NSEND > 0 ? NSEND : 1];
 #pragma unroll
             for (int w = 0; w < NSEND; ++w) send[w] = V[AQ + SR - kSendD[w]][kSendOff[w]];
-            if (write_top && Z.colok) {
+            if (write_top && Z.colok && inwin) {
 #pragma unroll
                 for (int w = 0; w < NSEND; ++w) top_out[(size_t)j * NSEND + w] = send[w];
                 // publish in groups of 8 columns: the fence costs far more than the stores, and the
                 // consumer runs at least 32 columns behind anyway
-                if (W > 1 && ((j & 7) == 7 || j == T)) {
+                if (W > 1 && ((j & 7) == 7 || j == c1)) {
                     __threadfence_block();   // the rows are written before the counter moves
                     vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                 }
@@ -372,21 +415,35 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
                 if (lane == 0) recv[w] = upin[w];   // column s + 1 of the sweep above (unused in sweep 0)
             }
             // every kept column moves one place back; column 0 of the virtual rows is what arrived
+            if (live) {
 #pragma unroll
-            for (int r = 0; r < NROWS; ++r)
+                for (int r = 0; r < NROWS; ++r)
 #pragma unroll
-                for (int st = 0; st < S; ++st)
-                    if (kVD[st] >= 1) {
+                    for (int st = 0; st < S; ++st)
+                        if (kVD[st] >= 1) {
 #pragma unroll
-                        for (int k = (kVD[st] >= 1 ? kVD[st] : 1); k >= 1; --k)
+                            for (int k = (kVD[st] >= 1 ? kVD[st] : 1); k >= 1; --k)
 #pragma unroll
-                            for (int w = 0; w < kNW[st]; ++w)
-                                V[r][kVOff[st] + k * kNW[st] + w] = V[r][kVOff[st] + (k - 1) * kNW[st] + w];
-                    }
-            place_up(recv);
+                                for (int w = 0; w < kNW[st]; ++w)
+                                    V[r][kVOff[st] + k * kNW[st] + w] = V[r][kVOff[st] + (k - 1) * kNW[st] + w];
+                        }
+                place_up(recv);
+            }
+            if constexpr (kWinMode == 1) {
+                // last column of a window (wcols is a power of two): V now holds everything column j + 1
+                // of my rows depends on, the hand-off from the lane above included
+                if (Z.colok && j < T && ((j + 1) & (wcols - 1)) == 0) {
+                    int32_t *cp = ck + (((size_t)((j + 1) / wcols - 1) * all_sweeps + sweep) * CKW) * 32 + lane;
+#pragma unroll
+                    for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+                        for (int x = 0; x < VW; ++x) cp[(size_t)(r * VW + x) * 32] = V[r][x];
+                }
+            }
         }
         __syncwarp();
     }
+    if constexpr (kWinMode == 2) return;   // (END is known: the cursor came from pass 1)
     int best = bst.score, best_i = bst.i, best_j = bst.j, best_start = bst.start;
     // lexicographic reduction: max score, then min j, then min i
 #pragma unroll

@@ -32,6 +32,23 @@ struct GenOut {
     int32_t score, end_i, end_j, start_i, start_j, flags;
 };
 
+// Column windows of the systolic PATH pass (generic_jit_systolic.cuh, JIT_SYS_WIN), one per lattice
+// of the launch: pass 1 leaves a checkpoint of the register lattice after every `wcols` columns, the
+// PATH pass refills columns [c0, c1] of strips 0 .. nsweeps - 1 from the checkpoint left of c0.
+struct GenWin {
+    int32_t *ck;         // [window boundary][strip][word][lane]
+    int32_t wcols;       // window width, a power of two
+    int32_t c0, c1;      // columns of this refill (c0 a multiple of wcols; c1 = the cursor's column)
+    int32_t nsweeps;     // strips down to the cursor's (0: nothing to do for this lattice)
+    int32_t reserved;
+};
+
+// traceback cursor of a windowed lattice between rounds (generic_window_walk_kernel)
+struct GenWalk {
+    int32_t i, j, state;     // next: look up the winner of `state` at cell (i, j)
+    int32_t n_runs, last_t, status, done, reserved;
+};
+
 struct GenTables {
     c4b_model model;
     c4b_scoring scoring;

@@ -391,6 +391,119 @@ __global__ void generic_traceback_kernel(const GenPair *__restrict__ pairs, cons
     results[J.result] = res;
 }
 
+// ---- windowed traceback of lattices whose whole PATH record would not fit (JIT_SYS_WIN) ------
+// Cursors start at the END cell pass 1 found (checks of generic_traceback_kernel: optimal.c:394-411).
+__global__ void generic_window_walk_init_kernel(const GenPair *__restrict__ pairs, const GenOut *__restrict__ outs,
+                                                const GenOut *__restrict__ reg_outs, const GenJob *__restrict__ jobs,
+                                                const int32_t *__restrict__ big, int n, const GenTables *__restrict__ tables,
+                                                int threshold, GenWalk *__restrict__ walk,
+                                                c4b_result *__restrict__ results) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const GenJob J = jobs[big[g]];
+    const GenPair P = pairs[g];
+    const GenOut o = outs[P.out_index];
+    c4b_result res;
+    res.score = o.score; res.status = 0; res.reserved = 0; res.n_ops = 0; res.ops_offset = J.ops_off;
+    res.query_start = P.q_start; res.target_start = P.t_start;
+    res.query_end = P.q_start + o.end_i; res.target_end = P.t_start + o.end_j;
+    if (J.expect) {
+        const GenOut r = reg_outs[J.score_slot];
+        res.score = r.score;
+        if (r.score < threshold) res.status = 1;
+        else if (r.score != o.score) res.status = 3;
+    }
+    if (res.status == 0 && o.flags) res.status = 2;
+    GenWalk W;
+    W.i = o.end_i; W.j = o.end_j; W.state = tables->model.end_state;
+    W.n_runs = 0; W.last_t = -1; W.status = res.status; W.done = res.status != 0; W.reserved = 0;
+    walk[g] = W;
+    results[J.result] = res;   // (final for rejected lattices; the walk overwrites it when it finishes)
+}
+
+// Viterbi_Data_create_Alignment (viterbi.c:342-392) inside the window that was just refilled: one
+// thread per lattice walks END -> START until the cursor leaves the window on its left (the next
+// round refills the window it is then in) or reaches START.
+__global__ void generic_window_walk_kernel(const GenPair *__restrict__ pairs, const GenOut *__restrict__ outs,
+                                           const GenJob *__restrict__ jobs, const int32_t *__restrict__ big,
+                                           const GenWin *__restrict__ wins, int n,
+                                           const GenTables *__restrict__ tables, GenWalk *__restrict__ walk,
+                                           c4b_result *__restrict__ results, int32_t *__restrict__ ops) {
+    __shared__ short s_bit_off[C4B_MAX_STATES], s_bit_n[C4B_MAX_STATES];
+    __shared__ unsigned char s_rank2tr[C4B_MAX_STATES][C4B_MAX_TRANSITIONS + 1];
+    __shared__ int s_row_bits;
+    const c4b_model &m = tables->model;
+    const int S = m.n_states;
+    if (threadIdx.x == 0) {   // the rank-bit record's decode tables, as in generic_traceback_kernel
+        int row_bits = 0;
+        for (int s = 0; s < S; ++s) {
+            int n_in = 0, b = 0;
+            for (int k = 0; k < m.n_transitions; ++k)
+                if (m.transitions[k].output == s) s_rank2tr[s][++n_in] = (unsigned char)k;
+            s_rank2tr[s][0] = 0xFF;
+            while ((1 << b) < n_in + 1) ++b;
+            s_bit_off[s] = (short)row_bits; s_bit_n[s] = (short)b; row_bits += b;
+        }
+        s_row_bits = row_bits;
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    GenWalk W = walk[g];
+    if (W.done) return;
+    const GenJob J = jobs[big[g]];
+    const GenPair P = pairs[g];
+    const GenWin win = wins[g];
+    int32_t *out = ops + 2 * J.ops_off;
+    int i = W.i, j = W.j, state = W.state, n_runs = W.n_runs, last_t = W.last_t, status = 0;
+    bool finished = false;
+    const int row_bits = s_row_bits;
+    auto winner = [&](int ci, int cj, int st) -> int {   // records of the window: a lattice of wcols columns
+        const int nb = s_bit_n[st];
+        if (nb == 0) return 0xFF;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(
+            P.tb + GEN_TBS_CHUNK(ci, cj - win.c0, win.wcols - 1, P.tb_rows, P.tb_chunk));
+        const int pos = (ci % P.tb_rows) * row_bits + s_bit_off[st];
+        uint64_t v = w[pos / 32];
+        if (pos % 32 + nb > 32) v |= (uint64_t)w[pos / 32 + 1] << 32;
+        return s_rank2tr[st][(int)((v >> (pos % 32)) & ((1u << nb) - 1u))];
+    };
+    while (j >= win.c0) {
+        const int tr = winner(i, j, state);
+        if (tr == 0xFF) { finished = true; break; }
+        if (tr == last_t) out[2 * (n_runs - 1) + 1] += 1;
+        else if (n_runs < J.ops_cap) { out[2 * n_runs] = tr; out[2 * n_runs + 1] = 1; ++n_runs; last_t = tr; }
+        else { status = 4; break; }
+        const c4b_transition &t = m.transitions[tr];
+        i -= t.advance_query;
+        j -= t.advance_target;
+        if (t.input == m.start_state) { finished = true; break; }
+        if (i < 0 || j < 0) { status = 4; break; }
+        state = t.input;
+    }
+    if (finished || status) {
+        const GenOut o = outs[P.out_index];
+        c4b_result res = results[J.result];   // score / end as the init kernel left them
+        res.status = status;
+        if (!status) {
+            for (int a = 0, b = n_runs - 1; a < b; ++a, --b) {
+                const int t0 = out[2 * a], l0 = out[2 * a + 1];
+                out[2 * a] = out[2 * b]; out[2 * a + 1] = out[2 * b + 1];
+                out[2 * b] = t0; out[2 * b + 1] = l0;
+            }
+            res.query_start = P.q_start + max(i, 0);
+            res.target_start = P.t_start + max(j, 0);
+        }
+        res.query_end = P.q_start + o.end_i; res.target_end = P.t_start + o.end_j;
+        res.n_ops = n_runs;
+        results[J.result] = res;
+        W.done = 1;
+        W.status = status;
+    }
+    W.i = i; W.j = j; W.state = state; W.n_runs = n_runs; W.last_t = last_t;
+    walk[g] = W;
+}
+
 __global__ void generic_score_results_kernel(const GenPair *__restrict__ pairs, const GenOut *__restrict__ outs,
                                              int n, c4b_result *__restrict__ results) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

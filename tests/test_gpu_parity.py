@@ -95,6 +95,67 @@ def test_golden_vectors_specialised_kernel(eng, name, params, scoring, monkeypat
         assert helpers.report_line("vulgar", model, "qy", "tg", *strands(name), r) == ref["vulgar"]
 
 
+@pytest.mark.parametrize("wcols", ["32", "128", "1024"])
+def test_windowed_path_on_the_table_driven_kernel(eng, params, scoring, monkeypatch, wcols):
+    """PATH records that do not fit the device budget (forced here with a 1 kB budget): the systolic
+    specialisation leaves column checkpoints of its register lattice and the traceback refills one
+    window at a time under the cursor -- the reference recurses through checkpoint rows for the
+    same reason (optimal.c:183-345) and results do not depend on it.  Golden cases of every model
+    (op for op against the reference) and larger spliced lattices against the whole-record pass:
+    several strips, windows narrower than an intron, ANYWHERE scopes (REGION + box) and global ones."""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
+    monkeypatch.setenv("C4B_GENERIC_JIT", "1")
+    monkeypatch.setenv("C4B_GENERIC_WINDOW_COLS", wcols)
+
+    def both(model, pairs):
+        opt = Optimal(eng, model, scoring)
+        monkeypatch.delenv("C4B_GENERIC_TB_BUDGET_KB", raising=False)
+        whole = opt.find_path(pairs)
+        monkeypatch.setenv("C4B_GENERIC_TB_BUDGET_KB", "1")
+        b = Batch(eng, model, scoring, pairs, want_path=True)
+        b.run()
+        assert b.kernel_name == "generic_jit_systolic"
+        b.close()
+        return whole, opt.find_path(pairs)
+
+    if wcols == "128":
+        for name in ("affine_local_dna", "affine_global_dna", "est2genome", "protein2genome", "coding2coding"):
+            model, _ = helpers.load_model(name, params)
+            cases = helpers.load_cases(name)
+            pairs = PairSet([c["q"] for c in cases], [c["t"] for c in cases], splice=[splice_for(name, c) for c in cases])
+            whole, win = both(model, pairs)
+            for c, w, r in zip(cases, whole, win):
+                assert r == w, (name, c["name"])
+                assert r["score"] == c["path"]["score"] and r["ops"] == [tuple(o) for o in c["path"]["ops"]], (name, c["name"])
+    rng = random.Random(91)
+    for name in ("protein2genome", "est2genome", "coding2coding", "affine_global_dna"):
+        model, _ = helpers.load_model(name, params)
+        qs, ts, sp = [], [], []
+        for k in range(4):
+            if name == "protein2genome":
+                q, t = bench_p2g_pair(7000 + k, rng.choice([120, 330]), rng.choice([5000, 9000]))
+            elif name == "est2genome":
+                q, t = helpers.gene_pair(7100 + k, rng.choice([300, 700]), rng.choice([6000, 12000]), n_exons=3, rate=0.02,
+                                         reverse=bool(k & 1))
+            else:
+                q, t = helpers.dna_pair(7200 + k, rng.choice([200, 450]), rng.choice([1500, 3000]))
+            qs.append(q); ts.append(t)
+            sp.append(splice_arrays(t) if name in ("protein2genome", "est2genome") else None)
+        whole, win = both(model, PairSet(qs, ts, splice=sp))
+        assert any(len(r["ops"]) > 3 for r in whole), name
+        for k, (w, r) in enumerate(zip(whole, win)):
+            assert r == w, (name, k, wcols)
+
+
+def bench_p2g_pair(seed, qlen, tlen):
+    """one pair of bench.py's protein2genome generator (a planted spliced gene)"""
+    import bench
+    q, t = bench.make_batch_p2g(seed, 1, qlen, tlen)
+    return bytes(q[0]).decode(), bytes(t[0]).decode()
+
+
 def test_specialised_kernel_matches_interpreter_at_size(eng, params, scoring, monkeypatch):
     """protein2genome and coding2coding on lattices with several rows per thread
     (query longer than the 512-thread CTA) and suboptimal-blocked cells: the
@@ -706,7 +767,8 @@ E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257
               (513, 3000), (600, 5000), (1000, 6000), (1300, 2500), (2047, 2400)]
 
 
-@pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_packed16:full", "e2g_systolic"])
+@pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_packed16:full", "e2g_packed16:rows8", "e2g_packed16:rows16",
+                                    "e2g_packed16:rows8:full", "e2g_packed16:rows8:warps1", "e2g_systolic"])
 def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel):
     """The hand-specialised est2genome kernels -- e2g_packed16 (both strands per
     register, one warp per lattice, 512-row sweeps) and the int32 e2g_systolic
@@ -732,9 +794,16 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel
     opt = Optimal(eng, model, scoring)
     if kernel == "e2g_systolic":
         monkeypatch.setenv("C4B_E2G_PACK16", "0")
-    if kernel.endswith(":full"):     # records for the whole lattice instead of checkpoints + windows
-        monkeypatch.setenv("C4B_E2G_WINDOWS", "0")
-        kernel = kernel.split(":")[0]
+    # rows per lane: 16 (512-row sweeps) or 8 (256-row sweeps on up to four pipelined warps, the
+    # small-batch shape); unset = the library's choice by batch size
+    for opt_ in kernel.split(":")[1:]:
+        if opt_ == "full":           # records for the whole lattice instead of checkpoints + windows
+            monkeypatch.setenv("C4B_E2G_WINDOWS", "0")
+        elif opt_.startswith("rows"):
+            monkeypatch.setenv("C4B_E2G_ROWS", opt_[4:])
+        elif opt_.startswith("warps"):
+            monkeypatch.setenv("C4B_E2G_WARPS", opt_[5:])
+    kernel = kernel.split(":")[0]
 
     def check(idx):
         pairs = PairSet([qs[k] for k in idx], [ts[k] for k in idx], splice=[sp[k] for k in idx])
@@ -791,8 +860,10 @@ def test_est2genome_intron_gain_leaves_the_packed_kernel(eng, params, scoring):
     b.close()
 
 
-def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkeypatch):
-    """find_path on long targets: pass 1 saves column checkpoints every 1024 columns, the
+@pytest.mark.parametrize("rows", ["8", "16"])
+def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkeypatch, rows):
+    """(rows per lane 8: the small-batch shape, window refills on independent warps.)
+    find_path on long targets: pass 1 saves column checkpoints every 1024 columns, the
     traceback refills only the windows under the path and crosses introns in one jump
     (the checkpoint holds the intron's age).  Introns of 3 .. 40 kbp (the 16-bit age
     saturates at 32767: no jump, window-by-window walk), both strands; against the
@@ -809,6 +880,7 @@ def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkey
         ts.append(t)
     sp = [splice_arrays(t) for t in ts]
     pairs = PairSet(qs, ts, splice=sp)
+    monkeypatch.setenv("C4B_E2G_ROWS", rows)
     got = opt.find_path(pairs)
     monkeypatch.setenv("C4B_E2G_WINDOWS", "0")
     want = opt.find_path(pairs)
