@@ -359,17 +359,30 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     // windowed traceback: per lattice checkpoints + one window of records, all resident
     std::vector<size_t> ck_off(n, 0);
     size_t ck_words = 0;
+    b->mdl.win_cols = kE2pWinMax;
     if (packed && want_path) {
         const char *env = getenv("C4B_E2G_WINDOWS");
-        size_t max_sweeps = 1;
-        for (int p = 0; p < n; ++p) {
-            const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * RW - 1) / (32 * RW);
-            const size_t nwin = (size_t)pairs[p].target_length / kE2pWin + 1;
-            max_sweeps = std::max(max_sweeps, sweeps);
-            ck_off[p] = ck_words;
-            ck_words += (nwin - 1) * sweeps * 32 * RW * kE2pCkWords;
+        // window width: the narrowest whose checkpoints fit a quarter of the record budget (a refill
+        // covers at most one window per cursor and round: narrow windows refill fewer cells per exon)
+        int wc = 256;
+        if (const char *wenv = getenv("C4B_E2G_WINDOW_COLS")) {
+            wc = std::max(64, std::min(kE2pWinMax, atoi(wenv)));
+            while (wc & (wc - 1)) wc &= wc - 1;
         }
-        b->win_stride = max_sweeps * kE2pWinSteps * 32 * RW;
+        for (;; wc <<= 1) {
+            size_t max_sweeps = 1;
+            ck_words = 0;
+            for (int p = 0; p < n; ++p) {
+                const size_t sweeps = ((size_t)pairs[p].query_length + 1 + 32 * RW - 1) / (32 * RW);
+                const size_t nwin = (size_t)pairs[p].target_length / wc + 1;
+                max_sweeps = std::max(max_sweeps, sweeps);
+                ck_off[p] = ck_words;
+                ck_words += (nwin - 1) * sweeps * 32 * RW * kE2pCkWords;
+            }
+            b->win_stride = max_sweeps * (size_t)(wc + 31) * 32 * RW;
+            if (ck_words * 4 <= budget_hw / 4 || wc >= kE2pWinMax) break;
+        }
+        b->mdl.win_cols = wc;
         const size_t need = ck_words * 4 + (size_t)n * b->win_stride * 2;
         b->windowed = !(env && atoi(env) == 0) && need / 2 < budget_hw;
     }
@@ -549,7 +562,7 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
                                                                        b->d_walk.p, b->d_results.p);
             (*b->launches) += 3;
             C4B_CUDA(cudaGetLastError());
-            const int round_cap = 4 * (b->max_target / kE2pWin + 1) + 16;
+            const int round_cap = 4 * (b->max_target / b->mdl.win_cols + 1) + 16;
             for (int round = 0;; ++round) {
                 int cnt = 0;
                 C4B_CUDA(cudaMemsetAsync(b->d_count.p, 0, sizeof(int32_t), st));

@@ -54,13 +54,16 @@ struct E2pPair {
 
 // Windowed traceback (find_path on long targets): pass 1 is the score-only fill, which
 // also saves the complete column state {G, N, age (two columns each), D} of every row at
-// the last column of each window of kE2pWin columns.  The traceback then refills ONLY
+// the last column of each window of win_cols columns.  The traceback then refills ONLY
 // the windows the path crosses, from the checkpoint to their left, with records -- and
 // an intron is crossed in one jump, because the checkpoint holds its age (= length so
 // far).  Record memory is 2 MB per lattice instead of 2 B per cell, so every lattice of
 // a batch is resident at once and the refilled area is a few per cent of the lattice.
-constexpr int kE2pWin = 1024;
-constexpr int kE2pWinSteps = kE2pWin + 31;
+// Window width (E2gModel::win_cols, a power of two, per batch): the refill of a round covers at most one
+// window under each cursor, so narrow windows refill fewer cells per exon crossed; the checkpoints (one
+// register state per row per window) are what limits how narrow -- 256 columns when they fit a quarter
+// of the record budget, else 512 / 1024 (e2g_batch_create).
+constexpr int kE2pWinMax = 1024;
 constexpr int kE2pCkWords = 7;
 
 struct E2pWalk {       // traceback cursor of one lattice between rounds
@@ -127,11 +130,11 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
     int c0 = 0, c1 = T, nsweeps = all_sweeps;
     if (WIN) {
         const E2pWalk W = walk[pidx];
-        c0 = (W.j / kE2pWin) * kE2pWin;
+        c0 = W.j & ~(mdl.win_cols - 1);
         c1 = W.j;                                   // the path never moves right or down
         nsweeps = min(all_sweeps, W.i / rows_per_sweep + 1);
     }
-    const uint32_t *ck_in = (WIN && c0 > 0) ? P.ck + (size_t)(c0 / kE2pWin - 1) * all_sweeps * 32 * R * kE2pCkWords
+    const uint32_t *ck_in = (WIN && c0 > 0) ? P.ck + (size_t)(c0 / mdl.win_cols - 1) * all_sweeps * 32 * R * kE2pCkWords
                                             : nullptr;
 
     // first strict maximum of END per strand, tracked on G = M + open
@@ -197,9 +200,12 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         int in_code = kTargetNone, code0 = (c0 >= 1) ? (int)P.t[c0 - 1] : kTargetNone;
         uint32_t in_sp = 0u, sp0 = (c0 >= 2) ? P.sp[c0 - 2] : 0u;
         uint2 top0v = make_uint2(kNeg16x2, kNeg16x2);
-        // hand-off columns fetched ahead of their step: a step of 8 rows is shorter than an L2 round
-        // trip, so the 8-row shape keeps the next PF columns in flight (tq = columns s+1 .. s+PF-1)
-        constexpr int PF = (R == 8) ? 4 : 1;
+        // hand-off columns are fetched PF steps ahead of their use (tq = columns s+1 .. s+PF-1).  A step
+        // of 8 rows is shorter than an L2 round trip, but PF = 4 measured 4 % SLOWER than 1 on the B200
+        // (125 lattices 238 -> 228 GCUPS: the queue moves cost more than the latency they hide; ncu
+        // puts the pipelined shape's loss in exposed branch / fixed-latency stalls of a warp that is
+        // alone on its scheduler, profiles/r02_e2g_small.md), so the depth stays 1
+        constexpr int PF = 1;
         uint2 tq[PF > 1 ? PF - 1 : 1];
         // diagonal input of my first row at column c0: G of the row above at column c0-1
         if (WIN && ck_in && lane > 0)
@@ -216,7 +222,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
         uint4 *tbp = nullptr;
         if (MODE == E2P_FULL_TB) tbp = reinterpret_cast<uint4 *>(P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R);
         if (WIN) tbp = reinterpret_cast<uint4 *>(winbuf + (size_t)blockIdx.x * win_stride +
-                                                 (((size_t)sweep * kE2pWinSteps) * 32 + lane) * R);
+                                                 (((size_t)sweep * (mdl.win_cols + 31)) * 32 + lane) * R);
 
         auto step = [&](const int s, auto PAR) {
             constexpr int p = decltype(PAR)::value, o = p ^ 1;
@@ -225,7 +231,16 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             const uint32_t spw = (lane == 0) ? sp0 : in_sp;  // splice word of column j-2
             if (later_sweep && lane == 0) { topG = top0v.x; topI = top0v.y; }
             if (s + 1 <= T) {
-                code0 = (int)P.t[s];
+                if constexpr (R == 8) {
+                    // the byte as a 32-bit load result: nvcc otherwise masks it (LOP3 & 0xff) right behind the
+                    // load, and a warp that is alone on its scheduler then sits out the whole load latency in
+                    // every step (ncu: 10 % of the small-batch kernel's samples on that one instruction)
+                    unsigned v;
+                    asm("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(P.t + s));
+                    code0 = (int)v;
+                } else {
+                    code0 = (int)P.t[s];
+                }
                 sp0 = (s >= 1) ? P.sp[s - 1] : 0u;   // source column (s+1)-2
                 if (later_sweep) {
                     uint2 nv = make_uint2(kNeg16x2, kNeg16x2);
@@ -333,9 +348,9 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                         vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                     }
                 }
-                if (CK && ((j + 1) & (kE2pWin - 1)) == 0 && j < T) {
+                if (CK && ((j + 1) & (mdl.win_cols - 1)) == 0 && j < T) {
                     // last column of a window: the state a later window refill starts from
-                    uint32_t *c = P.ck + ((size_t)(((j + 1) / kE2pWin - 1) * all_sweeps + sweep) * 32 + lane) * R * kE2pCkWords;
+                    uint32_t *c = P.ck + ((size_t)(((j + 1) / mdl.win_cols - 1) * all_sweeps + sweep) * 32 + lane) * R * kE2pCkWords;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         c[r * kE2pCkWords + 0] = G[p][r]; c[r * kE2pCkWords + 1] = G[o][r];
@@ -549,7 +564,7 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
     const E2gJob J = jobs[pidx];   // jobs are indexed like pairs (J.pair == pidx)
     const E2pPair P = pairs[pidx];
     E2pWalk W = walk[pidx];
-    const int c0 = (W.j / kE2pWin) * kE2pWin;
+    const int c0 = W.j & ~(mdl.win_cols - 1);
     const int all_sweeps = (P.Q + 1 + 32 * R - 1) / (32 * R);
     const uint16_t *rec_base = winbuf + (size_t)slot * win_stride;
     int32_t *out = ops + 2 * J.ops_off;
@@ -564,7 +579,7 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
     };
     auto record = [&](int ci, int cj) -> uint32_t {
         const int w = ci / (32 * R), ln = (ci / R) & 31, r = ci % R;
-        return rec_base[(((size_t)w * kE2pWinSteps + (cj - c0 + ln)) * 32 + ln) * R + r];
+        return rec_base[(((size_t)w * (mdl.win_cols + 31) + (cj - c0 + ln)) * 32 + ln) * R + r];
     };
     while (j >= c0) {
         const uint32_t f = (record(i, j) >> (7 * x)) & 127u;
@@ -590,7 +605,7 @@ __global__ void e2g16_walk_kernel(const E2pPair *__restrict__ pairs, const E2gOu
         // inside an intron at column j in {c0-1, c0-2}: the checkpoint left of this window
         // holds the intron's age there = j - (column the intron was opened from)
         const int w = i / (32 * R), ln = (i / R) & 31, r = i % R;
-        const uint32_t *c = P.ck + (((size_t)(c0 / kE2pWin - 1) * all_sweeps + w) * 32 + ln) * R * kE2pCkWords +
+        const uint32_t *c = P.ck + (((size_t)(c0 / mdl.win_cols - 1) * all_sweeps + w) * 32 + ln) * R * kE2pCkWords +
                             (size_t)r * kE2pCkWords;
         const uint32_t a2 = (j == c0 - 1) ? c[4] : c[5];
         const int rel = (int)(short)((a2 >> (16 * x)) & 0xFFFFu);   // stored relative to the threshold

@@ -55,6 +55,7 @@ struct E2gModel {
     // transition ids by role, forward then reverse strand
     int32_t tNopen[2], tNloop[2], tNclose[2], tMatch[2], tIopen[2], tDopen[2], tIext[2], tDext[2];
     int32_t tI2M[2], tD2M[2], tS2M[2], tM2E[2];
+    int32_t win_cols;   // packed kernel, windowed traceback: columns per checkpoint window (a power of two)
 };
 
 __device__ __forceinline__ int e2g_prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel) {

@@ -81,7 +81,7 @@ c4b_group *exonerate_b200_group(void){
 
 /* EXONERATE_B200_STATS=1: one line on stderr at exit */
 static glong stat_calls = 0, stat_cache_miss = 0;
-static gdouble stat_total = 0, stat_prepare = 0, stat_engine = 0;
+static gdouble stat_total = 0, stat_prepare = 0, stat_engine = 0, stat_prefetch = 0, stat_spans = 0;
 static gdouble now_seconds(void){
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -103,10 +103,12 @@ static void print_viterbi_stats(void){
     fprintf(stderr, "exonerate_b200: Viterbi_calculate calls %ld (%.3f s: prepare %.3f s, "
                     "engine %.3f s), targets flattened %ld, answered from the batch "
                     "prefetch %ld (prefetched but not usable %ld); BSDP region fills prefetched %ld "
-                    "in %ld batch(es), answered from them %ld\n",
+                    "in %ld batch(es), answered from them %ld (terminal / join batches %.3f s, span "
+                    "batches %.3f s)\n",
             stat_calls, stat_total, stat_prepare, stat_engine, stat_cache_miss,
             b200_stat_prefetch_hits, b200_stat_prefetch_misses,
-            b200_stat_score_prefetched, b200_stat_score_batches, b200_stat_score_hits);
+            b200_stat_score_prefetched, b200_stat_score_batches, b200_stat_score_hits,
+            stat_prefetch, stat_spans);
     }
 
 /* Flattened sequences (they are virtual in the reference: revcomp / subseq / translate
@@ -687,6 +689,7 @@ void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer u
     gint nb;
     c4b_batch *batch = NULL;
     c4b_scoring scoring;
+    register gdouble t_begin = now_seconds();
     if((n <= 0) || (viterbi->mode != Viterbi_Mode_FIND_SCORE) || model_is_bound(viterbi->model)
     || viterbi->model->start_state->cell_start_func || viterbi->model->end_state->cell_end_func)
         return;
@@ -746,6 +749,7 @@ void b200_prefetch_scores(Viterbi *viterbi, gint n, Region **regions, gpointer u
     g_free(entry);
     g_free(results);
     g_free(pairs);
+    stat_prefetch += now_seconds() - t_begin;
     return;
     }
 
@@ -782,6 +786,7 @@ void b200_span_scores(gpointer heuristic_span, gint n, Region **src_regions, Reg
     register c4b_span_job *jobs = g_new0(c4b_span_job, n);
     register gint32 **lists = g_new0(gint32*, 4*n);
     register gint i;
+    register gdouble t_begin = now_seconds();
     c4b_scoring scoring;
     pair_cache_fetch(ud, with_splice);
     b200_fill_scoring(ud->mas, &scoring);
@@ -803,6 +808,7 @@ void b200_span_scores(gpointer heuristic_span, gint n, Region **src_regions, Reg
     g_free(jobs);
     b200_stat_score_prefetched += 2*n;
     b200_stat_score_batches++;
+    stat_spans += now_seconds() - t_begin;
     return;
     }
 

@@ -768,7 +768,8 @@ E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257
 
 
 @pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_packed16:full", "e2g_packed16:rows8", "e2g_packed16:rows16",
-                                    "e2g_packed16:rows8:full", "e2g_packed16:rows8:warps1", "e2g_systolic"])
+                                    "e2g_packed16:rows8:full", "e2g_packed16:rows8:warps1", "e2g_packed16:wcols64",
+                                    "e2g_packed16:rows8:wcols1024", "e2g_systolic"])
 def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel):
     """The hand-specialised est2genome kernels -- e2g_packed16 (both strands per
     register, one warp per lattice, 512-row sweeps) and the int32 e2g_systolic
@@ -803,6 +804,8 @@ def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel
             monkeypatch.setenv("C4B_E2G_ROWS", opt_[4:])
         elif opt_.startswith("warps"):
             monkeypatch.setenv("C4B_E2G_WARPS", opt_[5:])
+        elif opt_.startswith("wcols"):   # checkpoint window width of the windowed traceback (default: by memory)
+            monkeypatch.setenv("C4B_E2G_WINDOW_COLS", opt_[5:])
     kernel = kernel.split(":")[0]
 
     def check(idx):

@@ -11,9 +11,14 @@ Reports wall time end to end and, from the binding's counters (EXONERATE_B200_ST
 host-visible time of every Viterbi_calculate / batched region fill.  What is left is the reference's own
 host code (FASTA, seeding, SAR graph, printing), which north_star keeps as-is.
 
+Several processes on ONE GPU time-slice it (every batch's synchronise waits for the other contexts' slices);
+--mps starts the CUDA MPS daemon for the run so their kernels overlap instead.  The model-specialised kernels
+are compiled once into C4B_JIT_CACHE_DIR by an untimed one-query run (the counterpart of the reference's
+bootstrapper step, reported separately).
+
 usage: python tools/config4_bench.py [--queries 1000] [--aa 500] [--target 1000000] [--planted 100]
-                                     [--gpus 1] [--procs 8] [--no-reference]"""
-import argparse, os, re, subprocess, sys, tempfile, time
+                                     [--gpus 1] [--procs 8] [--mps] [--no-reference]"""
+import argparse, os, re, shutil, subprocess, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODON = {"A": "GCT", "R": "CGT", "N": "AAC", "D": "GAC", "C": "TGC", "Q": "CAG", "E": "GAG", "G": "GGT",
@@ -71,8 +76,9 @@ def run_chunks(exe, args, procs, gpus):
     ps = []
     for c in range(procs):
         env = dict(os.environ, EXONERATE_B200_STATS="1")
-        if gpus:
-            env["EXONERATE_B200_DEVICE"] = str(c % gpus)
+        if gpus:   # one visible device per process: the driver initialises only that one
+            env["CUDA_VISIBLE_DEVICES"] = str(c % gpus)
+            env["EXONERATE_B200_DEVICE"] = "0"
         ps.append(subprocess.Popen([exe] + args + ["--querychunkid", str(c + 1), "--querychunktotal", str(procs)],
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
     outs = [p.communicate() for p in ps]
@@ -92,6 +98,8 @@ def main():
     ap.add_argument("--procs", type=int, default=8)
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--mps", action="store_true")
+    ap.add_argument("--no-jit-cache", action="store_true")
     a = ap.parse_args()
     base = os.path.join(ROOT, "gpurun_out")
     tmp = tempfile.mkdtemp(prefix="config4_", dir=base if os.path.isdir(base) else None)
@@ -103,13 +111,43 @@ def main():
               a.queries, a.aa, a.target, 2 * a.queries, a.planted, a.procs, a.gpus, os.cpu_count() or 0))
     ours = os.path.join(ROOT, "integration", "_build", "exonerate_b200")
     ref = os.path.join(ROOT, "oracle", "_ref", "exonerate_c")
-    wall, outs, errs = run_chunks(ours, args, a.procs, a.gpus)
+    if not a.no_jit_cache:
+        os.environ["C4B_JIT_CACHE_DIR"] = os.path.join(tmp, "jit")
+        os.makedirs(os.environ["C4B_JIT_CACHE_DIR"], exist_ok=True)
+        wq = os.path.join(tmp, "warm.fa")
+        with open(qf) as f, open(wq, "w") as g:   # queries with a planted gene reach every derived model
+            lines = f.read().split(">")[1:]
+            g.write("".join(">" + x for x in lines if int(x.split()[0][1:]) < max(1, min(4, a.planted))))
+        t0 = time.perf_counter()
+        subprocess.run([ours, wq] + args[1:], capture_output=True, env=dict(os.environ, EXONERATE_B200_DEVICE="0"))
+        print("kernel specialisation (one untimed run, %d cubins kept in C4B_JIT_CACHE_DIR): %.1f s" % (
+            len(os.listdir(os.environ["C4B_JIT_CACHE_DIR"])), time.perf_counter() - t0))
+    mps = None
+    if a.mps or a.procs > a.gpus:   # several contexts on one GPU: let their kernels overlap
+        ctl = shutil.which("nvidia-cuda-mps-control")
+        if ctl:
+            os.environ["CUDA_MPS_PIPE_DIRECTORY"] = os.path.join(tmp, "mps")
+            os.environ["CUDA_MPS_LOG_DIRECTORY"] = os.path.join(tmp, "mps_log")
+            os.makedirs(os.environ["CUDA_MPS_PIPE_DIRECTORY"], exist_ok=True)
+            os.makedirs(os.environ["CUDA_MPS_LOG_DIRECTORY"], exist_ok=True)
+            mps = subprocess.run([ctl, "-d"], capture_output=True, text=True)
+            print("CUDA MPS daemon: rc %d %s" % (mps.returncode, (mps.stderr or mps.stdout).strip()[:200]))
+            time.sleep(1.0)
+        else:
+            print("CUDA MPS daemon: nvidia-cuda-mps-control not found, processes time-slice the GPU")
+    try:
+        wall, outs, errs = run_chunks(ours, args, a.procs, a.gpus)
+    finally:
+        if mps is not None and mps.returncode == 0:
+            subprocess.run([shutil.which("nvidia-cuda-mps-control")], input="quit\n", capture_output=True, text=True)
+            for k in ("CUDA_MPS_PIPE_DIRECTORY", "CUDA_MPS_LOG_DIRECTORY"):
+                os.environ.pop(k, None)
     n_aln = sum(o.count("vulgar:") for o in outs)
     dp = fills = batches = 0.0
     for e in errs:
         for m in re.finditer(r"Viterbi_calculate calls (\d+) \(([\d.]+) s", e):
             dp += float(m.group(2))
-        for m in re.finditer(r"(\d+) fills in (\d+) batches", e):
+        for m in re.finditer(r"fills prefetched (\d+) in (\d+) batch", e):
             fills += int(m.group(1)); batches += int(m.group(2))
     print("exonerate_b200: wall %.2f s end to end (%.1f comparisons/s), %d alignments; DP-only (host-visible time of all "
           "Viterbi_calculate calls, summed over processes) %.2f s; %d region fills in %d device batches" % (
