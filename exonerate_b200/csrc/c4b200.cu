@@ -1478,10 +1478,14 @@ int c4b_model_specialise(const c4b_model *model, int32_t mode, int32_t cta_threa
         if (L.ok && !(env && atoi(env) == 0)) {
             // (for the strip counts of queries that fill cta_threads rows of the thread-per-row kernel)
             // + the column-window variants: checkpointing score pass / PATH over one window
-            for (int win = 0; win < 3; ++win) {
+            // + the SubOpt form of the whole-lattice pass (blocked cells as per-strip entries): what every
+            // iteration after the first of a `--subopt yes` run (the CLI default) launches
+            for (int v = 0; v < 4; ++v) {
+                const int win = v < 3 ? v : 0;
+                const bool blk = v == 3;
                 if ((win == 1 && mode != GEN_SCORE) || (win == 2 && mode != GEN_PATH)) continue;
                 const std::string src = jit_sys_program_source(*model, mode, mode == GEN_REGION, L,
-                                                               jit_sys_warps(L, cta_threads - 1), win);
+                                                               jit_sys_warps(L, cta_threads - 1), win, blk);
                 if (!jit_compile(src, &cubin, &log)) {
                     set_error("systolic model specialisation failed: " + log);
                     return -1;

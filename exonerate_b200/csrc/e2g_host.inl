@@ -364,7 +364,7 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         const char *env = getenv("C4B_E2G_WINDOWS");
         // window width: the narrowest whose checkpoints fit a quarter of the record budget (a refill
         // covers at most one window per cursor and round: narrow windows refill fewer cells per exon)
-        int wc = 256;
+        int wc = 512;   // (measured at 1000 lattices of 1 kbp x 100 kbp: 256 / 512 / 1024 columns 585 / 595 / 573 GCUPS)
         if (const char *wenv = getenv("C4B_E2G_WINDOW_COLS")) {
             wc = std::max(64, std::min(kE2pWinMax, atoi(wenv)));
             while (wc & (wc - 1)) wc &= wc - 1;

@@ -46,11 +46,19 @@ struct GenericBatch {
     DevBuf<int32_t> d_wbig, d_wck;
     DevBuf<uint8_t> d_wtb;
     int windowed_lattices = 0, window_cols = 0, window_rounds = 0;
+    // SubOpt blocked cells on the systolic kernel (JIT_SYS_BLK): the callers' lists (kept: the entries
+    // are rebuilt per pass, for the full lattices and for the alignment boxes) and their device form
+    bool sys_blk = false;
+    std::vector<int32_t> h_blk_q, h_blk_t;
+    std::vector<size_t> h_blk_at;
+    DevBuf<int2> d_sblk_a, d_sblk_b;
+    DevBuf<int32_t> d_sblk_off_a, d_sblk_off_b;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     double fill_ms = -1;
     ~GenericBatch() {
         d_endm.release(); d_startc.release(); d_top.release();
         d_wpairs.release(); d_wins.release(); d_wwalk.release(); d_wbig.release(); d_wck.release(); d_wtb.release();
+        d_sblk_a.release(); d_sblk_b.release(); d_sblk_off_a.release(); d_sblk_off_b.release();
         d_tables.release(); d_seq.release(); d_ints.release(); d_full.release(); d_box.release();
         d_out_a.release(); d_out_b.release(); d_jobs.release(); d_ring.release(); d_cursor.release();
         d_tb.release(); d_results.release(); d_ops_slots.release(); d_ops_packed.release();
@@ -259,8 +267,22 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     {
         const char *env = getenv("C4B_JIT_SYSTOLIC");
         g->plain = !start_cells && !end_cells && !dev;   // (set here: the descriptors are filled in below)
-        for (int p = 0; p < n; ++p) g->plain = g->plain && pairs[p].n_blocked == 0;
         if (g->use_jit && g->plain && !(env && atoi(env) == 0)) {
+            // SubOpt blocked cells ride along as per-strip {column, row mask} entries (JIT_SYS_BLK)
+            g->h_blk_at.assign((size_t)n + 1, 0);
+            for (int p = 0; p < n; ++p) {
+                g->sys_blk = g->sys_blk || pairs[p].n_blocked > 0;
+                g->h_blk_at[p + 1] = g->h_blk_at[p] + (size_t)pairs[p].n_blocked;
+            }
+            if (g->sys_blk) {
+                g->h_blk_q.resize(g->h_blk_at[n]);
+                g->h_blk_t.resize(g->h_blk_at[n]);
+                for (int p = 0; p < n; ++p)
+                    if (pairs[p].n_blocked) {
+                        memcpy(g->h_blk_q.data() + g->h_blk_at[p], pairs[p].blocked_query_pos, (size_t)pairs[p].n_blocked * 4);
+                        memcpy(g->h_blk_t.data() + g->h_blk_at[p], pairs[p].blocked_target_pos, (size_t)pairs[p].n_blocked * 4);
+                    }
+            }
             const bool pack_start = ((int64_t)maxQ + 1) * ((int64_t)g->max_t + 1) < ((int64_t)1 << 31);
             g->sys_score = jit_sys_layout(m, GEN_SCORE, false);
             g->sys_region = jit_sys_layout(m, GEN_REGION, pack_start);
@@ -316,6 +338,7 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
         G.out_index = p;
         G.tb_rows = 0;
         G.tb_chunk = 0;
+        G.blk = nullptr; G.blk_off = nullptr;
     }
     if ((start_cells || end_cells) && n == 1) {
         const size_t cells = ((size_t)pairs[0].query_length + 1) * ((size_t)pairs[0].target_length + 1) *
@@ -367,6 +390,60 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     return 0;
 }
 
+// SubOpt blocked cells (src/c4/subopt.c:250-338: region coordinates of the DESTINATION cell) of every
+// lattice in `lat` -> per lane strip {column, row mask} sorted by column, for the systolic kernel with R
+// rows per lane; lat[p].blk / blk_off are set (null for a lattice without blocked cells).  A lattice may
+// be a box inside the caller's region: list coordinates are lattice coordinates + (blk_dq, blk_dt).
+static int generic_build_sys_blk(GenericBatch *g, std::vector<GenPair> &lat, int R, DevBuf<int2> &d_blk,
+                                 DevBuf<int32_t> &d_off) {
+    const int n = g->n;
+    std::vector<int2> h_blk;
+    std::vector<int32_t> h_off;
+    std::vector<size_t> seg(n, (size_t)-1);
+    std::vector<std::array<int32_t, 3>> cells;   // (lane strip, column, row in strip)
+    for (int p = 0; p < n; ++p) {
+        GenPair &L = lat[p];
+        L.blk = nullptr; L.blk_off = nullptr;
+        const size_t nb = g->h_blk_at[p + 1] - g->h_blk_at[p];
+        if (!nb || (L.Q == 0 && L.T == 0)) continue;
+        const int32_t *bq = g->h_blk_q.data() + g->h_blk_at[p], *bt = g->h_blk_t.data() + g->h_blk_at[p];
+        const int nstrips = 32 * ((L.Q + 32 * R) / (32 * R));
+        cells.clear();
+        for (size_t k = 0; k < nb; ++k) {
+            const int64_t i = (int64_t)bq[k] - L.blk_dq, j = (int64_t)bt[k] - L.blk_dt;
+            if (i < 0 || i > L.Q || j < 0 || j > L.T) continue;   // never looked at
+            cells.push_back({(int32_t)(i / R), (int32_t)j, (int32_t)(i % R)});
+        }
+        std::sort(cells.begin(), cells.end());
+        seg[p] = h_off.size();
+        size_t c = 0;
+        for (int strip = 0; strip < nstrips; ++strip) {
+            h_off.push_back((int32_t)h_blk.size());
+            while (c < cells.size() && cells[c][0] == strip) {
+                const int j = cells[c][1];
+                uint32_t mask = 0;
+                for (; c < cells.size() && cells[c][0] == strip && cells[c][1] == j; ++c) mask |= 1u << cells[c][2];
+                h_blk.push_back(make_int2(j, (int)mask));
+            }
+        }
+        h_off.push_back((int32_t)h_blk.size());
+        if (h_blk.size() > (size_t)INT32_MAX / 2) {
+            set_error("too many SubOpt blocked cells in one batch");
+            return -1;
+        }
+    }
+    d_blk.release(); d_off.release();
+    if (d_blk.alloc(h_blk.size() + 1) || d_off.alloc(h_off.size() + 1)) return -1;
+    if (!h_blk.empty())
+        C4B_CUDA(cudaMemcpyAsync(d_blk.p, h_blk.data(), h_blk.size() * sizeof(int2), cudaMemcpyHostToDevice, g->stream));
+    if (!h_off.empty())
+        C4B_CUDA(cudaMemcpyAsync(d_off.p, h_off.data(), h_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    C4B_CUDA(cudaStreamSynchronize(g->stream));   // (the host vectors die here)
+    for (int p = 0; p < n; ++p)
+        if (seg[p] != (size_t)-1) { lat[p].blk = d_blk.p; lat[p].blk_off = d_off.p + seg[p]; }
+    return 0;
+}
+
 // win / wins: the column-window variants of the systolic kernel (JIT_SYS_WIN), one GenWin per lattice
 static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count, GenOut *outs, int mode,
                                int win = 0, const GenWin *wins = nullptr) {
@@ -385,7 +462,7 @@ static int generic_launch_fill(GenericBatch *g, const GenPair *pairs, int count,
         for (int p = 0; p < g->n; ++p) { maxQ = std::max(maxQ, g->h_full[p].Q); maxT = std::max(maxT, g->h_full[p].T); }
         const int nsweeps = (maxQ + 32 * SL.R) / (32 * SL.R);
         const int warps = jit_sys_warps(SL, maxQ);
-        if (JitKernel *jk = jit_get_sys(g->tables.model, mode, pack_start, SL, warps, win)) {
+        if (JitKernel *jk = jit_get_sys(g->tables.model, mode, pack_start, SL, warps, win, g->sys_blk)) {
             const size_t nsend = std::max<size_t>(1, SL.sendD.size());
             const size_t stride = nsweeps > 1 ? align_up(2 * ((size_t)maxT + 1) * nsend, 4) : 0;
             if (stride * (size_t)count > g->d_top.n) {
@@ -558,6 +635,14 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     const int n = g->n;
     const int S = g->tables.model.n_states;
     if (!n) return 0;
+    // SubOpt blocked cells in the systolic kernel's form, for the pass over the full lattices
+    if (g->sys_blk) {
+        const SysLayout &first = !g->want_path ? g->sys_score : (g->use_region ? g->sys_region : g->sys_path);
+        if (first.ok) {
+            if (generic_build_sys_blk(g, g->h_full, first.R, g->d_sblk_a, g->d_sblk_off_a)) return -1;
+            C4B_CUDA(cudaMemcpyAsync(g->d_full.p, g->h_full.data(), n * sizeof(GenPair), cudaMemcpyHostToDevice, st));
+        }
+    }
     C4B_CUDA(cudaEventRecord(g->ev_a, st));
     if (!g->want_path) {
         if (generic_launch_fill(g, g->d_full.p, n, g->d_out_a.p, GEN_SCORE)) return -1;
@@ -593,15 +678,18 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
     if (sys_tb)
         for (int p = 0; p < n; ++p) { box[p].tb_rows = g->sys_path.R; box[p].tb_chunk = g->sys_path.chunk; }
     size_t budget = 256ull << 20;  // small jobs (BSDP region fills) never need to ask the driver
+    size_t window_budget = budget; // what the windowed route may use (the real budget, also when testing)
     {
         size_t all = 0;
         for (int p = 0; p < n; ++p) all += align_up(tb_bytes(p), 16);
-        if (all > budget) {
+        const char *env = getenv("C4B_GENERIC_TB_BUDGET_KB");
+        if (all > budget || env) {
             size_t free_b = 0, total_b = 0;
             C4B_CUDA(cudaMemGetInfo(&free_b, &total_b));
             if (free_b > (3ull << 30)) budget = (free_b - (2ull << 30)) / 2;
         }
-        if (const char *env = getenv("C4B_GENERIC_TB_BUDGET_KB"))   // testing: force the chunked / windowed routes
+        window_budget = budget;
+        if (env)   // testing: force the chunked / windowed routes (the budget only decides the route)
             budget = std::max<size_t>(256, (size_t)atoll(env) << 10);
     }
     std::vector<size_t> tb_off(n);
@@ -624,7 +712,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
             // time under the traceback cursor (generic_batch_run_windows).
             if (!(sys_tb && g->plain && g->sys_score.ok)) {
                 set_error("traceback box of pair " + std::to_string(p) + " exceeds the device memory budget "
-                          "(column windows need the systolic specialisation: no SubOpt blocked cells or cell tables)");
+                          "(column windows need the systolic specialisation: a batch of >= 2^31 cells or C4B_GENERIC_JIT=1, no cell tables)");
                 return -1;
             }
             if (begin < p) chunks.push_back({begin, p});
@@ -646,6 +734,8 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         g->d_ops_packed.alloc(2 * (size_t)ops_cursor + 2) || g->d_new_off.alloc((size_t)n + 1))
         return -1;
     for (int p = 0; p < n; ++p) box[p].tb = g->d_tb.p + tb_off[p];
+    // (the boxes moved the lattice origins: their blocked-cell entries are built afresh)
+    if (g->sys_blk && sys_tb && generic_build_sys_blk(g, box, g->sys_path.R, g->d_sblk_b, g->d_sblk_off_b)) return -1;
     C4B_CUDA(cudaMemcpyAsync(g->d_box.p, box.data(), n * sizeof(GenPair), cudaMemcpyHostToDevice, st));
     C4B_CUDA(cudaMemcpyAsync(g->d_jobs.p, jobs.data(), n * sizeof(GenJob), cudaMemcpyHostToDevice, st));
     for (const Chunk &c : chunks) {
@@ -657,8 +747,7 @@ int generic_batch_run(GenericBatch *g, c4b_score threshold) {
         (*g->launches)++;
         C4B_CUDA(cudaGetLastError());
     }
-    // (a budget forced small for testing only decides the route: the windows themselves get real room)
-    if (!big.empty() && generic_batch_run_windows(g, box, big, std::max<size_t>(budget, 256ull << 20), threshold)) return -1;
+    if (!big.empty() && generic_batch_run_windows(g, box, big, window_budget, threshold)) return -1;
     C4B_CUDA(cudaEventRecord(g->ev_b, st));
     apply_threshold_kernel<<<(n + 127) / 128, 128, 0, st>>>(g->d_results.p, n, threshold);
     ops_scan_kernel<<<1, 1024, 0, st>>>(g->d_results.p, n, g->d_new_off.p, g->d_new_off.p + n);

@@ -262,8 +262,9 @@ static int jit_sys_warps(const SysLayout &L, int max_q) {
 
 // win: 0 whole-lattice pass, 1 score pass that leaves column checkpoints, 2 PATH over one column
 // window started from a checkpoint (JIT_SYS_WIN in generic_jit_systolic.cuh)
+// blk: lattices carry SubOpt blocked cells as {column, row mask} entries (JIT_SYS_BLK)
 static std::string jit_sys_program_source(const c4b_model &m, int mode, bool pack_start, const SysLayout &L,
-                                          int warps, int win = 0) {
+                                          int warps, int win = 0, bool blk = false) {
     // the tables of the thread-per-row kernel first (its calc / scope code is shared), then ours
     std::string base = jit_program_source(m, mode, 128, false, pack_start);
     const size_t cut = base.find(kJitSrc_generic_jit_kernel_cuh);
@@ -275,6 +276,7 @@ static std::string jit_sys_program_source(const c4b_model &m, int mode, bool pac
     o << "#define JIT_SYSTOLIC 1\n#define JIT_SYS_R " << L.R << "\n#define JIT_SYS_MINB " << minb
       << "\n#define JIT_SYS_WARPS " << warps << "\n";
     if (win) o << "#define JIT_SYS_WIN " << win << "\n";
+    if (blk) o << "#define JIT_SYS_BLK 1\n";
     o << "namespace c4bjit {\n";
     o << "constexpr int AQ = " << L.AQ << ", VW = " << L.VW << ", NSEND = " << L.sendD.size() << ";\n";
     auto arr = [&](const char *name, const std::vector<int> &v, size_t n) {
@@ -434,10 +436,10 @@ static JitKernel *jit_get(const c4b_model &m, int mode, int threads, bool smem_r
 
 // the systolic specialisation of (model, mode); nullptr = not available (reason on stderr once)
 static JitKernel *jit_get_sys(const c4b_model &m, int mode, bool pack_start, const SysLayout &L, int warps,
-                              int win = 0) {
+                              int win = 0, bool blk = false) {
     static std::mutex mu;
     static std::map<std::string, JitKernel *> cache;
-    const std::string src = jit_sys_program_source(m, mode, pack_start, L, warps, win);
+    const std::string src = jit_sys_program_source(m, mode, pack_start, L, warps, win, blk);
     int device = 0;
     cudaGetDevice(&device);
     const std::string key = std::to_string(device) + ":" + src;

@@ -25,8 +25,13 @@
 // strict maximum in (target outer, query inner) order (:778-791).  calc_score<> and the
 // scope tests are the ones of generic_jit_kernel.cuh (included in front of this file).
 //
-// Not handled here (the host keeps generic_jit_kernel.cuh for them): SubOpt blocked
-// cells, START / END cell tables of BSDP's derived models.
+// SubOpt blocked cells (JIT_SYS_BLK; src/c4/subopt.h:77-80, viterbi.c:701-704: a MATCH-labelled
+// transition is skipped at a blocked DESTINATION cell): the host turns a lattice's list into {column,
+// row mask} entries per lane strip, sorted by column (GenPair::blk / blk_off); a lane walks its strip's
+// entries with one cursor and the mask of the current column gates the match transitions of its rows --
+// the scheme of affine_fill_kernel's BLK variant.
+// Not handled here (the host keeps generic_jit_kernel.cuh for them): START / END cell tables of
+// BSDP's derived models.
 //
 // JIT_SYS_WIN -- a PATH record for lattices whose whole record would not fit device memory (the
 // reference recurses through checkpoint rows for the same reason, src/c4/optimal.c:183-345,
@@ -49,10 +54,14 @@
 #ifndef JIT_SYS_WIN
 #define JIT_SYS_WIN 0
 #endif
+#ifndef JIT_SYS_BLK
+#define JIT_SYS_BLK 0
+#endif
 
 namespace c4bjit {
 
 constexpr int kWinMode = JIT_SYS_WIN;
+constexpr bool kBlk = JIT_SYS_BLK != 0;
 static_assert(kWinMode == 0 || (kWinMode == 1 && JIT_MODE == GEN_SCORE) || (kWinMode == 2 && JIT_MODE == GEN_PATH),
               "checkpoints are written by the score pass and consumed by the PATH pass");
 constexpr int SR = JIT_SYS_R;
@@ -94,6 +103,7 @@ struct SysCtx {
     bool has_up;       // some lattice row lies above my strip
     int j;             // my column this step
     bool colok;        // 0 <= j <= T
+    unsigned bmask;    // JIT_SYS_BLK: rows of my strip whose cell in this column is SubOpt-blocked
 };
 
 template <int K, int ROW>
@@ -164,7 +174,9 @@ __device__ __forceinline__ void sys_transitions(const SysCtx &Z, const int (&V)[
         // "first valid transition assigns, later ones replace only if strictly greater"
         // (viterbi.c:766-775) as a max: an unset state holds UNSET, below every candidate, and an
         // invalid transition offers UNSET.  (t is never UNSET: scores stay above 2 * LOWV.)
-        const int teff = tested ? (valid ? t : UNSET) : t;
+        int teff = tested ? (valid ? t : UNSET) : t;
+        if constexpr (kBlk && kTrLabel[K] == C4B_LABEL_MATCH)   // viterbi.c:701-704
+            teff = ((Z.bmask >> ROW) & 1u) ? UNSET : teff;
         constexpr bool carries = (JIT_MODE == GEN_PATH) || kRegion || (kNW[out] > 1);
         if constexpr (carries) {
             const bool take = teff > c.v[out][0];
@@ -286,6 +298,7 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
     Z.X.blk_q = nullptr; Z.X.blk_t = nullptr;
     Z.X.n_blocked = 0; Z.X.blk_dq = 0; Z.X.blk_dt = 0;
     Z.X.q_start = P.q_start; Z.X.t_start = P.t_start; Z.X.Q = P.Q; Z.X.T = P.T;
+    Z.bmask = 0u;
     const int Q = P.Q, T = P.T;
     constexpr int rows_per_sweep = 32 * SR;
     const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
@@ -363,6 +376,23 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             load_top(c0);
             if (lane == 0) place_up(upin);
         }
+        // SubOpt: cursor into my strip's blocked columns
+        int blk_cur = 0, blk_end = 0, blk_next = 0x7fffffff;
+        if constexpr (kBlk) {
+            if (P.blk_off != nullptr) {
+                blk_cur = P.blk_off[sweep * 32 + lane];
+                blk_end = P.blk_off[sweep * 32 + lane + 1];
+                if constexpr (kWinMode == 2) {   // first entry at or after the window's first column
+                    int lo = blk_cur, hi = blk_end;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (P.blk[mid].x < c0) lo = mid + 1; else hi = mid;
+                    }
+                    blk_cur = lo;
+                }
+                if (blk_cur < blk_end) blk_next = P.blk[blk_cur].x;
+            }
+        }
         unsigned char *tbp = nullptr;
         constexpr int TBCH = TB_CHUNK;   // traceback bytes per lane per step
         if constexpr (JIT_MODE == GEN_PATH)
@@ -385,6 +415,14 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             uint32_t tbw[TBCH / 4];
 #pragma unroll
             for (int k = 0; k < TBCH / 4; ++k) tbw[k] = 0u;
+            if constexpr (kBlk) {
+                Z.bmask = 0u;
+                if (j == blk_next) {
+                    Z.bmask = (unsigned)P.blk[blk_cur].y;
+                    ++blk_cur;
+                    blk_next = (blk_cur < blk_end) ? P.blk[blk_cur].x : 0x7fffffff;
+                }
+            }
             if (live) sys_rows<0>(Z, V, bst, tbw);
 
             if constexpr (JIT_MODE == GEN_PATH) {

@@ -26,6 +26,12 @@ struct GenPair {
     // PATH record layout: 0 = by anti-diagonal, one byte per state (GEN_TB_CELL); r > 0 = the systolic
     // kernel's skewed bit-packed layout with r rows per lane (GEN_TBS_CHUNK)
     int32_t tb_rows, tb_chunk;
+    // SubOpt blocked cells for the systolic kernel (JIT_SYS_BLK): per lane strip (strip * 32 + lane) the
+    // blocked MATCH destination cells of THIS lattice as {column, row mask} sorted by column; blk_off has
+    // one entry per lane strip + 1.  Null when the lattice has none (or on the other kernels, which
+    // search blk_q / blk_t instead).
+    const int2 *blk;
+    const int32_t *blk_off;
 };
 
 struct GenOut {

@@ -118,8 +118,8 @@ def test_every_scope_combination_specialises():
 def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
     """With C4B_JIT_CACHE_DIR set, c4b_model_specialise leaves every variant's cubin in the cache
     (thread-per-row kernel: ring in shared memory / L2, and both start-slot layouts for FIND_REGION;
-    plus the systolic kernel of the mode and its column-window variant: the checkpointing score
-    pass for FIND_SCORE, the one-window pass for FIND_PATH) -- the device analogue of running the reference's
+    plus the systolic kernel of the mode, its SubOpt form and its column-window variant: the
+    checkpointing score pass for FIND_SCORE, the one-window pass for FIND_PATH) -- the device analogue of running the reference's
     bootstrapper once -- and a second call rewrites the same files (names are a hash of the
     generated source)."""
     from exonerate_b200 import load_library
@@ -129,13 +129,13 @@ def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
     model, _ = host_model("coding2coding")
     assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
     first = sorted(os.listdir(tmp_path))
-    assert len(first) == 4 and all(f.startswith("c4bjit_") and f.endswith(".cubin") for f in first)
+    assert len(first) == 5 and all(f.startswith("c4bjit_") and f.endswith(".cubin") for f in first)
     assert lib.c4b_model_specialise(C.byref(model), 2, 128, None) == 0
-    assert len(os.listdir(tmp_path)) == 4 + 5
+    assert len(os.listdir(tmp_path)) == 5 + 6
     assert lib.c4b_model_specialise(C.byref(model), 0, 128, None) == 0
-    assert len(os.listdir(tmp_path)) == 9
+    assert len(os.listdir(tmp_path)) == 11
     assert lib.c4b_model_specialise(C.byref(model), 1, 128, None) == 0
-    assert len(os.listdir(tmp_path)) == 9 + 4
+    assert len(os.listdir(tmp_path)) == 11 + 5
     monkeypatch.setenv("C4B_JIT_SYSTOLIC", "0")   # the thread-per-row variants alone
     other = tmp_path / "no_systolic"
     other.mkdir()

@@ -597,6 +597,64 @@ def _subopt_series(opt, model, scoring, q, t, rounds, region=None):
     return done
 
 
+@pytest.mark.parametrize("route", ["box", "direct", "windows"])
+def test_subopt_on_the_systolic_table_driven_kernel(eng, params, scoring, monkeypatch, route):
+    """SubOpt blocked cells on the systolic specialisation (JIT_SYS_BLK: the callers' lists as {column, row
+    mask} entries per lane strip, rebuilt for the alignment boxes): the --subopt series against the oracle for
+    protein2genome, coding2coding, est2genome and affine:local forced onto the table-driven path -- REGION +
+    box, one PATH pass over the full lattice, and column windows; several strips, a sub-region with its own
+    list.  (CLI default --subopt yes: every iteration after the first carries such a list.)"""
+    from exonerate_b200 import Batch, Optimal, PairSet
+    from exonerate_b200.models import splice_arrays
+    monkeypatch.setenv("C4B_FORCE_GENERIC", "1")
+    monkeypatch.setenv("C4B_GENERIC_JIT", "1")
+    if route == "windows":
+        monkeypatch.setenv("C4B_GENERIC_TB_BUDGET_KB", "1")
+        monkeypatch.setenv("C4B_GENERIC_WINDOW_COLS", "64")
+    else:
+        monkeypatch.setenv("C4B_GENERIC_DIRECT_PATH", "1" if route == "direct" else "0")
+    for name in ("protein2genome", "coding2coding", "est2genome", "affine_local_dna"):
+        model, _ = helpers.load_model(name, params)
+        if name == "protein2genome":
+            q, t = bench_p2g_pair(8100, 150, 3000)
+        elif name == "est2genome":
+            q, t = helpers.gene_pair(8101, 400, 4000, n_exons=3, rate=0.02)
+        else:
+            q, t = helpers.dna_pair(8102, 420 if name == "coding2coding" else 700, 2500)
+        sp = splice_arrays(t) if name in ("protein2genome", "est2genome") else None
+
+        class Opt:   # _subopt_series builds its own PairSet: give it the splice arrays
+            def find_path(self, pairs):
+                ps = PairSet([q], [t], splice=[sp] if sp is not None else None, blocked=[self.pts], regions=self.regions)
+                if len(self.pts) and not self.checked:
+                    b = Batch(eng, model, scoring, ps, want_path=True)
+                    b.run()
+                    assert b.kernel_name == "generic_jit_systolic", name
+                    b.close()
+                    self.checked = True
+                return Optimal(eng, model, scoring).find_path(ps)
+        o = Opt()
+        o.checked = False
+        done = []
+        for region in (None, (len(q) // 8, len(t) // 10, len(q) - len(q) // 8 - 3, len(t) - len(t) // 10 - 7)):
+            done = []
+            for _ in range(3):
+                pts = blocked_points(model, done)
+                if region:
+                    pts = [(a - region[0], b - region[1]) for a, b in pts
+                           if 0 <= a - region[0] <= region[2] and 0 <= b - region[1] <= region[3]]
+                o.pts, o.regions = pts, [region] if region else None
+                want = helpers.oracle_viterbi(model, scoring, helpers.PairBuf(q, t, splice=sp, blocked=pts, region=region),
+                                              abi.MODE_FIND_PATH, max_ops=len(q) + len(t) + 8)
+                got = o.find_path(None)[0]
+                assert got["score"] == want["score"] and got["region"] == want["region"], (name, route, region)
+                assert got["ops"] == want["ops"], (name, route, region)
+                if not want["ops"]:
+                    break
+                done.append(want)
+        assert o.checked and len(done) >= 1, name
+
+
 @pytest.mark.parametrize("name,shape", [("affine_local_dna", (300, 900)), ("affine_local_dna", (1000, 20000)),
                                         ("affine_local_dna", (1500, 1700)), ("affine_global_dna", (120, 150)),
                                         ("affine_bestfit_dna", (90, 400)), ("affine_overlap_dna", (200, 260)),
