@@ -90,6 +90,43 @@ static unsigned host_threads() {
     return hw;
 }
 
+// Grow-only pinned staging memory of this host thread (pinning is far too slow to
+// repeat per batch); `busy` is the last copy that read it.
+struct PinnedScratch {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t busy = nullptr;
+    uint8_t *get(size_t bytes) {
+        if (busy) cudaEventSynchronize(busy);
+        if (cap < bytes) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            if (cudaMallocHost(&p, bytes + bytes / 8) != cudaSuccess) return nullptr;
+            cap = bytes + bytes / 8;
+        }
+        return p;
+    }
+    void mark(cudaStream_t st) {
+        if (!busy) cudaEventCreateWithFlags(&busy, cudaEventDisableTiming);
+        cudaEventRecord(busy, st);
+    }
+};
+
+template <typename F>
+static void parallel_for(int n, F f) {
+    const unsigned nt = std::max(1u, std::min<unsigned>(host_threads(), (unsigned)n));
+    if (nt <= 1) {
+        for (int k = 0; k < n; ++k) f(k);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t)
+        th.emplace_back([&, t] { for (int k = (int)t; k < n; k += (int)nt) f(k); });
+    for (int k = 0; k < n; k += (int)nt) f(k);
+    for (auto &x : th) x.join();
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;

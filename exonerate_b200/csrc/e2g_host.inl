@@ -79,43 +79,7 @@ static bool analyze_est2genome(const c4b_model &m, const c4b_scoring &sc, E2gMod
     return true;
 }
 
-// Grow-only pinned staging memory of this host thread (pinning is far too slow to
-// repeat per batch); `busy` is the last copy that read it.
-struct PinnedScratch {
-    uint8_t *p = nullptr;
-    size_t cap = 0;
-    cudaEvent_t busy = nullptr;
-    uint8_t *get(size_t bytes) {
-        if (busy) cudaEventSynchronize(busy);
-        if (cap < bytes) {
-            if (p) cudaFreeHost(p);
-            p = nullptr;
-            cap = 0;
-            if (cudaMallocHost(&p, bytes + bytes / 8) != cudaSuccess) return nullptr;
-            cap = bytes + bytes / 8;
-        }
-        return p;
-    }
-    void mark(cudaStream_t st) {
-        if (!busy) cudaEventCreateWithFlags(&busy, cudaEventDisableTiming);
-        cudaEventRecord(busy, st);
-    }
-};
 static thread_local PinnedScratch tl_e2g_scratch;
-
-template <typename F>
-static void parallel_for(int n, F f) {
-    const unsigned nt = std::max(1u, std::min<unsigned>(host_threads(), (unsigned)n));
-    if (nt <= 1) {
-        for (int k = 0; k < n; ++k) f(k);
-        return;
-    }
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t)
-        th.emplace_back([&, t] { for (int k = (int)t; k < n; k += (int)nt) f(k); });
-    for (int k = 0; k < n; k += (int)nt) f(k);
-    for (auto &x : th) x.join();
-}
 
 struct E2gBatch {
     cudaStream_t stream = nullptr;
@@ -286,6 +250,11 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         std::vector<std::pair<SeqKey, size_t>> qlist(qmap.begin(), qmap.end()), tlist(tmap.begin(), tmap.end());
         std::map<SeqKey, int> owner;  // target slice -> a pair that carries its splice arrays
         for (int p = 0; p < n; ++p) owner[SeqKey(pairs[p].target + pairs[p].target_start, pairs[p].target_length)] = p;
+        // targets in slot order: a run of them is one contiguous range of the staging block, so the DMA
+        // of a packed run goes out while the host threads pack the next one
+        std::sort(tlist.begin(), tlist.end(), [](const std::pair<SeqKey, size_t> &a, const std::pair<SeqKey, size_t> &c) {
+            return a.second < c.second;
+        });
         std::vector<const c4b_pair *> towner(tlist.size());
         for (size_t k = 0; k < tlist.size(); ++k) towner[k] = &pairs[owner[tlist[k].first]];
         for (auto &kv : qlist) {
@@ -294,12 +263,27 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
             memset(hseq + kv.second + len, qfill, slot - len);
         }
         memset(hseq + qbytes + tbytes, tfill, 64);
+        memset(hsp + tbytes, 0, 16 * sizeof(uint32_t));
+        if (b->d_seq.alloc(qbytes + tbytes + 64) || b->d_sp.alloc(tbytes + 16)) {
+            delete b;
+            return -1;
+        }
+        bool copied = true;
+        if (qbytes) copied = cudaMemcpyAsync(b->d_seq.p, hseq, qbytes, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        copied = copied && cudaMemcpyAsync(b->d_seq.p + qbytes + tbytes, hseq + qbytes + tbytes, 64,
+                                           cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        copied = copied && cudaMemcpyAsync(b->d_sp.p + tbytes, hsp + tbytes, 16 * sizeof(uint32_t),
+                                           cudaMemcpyHostToDevice, stream) == cudaSuccess;
         std::atomic<bool> out_of_range(false);
         // the 16-bit value bound assumes an intron never GAINS score: intron_open + 5'ss + 3'ss <= 0
         // on either strand (true for the default --intronpenalty -30; with e.g. 0, introns chain
         // without consuming query and the score grows with their number: halfword adds would wrap)
         std::atomic<int> max_gain(INT32_MIN);
-        parallel_for((int)tlist.size(), [&](int k) {
+        const int n_t = (int)tlist.size(), run = std::max(1, (n_t + 7) / 8);
+        for (int first = 0; first < n_t; first += run) {
+        const int last = std::min(n_t, first + run);
+        parallel_for(last - first, [&](int kk) {
+            const int k = first + kk;
             const size_t off = tlist[k].second, len = (size_t)tlist[k].first.second, slot = align_up(len, 16) + 16;
             memcpy(hseq + qbytes + off, tlist[k].first.first, len);
             memset(hseq + qbytes + off + len, tfill, slot - len);
@@ -324,6 +308,19 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
                 while (g > cur && !max_gain.compare_exchange_weak(cur, g)) {}
             }
         });
+        const size_t lo = tlist[first].second;
+        const size_t hi = tlist[last - 1].second + align_up((size_t)tlist[last - 1].first.second, 16) + 16;
+        copied = copied && cudaMemcpyAsync(b->d_seq.p + qbytes + lo, hseq + qbytes + lo, hi - lo, cudaMemcpyHostToDevice,
+                                           stream) == cudaSuccess;
+        copied = copied && cudaMemcpyAsync(b->d_sp.p + lo, hsp + lo, (hi - lo) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                           stream) == cudaSuccess;
+        }
+        tl_e2g_scratch.mark(stream);   // (a retry on another kernel below reuses the scratch)
+        if (!copied) {
+            set_error("staging the est2genome batch failed");
+            delete b;
+            return -1;
+        }
         if (out_of_range) {
             delete b;
             return 1;
@@ -415,8 +412,6 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         b->chunks.push_back({0, n});
     }
     int rc = 0;
-    rc |= b->d_seq.alloc(qbytes + tbytes + 64);
-    rc |= b->d_sp.alloc(tbytes + 16);
     rc |= b->d_lut.alloc(512);
     rc |= b->d_xtab.alloc(25);
     rc |= b->d_bad.alloc(1);
@@ -481,9 +476,7 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         }
         ok &= cudaMemcpyAsync(b->d_pairs16.p, hp16.data(), n * sizeof(E2pPair), cudaMemcpyHostToDevice, stream) == cudaSuccess;
     }
-    ok &= cudaMemcpyAsync(b->d_seq.p, hseq, qbytes + tbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    ok &= cudaMemcpyAsync(b->d_sp.p, hsp, (tbytes + 16) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
-    tl_e2g_scratch.mark(stream);
+    tl_e2g_scratch.mark(stream);   // (sequences and splice words went out run by run while they were packed)
     ok &= cudaMemcpyAsync(b->d_lut.p, lut.data(), 512, cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(b->d_xtab.p, xt.data(), 25 * sizeof(uint2), cudaMemcpyHostToDevice, stream) == cudaSuccess;
     ok &= cudaMemsetAsync(b->d_bad.p, 0, sizeof(int), stream) == cudaSuccess;
@@ -510,20 +503,28 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
     return 0;
 }
 
-// the packed fill kernel for a batch's rows per lane / warps per lattice
+// the packed fill kernel for a batch's rows per lane / warps per lattice (the whole-lattice record pass
+// E2P_FULL_TB is always one warp per lattice: its pipelined forms are not instantiated)
+template <int MODE, int ROWS>
+static void e2p_launch_rows(int warps, int grid, cudaStream_t st, const E2pPair *pairs, E2gOut *outs,
+                            const E2gModel &mdl, const uint2 *xtab, const int32_t *active, const E2pWalk *walk,
+                            uint16_t *winbuf, size_t win_stride) {
+    if constexpr (MODE != E2P_FULL_TB) {
+        if (warps > 1) {
+            e2g_fill16_kernel<MODE, true, ROWS><<<grid, 32 * warps, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf,
+                                                                            win_stride);
+            return;
+        }
+    }
+    e2g_fill16_kernel<MODE, false, ROWS><<<grid, 32, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+}
+
 template <int MODE>
 static void e2p_launch(int rows, int warps, int grid, cudaStream_t st, const E2pPair *pairs, E2gOut *outs,
                        const E2gModel &mdl, const uint2 *xtab, const int32_t *active, const E2pWalk *walk,
                        uint16_t *winbuf, size_t win_stride) {
-    const int threads = 32 * warps;
-    if constexpr (MODE == E2P_FULL_TB) warps = 1;   // (the whole-lattice record pass is one warp per lattice)
-    if (rows == 8) {
-        if (warps > 1) e2g_fill16_kernel<MODE, true, 8><<<grid, threads, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
-        else e2g_fill16_kernel<MODE, false, 8><<<grid, 32, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
-    } else {
-        if (warps > 1) e2g_fill16_kernel<MODE, true, kE2pR><<<grid, threads, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
-        else e2g_fill16_kernel<MODE, false, kE2pR><<<grid, 32, 0, st>>>(pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
-    }
+    if (rows == 8) e2p_launch_rows<MODE, 8>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+    else e2p_launch_rows<MODE, kE2pR>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
 }
 
 static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {

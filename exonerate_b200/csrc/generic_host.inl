@@ -68,6 +68,8 @@ struct GenericBatch {
     }
 };
 
+static thread_local PinnedScratch tl_gen_scratch;
+
 static bool model_needs_splice(const c4b_model &m) {
     for (int k = 0; k < m.n_calcs; ++k)
         if (m.calcs[k].kind == C4B_CALC_SPLICE_PRE || m.calcs[k].kind == C4B_CALC_SPLICE_POST) return true;
@@ -363,14 +365,39 @@ int generic_batch_create(cudaStream_t stream, int64_t *launch_counter, const c4b
     }
     bool staged = true;
     if (direct) {
-        staged = cudaMemsetAsync(g->d_seq.p, 0, sbytes + 64, stream) == cudaSuccess &&
-                 cudaMemsetAsync(g->d_ints.p, 0, (ints + 4) * sizeof(int32_t), stream) == cudaSuccess;
-        for (auto &kv : smap)
-            staged = staged && cudaMemcpyAsync(g->d_seq.p + kv.second, kv.first.first, (size_t)kv.first.second,
-                                               cudaMemcpyHostToDevice, stream) == cudaSuccess;
-        for (auto &kv : imap)
-            staged = staged && cudaMemcpyAsync(g->d_ints.p + kv.second, kv.first.first, kv.first.second * sizeof(int32_t),
-                                               cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        // gathered by the host threads into this thread's pinned scratch, then two DMAs: thousands of
+        // copies from pageable caller buffers (one per sequence and splice array: ~15 us each, staged by the
+        // driver one after the other) were a third of an end-to-end protein2genome step
+        const size_t seq_bytes = align_up(sbytes + 64, 256);
+        uint8_t *scratch = tl_gen_scratch.get(seq_bytes + (ints + 4) * sizeof(int32_t));
+        if (!scratch) {
+            set_error("pinned staging allocation failed");
+            delete g;
+            return -1;
+        }
+        int32_t *hints = reinterpret_cast<int32_t *>(scratch + seq_bytes);
+        typedef std::pair<std::pair<const uint8_t *, int>, size_t> SeqItem;
+        typedef std::pair<std::pair<const int32_t *, size_t>, size_t> IntItem;
+        std::vector<SeqItem> slist(smap.begin(), smap.end());
+        std::vector<IntItem> ilist(imap.begin(), imap.end());
+        parallel_for((int)(slist.size() + ilist.size()), [&](int k) {
+            if (k < (int)slist.size()) {   // slot = len + 4 rounded up to 16: the tail reads as zero
+                const size_t len = (size_t)slist[k].first.second, slot = align_up(len + 4, 16);
+                memcpy(scratch + slist[k].second, slist[k].first.first, len);
+                memset(scratch + slist[k].second + len, 0, slot - len);
+            } else {
+                const IntItem &it = ilist[k - slist.size()];
+                const size_t len = it.first.second, slot = align_up(len, 4);
+                memcpy(hints + it.second, it.first.first, len * sizeof(int32_t));
+                memset(hints + it.second + len, 0, (slot - len) * sizeof(int32_t));
+            }
+        });
+        memset(scratch + sbytes, 0, 64);
+        memset(hints + ints, 0, 4 * sizeof(int32_t));
+        staged = cudaMemcpyAsync(g->d_seq.p, scratch, sbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+                 cudaMemcpyAsync(g->d_ints.p, hints, (ints + 4) * sizeof(int32_t), cudaMemcpyHostToDevice, stream) ==
+                     cudaSuccess;
+        tl_gen_scratch.mark(stream);
     } else {
         staged = cudaMemcpyAsync(g->d_seq.p, hs.data(), sbytes + 64, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
                  cudaMemcpyAsync(g->d_ints.p, hi.data(), (ints + 4) * 4, cudaMemcpyHostToDevice, stream) == cudaSuccess;
