@@ -203,7 +203,10 @@ static int e2g_batch_create(cudaStream_t stream, int64_t *launch_counter, const 
         // (measured, 1 kbp x 100 kbp find_path GCUPS, 16 rows one warp -> 8 rows four warps: 125 lattices
         // 107 -> 183+, 250 210 -> 315+, 500 413 -> 447+, 1000 559 -> 540: profiles/r02_e2g_small.md)
         b->rows16 = ((int64_t)n * sweeps16 <= 1400 && sweeps8 > sweeps16) ? 8 : kE2pR;
-        if (const char *env = getenv("C4B_E2G_ROWS")) b->rows16 = (atoi(env) == 8) ? 8 : kE2pR;
+        // (4 rows on eight warps: 125 lattices find_score 280 -> 259 but find_path 196 -> 214 -- the window
+        // refills like the extra warps; equal at 250 lattices)
+        if (b->rows16 == 8 && want_path && (int64_t)n * sweeps16 <= 300 && (maxQ + 1 + 127) / 128 > sweeps8) b->rows16 = 4;
+        if (const char *env = getenv("C4B_E2G_ROWS")) b->rows16 = (atoi(env) == 8) ? 8 : (atoi(env) == 4 ? 4 : kE2pR);
     }
     const int RW = b->rows16;
     // ---- staging: region slices of query / target, packed splice words ---------------
@@ -523,7 +526,8 @@ template <int MODE>
 static void e2p_launch(int rows, int warps, int grid, cudaStream_t st, const E2pPair *pairs, E2gOut *outs,
                        const E2gModel &mdl, const uint2 *xtab, const int32_t *active, const E2pWalk *walk,
                        uint16_t *winbuf, size_t win_stride) {
-    if (rows == 8) e2p_launch_rows<MODE, 8>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+    if (rows == 4) e2p_launch_rows<MODE, 4>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
+    else if (rows == 8) e2p_launch_rows<MODE, 8>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
     else e2p_launch_rows<MODE, kE2pR>(warps, grid, st, pairs, outs, mdl, xtab, active, walk, winbuf, win_stride);
 }
 
@@ -535,10 +539,11 @@ static int e2g_batch_run(E2gBatch *b, c4b_score threshold) {
     // otherwise: see e2g_packed16.cuh for the measurements; C4B_E2G_WARPS / C4B_E2G_ROWS override)
     const int RW = b->rows16;
     const int sweeps16 = (b->max_query + 1 + 32 * RW - 1) / (32 * RW);
-    int warps16 = (RW == 8) ? std::max(1, std::min(kE2pMaxWarps, sweeps16)) : 1;
-    if (const char *env = getenv("C4B_E2G_WARPS")) warps16 = std::max(1, std::min(std::min(kE2pMaxWarps, sweeps16), atoi(env)));
+    const int max_warps = RW == 4 ? 8 : 4;   // (the kernels' launch bounds)
+    int warps16 = (RW <= 8) ? std::max(1, std::min(max_warps, sweeps16)) : 1;
+    if (const char *env = getenv("C4B_E2G_WARPS")) warps16 = std::max(1, std::min(std::min(max_warps, sweeps16), atoi(env)));
     // window refills: the sweeps of a refill are independent (hand-off rows kept from pass 1)
-    const int warps_win = (RW == 8) ? warps16 : 1;
+    const int warps_win = (RW <= 8) ? warps16 : 1;
     C4B_CUDA(cudaEventRecord(b->ev_a, st));
     if (b->packed) {
         if (!b->want_path) {

@@ -82,24 +82,24 @@ enum { E2P_SCORE = 0, E2P_FULL_TB = 1, E2P_SCORE_CK = 2, E2P_WINDOW_TB = 3 };
 // counter in shared memory, published every 8 columns; the scheme of affine_fill_kernel) -- so a
 // 1 kbp cDNA occupies two schedulers instead of one: small batches (a shard of the 1k-pair batch on
 // 8 GPUs is 125 lattices) leave most of the GPU idle with one warp per lattice.
-constexpr int kE2pMaxWarps = 4;
+constexpr int kE2pMaxWarps = 8;
 
 // PIPE = false is the one-warp kernel exactly as before (W folds to 1 at compile time): measured on
 // the B200, the pipelined form wins only while the batch leaves warp slots empty (find_path GCUPS,
 // one warp -> pipelined: 125 lattices 86 -> 118, 500 336 -> 350, 1000 487 -> 369, 4000 597 -> 452).
 //
-// RR = rows per lane.  16 (512-row sweeps) is the loaded-GPU shape.  8 (256-row sweeps) exists for
-// SMALL batches: a 1 kbp cDNA becomes four sweeps on four pipelined warps, and -- because the sweeps
+// RR = rows per lane.  16 (512-row sweeps) is the loaded-GPU shape.  8 / 4 (256- / 128-row sweeps) exist for
+// SMALL batches: a 1 kbp cDNA becomes four / eight sweeps on as many pipelined warps, and -- because the sweeps
 // of a window refill read the hand-off rows pass 1 left in L2 -- the window refills of a lattice run
 // on independent warps as well.  All record / checkpoint layouts are [..][lane][RR]: one batch uses
 // one RR throughout (E2gBatch::rows16).
 template <int MODE, bool PIPE = false, int RR = kE2pR>
-__global__ void __launch_bounds__(PIPE ? 32 * kE2pMaxWarps : 32)
+__global__ void __launch_bounds__(PIPE ? 32 * (RR == 4 ? 8 : 4) : 32)
 e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, const E2gModel mdl,
                   const uint2 *__restrict__ score_table, const int32_t *__restrict__ active,
                   const E2pWalk *__restrict__ walk, uint16_t *__restrict__ winbuf, size_t win_stride) {
     constexpr int R = RR;
-    static_assert(R == 8 || R == 16, "records are stored as uint4 groups of 8 rows");
+    static_assert(R == 4 || R == 8 || R == 16, "records are stored as uint4 groups of 8 rows (uint2 for 4)");
     constexpr bool TB = (MODE == E2P_FULL_TB || MODE == E2P_WINDOW_TB);
     constexpr bool WIN = (MODE == E2P_WINDOW_TB);
     constexpr bool CK = (MODE == E2P_SCORE_CK);
@@ -219,10 +219,9 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                                           : make_uint2(kNeg16x2, kNeg16x2);
             if (c0 >= 1 && lane == 0) topGprev = top_in[c0 - 1].x;
         }
-        uint4 *tbp = nullptr;
-        if (MODE == E2P_FULL_TB) tbp = reinterpret_cast<uint4 *>(P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R);
-        if (WIN) tbp = reinterpret_cast<uint4 *>(winbuf + (size_t)blockIdx.x * win_stride +
-                                                 (((size_t)sweep * (mdl.win_cols + 31)) * 32 + lane) * R);
+        uint16_t *tbp = nullptr;   // this lane's R halfwords of the current step
+        if (MODE == E2P_FULL_TB) tbp = P.tb + (((size_t)sweep * nsteps) * 32 + lane) * R;
+        if (WIN) tbp = winbuf + (size_t)blockIdx.x * win_stride + (((size_t)sweep * (mdl.win_cols + 31)) * 32 + lane) * R;
 
         auto step = [&](const int s, auto PAR) {
             constexpr int p = decltype(PAR)::value, o = p ^ 1;
@@ -231,7 +230,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
             const uint32_t spw = (lane == 0) ? sp0 : in_sp;  // splice word of column j-2
             if (later_sweep && lane == 0) { topG = top0v.x; topI = top0v.y; }
             if (s + 1 <= T) {
-                if constexpr (R == 8) {
+                if constexpr (R <= 8) {
                     // the byte as a 32-bit load result: nvcc otherwise masks it (LOP3 & 0xff) right behind the
                     // load, and a warp that is alone on its scheduler then sits out the whole load latency in
                     // every step (ncu: 10 % of the small-batch kernel's samples on that one instruction)
@@ -336,10 +335,15 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 botI = upI;
                 topGprev = topG;
                 if (TB) {
+                    if constexpr (R >= 8) {
 #pragma unroll
-                    for (int g = 0; g < R / 8; ++g)
-                        tbp[g] = make_uint4(rec[8 * g] | (rec[8 * g + 1] << 16), rec[8 * g + 2] | (rec[8 * g + 3] << 16),
-                                            rec[8 * g + 4] | (rec[8 * g + 5] << 16), rec[8 * g + 6] | (rec[8 * g + 7] << 16));
+                        for (int g = 0; g < R / 8; ++g)
+                            reinterpret_cast<uint4 *>(tbp)[g] =
+                                make_uint4(rec[8 * g] | (rec[8 * g + 1] << 16), rec[8 * g + 2] | (rec[8 * g + 3] << 16),
+                                           rec[8 * g + 4] | (rec[8 * g + 5] << 16), rec[8 * g + 6] | (rec[8 * g + 7] << 16));
+                    } else {
+                        *reinterpret_cast<uint2 *>(tbp) = make_uint2(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16));
+                    }
                 }
                 if (write_top) {
                     top_out[j] = make_uint2(botG, botI);
@@ -387,7 +391,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 }
             }
             if (first_row_lane) { topG = kNeg16x2; topI = kNeg16x2; }
-            if (TB) tbp += (R / 8) * 32;
+            if (TB) tbp += 32 * R;
             const uint32_t nG = __shfl_up_sync(0xffffffffu, botG, 1);
             const uint32_t nI = __shfl_up_sync(0xffffffffu, botI, 1);
             const int nC = __shfl_up_sync(0xffffffffu, code, 1);

@@ -827,6 +827,7 @@ E2G_SHAPES = [(1, 1), (1, 50), (30, 2), (20, 120), (255, 1500), (256, 900), (257
 
 @pytest.mark.parametrize("kernel", ["e2g_packed16", "e2g_packed16:full", "e2g_packed16:rows8", "e2g_packed16:rows16",
                                     "e2g_packed16:rows8:full", "e2g_packed16:rows8:warps1", "e2g_packed16:wcols64",
+                                    "e2g_packed16:rows4", "e2g_packed16:rows4:full", "e2g_packed16:rows4:warps3",
                                     "e2g_packed16:rows8:wcols1024", "e2g_systolic"])
 def test_est2genome_systolic_vs_oracle(eng, params, scoring, monkeypatch, kernel):
     """The hand-specialised est2genome kernels -- e2g_packed16 (both strands per
@@ -921,7 +922,7 @@ def test_est2genome_intron_gain_leaves_the_packed_kernel(eng, params, scoring):
     b.close()
 
 
-@pytest.mark.parametrize("rows", ["8", "16"])
+@pytest.mark.parametrize("rows", ["4", "8", "16"])
 def test_est2genome_windowed_traceback_long_introns(eng, params, scoring, monkeypatch, rows):
     """(rows per lane 8: the small-batch shape, window refills on independent warps.)
     find_path on long targets: pass 1 saves column checkpoints every 1024 columns, the

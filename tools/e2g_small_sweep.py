@@ -38,7 +38,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
 
 sizes = [int(a) for a in sys.argv[1:]] or [125, 250, 500, 1000]
 for n in sizes:
-    for rows, warps in ((None, None), ("16", "1"), ("16", "2"), ("8", "4"), ("8", "2"), ("8", "1")):
+    for rows, warps in ((None, None), ("16", "1"), ("8", "4"), ("4", "8"), ("4", "4")):
         env = dict(os.environ)
         for key, val in (("C4B_E2G_ROWS", rows), ("C4B_E2G_WARPS", warps)):
             if val: env[key] = val
