@@ -424,6 +424,7 @@ __device__ __forceinline__ void affine_fill16u_body(const AffPair *__restrict__ 
     const uint32_t openK = (uint32_t)(open * 0x10001), extDK = (uint32_t)(mdl.extD * 0x10001);
     const uint32_t extI2 = pack16(mdl.extI);  // per-half operand of VIADDMNMX.U16x2 (wraps per half)
     const int nsteps = T + 1 + 31;
+    const int pub_mask = (T >= 4096) ? 15 : 3;   // hand-off rows are published every 16 (4) columns
     const int rows_per_sweep = 32 * R;
     const int nsweeps = MULTI ? (max(QA, QB) + 1 + rows_per_sweep - 1) / rows_per_sweep : 1;
 
@@ -557,7 +558,7 @@ __device__ __forceinline__ void affine_fill16u_body(const AffPair *__restrict__ 
                 pend_j = j;
                 if (write_top) {
                     top_out[j] = make_uint2(botM, botI);
-                    if (MULTI && W > 1) {
+                    if (MULTI && W > 1 && ((j & pub_mask) == pub_mask || j == T)) {   // (groups: see affine_fill_kernel)
                         __threadfence_block();
                         vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                     }

@@ -118,6 +118,7 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
     const int rows_per_sweep = 32 * R;
     const int nsweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     const int nsteps = T + 1 + 31;
+    const int pub_mask = (T >= 4096) ? 15 : 3;   // hand-off rows are published every 16 (4) columns
 
     // first strict maximum of END in (target outer, query inner) order
     // (viterbi.c:778-791) == lexicographic max of (score, -j, -i); tracked on
@@ -332,8 +333,10 @@ affine_fill_kernel(const AffPair *__restrict__ pairs, AffOut *__restrict__ outs,
                 }
                 if (write_top) {
                     top_out[j] = make_int2(botM, botI);
-                    if (W > 1) {
-                        __threadfence_block();  // the row is written before the counter moves
+                    // published in groups of columns: the fence waits for the hand-off stores and costs a good
+                    // part of a step; a consumer trails by the lane skew + one group (short targets: small groups)
+                    if (W > 1 && ((j & pub_mask) == pub_mask || j == T)) {
+                        __threadfence_block();  // the rows are written before the counter moves
                         vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                     }
                 }

@@ -456,7 +456,8 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
         default: rc = go(affine_fill16u_multi_kernel<32>); break;
         }
     } else if (b->p16_unsigned) {
-        switch (b->R) {
+        switch (b->R16) {   // (4: queries of up to 127 symbols -- with 8 rows per lane half the lanes would hold padding)
+        case 4: rc = go(affine_fill16u_kernel<4>); break;
         case 8: rc = go(affine_fill16u_kernel<8>); break;
         case 16: rc = go(affine_fill16u_kernel<16>); break;
         default: rc = go(affine_fill16u_kernel<32>); break;
@@ -749,6 +750,8 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                 if ((r == 8 || r == 16 || r == 32) && r <= b->R) b->R16 = r;
             }
         }
+        // short queries: 4 rows per lane (the one-sweep score pass only; the traceback keeps R)
+        if (b->p16_unsigned && b->n16 > 0 && b->R16 == 8 && maxQ16 + 1 <= 128 && !getenv("C4B_P16_R")) b->R16 = 4;
         b->fill_warps16 = std::max(1, std::min(kAffMaxWarps, (maxQ16 + 1 + 32 * b->R16 - 1) / (32 * b->R16)));
         b->p16_multi = b->p16_unsigned && maxQ16 + 1 > 32 * b->R16;
         // fold: one warp per lattice instead of one per PAIR while the batch is small enough that
@@ -1181,7 +1184,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                  "%d int32 (%d rows/lane, %d warp(s) per lattice%s); traceback: %d banded (%s), %d single-pass (%s); "
                  "%d with SubOpt blocked cells",
                  n, b->n16, b->p16_fold ? "offset-binary, folded: one lattice per warp" : b->p16_unsigned ? "offset-binary" : "signed",
-                 b->p16_fold ? b->R / 2 : b->p16_multi ? b->R16 : b->R,
+                 b->p16_fold ? b->R / 2 : b->R16,
                  b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R, b->fill_warps,
                  b->any_blocked ? ", BLK variant" : "", b->want_path ? ns : 0, b->tb16_band ? "packed 16-bit" : "int32",
                  b->want_path ? nd : 0, b->tb16_direct ? "packed 16-bit" : "int32", nblk);

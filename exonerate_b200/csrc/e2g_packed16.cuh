@@ -126,6 +126,9 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
     const int rows_per_sweep = 32 * R;
     const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     const int nsteps = T + 1 + 31;
+    // the fence of a publish waits for the hand-off stores: groups of 32 columns (8 on short targets,
+    // where the pipeline's run-in counts)
+    const int pub_mask = (T >= 4096) ? 31 : 7;
     // column range [c0, c1] and sweeps of this launch
     int c0 = 0, c1 = T, nsweeps = all_sweeps;
     if (WIN) {
@@ -347,7 +350,7 @@ e2g_fill16_kernel(const E2pPair *__restrict__ pairs, E2gOut *__restrict__ outs, 
                 }
                 if (write_top) {
                     top_out[j] = make_uint2(botG, botI);
-                    if (PIPE && W > 1 && ((j & 7) == 7 || j == T)) {
+                    if (PIPE && W > 1 && ((j & pub_mask) == pub_mask || j == T)) {
                         __threadfence_block();   // the rows are written before the counter moves
                         vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                     }

@@ -304,6 +304,7 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
     const int all_sweeps = (Q + 1 + rows_per_sweep - 1) / rows_per_sweep;
     int nsweeps = all_sweeps;
     const int nsteps = T + 1 + 31;
+    const int pub_mask = (T >= 4096) ? 31 : 7;
     // column window [c0, c1] of this launch (the whole lattice unless JIT_SYS_WIN == 2)
     int c0 = 0, c1 = T, wcols = 0;
     int32_t *ck = nullptr;
@@ -439,9 +440,9 @@ c4b_jit_sys(const c4b::GenPair *__restrict__ pairs, int n_pairs, c4b::GenOut *__
             if (write_top && Z.colok && inwin) {
 #pragma unroll
                 for (int w = 0; w < NSEND; ++w) top_out[(size_t)j * NSEND + w] = send[w];
-                // publish in groups of 8 columns: the fence costs far more than the stores, and the
-                // consumer runs at least 32 columns behind anyway
-                if (W > 1 && ((j & 7) == 7 || j == c1)) {
+                // publish in groups of 32 (8 on short lattices) columns: the fence costs far more than the
+                // stores, and the consumer runs at least 32 columns behind anyway
+                if (W > 1 && ((j & pub_mask) == pub_mask || j == c1)) {
                     __threadfence_block();   // the rows are written before the counter moves
                     vprog[warp] = (long long)sweep * (T + 1) + j + 1;
                 }
