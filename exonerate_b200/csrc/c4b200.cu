@@ -311,6 +311,7 @@ struct c4b_batch {
     // small batches: ONE lattice per warp, the two register halves on the two halves of its rows
     // (affine_fill16f_kernel), so that a batch of n lattices is n warps instead of n / 2
     bool p16_fold = false;
+    int Rf = 16;                // folded score pass: rows per lane and half
     bool tb16_band = false, tb16_direct = false;  // traceback pass on affine_fill16tb_kernel
     std::vector<int> score_list, direct_list;  // original pair indices, cost-descending
     std::vector<Chunk> band_chunks, direct_chunks;
@@ -448,7 +449,14 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
             kernel<<<count, 32, 0, s>>>(pairs, outs, count, b->aff, b->d_score_table.p);
             return 0;
         };
-        rc = (b->R == 32) ? gof(affine_fill16f_kernel<16>) : gof(affine_fill16f_kernel<8>);
+        switch (b->Rf) {   // rows per lane and half, fitted to the longest query (even numbers)
+        case 6: rc = gof(affine_fill16f_kernel<6>); break;
+        case 8: rc = gof(affine_fill16f_kernel<8>); break;
+        case 10: rc = gof(affine_fill16f_kernel<10>); break;
+        case 12: rc = gof(affine_fill16f_kernel<12>); break;
+        case 14: rc = gof(affine_fill16f_kernel<14>); break;
+        default: rc = gof(affine_fill16f_kernel<16>); break;
+        }
     } else if (b->p16_unsigned && b->p16_multi) {   // some query is longer than one sweep of 32 R16 rows
         switch (b->R16) {
         case 8: rc = go(affine_fill16u_multi_kernel<8>); break;
@@ -456,10 +464,15 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
         default: rc = go(affine_fill16u_multi_kernel<32>); break;
         }
     } else if (b->p16_unsigned) {
-        switch (b->R16) {   // (4: queries of up to 127 symbols -- with 8 rows per lane half the lanes would hold padding)
+        switch (b->R16) {   // rows per lane fitted to the longest query (multiples of 4)
         case 4: rc = go(affine_fill16u_kernel<4>); break;
+        case 6: rc = go(affine_fill16u_kernel<6>); break;
         case 8: rc = go(affine_fill16u_kernel<8>); break;
+        case 12: rc = go(affine_fill16u_kernel<12>); break;
         case 16: rc = go(affine_fill16u_kernel<16>); break;
+        case 20: rc = go(affine_fill16u_kernel<20>); break;
+        case 24: rc = go(affine_fill16u_kernel<24>); break;
+        case 28: rc = go(affine_fill16u_kernel<28>); break;
         default: rc = go(affine_fill16u_kernel<32>); break;
         }
     } else {
@@ -750,8 +763,15 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                 if ((r == 8 || r == 16 || r == 32) && r <= b->R) b->R16 = r;
             }
         }
-        // short queries: 4 rows per lane (the one-sweep score pass only; the traceback keeps R)
-        if (b->p16_unsigned && b->n16 > 0 && b->R16 == 8 && maxQ16 + 1 <= 128 && !getenv("C4B_P16_R")) b->R16 = 4;
+        // The one-sweep score pass takes the smallest multiple of 4 rows per lane that holds the longest
+        // packed query (the traceback keeps R in {8, 16, 32}: its records are groups of 8 rows): a
+        // 600-symbol query runs 20 rows per lane instead of 32 -- rows beyond the query are padding that
+        // is computed like any other row.
+        if (b->p16_unsigned && b->n16 > 0 && !getenv("C4B_P16_R") && maxQ16 + 1 <= 32 * b->R16)
+        {
+            const int need = (maxQ16 + 1 + 31) / 32;
+            b->R16 = need <= 8 ? std::max(4, (need + 1) / 2 * 2) : (need + 3) / 4 * 4;   // 4, 6, 8, 12, 16, .. 32
+        }
         b->fill_warps16 = std::max(1, std::min(kAffMaxWarps, (maxQ16 + 1 + 32 * b->R16 - 1) / (32 * b->R16)));
         b->p16_multi = b->p16_unsigned && maxQ16 + 1 > 32 * b->R16;
         // fold: one warp per lattice instead of one per PAIR while the batch is small enough that
@@ -765,6 +785,9 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                       (int64_t)(b->n16 + 1) / 2 * 10 < (int64_t)e->sm_count * 12 * (b->R == 32 ? 24 : 10);
         if (const char *env = getenv("C4B_P16_FOLD"))
             b->p16_fold = b->p16_unsigned && !b->p16_multi && b->R >= 16 && b->n16 > 0 && atoi(env) != 0;
+        // the folded kernel's halves hold 32 Rf rows each: the smallest even Rf that takes the longest query
+        b->Rf = std::min(b->R / 2, std::max(6, ((maxQ16 + 1 + 63) / 64 + 1) / 2 * 2));
+        if (getenv("C4B_P16_R")) b->Rf = b->R / 2;
         // packed traceback pass (tagged unsigned halfwords, 8 * value + 1024): whole lists only
         const char *tv = getenv("C4B_AFFINE_TB16");
         const bool tb_ok = model_ok && nonneg && b->aff.openI <= b->aff.extI && b->aff.openD >= -24 &&
@@ -1184,7 +1207,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                  "%d int32 (%d rows/lane, %d warp(s) per lattice%s); traceback: %d banded (%s), %d single-pass (%s); "
                  "%d with SubOpt blocked cells",
                  n, b->n16, b->p16_fold ? "offset-binary, folded: one lattice per warp" : b->p16_unsigned ? "offset-binary" : "signed",
-                 b->p16_fold ? b->R / 2 : b->R16,
+                 b->p16_fold ? b->Rf : b->R16,
                  b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R, b->fill_warps,
                  b->any_blocked ? ", BLK variant" : "", b->want_path ? ns : 0, b->tb16_band ? "packed 16-bit" : "int32",
                  b->want_path ? nd : 0, b->tb16_direct ? "packed 16-bit" : "int32", nblk);

@@ -311,7 +311,9 @@ def test_packed16_score_pass(eng, params, scoring, monkeypatch):
     model, _ = helpers.load_model("affine_local_dna", params)
     opt = Optimal(eng, model, scoring)
     rng = random.Random(77)
-    for maxq in (30, 250, 500, 1023):
+    # (the one-sweep score pass runs the smallest multiple of 4 rows per lane that holds the longest query:
+    # 4 .. 32 rows, one instantiation each)
+    for maxq in (30, 100, 128, 250, 370, 500, 630, 760, 890, 1023):
         qs, ts = [], []
         shapes = [(maxq, 700), (1, 1), (maxq, 40), (max(1, maxq // 3), 2500), (max(1, maxq - 1), 33)]
         shapes += [(rng.randrange(1, maxq + 1), rng.randrange(1, 1800)) for _ in range(8)]
@@ -331,6 +333,20 @@ def test_packed16_score_pass(eng, params, scoring, monkeypatch):
         paths32 = opt.find_path(pairs)
         monkeypatch.delenv("C4B_AFFINE_PACK16")
         assert scores == scores32 and paths == paths32
+        monkeypatch.setenv("C4B_P16_FOLD", "0")         # two lattices per warp also where a small batch would fold
+        from exonerate_b200 import Batch
+        b = Batch(eng, model, scoring, pairs, want_path=False)
+        need = (maxq + 1 + 31) // 32
+        assert "%d rows/lane" % (max(4, (need + 1) // 2 * 2) if need <= 8 else (need + 3) // 4 * 4) in b.description, b.description
+        b.close()
+        assert opt.find_score(pairs) == scores and opt.find_path(pairs) == paths
+        monkeypatch.setenv("C4B_P16_FOLD", "1")         # ... and one lattice per warp, folded (queries of > 255 symbols)
+        b = Batch(eng, model, scoring, pairs, want_path=False)
+        if maxq > 255:
+            assert "folded" in b.description and "%d rows/lane" % max(6, ((maxq + 1 + 63) // 64 + 1) // 2 * 2) in b.description
+        b.close()
+        assert opt.find_score(pairs) == scores and opt.find_path(pairs) == paths
+        monkeypatch.delenv("C4B_P16_FOLD")
         monkeypatch.setenv("C4B_P16_VARIANT", "s")      # signed-halfword variant of the packed kernel
         assert opt.find_score(pairs) == scores and opt.find_path(pairs) == paths
         monkeypatch.delenv("C4B_P16_VARIANT")

@@ -34,10 +34,9 @@ say("| query | target | pairs%s | find_score GCUPS | find_path GCUPS | vs 20 B/c
 say("|---:|---:|---:|---:|---:|---:|")
 only = os.environ.get("SWEEP_ONLY")   # e.g. "2048x1000000,4096x1000000": a subset of the grid (tuning aid)
 only = {tuple(int(v) for v in item.split("x")) for item in only.split(",")} if only else None
-for qlen in (128, 512, 1000, 2048, 4096, 16384):
-    for tlen in (1000, 10000, 100000, 1000000):
-        if only and (qlen, tlen) not in only:
-            continue
+grid = sorted(only) if only else [(q, t) for q in (128, 512, 1000, 2048, 4096, 16384) for t in (1000, 10000, 100000, 1000000)]
+for qlen, tlen in grid:
+    if True:
         n = int(max(2, world, min(40000, budget // (qlen * tlen))))
         if n * (qlen + tlen) > 3e9:
             n = int(3e9 // (qlen + tlen))
