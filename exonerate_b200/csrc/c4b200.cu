@@ -461,6 +461,9 @@ int launch_fill16(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, c
         switch (b->R16) {
         case 8: rc = go(affine_fill16u_multi_kernel<8>); break;
         case 16: rc = go(affine_fill16u_multi_kernel<16>); break;
+        case 20: rc = go(affine_fill16u_multi_kernel<20>); break;
+        case 24: rc = go(affine_fill16u_multi_kernel<24>); break;
+        case 28: rc = go(affine_fill16u_multi_kernel<28>); break;
         default: rc = go(affine_fill16u_multi_kernel<32>); break;
         }
     } else if (b->p16_unsigned) {
@@ -771,6 +774,13 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         {
             const int need = (maxQ16 + 1 + 31) / 32;
             b->R16 = need <= 8 ? std::max(4, (need + 1) / 2 * 2) : (need + 3) / 4 * 4;   // 4, 6, 8, 12, 16, .. 32
+        }
+        // ... and a query of several sweeps keeps its sweep count but takes the fewest rows per lane that
+        // still cover it (2049 rows: 3 sweeps of 24 rows per lane instead of 32)
+        if (b->p16_unsigned && b->n16 > 0 && !getenv("C4B_P16_R") && b->R16 == 32 && maxQ16 + 1 > 32 * 32) {
+            const int sweeps = (maxQ16 + 1 + 1023) / 1024;
+            const int need = (maxQ16 + 1 + 32 * sweeps - 1) / (32 * sweeps);
+            b->R16 = std::min(32, std::max(16, (need + 3) / 4 * 4));
         }
         b->fill_warps16 = std::max(1, std::min(kAffMaxWarps, (maxQ16 + 1 + 32 * b->R16 - 1) / (32 * b->R16)));
         b->p16_multi = b->p16_unsigned && maxQ16 + 1 > 32 * b->R16;

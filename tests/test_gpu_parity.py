@@ -432,6 +432,25 @@ def test_long_queries_pipelined_sweeps(eng, params, scoring, monkeypatch):
             want = oracle_path(model, scoring, qs[k], ts[k])
             assert got["8"][0][k] == want["score"], (name, k)
             assert got["8"][1][k]["region"] == want["region"] and got["8"][1][k]["ops"] == want["ops"], (name, k)
+    # the packed multi-sweep score pass keeps the sweep count and takes the fewest rows per lane that cover
+    # the longest query: 20 / 24 / 28 rows per lane (1201 / 2050 / 2601 lattice rows)
+    from exonerate_b200 import Batch
+    model, _ = helpers.load_model("affine_local_dna", params)
+    opt = Optimal(eng, model, scoring)
+    for maxq, rows in ((1200, 20), (2049, 24), (2600, 28)):
+        qs, ts = [], []
+        for k, (ql, tl) in enumerate([(maxq, 1500), (maxq // 2, 900), (maxq - 7, 2100)]):
+            q, t = helpers.dna_pair(62000 + maxq + k, ql, tl, rate=0.1)
+            qs.append(q)
+            ts.append(t)
+        pairs = PairSet(qs, ts)
+        b = Batch(eng, model, scoring, pairs, want_path=False)
+        assert "%d rows/lane" % rows in b.description, b.description
+        b.close()
+        scores, paths = opt.find_score(pairs), opt.find_path(pairs)
+        for k in range(pairs.n):
+            want = oracle_path(model, scoring, qs[k], ts[k])
+            assert scores[k] == want["score"] and paths[k]["region"] == want["region"] and paths[k]["ops"] == want["ops"], (maxq, k)
 
 
 def test_mixed_alphabets_share_a_batch(eng, params, scoring):
