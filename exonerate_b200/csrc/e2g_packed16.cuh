@@ -61,8 +61,8 @@ struct E2pPair {
 // a batch is resident at once and the refilled area is a few per cent of the lattice.
 // Window width (E2gModel::win_cols, a power of two, per batch): the refill of a round covers at most one
 // window under each cursor, so narrow windows refill fewer cells per exon crossed; the checkpoints (one
-// register state per row per window) are what limits how narrow -- 256 columns when they fit a quarter
-// of the record budget, else 512 / 1024 (e2g_batch_create).
+// register state per row per window) are what limits how narrow -- 512 columns when they fit a quarter
+// of the record budget, else 1024 (e2g_batch_create; measured 256 / 512 / 1024: 585 / 595 / 573 GCUPS).
 constexpr int kE2pWinMax = 1024;
 constexpr int kE2pCkWords = 7;
 
@@ -76,17 +76,17 @@ enum { E2P_SCORE = 0, E2P_FULL_TB = 1, E2P_SCORE_CK = 2, E2P_WINDOW_TB = 3 };
 // MODE: E2P_SCORE (END cell only), E2P_FULL_TB (records for the whole lattice),
 // E2P_SCORE_CK (END cell + column checkpoints), E2P_WINDOW_TB (records for one window
 // of one lattice, started from a checkpoint; active = list of lattices, walk = cursors).
-// blockDim.x = 32 W (W <= kE2pMaxWarps; W = 1 for E2P_WINDOW_TB): the W warps of a CTA take the
-// sweeps (strips of 512 rows) of ONE lattice round-robin and run them as a pipeline -- sweep k+1
-// follows sweep k at >= 32 columns, reading the hand-off row the moment it is published (monotone
-// counter in shared memory, published every 8 columns; the scheme of affine_fill_kernel) -- so a
-// 1 kbp cDNA occupies two schedulers instead of one: small batches (a shard of the 1k-pair batch on
-// 8 GPUs is 125 lattices) leave most of the GPU idle with one warp per lattice.
+// blockDim.x = 32 W (W <= kE2pMaxWarps): the W warps of a CTA take the sweeps (strips of 32 RR rows)
+// of ONE lattice round-robin and run them as a pipeline -- sweep k+1 follows sweep k at >= 32 columns,
+// reading the hand-off row the moment it is published (monotone counter in shared memory, published in
+// groups of columns; the scheme of affine_fill_kernel) -- so a 1 kbp cDNA occupies several schedulers
+// instead of one: small batches (a shard of the 1k-pair batch on 8 GPUs is 125 lattices) leave most of
+// the GPU idle with one warp per lattice.
 constexpr int kE2pMaxWarps = 8;
 
-// PIPE = false is the one-warp kernel exactly as before (W folds to 1 at compile time): measured on
-// the B200, the pipelined form wins only while the batch leaves warp slots empty (find_path GCUPS,
-// one warp -> pipelined: 125 lattices 86 -> 118, 500 336 -> 350, 1000 487 -> 369, 4000 597 -> 452).
+// PIPE = false is the one-warp kernel (W folds to 1 at compile time): measured on the B200, the pipelined
+// forms win only while the batch leaves warp slots empty (profiles/r02_e2g_small.md; 16 rows on two warps,
+// the first pipelined shape, lost from 500 lattices up and is no longer chosen by the host).
 //
 // RR = rows per lane.  16 (512-row sweeps) is the loaded-GPU shape.  8 / 4 (256- / 128-row sweeps) exist for
 // SMALL batches: a 1 kbp cDNA becomes four / eight sweeps on as many pipelined warps, and -- because the sweeps
