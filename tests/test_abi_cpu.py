@@ -115,6 +115,21 @@ def test_every_scope_combination_specialises():
             assert rc == 0, (start, end, mode, lib.c4b_last_error().decode()[:1500])
 
 
+def test_path_pass_variants_compile_for_the_spliced_models():
+    """FIND_PATH of the systolic specialisation has three forms -- whole lattice, one column window started
+    from a checkpoint (JIT_SYS_WIN), SubOpt blocked cells as per-strip entries (JIT_SYS_BLK) -- and all of
+    them must compile for the models with shadows, codon calcs and 2- / 3-column advances (protein2genome,
+    coding2coding); est2genome's are compiled by the scope test above.  nvcc never sees this source."""
+    from exonerate_b200 import load_library
+    from exonerate_b200.models import host_model
+    lib = load_library()
+    for name, protein in (("protein2genome", True), ("coding2coding", False)):
+        model, _ = host_model(name, query_is_protein=protein)
+        size = C.c_int64(0)
+        assert lib.c4b_model_specialise(C.byref(model), 1, 128, C.byref(size)) == 0, lib.c4b_last_error().decode()[:800]
+        assert size.value > 10000
+
+
 def test_specialise_fills_the_disk_cache(tmp_path, monkeypatch):
     """With C4B_JIT_CACHE_DIR set, c4b_model_specialise leaves every variant's cubin in the cache
     (thread-per-row kernel: ring in shared memory / L2, and both start-slot layouts for FIND_REGION;
