@@ -301,6 +301,7 @@ struct c4b_batch {
     AffModel aff;
     int R = 32, score_mode = SCORE_PRMT, max_sub = 0, gap_min = 0;
     int fill_warps = 1;  // warps per lattice of the int32 fill (concurrent sweeps of long queries)
+    int R32s = 32;       // rows per lane of the int32 SCORE pass (fitted to the longest query; the recording pass keeps R)
     int n16 = 0;  // leading lattices of score_list that take the packed 16-bit score pass
     bool p16_unsigned = false;  // offset-binary variant (affine_fill16u_kernel) is applicable
     bool p16_multi = false;     // some packed lattice needs more than one sweep
@@ -407,6 +408,17 @@ void launch_fill_r(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, 
     }
 }
 
+// score pass only, no SubOpt lists: the rows-per-lane values that exist for fitting a query (R32s)
+template <int R>
+void launch_fill_score(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, cudaStream_t s) {
+    const int threads = 32 * b->fill_warps;
+    const bool any = (b->aff.end_scope == C4B_SCOPE_ANYWHERE), prmt = (b->score_mode == SCORE_PRMT);
+    if (any && prmt) affine_fill_kernel<R, false, END_ANYWHERE, SCORE_PRMT><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+    else if (any) affine_fill_kernel<R, false, END_ANYWHERE, SCORE_SMEM><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+    else if (prmt) affine_fill_kernel<R, false, END_RESTRICTED, SCORE_PRMT><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+    else affine_fill_kernel<R, false, END_RESTRICTED, SCORE_SMEM><<<count, threads, 0, s>>>(pairs, outs, b->aff, b->d_score_table.p);
+}
+
 // timed = bracket the launch with an event pair on its stream (c4b_batch_last_fill_ms)
 int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, bool tb, cudaStream_t s,
                 bool timed) {
@@ -422,9 +434,13 @@ int launch_fill(c4b_batch *b, const AffPair *pairs, AffOut *outs, int count, boo
         ev = &b->fill_events[b->fill_events_used++];
         C4B_CUDA(cudaEventRecord(ev->a, s));
     }
-    switch (b->R) {
+    switch (tb ? b->R : b->R32s) {
     case 8: launch_fill_r<8>(b, pairs, outs, count, tb, s); break;
+    case 12: launch_fill_score<12>(b, pairs, outs, count, s); break;
     case 16: launch_fill_r<16>(b, pairs, outs, count, tb, s); break;
+    case 20: launch_fill_score<20>(b, pairs, outs, count, s); break;
+    case 24: launch_fill_score<24>(b, pairs, outs, count, s); break;
+    case 28: launch_fill_score<28>(b, pairs, outs, count, s); break;
     default: launch_fill_r<32>(b, pairs, outs, count, tb, s); break;
     }
     C4B_CUDA(cudaGetLastError());
@@ -646,6 +662,13 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
         const int r = atoi(env);
         if (r == 8 || r == 16 || r == 32) b->R = r;
     }
+    // The int32 score pass (proteins, N-rich queries, global / bestfit / overlap scopes) takes the smallest
+    // multiple of 4 rows per lane that holds the longest query in ONE sweep, like the packed score pass
+    // (a 300-residue protein: 12 rows per lane instead of 16); the recording pass keeps R (records are
+    // groups of 8 rows), and so do batches with SubOpt lists (their entries are laid out per R rows).
+    b->R32s = b->R;
+    if (!b->any_blocked && !getenv("C4B_AFFINE_R") && maxQ + 1 <= 32 * b->R)
+        b->R32s = std::min(b->R, std::max(8, ((maxQ + 1 + 31) / 32 + 3) / 4 * 4));
     b->fill_warps = std::max(1, std::min(kAffMaxWarps, (maxQ + 1 + 32 * b->R - 1) / (32 * b->R)));
     if (const char *env = getenv("C4B_AFFINE_WARPS")) b->fill_warps = std::max(1, std::min(kAffMaxWarps, atoi(env)));
 
@@ -1218,7 +1241,7 @@ int affine_create(c4b_batch *b, const c4b_pair *pairs, int match_kind) {
                  "%d with SubOpt blocked cells",
                  n, b->n16, b->p16_fold ? "offset-binary, folded: one lattice per warp" : b->p16_unsigned ? "offset-binary" : "signed",
                  b->p16_fold ? b->Rf : b->R16,
-                 b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R, b->fill_warps,
+                 b->p16_multi ? b->fill_warps16 : 1, ns - b->n16, b->R32s, b->fill_warps,
                  b->any_blocked ? ", BLK variant" : "", b->want_path ? ns : 0, b->tb16_band ? "packed 16-bit" : "int32",
                  b->want_path ? nd : 0, b->tb16_direct ? "packed 16-bit" : "int32", nblk);
         b->description = buf;
